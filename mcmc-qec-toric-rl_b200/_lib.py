@@ -1,0 +1,205 @@
+"""ctypes binding of libqecmc.so (include/qecmc.h).  There is no CPU fallback: if the
+library is missing or no CUDA device is present, every entry point raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "csrc", "libqecmc.so")
+
+TORIC, PLANAR, ROTATED, XZZX = 0, 1, 2, 3
+GEOM_NAMES = {"toric": TORIC, "planar": PLANAR, "rotated": ROTATED, "xzzx": XZZX}
+POW_NUMBA, POW_LIBM = 0, 1
+
+
+class QecmcError(RuntimeError):
+    pass
+
+
+class DevInfo(C.Structure):
+    _fields_ = [("device", C.c_int32), ("sm_count", C.c_int32), ("sm_clock_khz", C.c_int32), ("cc_major", C.c_int32),
+                ("cc_minor", C.c_int32), ("total_mem", C.c_int64), ("free_mem", C.c_int64), ("name", C.c_char * 64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("metropolis_steps", C.c_int64), ("accepted", C.c_int64), ("samples", C.c_int64),
+                ("distinct", C.c_int64), ("table_slots", C.c_int64), ("waves", C.c_int64),
+                ("kernel_launches", C.c_int64), ("chain_kernel_ms", C.c_double), ("total_ms", C.c_double)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class ChainCfg(C.Structure):
+    _fields_ = [("geom_chain", C.c_int32), ("L", C.c_int32), ("pow_kind", C.c_int32), ("reserved", C.c_int32),
+                ("p", C.c_double), ("seed", C.c_uint64), ("stream_offset", C.c_uint64)]
+
+
+class StdcCfg(C.Structure):
+    _fields_ = [("geom_code", C.c_int32), ("geom_chain", C.c_int32), ("L", C.c_int32), ("droplets", C.c_int32),
+                ("iters", C.c_int32), ("per_class_inits", C.c_int32), ("randomize", C.c_int32), ("reserved", C.c_int32),
+                ("steps", C.c_int64), ("p_error", C.c_double), ("p_sampling", C.c_double), ("conv_mult", C.c_double),
+                ("seed", C.c_uint64), ("u_nb", C.c_void_p), ("u_np", C.c_void_p)]
+
+
+_lib = None
+
+
+def load():
+    """Load libqecmc.so; raises QecmcError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO):
+        raise QecmcError(f"{SO} not found: build it with `python __graft_entry__.py` "
+                         "(nvcc, sm_100a); there is no CPU fallback")
+    L = C.CDLL(SO)
+    L.qecmc_last_error.restype = C.c_char_p
+    L.qecmc_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.qecmc_destroy.argtypes = [C.c_void_p]
+    L.qecmc_destroy.restype = None
+    L.qecmc_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.qecmc_set_table_budget.argtypes = [C.c_void_p, C.c_int64]
+    L.qecmc_device_info.argtypes = [C.c_void_p, C.POINTER(DevInfo)]
+    L.qecmc_chain_update.argtypes = [C.c_void_p, C.POINTER(ChainCfg), C.c_void_p, C.c_int64, C.c_int64, C.POINTER(Stats)]
+    L.qecmc_replay_chain.argtypes = [C.c_void_p, C.POINTER(ChainCfg), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.qecmc_stdc.argtypes = [C.c_void_p, C.POINTER(StdcCfg), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(Stats)]
+    L.qecmc_stdc_dev.argtypes = L.qecmc_stdc.argtypes
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise QecmcError(f"libqecmc error {rc}: {load().qecmc_last_error().decode()}")
+
+
+def nsites(geom, L):
+    return 2 * L * L if geom in (TORIC, PLANAR) else L * L
+
+
+def neq(geom):
+    return 16 if geom == TORIC else 4
+
+
+def ndraws(geom):
+    return 3 if geom in (TORIC, PLANAR) else 5
+
+
+class Context:
+    """One per GPU; not thread-safe (include/qecmc.h)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        _check(load().qecmc_create(device, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            load().qecmc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(load().qecmc_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_table_budget(self, nbytes):
+        _check(load().qecmc_set_table_budget(self._h, int(nbytes)))
+
+    def device_info(self):
+        d = DevInfo()
+        _check(load().qecmc_device_info(self._h, C.byref(d)))
+        out = {f: getattr(d, f) for f, _ in d._fields_}
+        out["name"] = d.name.decode()
+        return out
+
+    # ---- plain chains -------------------------------------------------
+    def chain_update(self, geom_chain, L, qm, p, iters, seed=0, stream_offset=0, pow_kind=POW_NUMBA):
+        """qm: uint8 [chains, n_sites] (C-contiguous), updated in place.  Returns stats dict."""
+        _require_u8(qm)
+        chains = qm.shape[0]
+        cfg = ChainCfg(geom_chain, L, pow_kind, 0, p, seed, stream_offset)
+        st = Stats()
+        _check(load().qecmc_chain_update(self._h, C.byref(cfg), qm.ctypes.data, chains, iters, C.byref(st)))
+        return st.as_dict()
+
+    def replay_chain(self, geom_chain, L, qm0, u, p, pow_kind=POW_NUMBA, want_traj=False):
+        """qm0 [chains, n_sites]; u [chains, iters, k+1].  Returns (qm_final, dE, accepted[, traj])."""
+        _require_u8(qm0)
+        u = np.ascontiguousarray(u, np.float64)
+        chains, iters = u.shape[0], u.shape[1]
+        assert u.shape[2] == ndraws(geom_chain) + 1 and qm0.shape[0] == chains
+        cfg = ChainCfg(geom_chain, L, pow_kind, 0, p, 0, 0)
+        out = np.empty_like(qm0)
+        dE = np.zeros((chains, iters), np.int8)
+        acc = np.zeros((chains, iters), np.uint8)
+        traj = np.zeros((chains, iters, qm0.shape[1]), np.uint8) if want_traj else None
+        _check(load().qecmc_replay_chain(self._h, C.byref(cfg), qm0.ctypes.data, u.ctypes.data, chains, iters,
+                                         out.ctypes.data, dE.ctypes.data, acc.ctypes.data,
+                                         traj.ctypes.data if want_traj else None))
+        return (out, dE, acc, traj) if want_traj else (out, dE, acc)
+
+    # ---- STDC -----------------------------------------------------------
+    def _stdc_cfg(self, geom_code, geom_chain, L, droplets, steps, p_error, p_sampling, iters, per_class, randomize,
+                  conv_mult, seed, u_nb, u_np):
+        return StdcCfg(geom_code, geom_chain, L, droplets, iters, int(per_class), int(randomize), 0, steps, p_error,
+                       p_sampling, conv_mult, seed, u_nb, u_np)
+
+    def stdc(self, geom_code, geom_chain, L, qm, p_error, p_sampling, droplets, steps, iters=5, per_class=False,
+             randomize=True, conv_mult=0.0, seed=0, u_nb=None, u_np=None, want_hist=False):
+        """Host buffers in, host buffers out.  qm: [S, n_sites] or [S, n_eq, n_sites] uint8.
+        Returns (eqdistr [S, n_eq] float64, stats dict[, N_hist [S, n_eq, n_sites+1] uint32])."""
+        _require_u8(qm)
+        S = qm.shape[0]
+        n_eq, n = neq(geom_code), nsites(geom_code, L)
+        assert qm.size == S * (n_eq if per_class else 1) * n, "qubit_matrix batch has the wrong shape"
+        keep = []
+        if u_nb is not None:
+            u_nb = np.ascontiguousarray(u_nb, np.float64)
+            keep.append(u_nb)
+            assert u_nb.size == S * n_eq * droplets * steps * iters * (ndraws(geom_chain) + 1)
+        if u_np is not None:
+            u_np = np.ascontiguousarray(u_np, np.float64)
+            keep.append(u_np)
+            assert u_np.size == S * n_eq * droplets * 2 * L * L
+        cfg = self._stdc_cfg(geom_code, geom_chain, L, droplets, steps, p_error, p_sampling, iters, per_class, randomize,
+                             conv_mult, seed, u_nb.ctypes.data if u_nb is not None else None,
+                             u_np.ctypes.data if u_np is not None else None)
+        out = np.zeros((S, n_eq), np.float64)
+        hist = np.zeros((S, n_eq, n + 1), np.uint32) if want_hist else None
+        st = Stats()
+        _check(load().qecmc_stdc(self._h, C.byref(cfg), qm.ctypes.data, S, out.ctypes.data,
+                                 hist.ctypes.data if want_hist else None, C.byref(st)))
+        return (out, st.as_dict(), hist) if want_hist else (out, st.as_dict())
+
+    def stdc_dev(self, geom_code, geom_chain, L, d_qm_ptr, S, d_out_ptr, p_error, p_sampling, droplets, steps, iters=5,
+                 per_class=False, randomize=True, seed=0, want_stats=True):
+        """Device pointers (e.g. torch tensors' data_ptr()); work is enqueued on the context's stream."""
+        cfg = self._stdc_cfg(geom_code, geom_chain, L, droplets, steps, p_error, p_sampling, iters, per_class, randomize,
+                             0.0, seed, None, None)
+        st = Stats()
+        _check(load().qecmc_stdc_dev(self._h, C.byref(cfg), C.c_void_p(d_qm_ptr), S, C.c_void_p(d_out_ptr), None,
+                                     C.byref(st) if want_stats else None))
+        return st.as_dict() if want_stats else None
+
+
+def _require_u8(a):
+    # the reference's njit signatures reject anything but C-contiguous uint8
+    if not isinstance(a, np.ndarray) or a.dtype != np.uint8 or not a.flags["C_CONTIGUOUS"]:
+        raise TypeError("qubit_matrix must be a C-contiguous numpy uint8 array")
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]

@@ -1,0 +1,530 @@
+// qecmc_api.cu -- C ABI (include/qecmc.h) over the CUDA kernels: context, device
+// memory, wave scheduling of the distinct-chain tables, host<->device staging.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <map>
+#include <tuple>
+#include <vector>
+
+#include "../../include/qecmc.h"
+#include "qecmc_kernels.cuh"
+
+using namespace qecmc;
+
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_OK(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return set_err(QECMC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define QTRY(call)            \
+    do {                      \
+        int r_ = (call);      \
+        if (r_ != 0) return r_; \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return set_err(QECMC_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        cap = bytes;
+        return 0;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct qecmc_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaDeviceProp prop;
+    int64_t table_budget = 0;
+    DevBuf packed, tables, Z, counters, qm_in, out_f64, out_u32, replay_a, replay_b, scratch;
+    std::map<std::tuple<int, int, int>, uint64_t *> stab_hash;  // (geom, L, wide) -> device table
+    cudaEvent_t ev[4];
+    uint64_t hash_seed = 0x5EEDC0DE2020ull;
+    int64_t launches = 0;
+};
+
+// ------------------------------ helpers ------------------------------
+static double numba_pow(double a, int64_t b)
+{
+    // numba lowers float64 ** int64 to square-and-multiply (reciprocal for negative exponents);
+    // this is what _update_chain_fast (src/mcmc.py:158) evaluates.
+    double r = 1.0;
+    bool inv = b < 0;
+    uint64_t e = inv ? (uint64_t)(-b) : (uint64_t)b;
+    while (e) {
+        if (e & 1) r *= a;
+        e >>= 1;
+        a *= a;
+    }
+    return inv ? 1.0 / r : r;
+}
+
+static void make_thr(double p, int pow_kind, Thr &t)
+{
+    double factor = (p / 3.0) / (1.0 - p);  // src/mcmc.py:16
+    for (int i = 0; i < QECMC_THR_N; i++) {
+        int dE = i - QECMC_THR_OFF;
+        double v = pow_kind == QECMC_POW_NUMBA ? numba_pow(factor, dE) : pow(factor, (double)dE);
+        t.d[i] = v;
+        if (!(v < 1.0)) t.u32[i] = 0xFFFFFFFFu;  // u < v always holds for u in [0,1)
+        else {
+            double x = ceil(v * 4294967296.0);  // u32/2^32 < v  <=>  u32 <= ceil(v*2^32) - 1
+            t.u32[i] = x < 1.0 ? 0u : (uint32_t)(x - 1.0);
+        }
+    }
+}
+
+static int check_geom(int geom, int L)
+{
+    if (geom < 0 || geom > 3) return set_err(QECMC_ERR_ARG, "unknown geometry %d", geom);
+    if (L < 2 || L > 32) return set_err(QECMC_ERR_ARG, "system size L=%d outside [2, 32]", L);
+    if ((geom == ROTATED || geom == XZZX) && (L < 3 || (L % 2) == 0))
+        return set_err(QECMC_ERR_ARG, "rotated/XZZX codes need odd L >= 3 (got %d)", L);
+    return 0;
+}
+
+template <typename W> static int pack_lattices(qecmc_ctx *c, const uint8_t *d_qm, int64_t n_lat, const Geo &g, void *d_out)
+{
+    int64_t n_words = n_lat * g.nw;
+    QTRY(c->scratch.ensure(sizeof(int)));
+    CUDA_OK(cudaMemsetAsync(c->scratch.p, 0, sizeof(int), c->stream));
+    int T = 256;
+    pack_kernel<W><<<(unsigned)((n_words + T - 1) / T), T, 0, c->stream>>>(d_qm, (W *)d_out, n_words, g.L, (int *)c->scratch.p);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    int bad = 0;
+    CUDA_OK(cudaMemcpyAsync(&bad, c->scratch.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (bad) return set_err(QECMC_ERR_ARG, "qubit_matrix holds values outside 0..3");
+    return 0;
+}
+
+template <int GEOM, typename W> static int build_stab_hash(qecmc_ctx *c, const Geo &g, uint64_t **out)
+{
+    auto key = std::make_tuple(GEOM, g.L, (int)(sizeof(W) == 8));
+    auto it = c->stab_hash.find(key);
+    if (it != c->stab_hash.end()) { *out = it->second; return 0; }
+    uint64_t *d = nullptr;
+    CUDA_OK(cudaMalloc(&d, sizeof(uint64_t) * g.nstab));
+    stab_hash_kernel<GEOM, W><<<(g.nstab + 127) / 128, 128, 0, c->stream>>>(g, c->hash_seed, d);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    c->stab_hash[key] = d;
+    *out = d;
+    return 0;
+}
+
+static int pick_threads(size_t bytes_per_chain, size_t fixed, const cudaDeviceProp &prop, int *threads, int *blocks_per_sm)
+{
+    // largest resident chain count per SM within the shared-memory budget, 256-thread CTAs preferred
+    size_t budget = prop.sharedMemPerMultiprocessor;
+    int best_T = 0, best_res = 0;
+    for (int T : {256, 128, 64}) {
+        size_t per_block = bytes_per_chain * T + fixed + 1024;  // +1 KiB reserved per CTA
+        if (bytes_per_chain * T + fixed > prop.sharedMemPerBlockOptin) continue;
+        int nb = (int)(budget / per_block);
+        int max_thr = prop.maxThreadsPerMultiProcessor;
+        if (nb * T > max_thr) nb = max_thr / T;
+        if (nb * T > best_res) { best_res = nb * T; best_T = T; *blocks_per_sm = nb; }
+    }
+    if (!best_T) return set_err(QECMC_ERR_UNSUPPORTED, "lattice does not fit in shared memory");
+    *threads = best_T;
+    return 0;
+}
+
+// ------------------------------ context ------------------------------
+extern "C" int qecmc_abi_version(void) { return QECMC_ABI_VERSION; }
+extern "C" const char *qecmc_last_error(void) { return g_err; }
+
+extern "C" int qecmc_create(int device, qecmc_ctx **out)
+{
+    if (!out) return set_err(QECMC_ERR_ARG, "out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return set_err(QECMC_ERR_CUDA, "no CUDA device available (%s); libqecmc has no CPU fallback",
+                       e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= n) return set_err(QECMC_ERR_ARG, "device %d out of range (have %d)", device, n);
+    CUDA_OK(cudaSetDevice(device));
+    qecmc_ctx *c = new qecmc_ctx();
+    c->device = device;
+    CUDA_OK(cudaGetDeviceProperties(&c->prop, device));
+    CUDA_OK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    for (auto &ev : c->ev) CUDA_OK(cudaEventCreate(&ev));
+    *out = c;
+    return 0;
+}
+
+extern "C" void qecmc_destroy(qecmc_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (DevBuf *b : {&c->packed, &c->tables, &c->Z, &c->counters, &c->qm_in, &c->out_f64, &c->out_u32, &c->replay_a,
+                      &c->replay_b, &c->scratch})
+        b->release();
+    for (auto &kv : c->stab_hash) cudaFree(kv.second);
+    for (auto &ev : c->ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+extern "C" int qecmc_set_stream(qecmc_ctx *c, void *s)
+{
+    if (!c) return set_err(QECMC_ERR_ARG, "ctx is NULL");
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return 0;
+}
+
+extern "C" int qecmc_set_table_budget(qecmc_ctx *c, int64_t bytes)
+{
+    if (!c || bytes < 0) return set_err(QECMC_ERR_ARG, "bad arguments");
+    c->table_budget = bytes;
+    return 0;
+}
+
+extern "C" int qecmc_device_info(qecmc_ctx *c, qecmc_devinfo *o)
+{
+    if (!c || !o) return set_err(QECMC_ERR_ARG, "NULL argument");
+    CUDA_OK(cudaSetDevice(c->device));
+    memset(o, 0, sizeof(*o));
+    o->device = c->device;
+    o->sm_count = c->prop.multiProcessorCount;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device);
+    o->sm_clock_khz = khz;
+    o->cc_major = c->prop.major;
+    o->cc_minor = c->prop.minor;
+    size_t fr = 0, tot = 0;
+    CUDA_OK(cudaMemGetInfo(&fr, &tot));
+    o->total_mem = (int64_t)tot;
+    o->free_mem = (int64_t)fr;
+    strncpy(o->name, c->prop.name, sizeof(o->name) - 1);
+    return 0;
+}
+
+// ------------------------------ plain chains ------------------------------
+template <int GEOM, typename W, bool REPLAY>
+static int launch_chain(qecmc_ctx *c, ChainParams &p)
+{
+    int T = 0, nb = 0;
+    size_t per_chain = (size_t)p.g.nw * sizeof(W);
+    QTRY(pick_threads(per_chain, 256, c->prop, &T, &nb));
+    size_t smem = per_chain * T;
+    CUDA_OK(cudaFuncSetAttribute(chain_kernel<GEOM, W, REPLAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned grid = (unsigned)((p.chains + T - 1) / T);
+    chain_kernel<GEOM, W, REPLAY><<<grid, T, smem, c->stream>>>(p);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <typename W, bool REPLAY> static int launch_chain_geom(qecmc_ctx *c, ChainParams &p)
+{
+    switch (p.g.geom) {
+    case TORIC: return launch_chain<TORIC, W, REPLAY>(c, p);
+    case PLANAR: return launch_chain<PLANAR, W, REPLAY>(c, p);
+    case ROTATED: return launch_chain<ROTATED, W, REPLAY>(c, p);
+    default: return launch_chain<XZZX, W, REPLAY>(c, p);
+    }
+}
+
+static int chain_common(qecmc_ctx *c, const qecmc_chain_cfg *cfg, const uint8_t *qm_in, uint8_t *qm_out, const double *u,
+                        int64_t chains, int64_t iters, int8_t *dE, uint8_t *accepted, uint8_t *traj, qecmc_stats *stats)
+{
+    if (!c || !cfg || !qm_in || !qm_out) return set_err(QECMC_ERR_ARG, "NULL argument");
+    if (chains <= 0 || iters < 0) return set_err(QECMC_ERR_ARG, "chains must be > 0 and iters >= 0");
+    if (!(cfg->p > 0.0 && cfg->p < 1.0)) return set_err(QECMC_ERR_ARG, "p=%g outside (0,1)", cfg->p);
+    QTRY(check_geom(cfg->geom_chain, cfg->L));
+    CUDA_OK(cudaSetDevice(c->device));
+    c->launches = 0;
+    Geo g = make_geo(cfg->geom_chain, cfg->L);
+    bool wide = cfg->L > 16;
+    size_t wbytes = wide ? 8 : 4;
+    size_t nbytes = (size_t)chains * g.nsites;
+    QTRY(c->qm_in.ensure(nbytes));
+    QTRY(c->packed.ensure((size_t)chains * g.nw * wbytes));
+    QTRY(c->counters.ensure(8 * sizeof(unsigned long long)));
+    CUDA_OK(cudaMemcpyAsync(c->qm_in.p, qm_in, nbytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(unsigned long long), c->stream));
+    if (wide) QTRY(pack_lattices<uint64_t>(c, (const uint8_t *)c->qm_in.p, chains, g, c->packed.p));
+    else QTRY(pack_lattices<uint32_t>(c, (const uint8_t *)c->qm_in.p, chains, g, c->packed.p));
+    ChainParams p;
+    memset(&p, 0, sizeof(p));
+    p.g = g;
+    p.lat = c->packed.p;
+    p.chains = chains;
+    p.iters = iters;
+    make_thr(cfg->p, cfg->pow_kind, p.thr);
+    p.seed = cfg->seed;
+    p.offset = cfg->stream_offset;
+    p.counters = (unsigned long long *)c->counters.p;
+    int k = (cfg->geom_chain == TORIC || cfg->geom_chain == PLANAR) ? 3 : 5;
+    size_t n_u = (size_t)chains * iters * (k + 1);
+    if (u) {
+        QTRY(c->replay_a.ensure(n_u * sizeof(double) + 8));
+        CUDA_OK(cudaMemcpyAsync(c->replay_a.p, u, n_u * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        p.u = (const double *)c->replay_a.p;
+        size_t trace = (size_t)chains * iters;
+        size_t need = (dE ? trace : 0) + (accepted ? trace : 0) + (traj ? trace * g.nsites : 0);
+        QTRY(c->out_u32.ensure(need + 16));
+        uint8_t *base = (uint8_t *)c->out_u32.p;
+        if (dE) { p.dE = (int8_t *)base; base += trace; }
+        if (accepted) { p.acc = base; base += trace; }
+        if (traj) p.traj = base;
+    }
+    CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
+    if (u) { if (wide) QTRY((launch_chain_geom<uint64_t, true>(c, p))); else QTRY((launch_chain_geom<uint32_t, true>(c, p))); }
+    else { if (wide) QTRY((launch_chain_geom<uint64_t, false>(c, p))); else QTRY((launch_chain_geom<uint32_t, false>(c, p))); }
+    CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
+    int T = 256;
+    int64_t n_words = chains * g.nw;
+    if (wide) unpack_kernel<uint64_t><<<(unsigned)((n_words + T - 1) / T), T, 0, c->stream>>>((uint64_t *)c->packed.p, (uint8_t *)c->qm_in.p, n_words, g.L);
+    else unpack_kernel<uint32_t><<<(unsigned)((n_words + T - 1) / T), T, 0, c->stream>>>((uint32_t *)c->packed.p, (uint8_t *)c->qm_in.p, n_words, g.L);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(qm_out, c->qm_in.p, nbytes, cudaMemcpyDeviceToHost, c->stream));
+    size_t trace = (size_t)chains * iters;
+    if (p.dE) CUDA_OK(cudaMemcpyAsync(dE, p.dE, trace, cudaMemcpyDeviceToHost, c->stream));
+    if (p.acc) CUDA_OK(cudaMemcpyAsync(accepted, p.acc, trace, cudaMemcpyDeviceToHost, c->stream));
+    if (p.traj) CUDA_OK(cudaMemcpyAsync(traj, p.traj, trace * g.nsites, cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long cnt[8] = {0};
+    CUDA_OK(cudaMemcpyAsync(cnt, c->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->metropolis_steps = chains * iters;
+        stats->accepted = (int64_t)cnt[0];
+        stats->kernel_launches = c->launches;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+        stats->chain_kernel_ms = ms;
+        stats->total_ms = ms;
+    }
+    return 0;
+}
+
+extern "C" int qecmc_chain_update(qecmc_ctx *c, const qecmc_chain_cfg *cfg, uint8_t *qm, int64_t chains, int64_t iters,
+                                  qecmc_stats *stats)
+{
+    return chain_common(c, cfg, qm, qm, nullptr, chains, iters, nullptr, nullptr, nullptr, stats);
+}
+
+extern "C" int qecmc_replay_chain(qecmc_ctx *c, const qecmc_chain_cfg *cfg, const uint8_t *qm0, const double *u,
+                                  int64_t chains, int64_t iters, uint8_t *qm_final, int8_t *dE, uint8_t *accepted,
+                                  uint8_t *traj)
+{
+    if (!u) return set_err(QECMC_ERR_ARG, "replay needs the uniform draws u");
+    return chain_common(c, cfg, qm0, qm_final, u, chains, iters, dE, accepted, traj, nullptr);
+}
+
+// ------------------------------ STDC ------------------------------
+template <int GEOM, typename W, bool REPLAY>
+static int launch_stdc(qecmc_ctx *c, StdcParams &p)
+{
+    int T = 0, nb = 0;
+    size_t per_chain = (size_t)p.gchain.nw * sizeof(W);
+    size_t fixed = (size_t)p.gchain.nstab * 8 + 16;
+    QTRY(pick_threads(per_chain, fixed + 256, c->prop, &T, &nb));
+    size_t smem = ((per_chain * T + 15) & ~(size_t)15) + fixed;
+    CUDA_OK(cudaFuncSetAttribute(stdc_kernel<GEOM, W, REPLAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned grid = (unsigned)((p.n_chains + T - 1) / T);
+    stdc_kernel<GEOM, W, REPLAY><<<grid, T, smem, c->stream>>>(p);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <typename W, bool REPLAY> static int launch_stdc_geom(qecmc_ctx *c, StdcParams &p)
+{
+    switch (p.gchain.geom) {
+    case TORIC: QTRY((build_stab_hash<TORIC, W>(c, p.gchain, (uint64_t **)&p.stab_hash))); return launch_stdc<TORIC, W, REPLAY>(c, p);
+    case PLANAR: QTRY((build_stab_hash<PLANAR, W>(c, p.gchain, (uint64_t **)&p.stab_hash))); return launch_stdc<PLANAR, W, REPLAY>(c, p);
+    case ROTATED: QTRY((build_stab_hash<ROTATED, W>(c, p.gchain, (uint64_t **)&p.stab_hash))); return launch_stdc<ROTATED, W, REPLAY>(c, p);
+    default: QTRY((build_stab_hash<XZZX, W>(c, p.gchain, (uint64_t **)&p.stab_hash))); return launch_stdc<XZZX, W, REPLAY>(c, p);
+    }
+}
+
+static uint64_t next_pow2(uint64_t x)
+{
+    uint64_t p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+extern "C" int qecmc_stdc_dev(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, const uint8_t *d_qm, int64_t S, double *d_eqdistr,
+                              uint32_t *d_N_hist, qecmc_stats *stats)
+{
+    if (!c || !cfg || !d_qm || !d_eqdistr) return set_err(QECMC_ERR_ARG, "NULL argument");
+    if (S <= 0) return set_err(QECMC_ERR_ARG, "S must be > 0");
+    QTRY(check_geom(cfg->geom_code, cfg->L));
+    QTRY(check_geom(cfg->geom_chain, cfg->L));
+    Geo gcode = make_geo(cfg->geom_code, cfg->L), gchain = make_geo(cfg->geom_chain, cfg->L);
+    if (gcode.layers != gchain.layers) return set_err(QECMC_ERR_ARG, "geom_code and geom_chain have different lattice shapes");
+    if (cfg->droplets <= 0 || cfg->steps <= 0 || cfg->iters <= 0) return set_err(QECMC_ERR_ARG, "droplets, steps, iters must be > 0");
+    if (!(cfg->p_error > 0 && cfg->p_error < 1) || !(cfg->p_sampling > 0 && cfg->p_sampling < 1))
+        return set_err(QECMC_ERR_ARG, "p_error / p_sampling outside (0,1)");
+    if (cfg->conv_mult != 0.0) return set_err(QECMC_ERR_UNSUPPORTED, "conv_mult != 0 is not implemented on the device path yet");
+    if (cfg->randomize && cfg->geom_code != TORIC && cfg->geom_code != PLANAR)
+        return set_err(QECMC_ERR_ARG, "apply_stabilizers_uniform exists only for toric/planar codes");
+    if (cfg->randomize && cfg->u_nb && !cfg->u_np) return set_err(QECMC_ERR_ARG, "replay with randomize needs u_np");
+    CUDA_OK(cudaSetDevice(c->device));
+    c->launches = 0;
+    const bool wide = cfg->L > 16;
+    const size_t wbytes = wide ? 8 : 4;
+    const int n_eq = gcode.neq;
+
+    // distinct-chain tables: capacity covers the worst case (every sample distinct) at load <= 0.8
+    uint64_t max_keys = (uint64_t)cfg->droplets * (uint64_t)cfg->steps;
+    uint64_t cap = next_pow2(max_keys + max_keys / 4 + 1);
+    if (cap < 1024) cap = 1024;
+    size_t fr = 0, tot = 0;
+    CUDA_OK(cudaMemGetInfo(&fr, &tot));
+    int64_t budget = c->table_budget ? c->table_budget : (int64_t)((double)(fr + c->tables.cap) * 0.85);
+    int64_t per_syndrome = (int64_t)n_eq * (int64_t)cap * 8;
+    int64_t wave = budget / per_syndrome;
+    if (wave < 1)
+        return set_err(QECMC_ERR_NOMEM, "distinct-chain tables need %lld bytes per syndrome, budget is %lld",
+                       (long long)per_syndrome, (long long)budget);
+    if (wave > S) wave = S;
+    QTRY(c->tables.ensure((size_t)wave * per_syndrome));
+    int64_t n_lat = cfg->per_class_inits ? S * n_eq : S;
+    QTRY(c->packed.ensure((size_t)n_lat * gcode.nw * wbytes));
+    QTRY(c->Z.ensure((size_t)S * n_eq * sizeof(double)));
+    QTRY(c->counters.ensure(8 * sizeof(unsigned long long)));
+    CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
+    CUDA_OK(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(unsigned long long), c->stream));
+    if (wide) QTRY(pack_lattices<uint64_t>(c, d_qm, n_lat, gcode, c->packed.p));
+    else QTRY(pack_lattices<uint32_t>(c, d_qm, n_lat, gcode, c->packed.p));
+
+    StdcParams p;
+    memset(&p, 0, sizeof(p));
+    p.gcode = gcode;
+    p.gchain = gchain;
+    p.per_class = cfg->per_class_inits;
+    p.randomize = cfg->randomize;
+    p.droplets = cfg->droplets;
+    p.iters = cfg->iters;
+    p.steps = cfg->steps;
+    p.seed = cfg->seed;
+    p.hash_seed = c->hash_seed;
+    p.tables = (unsigned long long *)c->tables.p;
+    p.cap_mask = cap - 1;
+    make_thr(cfg->p_sampling, QECMC_POW_NUMBA, p.thr);
+    p.u_nb = cfg->u_nb;
+    p.u_np = cfg->u_np;
+    p.counters = (unsigned long long *)c->counters.p;
+    const double beta = -log((cfg->p_error / 3) / (1 - cfg->p_error));  // decoders.py:299
+
+    float chain_ms = 0;
+    int64_t waves = 0;
+    for (int64_t s0 = 0; s0 < S; s0 += wave, waves++) {
+        int64_t sw = S - s0 < wave ? S - s0 : wave;
+        CUDA_OK(cudaMemsetAsync(c->tables.p, 0, (size_t)sw * per_syndrome, c->stream));
+        p.lat0 = (const char *)c->packed.p + (size_t)(cfg->per_class_inits ? s0 * n_eq : s0) * gcode.nw * wbytes;
+        p.n_chains = sw * n_eq * cfg->droplets;
+        p.chain_offset = s0 * n_eq * cfg->droplets;
+        CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
+        if (cfg->u_nb) { if (wide) QTRY((launch_stdc_geom<uint64_t, true>(c, p))); else QTRY((launch_stdc_geom<uint32_t, true>(c, p))); }
+        else { if (wide) QTRY((launch_stdc_geom<uint64_t, false>(c, p))); else QTRY((launch_stdc_geom<uint32_t, false>(c, p))); }
+        CUDA_OK(cudaEventRecord(c->ev[3], c->stream));
+        table_hist_kernel<<<(unsigned)(sw * n_eq), 512, (gcode.nsites + 1) * sizeof(uint32_t), c->stream>>>(
+            (const unsigned long long *)c->tables.p, cap, gcode.nsites, beta, (double *)c->Z.p + s0 * n_eq,
+            d_N_hist ? d_N_hist + (size_t)s0 * n_eq * (gcode.nsites + 1) : nullptr, (unsigned long long *)c->counters.p + 3);
+        c->launches++;
+        CUDA_OK(cudaGetLastError());
+        if (stats) {  // per-wave chain-kernel time (synchronises; waves are seconds long)
+            CUDA_OK(cudaEventSynchronize(c->ev[3]));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
+            chain_ms += ms;
+        }
+    }
+    normalize_kernel<<<(unsigned)((S + 127) / 128), 128, 0, c->stream>>>((const double *)c->Z.p, d_eqdistr, S, n_eq);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
+    if (stats) {
+        unsigned long long cnt[8] = {0};
+        CUDA_OK(cudaMemcpyAsync(cnt, c->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        memset(stats, 0, sizeof(*stats));
+        stats->metropolis_steps = S * n_eq * (int64_t)cfg->droplets * cfg->steps * cfg->iters;
+        stats->accepted = (int64_t)cnt[0];
+        stats->samples = (int64_t)cnt[1];
+        stats->distinct = (int64_t)cnt[3];
+        stats->table_slots = (int64_t)cap;
+        stats->waves = waves;
+        stats->kernel_launches = c->launches;
+        stats->chain_kernel_ms = chain_ms;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+        stats->total_ms = ms;
+    }
+    return 0;
+}
+
+extern "C" int qecmc_stdc(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, const uint8_t *qm, int64_t S, double *eqdistr,
+                          uint32_t *N_hist, qecmc_stats *stats)
+{
+    if (!c || !cfg || !qm || !eqdistr) return set_err(QECMC_ERR_ARG, "NULL argument");
+    if (S <= 0) return set_err(QECMC_ERR_ARG, "S must be > 0");
+    QTRY(check_geom(cfg->geom_code, cfg->L));
+    CUDA_OK(cudaSetDevice(c->device));
+    Geo g = make_geo(cfg->geom_code, cfg->L);
+    int64_t n_lat = cfg->per_class_inits ? S * g.neq : S;
+    size_t in_bytes = (size_t)n_lat * g.nsites;
+    size_t hist_elems = (size_t)S * g.neq * (g.nsites + 1);
+    QTRY(c->qm_in.ensure(in_bytes));
+    QTRY(c->out_f64.ensure((size_t)S * g.neq * sizeof(double)));
+    if (N_hist) QTRY(c->out_u32.ensure(hist_elems * sizeof(uint32_t)));
+    CUDA_OK(cudaMemcpyAsync(c->qm_in.p, qm, in_bytes, cudaMemcpyHostToDevice, c->stream));
+    qecmc_stdc_cfg dcfg = *cfg;
+    if (cfg->u_nb) {
+        if (cfg->droplets <= 0 || cfg->steps <= 0 || cfg->iters <= 0) return set_err(QECMC_ERR_ARG, "droplets, steps, iters must be > 0");
+        int k = (cfg->geom_chain == TORIC || cfg->geom_chain == PLANAR) ? 3 : 5;
+        size_t chains = (size_t)S * g.neq * cfg->droplets;
+        size_t nb = chains * (size_t)cfg->steps * cfg->iters * (k + 1) * sizeof(double);
+        QTRY(c->replay_a.ensure(nb));
+        CUDA_OK(cudaMemcpyAsync(c->replay_a.p, cfg->u_nb, nb, cudaMemcpyHostToDevice, c->stream));
+        dcfg.u_nb = (const double *)c->replay_a.p;
+        if (cfg->u_np) {
+            size_t np_ = chains * 2 * (size_t)cfg->L * cfg->L * sizeof(double);
+            QTRY(c->replay_b.ensure(np_));
+            CUDA_OK(cudaMemcpyAsync(c->replay_b.p, cfg->u_np, np_, cudaMemcpyHostToDevice, c->stream));
+            dcfg.u_np = (const double *)c->replay_b.p;
+        }
+    }
+    QTRY(qecmc_stdc_dev(c, &dcfg, (const uint8_t *)c->qm_in.p, S, (double *)c->out_f64.p,
+                        N_hist ? (uint32_t *)c->out_u32.p : nullptr, stats));
+    CUDA_OK(cudaMemcpyAsync(eqdistr, c->out_f64.p, (size_t)S * g.neq * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (N_hist) CUDA_OK(cudaMemcpyAsync(N_hist, c->out_u32.p, hist_elems * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}

@@ -1,0 +1,322 @@
+// qecmc_kernels.cuh -- CUDA kernels (sm_100a) for the Metropolis-chain decoders.
+//
+// One thread owns one chain.  The chain's 2-bit-packed lattice lives in shared memory
+// ([row word][thread], bank-conflict free); proposals come from per-thread Philox4x32-10
+// (native) or from the reference's own uniform draws (replay, bit-exact); the weight
+// change is a popcount difference on the touched row words; accepted moves update an
+// incremental length and a GF(2)-linear fingerprint; every `iters` steps the chain offers
+// its fingerprint to the (syndrome, class) distinct-chain set in HBM.
+#pragma once
+#include "qecmc_device.cuh"
+
+namespace qecmc {
+
+struct Thr {
+    uint32_t u32[QECMC_THR_N];  // native: accept iff philox_word <= u32[dE + 4]
+    double d[QECMC_THR_N];      // replay: accept iff u < d[dE + 4] (the reference's own doubles)
+};
+
+// ------------------------------ pack / unpack ------------------------------
+template <typename W>
+__global__ void pack_kernel(const uint8_t *__restrict__ qm, W *__restrict__ out, int64_t n_words, int L, int *bad)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_words) return;
+    const uint8_t *row = qm + i * L;
+    W w = 0;
+    int b = 0;
+    for (int c = 0; c < L; c++) {
+        uint8_t v = row[c];
+        b |= v > 3;
+        w |= (W)((W)(v & 3) << (2 * c));
+    }
+    out[i] = w;
+    if (b) *bad = 1;
+}
+
+template <typename W>
+__global__ void unpack_kernel(const W *__restrict__ in, uint8_t *__restrict__ qm, int64_t n_words, int L)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_words) return;
+    W w = in[i];
+    for (int c = 0; c < L; c++) qm[i * L + c] = (uint8_t)((w >> (2 * c)) & 3);
+}
+
+template <int GEOM, typename W> __global__ void stab_hash_kernel(Geo g, uint64_t seed, uint64_t *out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < g.nstab) out[i] = stab_hash<GEOM, W>(g, i, seed);
+}
+
+// apply stabilizer (row, col, op) of a runtime geometry; cold paths only (rain)
+template <typename W, typename A> __device__ int apply_rco_rt(const Geo &g, A &a, int row, int col, int op)
+{
+    Upd<W> u;
+    switch (g.geom) {
+    case TORIC: decode<TORIC, W>(g, row, col, op, u); return lat_apply<TORIC, W>(a, u);
+    case PLANAR: decode<PLANAR, W>(g, row, col, op, u); return lat_apply<PLANAR, W>(a, u);
+    case ROTATED: decode<ROTATED, W>(g, row, col, op, u); return lat_apply<ROTATED, W>(a, u);
+    default: decode<XZZX, W>(g, row, col, op, u); return lat_apply<XZZX, W>(a, u);
+    }
+}
+template <typename W, typename A> __device__ void to_class_rt(const Geo &g, A &a, int eq)
+{
+    switch (g.geom) {
+    case TORIC: lat_to_class<TORIC, W>(g, a, eq); break;
+    case PLANAR: lat_to_class<PLANAR, W>(g, a, eq); break;
+    case ROTATED: lat_to_class<ROTATED, W>(g, a, eq); break;
+    default: lat_to_class<XZZX, W>(g, a, eq); break;
+    }
+}
+__device__ inline bool rain_legal_rt(const Geo &g, int o, int r, int c)
+{
+    return g.geom == PLANAR ? rain_legal<PLANAR>(g, o, r, c) : true;
+}
+
+// One Metropolis proposal on the thread's lattice.  Returns dE; commits when accepted.
+template <int GEOM, typename W>
+__device__ __forceinline__ bool metropolis(const Geo &g, SmemLat<W> &lat, int row, int col, int op, int &dE_out,
+                                           const uint32_t *thr_u32, uint32_t r_acc, const double *thr_d, double u_acc,
+                                           bool replay)
+{
+    constexpr int NU = NumUpd<GEOM>::value;
+    Upd<W> u;
+    decode<GEOM, W>(g, row, col, op, u);
+    W nv[NU];
+    int dE = 0;
+#pragma unroll
+    for (int i = 0; i < NU; i++) {
+        W o = lat.get(u.w[i]);
+        nv[i] = (W)(o ^ u.m[i]);
+        dE += weight<W>(nv[i]) - weight<W>(o);
+    }
+    dE_out = dE;
+    bool acc = replay ? (u_acc < thr_d[dE + QECMC_THR_OFF]) : (r_acc <= thr_u32[dE + QECMC_THR_OFF]);
+    if (acc) {
+#pragma unroll
+        for (int i = 0; i < NU; i++) lat.set(u.w[i], nv[i]);
+    }
+    return acc;
+}
+
+// ------------------------------ plain chains ------------------------------
+// Chain.update_chain_fast / _update_chain_fast (src/mcmc.py:45-46,152-160).
+struct ChainParams {
+    Geo g;
+    void *lat;  // packed [chains][nw], in/out
+    int64_t chains, iters;
+    Thr thr;
+    uint64_t seed, offset;
+    const double *u;  // replay: [chains][iters][k+1]
+    int8_t *dE;
+    uint8_t *acc;
+    uint8_t *traj;
+    unsigned long long *counters;  // [0] accepted
+};
+
+template <int GEOM, typename W, bool REPLAY> __global__ void chain_kernel(ChainParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int T = blockDim.x, tid = threadIdx.x;
+    W *tile = reinterpret_cast<W *>(smem);
+    __shared__ uint32_t s_thr[QECMC_THR_N];
+    __shared__ double s_thrd[QECMC_THR_N];
+    if (tid < QECMC_THR_N) { s_thr[tid] = p.thr.u32[tid]; s_thrd[tid] = p.thr.d[tid]; }
+    __syncthreads();
+    int64_t ch = (int64_t)blockIdx.x * T + tid;
+    if (ch >= p.chains) return;
+    const Geo g = p.g;
+    SmemLat<W> lat{tile + tid, T};
+    W *gl = reinterpret_cast<W *>(p.lat) + ch * g.nw;
+    for (int w = 0; w < g.nw; w++) lat.set(w, gl[w]);
+    constexpr int K = NumDraws<GEOM>::value;
+    unsigned long long nacc = 0;
+    for (int64_t t = 0; t < p.iters; t++) {
+        int row, col, op, dE;
+        bool acc;
+        if (REPLAY) {
+            const double *u = p.u + (ch * p.iters + t) * (K + 1);
+            propose_replay<GEOM>(g, u, row, col, op);
+            acc = metropolis<GEOM, W>(g, lat, row, col, op, dE, s_thr, 0u, s_thrd, u[K], true);
+        } else {
+            uint64_t tg = p.offset + (uint64_t)t;
+            uint64_t call = tg >> 1;
+            uint4 r = philox4x32_10((uint32_t)call, (uint32_t)(call >> 32), (uint32_t)ch, (uint32_t)((uint64_t)ch >> 32),
+                                    (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+            uint32_t ra = (tg & 1) ? r.z : r.x, rb = (tg & 1) ? r.w : r.y;
+            int idx = (int)__umulhi(ra, (uint32_t)g.nstab);
+            idx_to_rco<GEOM>(g, idx, row, col, op);
+            acc = metropolis<GEOM, W>(g, lat, row, col, op, dE, s_thr, rb, s_thrd, 0.0, false);
+        }
+        nacc += acc;
+        if (p.dE) p.dE[ch * p.iters + t] = (int8_t)dE;
+        if (p.acc) p.acc[ch * p.iters + t] = (uint8_t)acc;
+        if (p.traj) {
+            uint8_t *o = p.traj + (ch * p.iters + t) * (int64_t)g.nsites;
+            for (int w = 0; w < g.nw; w++) unpack_row<W>(lat.get(w), o + w * g.L, g.L);
+        }
+    }
+    for (int w = 0; w < g.nw; w++) gl[w] = lat.get(w);
+    if (p.counters && nacc) atomicAdd(p.counters, nacc);
+}
+
+// ------------------------------ STDC ------------------------------
+// STDC_droplet (decoders.py:236-265) for every (syndrome, class, droplet) of a wave.
+struct StdcParams {
+    Geo gcode, gchain;
+    const void *lat0;  // packed [S_wave][nw] or [S_wave][n_eq][nw]
+    int per_class, randomize, droplets, iters;
+    int64_t steps;
+    int64_t n_chains;      // chains in this wave
+    int64_t chain_offset;  // global index of the wave's first chain (RNG stream / replay arrays)
+    uint64_t seed, hash_seed;
+    unsigned long long *tables;  // [S_wave * n_eq][cap]
+    uint64_t cap_mask;
+    const uint64_t *stab_hash;  // [gchain.nstab]
+    Thr thr;
+    const double *u_nb, *u_np;
+    unsigned long long *counters;  // [0] accepted [1] offered [2] inserted
+};
+
+template <int GEOM, typename W, bool REPLAY>
+__global__ void __launch_bounds__(256) stdc_kernel(StdcParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int T = blockDim.x, tid = threadIdx.x;
+    const Geo g = p.gchain;
+    W *tile = reinterpret_cast<W *>(smem);
+    uint64_t *s_hs = reinterpret_cast<uint64_t *>(smem + (((size_t)g.nw * T * sizeof(W) + 15) & ~(size_t)15));
+    __shared__ uint32_t s_thr[QECMC_THR_N];
+    __shared__ double s_thrd[QECMC_THR_N];
+    for (int i = tid; i < g.nstab; i += T) s_hs[i] = p.stab_hash[i];
+    if (tid < QECMC_THR_N) { s_thr[tid] = p.thr.u32[tid]; s_thrd[tid] = p.thr.d[tid]; }
+    __syncthreads();
+    const int64_t local = (int64_t)blockIdx.x * T + tid;
+    if (local >= p.n_chains) return;
+    const int64_t gchain = p.chain_offset + local;
+    const int n_eq = p.gcode.neq;
+    const int64_t tab = local / p.droplets;  // (syndrome, class) within the wave
+    const int eq = (int)(tab % n_eq);
+    const int64_t sw = tab / n_eq;
+    SmemLat<W> lat{tile + tid, T};
+    {
+        const W *src = reinterpret_cast<const W *>(p.lat0) + (p.per_class ? tab : sw) * g.nw;
+        for (int w = 0; w < g.nw; w++) lat.set(w, src[w]);
+    }
+    const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
+    const uint32_t cl = (uint32_t)gchain, chh = (uint32_t)((uint64_t)gchain >> 32);
+
+    // class initialisation: Toric_code.to_class / apply_logical(class ^ eq) (decoders.py:286-288, 556-560)
+    if (!p.per_class) to_class_rt<W>(p.gcode, lat, eq);
+    // rain: apply_stabilizers_uniform(p = 0.5) with the code's own geometry (decoders.py:245-246)
+    if (p.randomize) {
+        const int L = g.L;
+        uint4 r = make_uint4(0, 0, 0, 0);
+        int i = 0;
+        for (int o = 0; o < 2; o++)
+            for (int rr = 0; rr < L; rr++)
+                for (int c = 0; c < L; c++, i++) {
+                    bool hit;
+                    if (REPLAY) {
+                        hit = p.u_np[gchain * (int64_t)(2 * L * L) + i] < 0.5;
+                    } else {
+                        if ((i & 127) == 0) r = philox4x32_10((uint32_t)(i >> 7), 0x80000000u, cl, chh, k0, k1);
+                        int wi = (i >> 5) & 3;
+                        uint32_t word = wi == 0 ? r.x : wi == 1 ? r.y : wi == 2 ? r.z : r.w;
+                        hit = (word >> (i & 31)) & 1;
+                    }
+                    if (hit && rain_legal_rt(p.gcode, o, rr, c)) apply_rco_rt<W>(p.gcode, lat, rr, c, o == 0 ? 3 : 1);
+                }
+    }
+    int n = lat_weight<W>(g, lat);
+    uint64_t h = lat_hash<W>(g, lat, p.hash_seed);
+    unsigned long long *table = p.tables + (uint64_t)tab * (p.cap_mask + 1);
+
+    unsigned long long nacc = 0, noff = 0, nins = 0;
+    bool dirty = true;  // the first sample is always new to the chain
+    int left = p.iters;
+    const uint64_t tsteps = (uint64_t)p.steps * (uint64_t)p.iters;
+
+#define QECMC_AFTER_STEP()                                                  \
+    if (acc) { n += dE; h ^= s_hs[idx]; dirty = true; nacc++; }             \
+    if (--left == 0) {                                                      \
+        left = p.iters;                                                     \
+        if (dirty) { noff++; nins += table_insert(table, p.cap_mask, make_key(h, n)); dirty = false; } \
+    }
+
+    if (REPLAY) {
+        constexpr int K = NumDraws<GEOM>::value;
+        const double *u = p.u_nb + (uint64_t)gchain * tsteps * (K + 1);
+        for (uint64_t t = 0; t < tsteps; t++, u += K + 1) {
+            int row, col, op, dE;
+            propose_replay<GEOM>(g, u, row, col, op);
+            int idx = rco_to_idx<GEOM>(g, row, col, op);
+            bool acc = metropolis<GEOM, W>(g, lat, row, col, op, dE, s_thr, 0u, s_thrd, u[K], true);
+            QECMC_AFTER_STEP()
+        }
+    } else {
+        uint32_t c0 = 0, c1 = 0;
+        for (uint64_t t = 0; t < tsteps; t += 2) {
+            uint4 r = philox4x32_10(c0, c1, cl, chh, k0, k1);
+            if (++c0 == 0) ++c1;
+            {
+                int row, col, op, dE;
+                int idx = (int)__umulhi(r.x, (uint32_t)g.nstab);
+                idx_to_rco<GEOM>(g, idx, row, col, op);
+                bool acc = metropolis<GEOM, W>(g, lat, row, col, op, dE, s_thr, r.y, s_thrd, 0.0, false);
+                QECMC_AFTER_STEP()
+            }
+            if (t + 1 < tsteps) {
+                int row, col, op, dE;
+                int idx = (int)__umulhi(r.z, (uint32_t)g.nstab);
+                idx_to_rco<GEOM>(g, idx, row, col, op);
+                bool acc = metropolis<GEOM, W>(g, lat, row, col, op, dE, s_thr, r.w, s_thrd, 0.0, false);
+                QECMC_AFTER_STEP()
+            }
+        }
+    }
+#undef QECMC_AFTER_STEP
+    // statistics: three atomics per chain at the very end (negligible)
+    atomicAdd(p.counters + 0, nacc);
+    atomicAdd(p.counters + 1, noff);
+    atomicAdd(p.counters + 2, nins);
+}
+
+// One block per (syndrome, class) table: N(n) histogram from the length field of the
+// keys, then Z_E = sum_n N(n) exp(-beta n) (decoders.py:317-318).
+__global__ void table_hist_kernel(const unsigned long long *__restrict__ tables, uint64_t cap, int nsites, double beta,
+                                  double *__restrict__ Z, uint32_t *__restrict__ N_hist, unsigned long long *distinct)
+{
+    extern __shared__ uint32_t s_hist[];
+    const unsigned long long *tab = tables + (uint64_t)blockIdx.x * cap;
+    for (int i = threadIdx.x; i <= nsites; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    for (uint64_t i = threadIdx.x; i < cap; i += blockDim.x) {
+        unsigned long long k = tab[i];
+        if (k) atomicAdd(&s_hist[(int)(k & QECMC_LEN_MASK)], 1u);
+    }
+    __syncthreads();
+    if (N_hist)
+        for (int i = threadIdx.x; i <= nsites; i += blockDim.x) N_hist[(uint64_t)blockIdx.x * (nsites + 1) + i] = s_hist[i];
+    if (threadIdx.x == 0) {
+        double z = 0;
+        unsigned long long cnt = 0;
+        for (int n = 0; n <= nsites; n++)
+            if (s_hist[n]) { z += (double)s_hist[n] * exp(-beta * (double)n); cnt += s_hist[n]; }
+        Z[blockIdx.x] = z;
+        if (distinct) atomicAdd(distinct, cnt);
+    }
+}
+
+// eqdistr = Z / sum(Z) * 100 per syndrome (decoders.py:322)
+__global__ void normalize_kernel(const double *__restrict__ Z, double *__restrict__ out, int64_t S, int n_eq)
+{
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    double tot = 0;
+    for (int e = 0; e < n_eq; e++) tot += Z[s * n_eq + e];
+    for (int e = 0; e < n_eq; e++) out[s * n_eq + e] = Z[s * n_eq + e] / tot * 100;
+}
+
+}  // namespace qecmc

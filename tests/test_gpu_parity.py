@@ -1,0 +1,195 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and against the
+golden vectors recorded from the reference.  Integer work (trajectories, weight changes,
+accept decisions, distinct-chain histograms) must match bit-exactly in replay mode; the
+float64 class distributions to 1e-9 relative (sums in a different order, device exp)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from mcmc_qec_toric_rl_b200 import _lib
+    return _lib.default_context(0)
+
+
+def rand_lattice(rng, g, L, p=0.15):
+    shape = (2, L, L) if g in (O.TORIC, O.PLANAR) else (L, L)
+    q = ((rng.random(shape) < p) * rng.integers(1, 4, shape)).astype(np.uint8)
+    if g == O.PLANAR:
+        q[1, -1, :] = 0
+        q[1, :, -1] = 0
+    return q
+
+
+def golden(variant):
+    z = np.load(os.path.join(HERE, "golden", f"golden_{variant}.npz"))
+    manifest = json.loads(str(z["manifest"]))
+    out = []
+    for i, meta in enumerate(manifest):
+        c = dict(meta)
+        for k in z.files:
+            if k.startswith(f"{i}."):
+                c[k.split(".", 1)[1]] = z[k]
+        out.append(c)
+    return out
+
+
+# ------------------------------------------------------------------ replay: chains
+@pytest.mark.parametrize("g,L", [(O.TORIC, 5), (O.TORIC, 15), (O.TORIC, 21), (O.PLANAR, 5), (O.PLANAR, 7),
+                                 (O.PLANAR, 21), (O.ROTATED, 5), (O.ROTATED, 25), (O.XZZX, 7), (O.XZZX, 21)])
+def test_replay_chain_matches_oracle(ctx, g, L):
+    rng = np.random.default_rng(1000 + 10 * g + L)
+    chains, iters = 48, 300
+    k = 3 if g in (O.TORIC, O.PLANAR) else 5
+    p = 0.3
+    factor = (p / 3.0) / (1.0 - p)
+    qm0 = np.stack([rand_lattice(rng, g, L).reshape(-1) for _ in range(chains)])
+    u = rng.random((chains, iters, k + 1))
+    fin, dE, acc, traj = ctx.replay_chain(g, L, qm0, u, p, want_traj=True)
+    for ch in range(chains):
+        want, wdE, wacc = O.update_chain_fast(g, L, qm0[ch], factor, iters, O.Stream.replay(u[ch].reshape(-1)), trace=True)
+        assert np.array_equal(dE[ch], wdE)
+        assert np.array_equal(acc[ch], wacc)
+        assert np.array_equal(fin[ch], want)
+        assert np.array_equal(traj[ch, -1], want)
+
+
+@pytest.mark.parametrize("variant", ["shipped", "toric"])
+def test_replay_chain_matches_reference_golden(ctx, variant):
+    """Feed the reference's own numba MT19937 draws: trajectories equal the recorded reference run."""
+    n = 0
+    for c in golden(variant):
+        if c["kind"] != "chain_fast":
+            continue
+        g = O.GEOM[c["chain_geom"]]
+        L, iters, blocks = c["L"], c["iters"], c["blocks"]
+        u = np.random.RandomState(c["nb_seed"]).random_sample(iters * blocks * 4).reshape(1, iters * blocks, 4)
+        qm0 = c["q"].reshape(1, -1).copy()
+        fin, dE, acc, traj = ctx.replay_chain(g, L, qm0, u, c["p"], want_traj=True)
+        snaps = traj[0, iters - 1::iters]
+        assert np.array_equal(snaps, c["out"].reshape(blocks, -1))
+        n += 1
+    assert n >= 1
+
+
+# ------------------------------------------------------------------ replay: STDC
+def _stdc_streams(rng, n_chains, steps, iters, k, L):
+    u_nb = rng.random((n_chains, steps * iters, k + 1))
+    u_np = rng.random((n_chains, 2 * L * L))
+    return u_nb, u_np
+
+
+@pytest.mark.parametrize("gcode,gchain,L,droplets,per_class", [
+    (O.TORIC, O.TORIC, 5, 1, False), (O.TORIC, O.TORIC, 5, 3, False), (O.TORIC, O.PLANAR, 5, 2, False),
+    (O.TORIC, O.TORIC, 7, 2, False), (O.PLANAR, O.PLANAR, 5, 3, True), (O.PLANAR, O.PLANAR, 5, 2, False),
+    (O.TORIC, O.TORIC, 17, 2, False), (O.ROTATED, O.ROTATED, 5, 2, False), (O.XZZX, O.XZZX, 5, 2, True)])
+def test_stdc_replay_matches_oracle(ctx, gcode, gchain, L, droplets, per_class):
+    rng = np.random.default_rng(77 + L + droplets)
+    S, steps, iters = 3, 120, 5
+    n_eq = O.neq(gcode)
+    k = 3 if gchain in (O.TORIC, O.PLANAR) else 5
+    randomize = gcode in (O.TORIC, O.PLANAR) and not per_class
+    qs = [rand_lattice(rng, gcode, L, 0.1) for _ in range(S)]
+    if per_class:
+        qm = np.stack([O.all_classes(gcode, L, q) for q in qs])
+    else:
+        qm = np.stack([q.reshape(-1) for q in qs])
+    n_chains = S * n_eq * droplets
+    u_nb, u_np = _stdc_streams(rng, n_chains, steps, iters, k, L)
+    out, st, hist = ctx.stdc(gcode, gchain, L, qm, 0.1, 0.25, droplets, steps, iters=iters, per_class=per_class,
+                             randomize=randomize, u_nb=u_nb, u_np=u_np, want_hist=True)
+    for s in range(S):
+        inits = qm[s] if per_class else O.all_classes(gcode, L, qs[s])
+        base = s * n_eq * droplets
+        nb = [O.Stream.replay(u_nb[base + i].reshape(-1)) for i in range(n_eq * droplets)]
+        np_ = [O.Stream.replay(u_np[base + i]) for i in range(n_eq * droplets)]
+        want, wdist, whist = O.stdc(gcode, gchain, L, inits, 0.1, 0.25, droplets, steps, nb, np_, iters=iters,
+                                    randomize=randomize, want_hist=True)
+        assert np.array_equal(hist[s].astype(np.int64), whist), f"N(n) histogram differs for syndrome {s}"
+        np.testing.assert_allclose(out[s], want, rtol=1e-9)
+    assert st["distinct"] == int(hist.sum())
+
+
+@pytest.mark.parametrize("variant", ["shipped", "toric"])
+def test_stdc_replay_matches_reference_golden(ctx, variant):
+    """STDC(droplets=1) of the seeded reference: same class distribution from its own draws."""
+    n = 0
+    for c in golden(variant):
+        if c["kind"] != "stdc" or c["conv_mult"] != 0:
+            continue
+        gcode, gchain, L = O.GEOM[c["geom"]], O.GEOM[c["chain_geom"]], c["L"]
+        n_eq, steps, iters = O.neq(gcode), c["steps"], 5
+        per_class = gcode != O.TORIC
+        # droplets=1 runs in-process: one global numba stream and one numpy stream, consumed class after class
+        u_nb = np.random.RandomState(c["nb_seed"]).random_sample(n_eq * steps * iters * 4).reshape(n_eq, steps * iters, 4)
+        u_np = np.random.RandomState(c["np_seed"]).random_sample(n_eq * 2 * L * L).reshape(n_eq, 2 * L * L)
+        qm = (c["inits"].reshape(1, n_eq, -1) if per_class else c["q"].reshape(1, -1)).copy()
+        out, st = ctx.stdc(gcode, gchain, L, qm, c["p_error"], c["p_sampling"], 1, steps, iters=iters,
+                           per_class=per_class, randomize=bool(c["randomize"]), u_nb=u_nb, u_np=u_np)
+        np.testing.assert_allclose(out[0], c["out"], rtol=1e-9)
+        n += 1
+    assert n >= 2
+
+
+# ------------------------------------------------------------------ native Philox
+def test_native_chain_statistics(ctx):
+    """Native Philox chains: acceptance rate and mean weight agree with the oracle's MT19937 chains
+    within 5 standard errors (independent chains, same start, same number of steps)."""
+    g, L, p = O.TORIC, 7, 0.25
+    rng = np.random.default_rng(5)
+    chains, iters = 4096, 400
+    q0 = rand_lattice(rng, g, L, 0.1).reshape(-1)
+    qm = np.tile(q0, (chains, 1))
+    st = ctx.chain_update(g, L, qm, p, iters, seed=1234)
+    gpu_w = (qm != 0).sum(1)
+    factor = (p / 3.0) / (1.0 - p)
+    n_or = 512
+    or_w, or_acc = [], 0
+    for i in range(n_or):
+        f, dE, acc = O.update_chain_fast(g, L, q0, factor, iters, O.Stream.mt(1000 + i), trace=True)
+        or_w.append((f != 0).sum())
+        or_acc += acc.sum()
+    or_w = np.array(or_w)
+    se = np.sqrt(gpu_w.var() / chains + or_w.var() / n_or)
+    assert abs(gpu_w.mean() - or_w.mean()) < 5 * se, (gpu_w.mean(), or_w.mean(), se)
+    r_gpu = st["accepted"] / (chains * iters)
+    r_or = or_acc / (n_or * iters)
+    assert abs(r_gpu - r_or) < 0.01, (r_gpu, r_or)
+    # syndrome is preserved: every chain stays in the start's class orbit (toric stabilizers)
+    assert all(O.eq_class(g, L, x) == O.eq_class(g, L, q0) for x in qm[:64])
+
+
+def test_native_stdc_agrees_with_oracle(ctx):
+    """Native STDC on toric d=5: class distributions close to the oracle's (different RNG, same algorithm)
+    and the same most-likely class on nearly every syndrome."""
+    g, L = O.TORIC, 5
+    rng = np.random.default_rng(11)
+    S, droplets, steps = 24, 4, 2000
+    qm = np.stack([rand_lattice(rng, g, L, 0.08).reshape(-1) for _ in range(S)])
+    out, st = ctx.stdc(g, g, L, qm, 0.08, 0.25, droplets, steps, seed=99)
+    want = O.stdc_batch(g, g, L, qm, 0.08, 0.25, droplets, steps, seed=7, threads=8)
+    assert np.allclose(out.sum(1), 100.0)
+    agree = (out.argmax(1) == want.argmax(1)).mean()
+    assert agree >= 0.9, agree
+    assert np.abs(out - want).max() < 12.0, np.abs(out - want).max()
+    assert np.abs(out - want).mean() < 1.0
+    assert st["metropolis_steps"] == S * 16 * droplets * steps * 5
+
+
+def test_errors_are_loud(ctx):
+    from mcmc_qec_toric_rl_b200 import _lib
+    with pytest.raises(TypeError):
+        ctx.chain_update(O.TORIC, 5, np.zeros((1, 50), np.int64), 0.1, 5)
+    bad = np.full((1, 50), 7, np.uint8)
+    with pytest.raises(_lib.QecmcError):
+        ctx.chain_update(O.TORIC, 5, bad, 0.1, 5)
+    with pytest.raises(_lib.QecmcError):
+        ctx.chain_update(O.ROTATED, 6, np.zeros((1, 36), np.uint8), 0.1, 5)
