@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(CSRC, "libqecmc.so")
 SOURCES = ["qecmc_api.cu"]
-HEADERS = ["qecmc_lattice.h", "qecmc_device.cuh", "qecmc_kernels.cuh", os.path.join("..", "..", "include", "qecmc.h")]
+HEADERS = ["qecmc_lattice.h", "qecmc_device.cuh", "qecmc_kernels.cuh", "qecmc_stdc_fast.cuh", os.path.join("..", "..", "include", "qecmc.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-shared", "-cudart", "static"]
 

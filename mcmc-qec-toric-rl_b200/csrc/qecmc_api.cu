@@ -10,6 +10,7 @@
 
 #include "../../include/qecmc.h"
 #include "qecmc_kernels.cuh"
+#include "qecmc_stdc_fast.cuh"
 
 using namespace qecmc;
 
@@ -63,6 +64,8 @@ struct qecmc_ctx {
     int64_t table_budget = 0;
     DevBuf packed, tables, Z, counters, qm_in, out_f64, out_u32, replay_a, replay_b, scratch;
     std::map<std::tuple<int, int, int>, uint64_t *> stab_hash;  // (geom, L, wide) -> device table
+    std::map<std::tuple<int, int, int>, uint2 *> stab_desc;     // (geom, L, wide) -> descriptor table
+    DevBuf lut;
     cudaEvent_t ev[4];
     uint64_t hash_seed = 0x5EEDC0DE2020ull;
     int64_t launches = 0;
@@ -190,6 +193,8 @@ extern "C" void qecmc_destroy(qecmc_ctx *c)
                       &c->replay_b, &c->scratch})
         b->release();
     for (auto &kv : c->stab_hash) cudaFree(kv.second);
+    for (auto &kv : c->stab_desc) cudaFree(kv.second);
+    c->lut.release();
     for (auto &ev : c->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->own_stream);
     delete c;
@@ -344,6 +349,107 @@ extern "C" int qecmc_replay_chain(qecmc_ctx *c, const qecmc_chain_cfg *cfg, cons
     return chain_common(c, cfg, qm0, qm_final, u, chains, iters, dE, accepted, traj, nullptr);
 }
 
+
+// ---- tables of the table-driven STDC kernel (qecmc_stdc_fast.cuh) ----
+static void make_philox_keys(uint64_t seed, PhiloxKeys &k)
+{
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; r++) { k.k0[r] = k0; k.k1[r] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+}
+
+// slot layout a=(w0,sh) b=(w0,sh2) c=(w1,sh) d=(w2,sh); verified against decode<>() mask by mask
+template <int GEOM, typename W> static int build_stab_desc(qecmc_ctx *c, const Geo &g, const uint2 **out)
+{
+    auto key = std::make_tuple(GEOM, g.L, (int)(sizeof(W) == 8));
+    auto it = c->stab_desc.find(key);
+    if (it != c->stab_desc.end()) { *out = it->second; return 0; }
+    const int L = g.L;
+    std::vector<uint2> tab(g.nstab);
+    for (int idx = 0; idx < g.nstab; idx++) {
+        int row, col, op;
+        idx_to_rco<GEOM>(g, idx, row, col, op);
+        int w0, w1, w2, sh = 2 * col, sh2;
+        bool pa = true, pb = true, pc = true, pd = true;
+        if (GEOM == TORIC) {
+            if (op == 1) { w0 = L + row; sh2 = 2 * (col == 0 ? L - 1 : col - 1); w1 = row; w2 = row == 0 ? L - 1 : row - 1; }
+            else { w0 = row; sh2 = 2 * (col == L - 1 ? 0 : col + 1); w1 = L + row; w2 = L + (row == L - 1 ? 0 : row + 1); }
+        } else {
+            if (op == 1) { w0 = L + row; pa = col < L - 1; pb = col > 0; sh2 = pb ? 2 * (col - 1) : sh; w1 = row; w2 = row + 1; }
+            else { w0 = row; sh2 = 2 * (col + 1); w1 = L + row; pc = row < L - 1; pd = row > 0; w2 = pd ? L + row - 1 : L + 1; }
+        }
+        uint32_t f_and = 0xFF, f_or = 0;
+        bool pres[4] = {pa, pb, pc, pd};
+        for (int i = 0; i < 4; i++)
+            if (!pres[i]) { f_and &= ~(1u << (2 * i)); f_or |= 2u << (2 * i); }
+        tab[idx].x = (uint32_t)sh | ((uint32_t)w0 << 8) | ((uint32_t)w1 << 16) | ((uint32_t)w2 << 24);
+        tab[idx].y = (uint32_t)sh2 | (f_and << 8) | (f_or << 16) | ((op == 3 ? 1u : 0u) << 24);
+        // self-check against the generic geometry
+        Upd<W> u;
+        decode<GEOM, W>(g, row, col, op, u);
+        std::map<int, W> want, got;
+        for (int i = 0; i < 3; i++) if (u.m[i]) want[u.w[i]] ^= u.m[i];
+        W v = (W)op;
+        if (pa) got[w0] ^= (W)(v << sh);
+        if (pb) got[w0] ^= (W)(v << sh2);
+        if (pc) got[w1] ^= (W)(v << sh);
+        if (pd) got[w2] ^= (W)(v << sh);
+        if (want != got || w0 == w1 || w0 == w2 || w1 == w2 || w0 >= g.nw || w1 >= g.nw || w2 >= g.nw)
+            return set_err(QECMC_ERR_UNSUPPORTED, "internal: stabilizer descriptor %d disagrees with the geometry", idx);
+    }
+    uint2 *d = nullptr;
+    CUDA_OK(cudaMalloc(&d, sizeof(uint2) * g.nstab));
+    CUDA_OK(cudaMemcpyAsync(d, tab.data(), sizeof(uint2) * g.nstab, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    c->stab_desc[key] = d;
+    *out = d;
+    return 0;
+}
+
+// thr[(v==3)*256 + f], dE[...]: weight change of flipping the four gathered fields f by Pauli v
+static int build_fast_lut(qecmc_ctx *c, const Thr &t, FastTables &ft)
+{
+    std::vector<unsigned char> host(512 * 4 + 512);
+    uint32_t *thr = (uint32_t *)host.data();
+    int8_t *dE = (int8_t *)(host.data() + 512 * 4);
+    for (int vs = 0; vs < 2; vs++)
+        for (int f = 0; f < 256; f++) {
+            int v = vs ? 3 : 1, d = 0;
+            for (int i = 0; i < 4; i++) {
+                int q = (f >> (2 * i)) & 3;
+                d += (q == 0) - (q == v);
+            }
+            thr[vs * 256 + f] = t.u32[d + QECMC_THR_OFF];
+            dE[vs * 256 + f] = (int8_t)d;
+        }
+    QTRY(c->lut.ensure(host.size()));
+    CUDA_OK(cudaMemcpyAsync(c->lut.p, host.data(), host.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    ft.thr = (const uint32_t *)c->lut.p;
+    ft.dE = (const int8_t *)((const char *)c->lut.p + 512 * 4);
+    return 0;
+}
+
+template <int GEOM, typename W, bool REPLAY>
+static int launch_stdc_fast(qecmc_ctx *c, StdcParams &p)
+{
+    FastTables ft;
+    QTRY((build_stab_desc<GEOM, W>(c, p.gchain, &ft.desc)));
+    QTRY(build_fast_lut(c, p.thr, ft));
+    PhiloxKeys keys;
+    make_philox_keys(p.seed, keys);
+    int T = 0, nb = 0;
+    size_t per_chain = (size_t)p.gchain.nw * sizeof(W);
+    size_t fixed = (size_t)p.gchain.nstab * 16 + 512 * 5 + 16;
+    QTRY(pick_threads(per_chain, fixed + 256, c->prop, &T, &nb));
+    size_t smem = ((per_chain * T + 15) & ~(size_t)15) + fixed;
+    CUDA_OK(cudaFuncSetAttribute(stdc_fast_kernel<GEOM, W, REPLAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned grid = (unsigned)((p.n_chains + T - 1) / T);
+    stdc_fast_kernel<GEOM, W, REPLAY><<<grid, T, smem, c->stream>>>(p, ft, keys);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 // ------------------------------ STDC ------------------------------
 template <int GEOM, typename W, bool REPLAY>
 static int launch_stdc(qecmc_ctx *c, StdcParams &p)
@@ -364,8 +470,8 @@ static int launch_stdc(qecmc_ctx *c, StdcParams &p)
 template <typename W, bool REPLAY> static int launch_stdc_geom(qecmc_ctx *c, StdcParams &p)
 {
     switch (p.gchain.geom) {
-    case TORIC: QTRY((build_stab_hash<TORIC, W>(c, p.gchain, (uint64_t **)&p.stab_hash))); return launch_stdc<TORIC, W, REPLAY>(c, p);
-    case PLANAR: QTRY((build_stab_hash<PLANAR, W>(c, p.gchain, (uint64_t **)&p.stab_hash))); return launch_stdc<PLANAR, W, REPLAY>(c, p);
+    case TORIC: QTRY((build_stab_hash<TORIC, W>(c, p.gchain, (uint64_t **)&p.stab_hash))); return launch_stdc_fast<TORIC, W, REPLAY>(c, p);
+    case PLANAR: QTRY((build_stab_hash<PLANAR, W>(c, p.gchain, (uint64_t **)&p.stab_hash))); return launch_stdc_fast<PLANAR, W, REPLAY>(c, p);
     case ROTATED: QTRY((build_stab_hash<ROTATED, W>(c, p.gchain, (uint64_t **)&p.stab_hash))); return launch_stdc<ROTATED, W, REPLAY>(c, p);
     default: QTRY((build_stab_hash<XZZX, W>(c, p.gchain, (uint64_t **)&p.stab_hash))); return launch_stdc<XZZX, W, REPLAY>(c, p);
     }
@@ -390,6 +496,7 @@ extern "C" int qecmc_stdc_dev(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, const uin
     if (cfg->droplets <= 0 || cfg->steps <= 0 || cfg->iters <= 0) return set_err(QECMC_ERR_ARG, "droplets, steps, iters must be > 0");
     if (!(cfg->p_error > 0 && cfg->p_error < 1) || !(cfg->p_sampling > 0 && cfg->p_sampling < 1))
         return set_err(QECMC_ERR_ARG, "p_error / p_sampling outside (0,1)");
+    if ((uint64_t)cfg->steps * (uint64_t)cfg->iters >= (1ull << 32)) return set_err(QECMC_ERR_UNSUPPORTED, "steps * iters must be < 2^32");
     if (cfg->conv_mult != 0.0) return set_err(QECMC_ERR_UNSUPPORTED, "conv_mult != 0 is not implemented on the device path yet");
     if (cfg->randomize && cfg->geom_code != TORIC && cfg->geom_code != PLANAR)
         return set_err(QECMC_ERR_ARG, "apply_stabilizers_uniform exists only for toric/planar codes");
@@ -404,6 +511,7 @@ extern "C" int qecmc_stdc_dev(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, const uin
     uint64_t max_keys = (uint64_t)cfg->droplets * (uint64_t)cfg->steps;
     uint64_t cap = next_pow2(max_keys + max_keys / 4 + 1);
     if (cap < 1024) cap = 1024;
+    if (cap > (1ull << 32)) return set_err(QECMC_ERR_UNSUPPORTED, "more than 2^32 slots per distinct-chain table");
     size_t fr = 0, tot = 0;
     CUDA_OK(cudaMemGetInfo(&fr, &tot));
     int64_t budget = c->table_budget ? c->table_budget : (int64_t)((double)(fr + c->tables.cap) * 0.85);

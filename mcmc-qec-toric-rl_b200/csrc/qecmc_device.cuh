@@ -33,6 +33,32 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     return make_uint4(c0, c1, c2, c3);
 }
 
+// Same generator with the ten round keys precomputed on the host (kernel parameters live in
+// the constant bank, so each key is a free LOP3 operand) and mul.wide issued explicitly.
+struct PhiloxKeys {
+    uint32_t k0[10], k1[10];
+};
+__device__ __forceinline__ void mulhilo32(uint32_t a, uint32_t b, uint32_t &hi, uint32_t &lo)
+{
+    uint64_t p;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(a), "r"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(p));
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys &k)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t h0, l0, h1, l1;
+        mulhilo32(0xD2511F53u, c0, h0, l0);
+        mulhilo32(0xCD9E8D57u, c2, h1, l1);
+        c0 = h1 ^ c1 ^ k.k0[r];
+        c2 = h0 ^ c3 ^ k.k1[r];
+        c1 = l1;
+        c3 = l0;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
 // This thread's lattice inside the block's shared-memory tile, laid out [word][thread]
 // so that a warp's accesses to any word index hit 32 distinct banks.
 template <typename W> struct SmemLat {
@@ -88,6 +114,12 @@ template <int GEOM> __device__ __forceinline__ void propose_replay(const Geo &g,
 __device__ __forceinline__ uint64_t make_key(uint64_t h, int n)
 {
     return (h & ~QECMC_LEN_MASK) | (uint64_t)n | (1ull << 63);
+}
+
+__device__ __forceinline__ void table_prefetch(const unsigned long long *tab, uint64_t mask, uint64_t key)
+{
+    const unsigned long long *p = tab + ((key >> QECMC_LEN_BITS) & mask);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 // returns true when the key was not present before

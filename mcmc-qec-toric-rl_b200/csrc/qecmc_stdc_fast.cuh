@@ -1,0 +1,230 @@
+// qecmc_stdc_fast.cuh -- table-driven STDC chain kernel for the two-layer codes (toric, planar),
+// i.e. every lattice the reference's fast path (_update_chain_fast, src/mcmc.py:152-160) accepts.
+//
+// Per Metropolis step the generic kernel spends most of its issue slots decoding the stabilizer
+// and popcounting weight changes.  Here both are table lookups in shared memory:
+//   * an 8-byte descriptor per stabilizer: three row-word indices, two column shifts, the Pauli
+//     and (planar boundary stabilizers) which of the four qubit slots exist;
+//   * the four touched 2-bit fields are gathered into one byte f, and a 512-entry table indexed
+//     by (Pauli, f) returns the Metropolis acceptance threshold for the resulting weight change
+//     directly (a second byte table returns the weight change itself, read only on accept).
+// Slots:  a = (w0, sh)  b = (w0, sh2)  c = (w1, sh)  d = (w2, sh).
+// A missing slot is forced to the field value 2 (Y), which neither X nor Z flips change in weight.
+#pragma once
+#include "qecmc_kernels.cuh"
+
+namespace qecmc {
+
+// descriptor words:  x = sh | w0<<8 | w1<<16 | w2<<24
+//                    y = sh2 | f_and<<8 | f_or<<16 | (v==3)<<24
+struct FastTables {
+    const uint2 *desc;       // [nstab]
+    const uint32_t *thr;     // [512] native thresholds by (v==3)*256 + f
+    const int8_t *dE;        // [512]
+};
+
+template <typename W> __device__ __forceinline__ uint32_t gather_fields(W o0, W o1, W o2, uint32_t x, uint32_t y);
+
+template <> __device__ __forceinline__ uint32_t gather_fields<uint32_t>(uint32_t o0, uint32_t o1, uint32_t o2, uint32_t x, uint32_t y)
+{
+    // rotate each word so its field lands at bits [2i, 2i+2) of slot i; the funnel shift uses the
+    // low five bits of the shift operand, so x / y are used as they are
+    uint32_t ta = __funnelshift_r(o0, o0, x);
+    uint32_t tb = __funnelshift_r(o0, o0, y - 2u);
+    uint32_t tc = __funnelshift_r(o1, o1, x - 4u);
+    uint32_t td = __funnelshift_r(o2, o2, x - 6u);
+    uint32_t s1 = (ta & 0x03u) | (tb & ~0x03u);
+    uint32_t s2 = (tc & 0x30u) | (td & ~0x30u);
+    return (s1 & 0x0Fu) | (s2 & ~0x0Fu);  // caller masks to 8 bits
+}
+
+template <> __device__ __forceinline__ uint32_t gather_fields<uint64_t>(uint64_t o0, uint64_t o1, uint64_t o2, uint32_t x, uint32_t y)
+{
+    uint32_t sh = x & 63u, sh2 = y & 63u;
+    uint32_t qa = (uint32_t)(o0 >> sh) & 3u, qb = (uint32_t)(o0 >> sh2) & 3u;
+    uint32_t qc = (uint32_t)(o1 >> sh) & 3u, qd = (uint32_t)(o2 >> sh) & 3u;
+    return qa | (qb << 2) | (qc << 4) | (qd << 6);
+}
+
+template <int GEOM, typename W, bool REPLAY>
+__global__ void __launch_bounds__(256) stdc_fast_kernel(StdcParams p, FastTables ft, PhiloxKeys keys)
+{
+    static_assert(GEOM == TORIC || GEOM == PLANAR, "table-driven kernel covers the two-layer codes");
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int T = blockDim.x, tid = threadIdx.x;
+    const Geo g = p.gchain;
+    W *tile = reinterpret_cast<W *>(smem);
+    unsigned char *sp = smem + (((size_t)g.nw * T * sizeof(W) + 15) & ~(size_t)15);
+    uint64_t *s_hs = reinterpret_cast<uint64_t *>(sp);
+    uint2 *s_desc = reinterpret_cast<uint2 *>(s_hs + g.nstab);
+    uint32_t *s_thr = reinterpret_cast<uint32_t *>(s_desc + g.nstab);
+    int8_t *s_dE = reinterpret_cast<int8_t *>(s_thr + 512);
+    __shared__ double s_thrd[QECMC_THR_N];
+    for (int i = tid; i < g.nstab; i += T) { s_hs[i] = p.stab_hash[i]; s_desc[i] = ft.desc[i]; }
+    for (int i = tid; i < 512; i += T) { s_thr[i] = ft.thr[i]; s_dE[i] = ft.dE[i]; }
+    if (tid < QECMC_THR_N) s_thrd[tid] = p.thr.d[tid];
+    __syncthreads();
+    const int64_t local = (int64_t)blockIdx.x * T + tid;
+    if (local >= p.n_chains) return;
+    const int64_t gchain = p.chain_offset + local;
+    const int n_eq = p.gcode.neq;
+    const int64_t tab = local / p.droplets;
+    const int eq = (int)(tab % n_eq);
+    const int64_t sw = tab / n_eq;
+    SmemLat<W> lat{tile + tid, T};
+    {
+        const W *src = reinterpret_cast<const W *>(p.lat0) + (p.per_class ? tab : sw) * g.nw;
+        for (int w = 0; w < g.nw; w++) lat.set(w, src[w]);
+    }
+    const uint32_t cl = (uint32_t)gchain, chh = (uint32_t)((uint64_t)gchain >> 32);
+    if (!p.per_class) to_class_rt<W>(p.gcode, lat, eq);
+    if (p.randomize) {
+        const int L = g.L;
+        uint4 r = make_uint4(0, 0, 0, 0);
+        int i = 0;
+        for (int o = 0; o < 2; o++)
+            for (int rr = 0; rr < L; rr++)
+                for (int c = 0; c < L; c++, i++) {
+                    bool hit;
+                    if (REPLAY) {
+                        hit = p.u_np[gchain * (int64_t)(2 * L * L) + i] < 0.5;
+                    } else {
+                        if ((i & 127) == 0) r = philox4x32_10((uint32_t)(i >> 7), 0x80000000u, cl, chh, keys);
+                        int wi = (i >> 5) & 3;
+                        uint32_t word = wi == 0 ? r.x : wi == 1 ? r.y : wi == 2 ? r.z : r.w;
+                        hit = (word >> (i & 31)) & 1;
+                    }
+                    if (hit && rain_legal_rt(p.gcode, o, rr, c)) apply_rco_rt<W>(p.gcode, lat, rr, c, o == 0 ? 3 : 1);
+                }
+    }
+    int n = lat_weight<W>(g, lat);
+    uint64_t h = lat_hash<W>(g, lat, p.hash_seed);
+    unsigned long long *table = p.tables + (uint64_t)tab * (p.cap_mask + 1);
+    const uint64_t cap_mask = p.cap_mask;
+
+    uint32_t nacc = 0, noff = 0;
+    bool dirty = true;  // the first sample is always new to the chain
+    int left = p.iters;
+    // Asynchronous distinct-set inserts: a sample's key goes straight to atomicCAS(slot, 0, key) and the
+    // returned word is only looked at one sample (>= iters Metropolis steps) later, so the chain never
+    // waits on HBM.  A collision re-issues the CAS on the next slot and stays pending.  Two entries in
+    // flight per chain; only if both are still colliding when a third key arrives is one drained in place.
+    uint64_t keyA = 0, prevA = 0, keyB = 0, prevB = 0;
+    uint32_t slotA = 0, slotB = 0;
+    const uint32_t smask = (uint32_t)cap_mask;  // host guarantees cap <= 2^32 slots
+    unsigned char *mybase = reinterpret_cast<unsigned char *>(tile + tid);
+    const uint32_t wstride = (uint32_t)T * sizeof(W);
+
+#define QECMC_PROBE_DONE(prev, key) ((prev) == 0ull || (prev) == (key))
+#define QECMC_PROBE_NEXT(slot, prev, key)                                              \
+    do {                                                                               \
+        slot = (slot + 1u) & smask;                                                    \
+        prev = atomicCAS(table + slot, 0ull, (unsigned long long)(key));               \
+    } while (0)
+    // predicated atom.cas, output-only: when the predicate is false `prev` is undefined, which is fine because
+    // an entry's `prev` is only read one sample after that entry issued a CAS.  Written this way the result
+    // register is not copied after the atomic, so nothing waits on HBM until `prev` is read a sample later.
+#define QECMC_CAS_IF(pred, prev, slot, key)                                                                   \
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %4, 0;\n\t@q atom.global.cas.b64 %0, [%1], %2, %3;\n\t}" \
+                 : "=l"(prev)                                                                                  \
+                 : "l"(table + (slot)), "l"(0ull), "l"(key), "r"((uint32_t)(pred)))
+
+    // one Metropolis step for stabilizer idx; r_acc / u_acc is the accept draw
+    auto step = [&](int idx, uint32_t r_acc, double u_acc) {
+        const uint2 d = s_desc[idx];
+        W *p0 = reinterpret_cast<W *>(mybase + ((d.x >> 8) & 0xFFu) * wstride);
+        W *p1 = reinterpret_cast<W *>(mybase + ((d.x >> 16) & 0xFFu) * wstride);
+        W *p2 = reinterpret_cast<W *>(mybase + (d.x >> 24) * wstride);
+        const W o0 = *p0, o1 = *p1, o2 = *p2;
+        uint32_t f = gather_fields<W>(o0, o1, o2, d.x, d.y);
+        uint32_t li;
+        if (GEOM == TORIC) li = (f & 0xFFu) | (d.y >> 16);                            // f_or carries (v==3) at bit 8
+        else li = (f & ((d.y >> 8) & 0xFFu)) | (d.y >> 16);
+        bool acc;
+        if (REPLAY) acc = u_acc < s_thrd[(int)s_dE[li] + QECMC_THR_OFF];
+        else acc = r_acc <= s_thr[li];
+        if (acc) {
+            const uint32_t sh = d.x & 63u, sh2 = d.y & 63u;
+            const W v = (d.y & 0x01000000u) ? (W)3 : (W)1;
+            W m0, m1, m2;
+            if (GEOM == TORIC) {
+                m1 = (W)(v << sh);
+                m2 = m1;
+                m0 = (W)(m1 | (W)(v << sh2));
+            } else {
+                const uint32_t fa = d.y >> 8;
+                m0 = (W)(((fa & 1u) ? (W)(v << sh) : (W)0) | ((fa & 4u) ? (W)(v << sh2) : (W)0));
+                m1 = (fa & 16u) ? (W)(v << sh) : (W)0;
+                m2 = (fa & 64u) ? (W)(v << sh) : (W)0;
+            }
+            *p0 = (W)(o0 ^ m0);
+            *p1 = (W)(o1 ^ m1);
+            *p2 = (W)(o2 ^ m2);
+            n += (int)s_dE[li];
+            h ^= s_hs[idx];
+            dirty = true;
+            nacc++;
+        }
+        if (--left == 0) {
+            left = p.iters;
+            // branch-free bookkeeping: each entry issues at most one (predicated) CAS per sample
+            const uint64_t nkey = make_key(h, n);
+            const uint32_t nslot = (uint32_t)(nkey >> QECMC_LEN_BITS) & smask;
+            const bool retryA = keyA != 0 && !QECMC_PROBE_DONE(prevA, keyA);
+            const bool retryB = keyB != 0 && !QECMC_PROBE_DONE(prevB, keyB);
+            if (dirty && retryA && retryB) {  // rare: both entries still colliding -> drain A in place
+                uint64_t pv = prevA;
+                uint32_t sl = slotA;
+                while (!QECMC_PROBE_DONE(pv, keyA)) QECMC_PROBE_NEXT(sl, pv, keyA);
+                keyA = nkey; slotA = nslot; prevA = nkey;  // placeholder "done" value until the CAS below lands
+                QECMC_CAS_IF(1, prevA, nslot, nkey);
+                QECMC_CAS_IF(1, prevB, (slotB + 1u) & smask, keyB);
+                slotB = (slotB + 1u) & smask;
+            } else {
+                const bool takeA = dirty && !retryA;
+                const bool takeB = dirty && retryA;   // then B is free (handled above otherwise)
+                const bool issueA = retryA || takeA, issueB = retryB || takeB;
+                slotA = takeA ? nslot : (slotA + 1u) & smask;
+                slotB = takeB ? nslot : (slotB + 1u) & smask;
+                keyA = issueA ? (takeA ? nkey : keyA) : 0ull;
+                keyB = issueB ? (takeB ? nkey : keyB) : 0ull;
+                QECMC_CAS_IF(issueA, prevA, slotA, keyA);
+                QECMC_CAS_IF(issueB, prevB, slotB, keyB);
+            }
+            noff += dirty;
+            dirty = false;
+        }
+    };
+
+    const uint64_t tsteps = (uint64_t)p.steps * (uint64_t)p.iters;
+    if (REPLAY) {
+        constexpr int K = NumDraws<GEOM>::value;
+        const double *u = p.u_nb + (uint64_t)gchain * tsteps * (K + 1);
+        for (uint64_t t = 0; t < tsteps; t++, u += K + 1) {
+            int row, col, op;
+            propose_replay<GEOM>(g, u, row, col, op);
+            step(rco_to_idx<GEOM>(g, row, col, op), 0u, u[K]);
+        }
+    } else {
+        const uint32_t ncalls = (uint32_t)(tsteps >> 1);  // host guarantees tsteps < 2^32
+        const uint32_t nstab = (uint32_t)g.nstab;
+        for (uint32_t c0 = 0; c0 < ncalls; c0++) {
+            uint4 r = philox4x32_10(c0, 0u, cl, chh, keys);
+            step((int)__umulhi(r.x, nstab), r.y, 0.0);
+            step((int)__umulhi(r.z, nstab), r.w, 0.0);
+        }
+        if (tsteps & 1) {
+            uint4 r = philox4x32_10(ncalls, 0u, cl, chh, keys);
+            step((int)__umulhi(r.x, nstab), r.y, 0.0);
+        }
+    }
+    if (keyA) while (!QECMC_PROBE_DONE(prevA, keyA)) QECMC_PROBE_NEXT(slotA, prevA, keyA);
+    if (keyB) while (!QECMC_PROBE_DONE(prevB, keyB)) QECMC_PROBE_NEXT(slotB, prevB, keyB);
+#undef QECMC_PROBE_DONE
+#undef QECMC_PROBE_NEXT
+#undef QECMC_CAS_IF
+    atomicAdd(p.counters + 0, (unsigned long long)nacc);
+    atomicAdd(p.counters + 1, (unsigned long long)noff);
+}
+
+}  // namespace qecmc
