@@ -136,6 +136,106 @@ int qecmc_stdc(qecmc_ctx *ctx, const qecmc_stdc_cfg *cfg, const uint8_t *qm, int
 int qecmc_stdc_dev(qecmc_ctx *ctx, const qecmc_stdc_cfg *cfg, const uint8_t *d_qm, int64_t S, double *d_eqdistr,
                    uint32_t *d_N_hist, qecmc_stats *stats);
 
+/* ------------------------------------------------------------------------------
+ * STRC / STRC_droplet (decoders.py:745-949): same chains and distinct set as STDC plus
+ * the visit histogram m(n) (every sample counted) and, per droplet, the shortest and
+ * next-shortest visited lengths; Z_E = sum_l m(l) exp(-beta_s*shortest + (beta_s-beta)*l)
+ * times the mean distinct/visited fraction of the two shortest lengths (decoders.py:931-946),
+ * droplets merged in the reference's order (decoders.py:882-928).
+ *   m_hist     [S][n_eq][n_sites+1]  optional
+ *   short_info [S][n_eq][4] = (shortest, next_shortest, #distinct shortest, #distinct next-shortest), optional
+ * ------------------------------------------------------------------------------ */
+int qecmc_strc(qecmc_ctx *ctx, const qecmc_stdc_cfg *cfg, const uint8_t *qm, int64_t S, double *eqdistr,
+               uint64_t *m_hist, int32_t *short_info, qecmc_stats *stats);
+
+/* ------------------------------------------------------------------------------
+ * single_temp (decoders.py:108-135): one chain per class at p = cfg->p_sampling, cfg->steps =
+ * max_iters samples of cfg->iters (5) fast-path steps; mean_length [S][n_eq] = average chain
+ * length over the first max_iters-1 samples.  droplets must be 1; p_error is ignored.
+ * ------------------------------------------------------------------------------ */
+int qecmc_single_temp(qecmc_ctx *ctx, const qecmc_stdc_cfg *cfg, const uint8_t *qm, int64_t S, double *mean_length,
+                      qecmc_stats *stats);
+
+/* ------------------------------------------------------------------------------
+ * Parallel-tempering ladders: Ladder / Ladder_alpha / Ladder_biased (src/mcmc.py:49-103,
+ * src/mcmc_alpha.py:77-137, src/mcmc_biased.py:66-124) over the slow-path chains
+ * Chain / Chain_alpha / Chain_biased .update_chain (mcmc.py:19-43, mcmc_alpha.py:27-70,
+ * mcmc_biased.py:21-59; the denominator of the alpha/biased accept ratio is frozen per call
+ * as in the reference).  Replica swaps happen on the device.
+ * ------------------------------------------------------------------------------ */
+enum qecmc_ladder_kind { QECMC_LADDER_DEPOLARIZING = 0, QECMC_LADDER_ALPHA = 1, QECMC_LADDER_BIASED = 2 };
+
+typedef struct qecmc_ladder_cfg {
+    int32_t geom;        /* the code's own geometry (the slow path proposes with it) */
+    int32_t L;
+    int32_t kind;        /* enum qecmc_ladder_kind */
+    int32_t Nc;          /* rungs, 1..32; rung p's = numpy.linspace(bottom, top, Nc), top = 0.75 / 1 / (eta+1)/(2eta+1) */
+    int32_t iters;       /* Metropolis steps per rung between swap sweeps (the decoders use 10) */
+    int32_t reserved;
+    double  bottom;      /* p (depolarizing, biased) or pz_tilde (alpha) of rung 0 */
+    double  param_b;     /* alpha (kind 1) or eta (kind 2); unused for kind 0 */
+    double  p_logical;   /* top rung proposes a random logical operator with this probability */
+    uint64_t seed;       /* Philox key (native mode) */
+    /* replay mode when u_nb != NULL: per ladder, the numba-stream and CPython-stream uniforms in the
+       order the reference consumes them: u_nb [ladders][n_nb], u_py [ladders][n_py] */
+    const double *u_nb, *u_py;
+    int64_t n_nb, n_py;
+} qecmc_ladder_cfg;
+
+/* `steps` calls of Ladder.step(iters) on S ladders, every rung starting from qm0[s] ([S][n_sites]).
+ * Optional outputs in rung order (rung 0 = coldest): rung_states [S][Nc][n_sites], flags [S][Nc],
+ * tops0 [S], n_eff [S][Nc] (alpha ladders), and the same after every step (tests):
+ * snap_states [S][steps][Nc][n_sites], snap_flags [S][steps][Nc], snap_tops0 [S][steps]. */
+int qecmc_ladder_run(qecmc_ctx *ctx, const qecmc_ladder_cfg *cfg, const uint8_t *qm0, int64_t S, int64_t steps,
+                     uint8_t *rung_states, int32_t *flags, int64_t *tops0, double *n_eff, uint8_t *snap_states,
+                     int32_t *snap_flags, int64_t *snap_tops0, qecmc_stats *stats);
+
+/* PTEQ / PTEQ_biased / PTEQ_alpha (decoders.py:25-105, decoders_biasednoise.py:28-90,175-237). */
+typedef struct qecmc_pteq_cfg {
+    qecmc_ladder_cfg ladder;
+    int32_t SEQ, TOPS, tops_burn;
+    int32_t use_conv;    /* 1: conv_criteria='error_based' (decoders.py:93-105); 0: run all `steps` */
+    double  eps;
+    int64_t steps;       /* cap on Ladder.step calls per syndrome */
+} qecmc_pteq_cfg;
+
+/* eqdistr [S][n_eq] uint8 = (class counts / (since_burn + 1) * 100) truncated, as the reference returns;
+ * eq_counts [S][n_eq] optional; info [S][4] = (steps used, since_burn, tops0, converged) optional. */
+int qecmc_pteq(qecmc_ctx *ctx, const qecmc_pteq_cfg *cfg, const uint8_t *qm, int64_t S, uint8_t *eqdistr,
+               int64_t *eq_counts, int64_t *info, qecmc_stats *stats);
+/* same with DEVICE qm / eqdistr; info stays a host pointer */
+int qecmc_pteq_dev(qecmc_ctx *ctx, const qecmc_pteq_cfg *cfg, const uint8_t *d_qm, int64_t S, uint8_t *d_eqdistr,
+                   int64_t *info, qecmc_stats *stats);
+
+/* PTDC / PTDC_droplet (decoders.py:138-233): per syndrome and class, `droplets` ladders (p_logical = 0)
+ * of `steps` Ladder.step(iters) calls, every rung's state offered to the class's distinct-chain set
+ * after every step; Z_E = sum exp(-beta n).  eqdistr [S][n_eq] in percent as float64 (the reference
+ * truncates to uint8; the Python mirror does that). */
+typedef struct qecmc_ptdc_cfg {
+    qecmc_ladder_cfg ladder;    /* kind must be depolarizing; bottom = p_sampling */
+    int32_t droplets;
+    int32_t per_class_inits;
+    int64_t steps;              /* already divided by Nc (decoders.py:196) */
+    double  p_error;
+} qecmc_ptdc_cfg;
+int qecmc_ptdc(qecmc_ctx *ctx, const qecmc_ptdc_cfg *cfg, const uint8_t *qm, int64_t S, double *eqdistr, qecmc_stats *stats);
+
+/* EWD-style STDC_Nall_n_alpha / STDC_droplet_alpha (decoders.py:510-581): one Chain_alpha per class,
+ * `steps` samples of Chain_alpha.update_chain(iters), distinct chains weighted by
+ * pz_tilde ** (nz + alpha (nx + ny)).  distinct [S][n_eq] optional. */
+typedef struct qecmc_alpha_cfg {
+    int32_t geom, L;
+    int32_t iters;              /* the reference uses 5 (decoders.py:521) */
+    int32_t per_class_inits;
+    int64_t steps;
+    double  pz_tilde_sampling, alpha, pz_tilde;
+    uint64_t seed;
+    const double *u_nb, *u_py;  /* replay, per (syndrome, class): [S*n_eq][n_nb], [S*n_eq][n_py] */
+    int64_t n_nb, n_py;
+} qecmc_alpha_cfg;
+int qecmc_stdc_alpha(qecmc_ctx *ctx, const qecmc_alpha_cfg *cfg, const uint8_t *qm, int64_t S, double *eqdistr,
+                     int64_t *distinct, qecmc_stats *stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,30 @@ class StdcCfg(C.Structure):
                 ("seed", C.c_uint64), ("u_nb", C.c_void_p), ("u_np", C.c_void_p)]
 
 
+class LadderCfg(C.Structure):
+    _fields_ = [("geom", C.c_int32), ("L", C.c_int32), ("kind", C.c_int32), ("Nc", C.c_int32), ("iters", C.c_int32),
+                ("reserved", C.c_int32), ("bottom", C.c_double), ("param_b", C.c_double), ("p_logical", C.c_double),
+                ("seed", C.c_uint64), ("u_nb", C.c_void_p), ("u_py", C.c_void_p), ("n_nb", C.c_int64), ("n_py", C.c_int64)]
+
+
+class PteqCfg(C.Structure):
+    _fields_ = [("ladder", LadderCfg), ("SEQ", C.c_int32), ("TOPS", C.c_int32), ("tops_burn", C.c_int32),
+                ("use_conv", C.c_int32), ("eps", C.c_double), ("steps", C.c_int64)]
+
+
+class PtdcCfg(C.Structure):
+    _fields_ = [("ladder", LadderCfg), ("droplets", C.c_int32), ("per_class_inits", C.c_int32), ("steps", C.c_int64),
+                ("p_error", C.c_double)]
+
+
+class AlphaCfg(C.Structure):
+    _fields_ = [("geom", C.c_int32), ("L", C.c_int32), ("iters", C.c_int32), ("per_class_inits", C.c_int32),
+                ("steps", C.c_int64), ("pz_tilde_sampling", C.c_double), ("alpha", C.c_double), ("pz_tilde", C.c_double),
+                ("seed", C.c_uint64), ("u_nb", C.c_void_p), ("u_py", C.c_void_p), ("n_nb", C.c_int64), ("n_py", C.c_int64)]
+
+
+LADDER_DEPOLARIZING, LADDER_ALPHA, LADDER_BIASED = 0, 1, 2
+
 _lib = None
 
 
@@ -67,6 +91,18 @@ def load():
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.qecmc_stdc.argtypes = [C.c_void_p, C.POINTER(StdcCfg), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(Stats)]
     L.qecmc_stdc_dev.argtypes = L.qecmc_stdc.argtypes
+    L.qecmc_strc.argtypes = [C.c_void_p, C.POINTER(StdcCfg), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                             C.POINTER(Stats)]
+    L.qecmc_single_temp.argtypes = [C.c_void_p, C.POINTER(StdcCfg), C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(Stats)]
+    L.qecmc_ladder_run.argtypes = [C.c_void_p, C.POINTER(LadderCfg), C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 7 + \
+        [C.POINTER(Stats)]
+    L.qecmc_pteq.argtypes = [C.c_void_p, C.POINTER(PteqCfg), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                             C.POINTER(Stats)]
+    L.qecmc_pteq_dev.argtypes = [C.c_void_p, C.POINTER(PteqCfg), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                 C.POINTER(Stats)]
+    L.qecmc_ptdc.argtypes = [C.c_void_p, C.POINTER(PtdcCfg), C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(Stats)]
+    L.qecmc_stdc_alpha.argtypes = [C.c_void_p, C.POINTER(AlphaCfg), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                   C.POINTER(Stats)]
     _lib = L
     return L
 
@@ -178,6 +214,147 @@ class Context:
         _check(load().qecmc_stdc(self._h, C.byref(cfg), qm.ctypes.data, S, out.ctypes.data,
                                  hist.ctypes.data if want_hist else None, C.byref(st)))
         return (out, st.as_dict(), hist) if want_hist else (out, st.as_dict())
+
+    def _replay_args(self, S, n_eq, geom_chain, L, droplets, steps, iters, u_nb, u_np):
+        keep = []
+        if u_nb is not None:
+            u_nb = np.ascontiguousarray(u_nb, np.float64)
+            keep.append(u_nb)
+            assert u_nb.size == S * n_eq * droplets * steps * iters * (ndraws(geom_chain) + 1)
+        if u_np is not None:
+            u_np = np.ascontiguousarray(u_np, np.float64)
+            keep.append(u_np)
+            assert u_np.size == S * n_eq * droplets * 2 * L * L
+        return (u_nb.ctypes.data if u_nb is not None else None, u_np.ctypes.data if u_np is not None else None, keep)
+
+    def strc(self, geom_code, geom_chain, L, qm, p_error, p_sampling, droplets, steps, iters=5, per_class=False,
+             randomize=True, conv_mult=0.0, seed=0, u_nb=None, u_np=None, want_hist=False):
+        """STRC over a batch.  Returns (eqdistr [S, n_eq], stats[, m_hist [S, n_eq, n_sites+1] uint64,
+        short_info [S, n_eq, 4] int32])."""
+        _require_u8(qm)
+        S = qm.shape[0]
+        n_eq, n = neq(geom_code), nsites(geom_code, L)
+        assert qm.size == S * (n_eq if per_class else 1) * n, "qubit_matrix batch has the wrong shape"
+        a, b, keep = self._replay_args(S, n_eq, geom_chain, L, droplets, steps, iters, u_nb, u_np)
+        cfg = self._stdc_cfg(geom_code, geom_chain, L, droplets, steps, p_error, p_sampling, iters, per_class, randomize,
+                             conv_mult, seed, a, b)
+        out = np.zeros((S, n_eq), np.float64)
+        mh = np.zeros((S, n_eq, n + 1), np.uint64) if want_hist else None
+        info = np.zeros((S, n_eq, 4), np.int32) if want_hist else None
+        st = Stats()
+        _check(load().qecmc_strc(self._h, C.byref(cfg), qm.ctypes.data, S, out.ctypes.data,
+                                 mh.ctypes.data if want_hist else None, info.ctypes.data if want_hist else None, C.byref(st)))
+        return (out, st.as_dict(), mh, info) if want_hist else (out, st.as_dict())
+
+    def single_temp(self, geom_code, geom_chain, L, qm, p, max_iters, iters=5, per_class=False, seed=0, u_nb=None):
+        """single_temp over a batch: mean chain length [S, n_eq] of one chain per class."""
+        _require_u8(qm)
+        S = qm.shape[0]
+        n_eq, n = neq(geom_code), nsites(geom_code, L)
+        assert qm.size == S * (n_eq if per_class else 1) * n, "qubit_matrix batch has the wrong shape"
+        a, _, keep = self._replay_args(S, n_eq, geom_chain, L, 1, max_iters, iters, u_nb, None)
+        cfg = self._stdc_cfg(geom_code, geom_chain, L, 1, max_iters, p, p, iters, per_class, False, 0.0, seed, a, None)
+        out = np.zeros((S, n_eq), np.float64)
+        st = Stats()
+        _check(load().qecmc_single_temp(self._h, C.byref(cfg), qm.ctypes.data, S, out.ctypes.data, C.byref(st)))
+        return out, st.as_dict()
+
+    # ---- tempering ladders ------------------------------------------------
+    @staticmethod
+    def _ladder_cfg(geom, L, kind, Nc, iters, bottom, param_b, p_logical, seed, u_nb, u_py, n_ladders):
+        keep = []
+        a = b = None
+        n_nb = n_py = 0
+        if u_nb is not None:
+            u_nb = np.ascontiguousarray(u_nb, np.float64).reshape(n_ladders, -1)
+            u_py = np.ascontiguousarray(u_py, np.float64).reshape(n_ladders, -1)
+            keep += [u_nb, u_py]
+            a, b, n_nb, n_py = u_nb.ctypes.data, u_py.ctypes.data, u_nb.shape[1], u_py.shape[1]
+        return LadderCfg(geom, L, kind, Nc, iters, 0, bottom, param_b, p_logical, seed, a, b, n_nb, n_py), keep
+
+    def ladder_run(self, geom, L, kind, qm0, bottom, Nc, steps, iters=10, param_b=0.0, p_logical=0.0, seed=0, u_nb=None,
+                   u_py=None, snapshots=False):
+        """`steps` Ladder.step(iters) calls on S ladders (qm0 [S, n_sites]).  Returns a dict with rung_states
+        [S, Nc, n_sites], flags [S, Nc], tops0 [S], n_eff [S, Nc], stats (+ snap_* after every step)."""
+        _require_u8(qm0)
+        S, n = qm0.shape[0], nsites(geom, L)
+        assert qm0.size == S * n
+        cfg, keep = self._ladder_cfg(geom, L, kind, Nc, iters, bottom, param_b, p_logical, seed, u_nb, u_py, S)
+        out = dict(rung_states=np.zeros((S, Nc, n), np.uint8), flags=np.zeros((S, Nc), np.int32), tops0=np.zeros(S, np.int64),
+                   n_eff=np.zeros((S, Nc), np.float64))
+        snap = [None, None, None]
+        if snapshots:
+            snap = [np.zeros((S, steps, Nc, n), np.uint8), np.zeros((S, steps, Nc), np.int32), np.zeros((S, steps), np.int64)]
+            out.update(snap_states=snap[0], snap_flags=snap[1], snap_tops0=snap[2])
+        st = Stats()
+        _check(load().qecmc_ladder_run(self._h, C.byref(cfg), qm0.ctypes.data, S, steps, out["rung_states"].ctypes.data,
+                                       out["flags"].ctypes.data, out["tops0"].ctypes.data, out["n_eff"].ctypes.data,
+                                       *[x.ctypes.data if x is not None else None for x in snap], C.byref(st)))
+        out["stats"] = st.as_dict()
+        return out
+
+    def pteq(self, geom, L, kind, qm, bottom, Nc=None, param_b=0.0, SEQ=2, TOPS=10, tops_burn=2, eps=0.1, steps=1000000,
+             iters=10, conv=True, p_logical=0.5, seed=0, u_nb=None, u_py=None):
+        """PTEQ / PTEQ_alpha / PTEQ_biased over a batch qm [S, n_sites].  Returns (percent uint8 [S, n_eq], info dict)."""
+        _require_u8(qm)
+        S, n, n_eq = qm.shape[0], nsites(geom, L), neq(geom)
+        assert qm.size == S * n
+        Nc = Nc or L
+        lc, keep = self._ladder_cfg(geom, L, kind, Nc, iters, bottom, param_b, p_logical, seed, u_nb, u_py, S)
+        cfg = PteqCfg(lc, SEQ, TOPS, tops_burn, int(bool(conv)), eps, int(steps))
+        pct = np.zeros((S, n_eq), np.uint8)
+        counts = np.zeros((S, n_eq), np.int64)
+        info = np.zeros((S, 4), np.int64)
+        st = Stats()
+        _check(load().qecmc_pteq(self._h, C.byref(cfg), qm.ctypes.data, S, pct.ctypes.data, counts.ctypes.data,
+                                 info.ctypes.data, C.byref(st)))
+        return pct, dict(steps=info[:, 0], since_burn=info[:, 1], tops0=info[:, 2], converged=info[:, 3], counts=counts,
+                         stats=st.as_dict())
+
+    def pteq_dev(self, geom, L, kind, d_qm_ptr, S, d_out_ptr, bottom, Nc=None, param_b=0.0, SEQ=2, TOPS=10, tops_burn=2,
+                 eps=0.1, steps=1000000, iters=10, conv=True, p_logical=0.5, seed=0):
+        Nc = Nc or L
+        lc, _ = self._ladder_cfg(geom, L, kind, Nc, iters, bottom, param_b, p_logical, seed, None, None, S)
+        cfg = PteqCfg(lc, SEQ, TOPS, tops_burn, int(bool(conv)), eps, int(steps))
+        info = np.zeros((S, 4), np.int64)
+        st = Stats()
+        _check(load().qecmc_pteq_dev(self._h, C.byref(cfg), C.c_void_p(d_qm_ptr), S, C.c_void_p(d_out_ptr), info.ctypes.data,
+                                     C.byref(st)))
+        return st.as_dict(), info
+
+    def ptdc(self, geom, L, qm, p_error, p_sampling, droplets, Nc, steps, iters=10, per_class=False, seed=0, u_nb=None,
+             u_py=None):
+        """PTDC over a batch; `steps` is the per-ladder step count (the reference's steps // Nc)."""
+        _require_u8(qm)
+        S, n, n_eq = qm.shape[0], nsites(geom, L), neq(geom)
+        assert qm.size == S * (n_eq if per_class else 1) * n
+        lc, keep = self._ladder_cfg(geom, L, LADDER_DEPOLARIZING, Nc, iters, p_sampling, 0.0, 0.0, seed, u_nb, u_py,
+                                    S * n_eq * droplets)
+        cfg = PtdcCfg(lc, droplets, int(per_class), int(steps), p_error)
+        out = np.zeros((S, n_eq), np.float64)
+        st = Stats()
+        _check(load().qecmc_ptdc(self._h, C.byref(cfg), qm.ctypes.data, S, out.ctypes.data, C.byref(st)))
+        return out, st.as_dict()
+
+    def stdc_alpha(self, geom, L, qm, pz_tilde_sampling, alpha, pz_tilde, steps, iters=5, per_class=False, seed=0, u_nb=None,
+                   u_py=None):
+        """EWD-style STDC_Nall_n_alpha over a batch.  Returns (eqdistr [S, n_eq], distinct [S, n_eq], stats)."""
+        _require_u8(qm)
+        S, n, n_eq = qm.shape[0], nsites(geom, L), neq(geom)
+        assert qm.size == S * (n_eq if per_class else 1) * n
+        keep, a, b, n_nb, n_py = [], None, None, 0, 0
+        if u_nb is not None:
+            u_nb = np.ascontiguousarray(u_nb, np.float64).reshape(S * n_eq, -1)
+            u_py = np.ascontiguousarray(u_py, np.float64).reshape(S * n_eq, -1)
+            keep += [u_nb, u_py]
+            a, b, n_nb, n_py = u_nb.ctypes.data, u_py.ctypes.data, u_nb.shape[1], u_py.shape[1]
+        cfg = AlphaCfg(geom, L, iters, int(per_class), int(steps), pz_tilde_sampling, alpha, pz_tilde, seed, a, b, n_nb, n_py)
+        out = np.zeros((S, n_eq), np.float64)
+        distinct = np.zeros((S, n_eq), np.int64)
+        st = Stats()
+        _check(load().qecmc_stdc_alpha(self._h, C.byref(cfg), qm.ctypes.data, S, out.ctypes.data, distinct.ctypes.data,
+                                       C.byref(st)))
+        return out, distinct, st.as_dict()
 
     def stdc_dev(self, geom_code, geom_chain, L, d_qm_ptr, S, d_out_ptr, p_error, p_sampling, droplets, steps, iters=5,
                  per_class=False, randomize=True, seed=0, want_stats=True):

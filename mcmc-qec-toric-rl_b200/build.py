@@ -1,30 +1,58 @@
-"""Compile csrc/ into csrc/libqecmc.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+"""Compile csrc/*.cu into csrc/libqecmc.so for sm_100a with nvcc (cross-compiles without a GPU).
+
+Each translation unit is compiled to an object in parallel, then linked into one shared library."""
+import glob
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "_obj")
 SO = os.path.join(CSRC, "libqecmc.so")
-SOURCES = ["qecmc_api.cu"]
-HEADERS = ["qecmc_lattice.h", "qecmc_device.cuh", "qecmc_kernels.cuh", "qecmc_stdc_fast.cuh", os.path.join("..", "..", "include", "qecmc.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-              "-shared", "-cudart", "static"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVCC_FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def headers():
+    return (glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) +
+            [os.path.join(HERE, "..", "include", "qecmc.h")])
+
+
+def _obj(src):
+    return os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
 
 
 def needs_build():
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    return any(os.path.getmtime(f) > t for f in sources() + headers())
 
 
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return SO
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + SOURCES
-    subprocess.check_call(cmd, cwd=CSRC)
+    os.makedirs(OBJ, exist_ok=True)
+    newest_hdr = max(os.path.getmtime(h) for h in headers())
+
+    def compile_one(src):
+        obj = _obj(src)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), newest_hdr):
+            return obj
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        subprocess.check_call(cmd, cwd=CSRC)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        objs = list(ex.map(compile_one, sources()))
+    subprocess.check_call([nvcc] + ARCH + ["-shared", "-cudart", "static", "-o", SO] + objs, cwd=CSRC)
     return SO
 
 

@@ -1,163 +1,18 @@
 // qecmc_api.cu -- C ABI (include/qecmc.h) over the CUDA kernels: context, device
 // memory, wave scheduling of the distinct-chain tables, host<->device staging.
-#include <math.h>
-#include <stdarg.h>
-#include <stdio.h>
-#include <string.h>
-#include <map>
-#include <tuple>
-#include <vector>
-
-#include "../../include/qecmc.h"
-#include "qecmc_kernels.cuh"
+#include "qecmc_internal.h"
 #include "qecmc_stdc_fast.cuh"
 
 using namespace qecmc;
 
 static thread_local char g_err[512] = "";
-static int set_err(int code, const char *fmt, ...)
+int qecmc_set_err(int code, const char *fmt, ...)
 {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
     return code;
-}
-#define CUDA_OK(call)                                                                                   \
-    do {                                                                                                \
-        cudaError_t e_ = (call);                                                                        \
-        if (e_ != cudaSuccess)                                                                          \
-            return set_err(QECMC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-    } while (0)
-#define QTRY(call)            \
-    do {                      \
-        int r_ = (call);      \
-        if (r_ != 0) return r_; \
-    } while (0)
-
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    int ensure(size_t bytes)
-    {
-        if (bytes <= cap) return 0;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        cudaError_t e = cudaMalloc(&p, bytes);
-        if (e != cudaSuccess) return set_err(QECMC_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
-        cap = bytes;
-        return 0;
-    }
-    void release()
-    {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-};
-
-struct qecmc_ctx {
-    int device = 0;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaDeviceProp prop;
-    int64_t table_budget = 0;
-    DevBuf packed, tables, Z, counters, qm_in, out_f64, out_u32, replay_a, replay_b, scratch;
-    std::map<std::tuple<int, int, int>, uint64_t *> stab_hash;  // (geom, L, wide) -> device table
-    std::map<std::tuple<int, int, int>, uint2 *> stab_desc;     // (geom, L, wide) -> descriptor table
-    DevBuf lut;
-    cudaEvent_t ev[4];
-    uint64_t hash_seed = 0x5EEDC0DE2020ull;
-    int64_t launches = 0;
-};
-
-// ------------------------------ helpers ------------------------------
-static double numba_pow(double a, int64_t b)
-{
-    // numba lowers float64 ** int64 to square-and-multiply (reciprocal for negative exponents);
-    // this is what _update_chain_fast (src/mcmc.py:158) evaluates.
-    double r = 1.0;
-    bool inv = b < 0;
-    uint64_t e = inv ? (uint64_t)(-b) : (uint64_t)b;
-    while (e) {
-        if (e & 1) r *= a;
-        e >>= 1;
-        a *= a;
-    }
-    return inv ? 1.0 / r : r;
-}
-
-static void make_thr(double p, int pow_kind, Thr &t)
-{
-    double factor = (p / 3.0) / (1.0 - p);  // src/mcmc.py:16
-    for (int i = 0; i < QECMC_THR_N; i++) {
-        int dE = i - QECMC_THR_OFF;
-        double v = pow_kind == QECMC_POW_NUMBA ? numba_pow(factor, dE) : pow(factor, (double)dE);
-        t.d[i] = v;
-        if (!(v < 1.0)) t.u32[i] = 0xFFFFFFFFu;  // u < v always holds for u in [0,1)
-        else {
-            double x = ceil(v * 4294967296.0);  // u32/2^32 < v  <=>  u32 <= ceil(v*2^32) - 1
-            t.u32[i] = x < 1.0 ? 0u : (uint32_t)(x - 1.0);
-        }
-    }
-}
-
-static int check_geom(int geom, int L)
-{
-    if (geom < 0 || geom > 3) return set_err(QECMC_ERR_ARG, "unknown geometry %d", geom);
-    if (L < 2 || L > 32) return set_err(QECMC_ERR_ARG, "system size L=%d outside [2, 32]", L);
-    if ((geom == ROTATED || geom == XZZX) && (L < 3 || (L % 2) == 0))
-        return set_err(QECMC_ERR_ARG, "rotated/XZZX codes need odd L >= 3 (got %d)", L);
-    return 0;
-}
-
-template <typename W> static int pack_lattices(qecmc_ctx *c, const uint8_t *d_qm, int64_t n_lat, const Geo &g, void *d_out)
-{
-    int64_t n_words = n_lat * g.nw;
-    QTRY(c->scratch.ensure(sizeof(int)));
-    CUDA_OK(cudaMemsetAsync(c->scratch.p, 0, sizeof(int), c->stream));
-    int T = 256;
-    pack_kernel<W><<<(unsigned)((n_words + T - 1) / T), T, 0, c->stream>>>(d_qm, (W *)d_out, n_words, g.L, (int *)c->scratch.p);
-    c->launches++;
-    CUDA_OK(cudaGetLastError());
-    int bad = 0;
-    CUDA_OK(cudaMemcpyAsync(&bad, c->scratch.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_OK(cudaStreamSynchronize(c->stream));
-    if (bad) return set_err(QECMC_ERR_ARG, "qubit_matrix holds values outside 0..3");
-    return 0;
-}
-
-template <int GEOM, typename W> static int build_stab_hash(qecmc_ctx *c, const Geo &g, uint64_t **out)
-{
-    auto key = std::make_tuple(GEOM, g.L, (int)(sizeof(W) == 8));
-    auto it = c->stab_hash.find(key);
-    if (it != c->stab_hash.end()) { *out = it->second; return 0; }
-    uint64_t *d = nullptr;
-    CUDA_OK(cudaMalloc(&d, sizeof(uint64_t) * g.nstab));
-    stab_hash_kernel<GEOM, W><<<(g.nstab + 127) / 128, 128, 0, c->stream>>>(g, c->hash_seed, d);
-    c->launches++;
-    CUDA_OK(cudaGetLastError());
-    c->stab_hash[key] = d;
-    *out = d;
-    return 0;
-}
-
-static int pick_threads(size_t bytes_per_chain, size_t fixed, const cudaDeviceProp &prop, int *threads, int *blocks_per_sm)
-{
-    // largest resident chain count per SM within the shared-memory budget, 256-thread CTAs preferred
-    size_t budget = prop.sharedMemPerMultiprocessor;
-    int best_T = 0, best_res = 0;
-    for (int T : {256, 128, 64}) {
-        size_t per_block = bytes_per_chain * T + fixed + 1024;  // +1 KiB reserved per CTA
-        if (bytes_per_chain * T + fixed > prop.sharedMemPerBlockOptin) continue;
-        int nb = (int)(budget / per_block);
-        int max_thr = prop.maxThreadsPerMultiProcessor;
-        if (nb * T > max_thr) nb = max_thr / T;
-        if (nb * T > best_res) { best_res = nb * T; best_T = T; *blocks_per_sm = nb; }
-    }
-    if (!best_T) return set_err(QECMC_ERR_UNSUPPORTED, "lattice does not fit in shared memory");
-    *threads = best_T;
-    return 0;
 }
 
 // ------------------------------ context ------------------------------
@@ -189,8 +44,8 @@ extern "C" void qecmc_destroy(qecmc_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf *b : {&c->packed, &c->tables, &c->Z, &c->counters, &c->qm_in, &c->out_f64, &c->out_u32, &c->replay_a,
-                      &c->replay_b, &c->scratch})
+    for (DevBuf *b : {&c->packed, &c->tables, &c->Z, &c->counters, &c->qm_in, &c->out_f64, &c->out_u32, &c->out_u64,
+                      &c->out_i32, &c->replay_a, &c->replay_b, &c->scratch, &c->nhist, &c->mhist, &c->shorts, &c->sums})
         b->release();
     for (auto &kv : c->stab_hash) cudaFree(kv.second);
     for (auto &kv : c->stab_desc) cudaFree(kv.second);
@@ -429,7 +284,7 @@ static int build_fast_lut(qecmc_ctx *c, const Thr &t, FastTables &ft)
     return 0;
 }
 
-template <int GEOM, typename W, bool REPLAY>
+template <int GEOM, typename W, bool REPLAY, int MODE>
 static int launch_stdc_fast(qecmc_ctx *c, StdcParams &p)
 {
     FastTables ft;
@@ -442,16 +297,16 @@ static int launch_stdc_fast(qecmc_ctx *c, StdcParams &p)
     size_t fixed = (size_t)p.gchain.nstab * 16 + 512 * 5 + 16;
     QTRY(pick_threads(per_chain, fixed + 256, c->prop, &T, &nb));
     size_t smem = ((per_chain * T + 15) & ~(size_t)15) + fixed;
-    CUDA_OK(cudaFuncSetAttribute(stdc_fast_kernel<GEOM, W, REPLAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_OK(cudaFuncSetAttribute(stdc_fast_kernel<GEOM, W, REPLAY, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned grid = (unsigned)((p.n_chains + T - 1) / T);
-    stdc_fast_kernel<GEOM, W, REPLAY><<<grid, T, smem, c->stream>>>(p, ft, keys);
+    stdc_fast_kernel<GEOM, W, REPLAY, MODE><<<grid, T, smem, c->stream>>>(p, ft, keys);
     c->launches++;
     CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 // ------------------------------ STDC ------------------------------
-template <int GEOM, typename W, bool REPLAY>
+template <int GEOM, typename W, bool REPLAY, int MODE>
 static int launch_stdc(qecmc_ctx *c, StdcParams &p)
 {
     int T = 0, nb = 0;
@@ -459,35 +314,44 @@ static int launch_stdc(qecmc_ctx *c, StdcParams &p)
     size_t fixed = (size_t)p.gchain.nstab * 8 + 16;
     QTRY(pick_threads(per_chain, fixed + 256, c->prop, &T, &nb));
     size_t smem = ((per_chain * T + 15) & ~(size_t)15) + fixed;
-    CUDA_OK(cudaFuncSetAttribute(stdc_kernel<GEOM, W, REPLAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_OK(cudaFuncSetAttribute(stdc_kernel<GEOM, W, REPLAY, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned grid = (unsigned)((p.n_chains + T - 1) / T);
-    stdc_kernel<GEOM, W, REPLAY><<<grid, T, smem, c->stream>>>(p);
+    stdc_kernel<GEOM, W, REPLAY, MODE><<<grid, T, smem, c->stream>>>(p);
     c->launches++;
     CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-template <typename W, bool REPLAY> static int launch_stdc_geom(qecmc_ctx *c, StdcParams &p)
+template <typename W, bool REPLAY, int MODE> static int launch_stdc_geom(qecmc_ctx *c, StdcParams &p)
 {
     switch (p.gchain.geom) {
-    case TORIC: QTRY((build_stab_hash<TORIC, W>(c, p.gchain, (uint64_t **)&p.stab_hash))); return launch_stdc_fast<TORIC, W, REPLAY>(c, p);
-    case PLANAR: QTRY((build_stab_hash<PLANAR, W>(c, p.gchain, (uint64_t **)&p.stab_hash))); return launch_stdc_fast<PLANAR, W, REPLAY>(c, p);
-    case ROTATED: QTRY((build_stab_hash<ROTATED, W>(c, p.gchain, (uint64_t **)&p.stab_hash))); return launch_stdc<ROTATED, W, REPLAY>(c, p);
-    default: QTRY((build_stab_hash<XZZX, W>(c, p.gchain, (uint64_t **)&p.stab_hash))); return launch_stdc<XZZX, W, REPLAY>(c, p);
+    case TORIC: QTRY((build_stab_hash<TORIC, W>(c, p.gchain, (uint64_t **)&p.stab_hash))); return launch_stdc_fast<TORIC, W, REPLAY, MODE>(c, p);
+    case PLANAR: QTRY((build_stab_hash<PLANAR, W>(c, p.gchain, (uint64_t **)&p.stab_hash))); return launch_stdc_fast<PLANAR, W, REPLAY, MODE>(c, p);
+    case ROTATED: QTRY((build_stab_hash<ROTATED, W>(c, p.gchain, (uint64_t **)&p.stab_hash))); return launch_stdc<ROTATED, W, REPLAY, MODE>(c, p);
+    default: QTRY((build_stab_hash<XZZX, W>(c, p.gchain, (uint64_t **)&p.stab_hash))); return launch_stdc<XZZX, W, REPLAY, MODE>(c, p);
     }
 }
 
-static uint64_t next_pow2(uint64_t x)
+template <int MODE> static int launch_stdc_mode(qecmc_ctx *c, StdcParams &p, bool wide, bool replay)
 {
-    uint64_t p = 1;
-    while (p < x) p <<= 1;
-    return p;
+    if (replay) return wide ? launch_stdc_geom<uint64_t, true, MODE>(c, p) : launch_stdc_geom<uint32_t, true, MODE>(c, p);
+    return wide ? launch_stdc_geom<uint64_t, false, MODE>(c, p) : launch_stdc_geom<uint32_t, false, MODE>(c, p);
 }
 
-extern "C" int qecmc_stdc_dev(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, const uint8_t *d_qm, int64_t S, double *d_eqdistr,
-                              uint32_t *d_N_hist, qecmc_stats *stats)
+
+// Shared driver of STDC / STRC / single_temp: all three run `droplets` chains per (syndrome, class) with a sample
+// every `iters` Metropolis steps and differ in what a sample feeds.  Device pointers throughout.
+struct StdcOut {
+    double *eqdistr = nullptr;           // [S][n_eq]  percent (STDC, STRC) or mean length (single_temp)
+    uint32_t *N_hist = nullptr;          // [S][n_eq][nsites+1]  optional
+    unsigned long long *m_hist = nullptr;// [S][n_eq][nsites+1]  STRC, optional
+    int32_t *short_info = nullptr;       // [S][n_eq][4]         STRC, optional
+};
+
+static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uint8_t *d_qm, int64_t S, const StdcOut &out,
+                    qecmc_stats *stats)
 {
-    if (!c || !cfg || !d_qm || !d_eqdistr) return set_err(QECMC_ERR_ARG, "NULL argument");
+    if (!c || !cfg || !d_qm || !out.eqdistr) return set_err(QECMC_ERR_ARG, "NULL argument");
     if (S <= 0) return set_err(QECMC_ERR_ARG, "S must be > 0");
     QTRY(check_geom(cfg->geom_code, cfg->L));
     QTRY(check_geom(cfg->geom_chain, cfg->L));
@@ -501,33 +365,49 @@ extern "C" int qecmc_stdc_dev(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, const uin
     if (cfg->randomize && cfg->geom_code != TORIC && cfg->geom_code != PLANAR)
         return set_err(QECMC_ERR_ARG, "apply_stabilizers_uniform exists only for toric/planar codes");
     if (cfg->randomize && cfg->u_nb && !cfg->u_np) return set_err(QECMC_ERR_ARG, "replay with randomize needs u_np");
+    if (mode == MODE_MEAN && cfg->steps < 2) return set_err(QECMC_ERR_ARG, "single_temp needs max_iters >= 2");
     CUDA_OK(cudaSetDevice(c->device));
     c->launches = 0;
     const bool wide = cfg->L > 16;
     const size_t wbytes = wide ? 8 : 4;
     const int n_eq = gcode.neq;
+    const int nh = gcode.nsites + 1;
 
     // distinct-chain tables: capacity covers the worst case (every sample distinct) at load <= 0.8
-    uint64_t max_keys = (uint64_t)cfg->droplets * (uint64_t)cfg->steps;
-    uint64_t cap = next_pow2(max_keys + max_keys / 4 + 1);
-    if (cap < 1024) cap = 1024;
-    if (cap > (1ull << 32)) return set_err(QECMC_ERR_UNSUPPORTED, "more than 2^32 slots per distinct-chain table");
-    size_t fr = 0, tot = 0;
-    CUDA_OK(cudaMemGetInfo(&fr, &tot));
-    int64_t budget = c->table_budget ? c->table_budget : (int64_t)((double)(fr + c->tables.cap) * 0.85);
-    int64_t per_syndrome = (int64_t)n_eq * (int64_t)cap * 8;
-    int64_t wave = budget / per_syndrome;
-    if (wave < 1)
-        return set_err(QECMC_ERR_NOMEM, "distinct-chain tables need %lld bytes per syndrome, budget is %lld",
-                       (long long)per_syndrome, (long long)budget);
-    if (wave > S) wave = S;
-    QTRY(c->tables.ensure((size_t)wave * per_syndrome));
+    uint64_t cap = 0;
+    int64_t per_syndrome = 0, wave = S;
+    if (mode != MODE_MEAN) {
+        uint64_t max_keys = (uint64_t)cfg->droplets * (uint64_t)cfg->steps;
+        cap = next_pow2(max_keys + max_keys / 4 + 1);
+        if (cap < 1024) cap = 1024;
+        if (cap > (1ull << 32)) return set_err(QECMC_ERR_UNSUPPORTED, "more than 2^32 slots per distinct-chain table");
+        size_t fr = 0, tot = 0;
+        CUDA_OK(cudaMemGetInfo(&fr, &tot));
+        int64_t budget = c->table_budget ? c->table_budget : (int64_t)((double)(fr + c->tables.cap) * 0.85);
+        per_syndrome = (int64_t)n_eq * (int64_t)cap * 8;
+        wave = budget / per_syndrome;
+        if (wave < 1)
+            return set_err(QECMC_ERR_NOMEM, "distinct-chain tables need %lld bytes per syndrome, budget is %lld",
+                           (long long)per_syndrome, (long long)budget);
+        if (wave > S) wave = S;
+        QTRY(c->tables.ensure((size_t)wave * per_syndrome));
+    }
     int64_t n_lat = cfg->per_class_inits ? S * n_eq : S;
     QTRY(c->packed.ensure((size_t)n_lat * gcode.nw * wbytes));
     QTRY(c->Z.ensure((size_t)S * n_eq * sizeof(double)));
     QTRY(c->counters.ensure(8 * sizeof(unsigned long long)));
+    const int64_t wave_chains = wave * n_eq * cfg->droplets;
+    uint32_t *d_nh = out.N_hist;
+    unsigned long long *d_mh = out.m_hist;
+    if (mode == MODE_STRC) {
+        if (!d_nh) { QTRY(c->nhist.ensure((size_t)S * n_eq * nh * sizeof(uint32_t))); d_nh = (uint32_t *)c->nhist.p; }
+        if (!d_mh) { QTRY(c->mhist.ensure((size_t)S * n_eq * nh * sizeof(unsigned long long))); d_mh = (unsigned long long *)c->mhist.p; }
+        QTRY(c->shorts.ensure((size_t)wave_chains * 2 * sizeof(int)));
+    }
+    if (mode == MODE_MEAN) QTRY(c->sums.ensure((size_t)wave_chains * sizeof(unsigned long long)));
     CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
     CUDA_OK(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(unsigned long long), c->stream));
+    if (mode == MODE_STRC) CUDA_OK(cudaMemsetAsync(d_mh, 0, (size_t)S * n_eq * nh * sizeof(unsigned long long), c->stream));
     if (wide) QTRY(pack_lattices<uint64_t>(c, d_qm, n_lat, gcode, c->packed.p));
     else QTRY(pack_lattices<uint32_t>(c, d_qm, n_lat, gcode, c->packed.p));
 
@@ -543,30 +423,55 @@ extern "C" int qecmc_stdc_dev(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, const uin
     p.seed = cfg->seed;
     p.hash_seed = c->hash_seed;
     p.tables = (unsigned long long *)c->tables.p;
-    p.cap_mask = cap - 1;
+    p.cap_mask = cap ? cap - 1 : 0;
     make_thr(cfg->p_sampling, QECMC_POW_NUMBA, p.thr);
     p.u_nb = cfg->u_nb;
     p.u_np = cfg->u_np;
     p.counters = (unsigned long long *)c->counters.p;
+    // diagnostic knob for roofline work (3 = chains without the distinct set: results are then meaningless)
+    p.insert_mode = getenv("QECMC_DEBUG_INSERT_MODE") ? atoi(getenv("QECMC_DEBUG_INSERT_MODE")) : 2;
+    p.max_length = 2 * cfg->L * cfg->L;  // decoders.py:747
+    p.short_out = (int *)c->shorts.p;
+    p.sum_out = (unsigned long long *)c->sums.p;
     const double beta = -log((cfg->p_error / 3) / (1 - cfg->p_error));  // decoders.py:299
+    const double beta_s = -log((cfg->p_sampling / 3) / (1 - cfg->p_sampling));
 
     float chain_ms = 0;
     int64_t waves = 0;
     for (int64_t s0 = 0; s0 < S; s0 += wave, waves++) {
         int64_t sw = S - s0 < wave ? S - s0 : wave;
-        CUDA_OK(cudaMemsetAsync(c->tables.p, 0, (size_t)sw * per_syndrome, c->stream));
+        if (mode != MODE_MEAN) CUDA_OK(cudaMemsetAsync(c->tables.p, 0, (size_t)sw * per_syndrome, c->stream));
         p.lat0 = (const char *)c->packed.p + (size_t)(cfg->per_class_inits ? s0 * n_eq : s0) * gcode.nw * wbytes;
         p.n_chains = sw * n_eq * cfg->droplets;
         p.chain_offset = s0 * n_eq * cfg->droplets;
+        p.m_hist = d_mh ? d_mh + (size_t)s0 * n_eq * nh : nullptr;
         CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
-        if (cfg->u_nb) { if (wide) QTRY((launch_stdc_geom<uint64_t, true>(c, p))); else QTRY((launch_stdc_geom<uint32_t, true>(c, p))); }
-        else { if (wide) QTRY((launch_stdc_geom<uint64_t, false>(c, p))); else QTRY((launch_stdc_geom<uint32_t, false>(c, p))); }
+        if (mode == MODE_STDC) QTRY(launch_stdc_mode<MODE_STDC>(c, p, wide, cfg->u_nb != nullptr));
+        else if (mode == MODE_STRC) QTRY(launch_stdc_mode<MODE_STRC>(c, p, wide, cfg->u_nb != nullptr));
+        else QTRY(launch_stdc_mode<MODE_MEAN>(c, p, wide, cfg->u_nb != nullptr));
         CUDA_OK(cudaEventRecord(c->ev[3], c->stream));
-        table_hist_kernel<<<(unsigned)(sw * n_eq), 512, (gcode.nsites + 1) * sizeof(uint32_t), c->stream>>>(
-            (const unsigned long long *)c->tables.p, cap, gcode.nsites, beta, (double *)c->Z.p + s0 * n_eq,
-            d_N_hist ? d_N_hist + (size_t)s0 * n_eq * (gcode.nsites + 1) : nullptr, (unsigned long long *)c->counters.p + 3);
-        c->launches++;
-        CUDA_OK(cudaGetLastError());
+        const int64_t tabs = sw * n_eq;
+        if (mode != MODE_MEAN) {
+            table_hist_kernel<<<(unsigned)tabs, 512, nh * sizeof(uint32_t), c->stream>>>(
+                (const unsigned long long *)c->tables.p, cap, gcode.nsites, beta, (double *)c->Z.p + s0 * n_eq,
+                d_nh ? d_nh + (size_t)s0 * n_eq * nh : nullptr, (unsigned long long *)c->counters.p + 3);
+            c->launches++;
+            CUDA_OK(cudaGetLastError());
+        }
+        if (mode == MODE_STRC) {
+            strc_finalize_kernel<<<(unsigned)((tabs + 127) / 128), 128, 0, c->stream>>>(
+                d_nh + (size_t)s0 * n_eq * nh, d_mh + (size_t)s0 * n_eq * nh, (const int *)c->shorts.p, tabs, cfg->droplets,
+                gcode.nsites, p.max_length, beta_s, beta_s - beta, (double *)c->Z.p + s0 * n_eq,
+                out.short_info ? out.short_info + (size_t)s0 * n_eq * 4 : nullptr);
+            c->launches++;
+            CUDA_OK(cudaGetLastError());
+        }
+        if (mode == MODE_MEAN) {
+            mean_kernel<<<(unsigned)((tabs + 127) / 128), 128, 0, c->stream>>>((const unsigned long long *)c->sums.p,
+                                                                               out.eqdistr + s0 * n_eq, tabs, cfg->steps);
+            c->launches++;
+            CUDA_OK(cudaGetLastError());
+        }
         if (stats) {  // per-wave chain-kernel time (synchronises; waves are seconds long)
             CUDA_OK(cudaEventSynchronize(c->ev[3]));
             float ms = 0;
@@ -574,9 +479,11 @@ extern "C" int qecmc_stdc_dev(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, const uin
             chain_ms += ms;
         }
     }
-    normalize_kernel<<<(unsigned)((S + 127) / 128), 128, 0, c->stream>>>((const double *)c->Z.p, d_eqdistr, S, n_eq);
-    c->launches++;
-    CUDA_OK(cudaGetLastError());
+    if (mode != MODE_MEAN) {
+        normalize_kernel<<<(unsigned)((S + 127) / 128), 128, 0, c->stream>>>((const double *)c->Z.p, out.eqdistr, S, n_eq);
+        c->launches++;
+        CUDA_OK(cudaGetLastError());
+    }
     CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
     if (stats) {
         unsigned long long cnt[8] = {0};
@@ -598,8 +505,18 @@ extern "C" int qecmc_stdc_dev(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, const uin
     return 0;
 }
 
-extern "C" int qecmc_stdc(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, const uint8_t *qm, int64_t S, double *eqdistr,
-                          uint32_t *N_hist, qecmc_stats *stats)
+extern "C" int qecmc_stdc_dev(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, const uint8_t *d_qm, int64_t S, double *d_eqdistr,
+                              uint32_t *d_N_hist, qecmc_stats *stats)
+{
+    StdcOut o;
+    o.eqdistr = d_eqdistr;
+    o.N_hist = d_N_hist;
+    return stdc_run(c, cfg, MODE_STDC, d_qm, S, o, stats);
+}
+
+// host-buffer front end shared by qecmc_stdc / qecmc_strc / qecmc_single_temp
+static int stdc_host(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uint8_t *qm, int64_t S, double *eqdistr,
+                     uint32_t *N_hist, uint64_t *m_hist, int32_t *short_info, qecmc_stats *stats)
 {
     if (!c || !cfg || !qm || !eqdistr) return set_err(QECMC_ERR_ARG, "NULL argument");
     if (S <= 0) return set_err(QECMC_ERR_ARG, "S must be > 0");
@@ -612,6 +529,8 @@ extern "C" int qecmc_stdc(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, const uint8_t
     QTRY(c->qm_in.ensure(in_bytes));
     QTRY(c->out_f64.ensure((size_t)S * g.neq * sizeof(double)));
     if (N_hist) QTRY(c->out_u32.ensure(hist_elems * sizeof(uint32_t)));
+    if (m_hist) QTRY(c->out_u64.ensure(hist_elems * sizeof(uint64_t)));
+    if (short_info) QTRY(c->out_i32.ensure((size_t)S * g.neq * 4 * sizeof(int32_t)));
     CUDA_OK(cudaMemcpyAsync(c->qm_in.p, qm, in_bytes, cudaMemcpyHostToDevice, c->stream));
     qecmc_stdc_cfg dcfg = *cfg;
     if (cfg->u_nb) {
@@ -629,10 +548,35 @@ extern "C" int qecmc_stdc(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, const uint8_t
             dcfg.u_np = (const double *)c->replay_b.p;
         }
     }
-    QTRY(qecmc_stdc_dev(c, &dcfg, (const uint8_t *)c->qm_in.p, S, (double *)c->out_f64.p,
-                        N_hist ? (uint32_t *)c->out_u32.p : nullptr, stats));
+    StdcOut o;
+    o.eqdistr = (double *)c->out_f64.p;
+    o.N_hist = N_hist ? (uint32_t *)c->out_u32.p : nullptr;
+    o.m_hist = m_hist ? (unsigned long long *)c->out_u64.p : nullptr;
+    o.short_info = short_info ? (int32_t *)c->out_i32.p : nullptr;
+    QTRY(stdc_run(c, &dcfg, mode, (const uint8_t *)c->qm_in.p, S, o, stats));
     CUDA_OK(cudaMemcpyAsync(eqdistr, c->out_f64.p, (size_t)S * g.neq * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (N_hist) CUDA_OK(cudaMemcpyAsync(N_hist, c->out_u32.p, hist_elems * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (m_hist) CUDA_OK(cudaMemcpyAsync(m_hist, c->out_u64.p, hist_elems * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    if (short_info) CUDA_OK(cudaMemcpyAsync(short_info, c->out_i32.p, (size_t)S * g.neq * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     return 0;
+}
+
+extern "C" int qecmc_stdc(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, const uint8_t *qm, int64_t S, double *eqdistr,
+                          uint32_t *N_hist, qecmc_stats *stats)
+{
+    return stdc_host(c, cfg, MODE_STDC, qm, S, eqdistr, N_hist, nullptr, nullptr, stats);
+}
+
+extern "C" int qecmc_strc(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, const uint8_t *qm, int64_t S, double *eqdistr,
+                          uint64_t *m_hist, int32_t *short_info, qecmc_stats *stats)
+{
+    return stdc_host(c, cfg, MODE_STRC, qm, S, eqdistr, nullptr, m_hist, short_info, stats);
+}
+
+extern "C" int qecmc_single_temp(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, const uint8_t *qm, int64_t S, double *mean_length,
+                                 qecmc_stats *stats)
+{
+    if (cfg && cfg->droplets != 1) return set_err(QECMC_ERR_ARG, "single_temp runs one chain per class (droplets must be 1)");
+    return stdc_host(c, cfg, MODE_MEAN, qm, S, mean_length, nullptr, nullptr, nullptr, stats);
 }

@@ -1,0 +1,165 @@
+// qecmc_internal.h -- host-side plumbing shared by the translation units of libqecmc:
+// error reporting, device buffers, the context, lattice packing.
+#pragma once
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <map>
+#include <tuple>
+#include <vector>
+
+#include "../../include/qecmc.h"
+#include "qecmc_kernels.cuh"
+
+int qecmc_set_err(int code, const char *fmt, ...);
+#define set_err qecmc_set_err
+#define CUDA_OK(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return set_err(QECMC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define QTRY(call)            \
+    do {                      \
+        int r_ = (call);      \
+        if (r_ != 0) return r_; \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return set_err(QECMC_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        cap = bytes;
+        return 0;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct qecmc_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaDeviceProp prop;
+    int64_t table_budget = 0;
+    DevBuf packed, tables, Z, counters, qm_in, out_f64, out_u32, out_u64, out_i32, replay_a, replay_b, scratch, nhist, mhist,
+        shorts, sums;
+    std::map<std::tuple<int, int, int>, uint64_t *> stab_hash;  // (geom, L, wide) -> device table
+    std::map<std::tuple<int, int, int>, uint2 *> stab_desc;     // (geom, L, wide) -> descriptor table
+    DevBuf lut;
+    cudaEvent_t ev[4];
+    uint64_t hash_seed = 0x5EEDC0DE2020ull;
+    int64_t launches = 0;
+};
+
+
+using namespace qecmc;
+
+// ------------------------------ helpers ------------------------------
+static inline double numba_pow(double a, int64_t b)
+{
+    // numba lowers float64 ** int64 to square-and-multiply (reciprocal for negative exponents);
+    // this is what _update_chain_fast (src/mcmc.py:158) evaluates.
+    double r = 1.0;
+    bool inv = b < 0;
+    uint64_t e = inv ? (uint64_t)(-b) : (uint64_t)b;
+    while (e) {
+        if (e & 1) r *= a;
+        e >>= 1;
+        a *= a;
+    }
+    return inv ? 1.0 / r : r;
+}
+
+static inline void make_thr(double p, int pow_kind, Thr &t)
+{
+    double factor = (p / 3.0) / (1.0 - p);  // src/mcmc.py:16
+    for (int i = 0; i < QECMC_THR_N; i++) {
+        int dE = i - QECMC_THR_OFF;
+        double v = pow_kind == QECMC_POW_NUMBA ? numba_pow(factor, dE) : pow(factor, (double)dE);
+        t.d[i] = v;
+        if (!(v < 1.0)) t.u32[i] = 0xFFFFFFFFu;  // u < v always holds for u in [0,1)
+        else {
+            double x = ceil(v * 4294967296.0);  // u32/2^32 < v  <=>  u32 <= ceil(v*2^32) - 1
+            t.u32[i] = x < 1.0 ? 0u : (uint32_t)(x - 1.0);
+        }
+    }
+}
+
+static inline int check_geom(int geom, int L)
+{
+    if (geom < 0 || geom > 3) return set_err(QECMC_ERR_ARG, "unknown geometry %d", geom);
+    if (L < 2 || L > 32) return set_err(QECMC_ERR_ARG, "system size L=%d outside [2, 32]", L);
+    if ((geom == ROTATED || geom == XZZX) && (L < 3 || (L % 2) == 0))
+        return set_err(QECMC_ERR_ARG, "rotated/XZZX codes need odd L >= 3 (got %d)", L);
+    return 0;
+}
+
+template <typename W> static int pack_lattices(qecmc_ctx *c, const uint8_t *d_qm, int64_t n_lat, const Geo &g, void *d_out)
+{
+    int64_t n_words = n_lat * g.nw;
+    QTRY(c->scratch.ensure(sizeof(int)));
+    CUDA_OK(cudaMemsetAsync(c->scratch.p, 0, sizeof(int), c->stream));
+    int T = 256;
+    pack_kernel<W><<<(unsigned)((n_words + T - 1) / T), T, 0, c->stream>>>(d_qm, (W *)d_out, n_words, g.L, (int *)c->scratch.p);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    int bad = 0;
+    CUDA_OK(cudaMemcpyAsync(&bad, c->scratch.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (bad) return set_err(QECMC_ERR_ARG, "qubit_matrix holds values outside 0..3");
+    return 0;
+}
+
+template <int GEOM, typename W> static int build_stab_hash(qecmc_ctx *c, const Geo &g, uint64_t **out)
+{
+    auto key = std::make_tuple(GEOM, g.L, (int)(sizeof(W) == 8));
+    auto it = c->stab_hash.find(key);
+    if (it != c->stab_hash.end()) { *out = it->second; return 0; }
+    uint64_t *d = nullptr;
+    CUDA_OK(cudaMalloc(&d, sizeof(uint64_t) * g.nstab));
+    stab_hash_kernel<GEOM, W><<<(g.nstab + 127) / 128, 128, 0, c->stream>>>(g, c->hash_seed, d);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    c->stab_hash[key] = d;
+    *out = d;
+    return 0;
+}
+
+static inline int pick_threads(size_t bytes_per_chain, size_t fixed, const cudaDeviceProp &prop, int *threads, int *blocks_per_sm)
+{
+    // largest resident chain count per SM within the shared-memory budget, 256-thread CTAs preferred
+    size_t budget = prop.sharedMemPerMultiprocessor;
+    int best_T = 0, best_res = 0;
+    for (int T : {256, 128, 64}) {
+        size_t per_block = bytes_per_chain * T + fixed + 1024;  // +1 KiB reserved per CTA
+        if (bytes_per_chain * T + fixed > prop.sharedMemPerBlockOptin) continue;
+        int nb = (int)(budget / per_block);
+        int max_thr = prop.maxThreadsPerMultiProcessor;
+        if (nb * T > max_thr) nb = max_thr / T;
+        if (nb * T > best_res) { best_res = nb * T; best_T = T; *blocks_per_sm = nb; }
+    }
+    if (!best_T) return set_err(QECMC_ERR_UNSUPPORTED, "lattice does not fit in shared memory");
+    *threads = best_T;
+    return 0;
+}
+
+
+static inline uint64_t next_pow2(uint64_t x)
+{
+    uint64_t p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}

@@ -177,9 +177,61 @@ struct StdcParams {
     Thr thr;
     const double *u_nb, *u_np;
     unsigned long long *counters;  // [0] accepted [1] offered [2] inserted
+    int insert_mode;               // 2 asynchronous CAS (default); diagnostics: 0 synchronous probe, 3 no inserts
+    // STRC (decoders.py:745-832): visits per length m(n), per droplet shortest / next-shortest visited length
+    unsigned long long *m_hist;    // [S_wave * n_eq][nsites + 1]
+    int *short_out;                // [n_chains][2]
+    int max_length;                // 2 * L * L (decoders.py:747)
+    // single_temp (decoders.py:108-135): sum of the chain length over the first steps-1 samples
+    unsigned long long *sum_out;   // [n_chains]
 };
 
-template <int GEOM, typename W, bool REPLAY>
+enum { MODE_STDC = 0, MODE_STRC = 1, MODE_MEAN = 2 };
+
+// Per-sample bookkeeping beyond the distinct set.
+template <int MODE> struct SampleAcct {
+    int sh, nsh, run_n;
+    uint32_t run_cnt;
+    unsigned long long *mh;
+    unsigned long long sum;
+    int64_t mean_left;
+    __device__ __forceinline__ void init(const StdcParams &p, int64_t tab)
+    {
+        sh = nsh = p.max_length;
+        run_n = -1;
+        run_cnt = 0;
+        mh = MODE == MODE_STRC ? p.m_hist + (uint64_t)tab * (p.gcode.nsites + 1) : nullptr;
+        sum = 0;
+        mean_left = p.steps - 1;
+    }
+    __device__ __forceinline__ void sample(int n)
+    {
+        if (MODE == MODE_STRC) {
+            if (n != run_n) {  // run-length aggregated m(n) += 1
+                if (run_cnt) atomicAdd(mh + run_n, (unsigned long long)run_cnt);
+                run_n = n;
+                run_cnt = 0;
+            }
+            run_cnt++;
+            if (n < sh) { nsh = sh; sh = n; }
+            else if (n > sh && n < nsh) nsh = n;
+        } else if (MODE == MODE_MEAN) {
+            if (mean_left > 0) { sum += (unsigned long long)n; mean_left--; }
+        }
+    }
+    __device__ __forceinline__ void finish(const StdcParams &p, int64_t local)
+    {
+        if (MODE == MODE_STRC) {
+            if (run_cnt) atomicAdd(mh + run_n, (unsigned long long)run_cnt);
+            p.short_out[2 * local] = sh;
+            p.short_out[2 * local + 1] = nsh;
+        } else if (MODE == MODE_MEAN) {
+            p.sum_out[local] = sum;
+        }
+    }
+};
+
+template <int GEOM, typename W, bool REPLAY, int MODE>
 __global__ void __launch_bounds__(256) stdc_kernel(StdcParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -232,6 +284,8 @@ __global__ void __launch_bounds__(256) stdc_kernel(StdcParams p)
     int n = lat_weight<W>(g, lat);
     uint64_t h = lat_hash<W>(g, lat, p.hash_seed);
     unsigned long long *table = p.tables + (uint64_t)tab * (p.cap_mask + 1);
+    SampleAcct<MODE> acct;
+    acct.init(p, tab);
 
     unsigned long long nacc = 0, noff = 0, nins = 0;
     bool dirty = true;  // the first sample is always new to the chain
@@ -242,7 +296,9 @@ __global__ void __launch_bounds__(256) stdc_kernel(StdcParams p)
     if (acc) { n += dE; h ^= s_hs[idx]; dirty = true; nacc++; }             \
     if (--left == 0) {                                                      \
         left = p.iters;                                                     \
-        if (dirty) { noff++; nins += table_insert(table, p.cap_mask, make_key(h, n)); dirty = false; } \
+        acct.sample(n);                                                     \
+        if (MODE != MODE_MEAN && dirty) { noff++; nins += table_insert(table, p.cap_mask, make_key(h, n)); } \
+        dirty = false;                                                      \
     }
 
     if (REPLAY) {
@@ -277,6 +333,7 @@ __global__ void __launch_bounds__(256) stdc_kernel(StdcParams p)
         }
     }
 #undef QECMC_AFTER_STEP
+    acct.finish(p, local);
     // statistics: three atomics per chain at the very end (negligible)
     atomicAdd(p.counters + 0, nacc);
     atomicAdd(p.counters + 1, noff);
@@ -285,7 +342,7 @@ __global__ void __launch_bounds__(256) stdc_kernel(StdcParams p)
 
 // One block per (syndrome, class) table: N(n) histogram from the length field of the
 // keys, then Z_E = sum_n N(n) exp(-beta n) (decoders.py:317-318).
-__global__ void table_hist_kernel(const unsigned long long *__restrict__ tables, uint64_t cap, int nsites, double beta,
+static __global__ void table_hist_kernel(const unsigned long long *__restrict__ tables, uint64_t cap, int nsites, double beta,
                                   double *__restrict__ Z, uint32_t *__restrict__ N_hist, unsigned long long *distinct)
 {
     extern __shared__ uint32_t s_hist[];
@@ -309,8 +366,51 @@ __global__ void table_hist_kernel(const unsigned long long *__restrict__ tables,
     }
 }
 
+// STRC per (syndrome, class): the order-dependent droplet merge of decoders.py:882-928 (the union of the
+// droplets' distinct shortest / next-shortest sets has N(shortest) / N(next_shortest) members),
+// then Z_E = sum_l m(l) exp(-beta_s * shortest + d_beta * l) * mean_fraction (decoders.py:931-946).
+static __global__ void strc_finalize_kernel(const uint32_t *__restrict__ N_hist, const unsigned long long *__restrict__ m_hist,
+                                     const int *__restrict__ short_in, int64_t tabs, int droplets, int nsites,
+                                     int max_length, double beta_s, double d_beta, double *__restrict__ Z,
+                                     int *__restrict__ short_info)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= tabs) return;
+    const int *sh = short_in + t * droplets * 2;
+    int shortest = max_length, next = max_length;
+    for (int d = 0; d < droplets; d++) {
+        if (sh[2 * d] < shortest) { next = shortest; shortest = sh[2 * d]; }
+        if (sh[2 * d + 1] < next) next = sh[2 * d + 1];
+    }
+    const uint32_t *N = N_hist + t * (nsites + 1);
+    const unsigned long long *m = m_hist + t * (nsites + 1);
+    double n0 = shortest <= nsites ? (double)N[shortest] : 0.0, n1 = next <= nsites ? (double)N[next] : 0.0;
+    double frac = n0 / (shortest <= nsites ? (double)m[shortest] : 0.0);
+    if (next != max_length) {
+        double nf = n1 / (double)m[next];
+        frac = 0.5 * (frac + nf * exp(-beta_s * (double)(next - shortest)));
+    }
+    double z = 0;
+    for (int l = 0; l <= nsites; l++)
+        if (m[l]) z += (double)m[l] * exp(-beta_s * (double)shortest + d_beta * (double)l);
+    Z[t] = z * frac;
+    if (short_info) {
+        short_info[4 * t] = shortest;
+        short_info[4 * t + 1] = next;
+        short_info[4 * t + 2] = (int)n0;
+        short_info[4 * t + 3] = (int)n1;
+    }
+}
+
+// single_temp: mean chain length over the first steps-1 samples (decoders.py:128-133)
+static __global__ void mean_kernel(const unsigned long long *__restrict__ sum, double *__restrict__ out, int64_t n, int64_t steps)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)sum[i] / (double)(steps - 1);
+}
+
 // eqdistr = Z / sum(Z) * 100 per syndrome (decoders.py:322)
-__global__ void normalize_kernel(const double *__restrict__ Z, double *__restrict__ out, int64_t S, int n_eq)
+static __global__ void normalize_kernel(const double *__restrict__ Z, double *__restrict__ out, int64_t S, int n_eq)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;

@@ -1,0 +1,523 @@
+// qecmc_ladder.cuh -- parallel-tempering ladders on the GPU.
+//
+// Reference: Ladder / Ladder_alpha / Ladder_biased (.step, .r_flip) and Chain / Chain_alpha /
+// Chain_biased (.update_chain) in src/mcmc.py:19-103, src/mcmc_alpha.py:27-137,
+// src/mcmc_biased.py:21-124; PTEQ's bookkeeping in decoders.py:25-105 and
+// decoders_biasednoise.py:28-237; PTDC_droplet in decoders.py:138-165; STDC_droplet_alpha in
+// decoders.py:510-534.
+//
+// Mapping.  One ladder = one group of G = 2^k >= Nc consecutive lanes of a warp, lane <-> one
+// replica.  A replica's 2-bit-packed lattice never moves: it stays in the lane's column of the
+// shared-memory tile ([row word][thread], conflict free).  A replica swap exchanges the two lanes'
+// RUNG INDICES (and, for the alpha ladder, the rung-owned n_eff, which the reference does not swap),
+// so the sequential top-to-bottom swap sweep is ballots + shuffles, never a lattice copy and never a
+// host round trip.  Replay mode consumes the reference's own numba (NB) and CPython (PY) uniform
+// streams in the reference's order and is bit-exact; native mode draws from
+// per-lane Philox4x32-10 streams.
+#pragma once
+#include "qecmc_device.cuh"
+
+namespace qecmc {
+
+enum { LK_DEPOL = 0, LK_ALPHA = 1, LK_BIASED = 2 };
+enum { ACCT_NONE = 0, ACCT_PTEQ = 1, ACCT_DC = 2 };
+
+struct LadderParams {
+    Geo g;
+    int kind, Nc, G, iters, acct;
+    double p_logical;       // top rung: probability of proposing a logical operator
+    int top_accept_all;     // kind 0: ladder[Nc-1] >= 0.75 (mcmc.py:30)
+    int64_t n_ladders, ladder_offset, steps;
+    const void *lat_in;     // packed [n_ladders][nw] (init_broadcast) or [n_ladders][Nc][nw]
+    int init_broadcast;
+    void *lat_out;          // packed [n_ladders][Nc][nw], rung order (optional)
+    int *flags_out;         // [n_ladders][Nc] (optional)
+    int2 *neff_out;         // [n_ladders][Nc] (nz, nx+ny) of the rung-owned n_eff (optional)
+    long long *tops0_out;   // [n_ladders] (optional)
+    void *snap_lat;         // tests: [n_ladders][steps][Nc][nw] after every Ladder.step
+    int *snap_flags;        // [n_ladders][steps][Nc]
+    long long *snap_tops0;  // [n_ladders][steps]
+    const double *thr_d;    // [Nc][9]  kind 0: pow(factor_r, dE), dE = -4..4 (libm, as CPython float ** int)
+    const uint32_t *thr_u;  // [Nc][9]  the same as 32-bit thresholds (native mode)
+    const double *thr_top_d;// [8L+1]   kind 0 top rung: pow(factor_top, dE), dE = -4L..4L (a toric logical
+                            //          acts on both layers: up to 2(2L-1) qubits)
+    const double *diff;     // [Nc-1]   p_diff (kind 0, 2) or pz_tilde[i]/pz_tilde[i+1] (kind 1)
+    double alpha;           // kind 1
+    const double *wtab;     // kinds 1, 2: [Nc][4][nsites+1] = px^k, py^k, pz^k, q0^(L*L-k)
+    uint64_t seed;
+    const double *u_nb, *u_py;  // replay: [n_ladders][n_nb], [n_ladders][n_py]
+    int n_nb, n_py;
+    // PTEQ
+    int SEQ, TOPS, tops_burn, use_conv;
+    double eps;
+    uint32_t *hist;         // [n_ladders][steps]  bottom-rung n_err (or nz | nxy << 16) after burn-in
+    long long *eq_counts;   // [n_ladders][n_eq]
+    long long *info;        // [n_ladders][4] = steps used, since_burn, tops0, converged
+    uint8_t *percent;       // [n_ladders][n_eq]
+    int cls_delta[8];       // raw class change of logical (layer, op)
+    // distinct-chain accounting (PTDC, EWD)
+    unsigned long long *tables;
+    uint64_t cap_mask;
+    int droplets, aux_bits;
+    const uint64_t *stab_hash;
+    uint64_t hash_seed;
+    unsigned long long *counters;  // [0] accepted [1] offered
+    int *status;                   // != 0: a replay stream ran dry
+};
+
+// raw class bits: XOR-linear in the lattice.  Equal to the class label except for XZZX, whose label
+// is a relabelling of (x, z) (xzzx_model.py:476-486): raw = x + 2z <-> label by swapping 2 and 3.
+__host__ __device__ inline int class_raw_to_label(int geom, int raw) { return (geom == XZZX && raw >= 2) ? 5 - raw : raw; }
+
+struct NativeRng {
+    uint32_t k0, k1, id_lo, id_hi, ctr;
+    uint4 buf;
+    int have;
+    __device__ __forceinline__ void init(uint64_t seed, uint64_t id)
+    {
+        k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
+        id_lo = (uint32_t)id; id_hi = (uint32_t)(id >> 32);
+        ctr = 0; have = 0;
+        buf = make_uint4(0, 0, 0, 0);
+    }
+    __device__ __forceinline__ uint32_t next32()
+    {
+        if (have == 0) { buf = philox4x32_10(ctr++, 0u, id_lo, id_hi, k0, k1); have = 4; }
+        uint32_t v = buf.x;
+        buf.x = buf.y; buf.y = buf.z; buf.z = buf.w;
+        have--;
+        return v;
+    }
+    __device__ __forceinline__ double nb() { return (double)next32() * 2.3283064365386963e-10; }
+    __device__ __forceinline__ double py() { return nb(); }
+};
+
+struct ReplayRng {
+    const double *nb_base, *py_base;
+    int nbp, pyp, n_nb, n_py;
+    int *status;
+    __device__ __forceinline__ double nb()
+    {
+        if (nbp >= n_nb) { *status = 1; nbp++; return 0.0; }
+        return nb_base[nbp++];
+    }
+    __device__ __forceinline__ double py()
+    {
+        if (pyp >= n_py) { *status = 2; pyp++; return 0.0; }
+        return py_base[pyp++];
+    }
+};
+
+// numba's float64 ** int64 (mcmc.py:149): square-and-multiply, reciprocal for negative exponents
+__device__ __forceinline__ double numba_pow_dev(double a, int b)
+{
+    double r = 1.0;
+    bool inv = b < 0;
+    unsigned e = inv ? (unsigned)(-b) : (unsigned)b;
+    while (e) {
+        if (e & 1) r = __dmul_rn(r, a);
+        e >>= 1;
+        a = __dmul_rn(a, a);
+    }
+    return inv ? __ddiv_rn(1.0, r) : r;
+}
+
+// P(state) of mcmc_alpha.py:40 / mcmc_biased.py:31 from host-made pow tables (bit-equal to libm's)
+__device__ __forceinline__ double chain_weight(const double *wt, int ns1, int nx, int ny, int nz)
+{
+    double a = __dmul_rn(wt[nx], wt[ns1 + ny]);
+    a = __dmul_rn(a, wt[2 * ns1 + nz]);
+    return __dmul_rn(a, wt[3 * ns1 + nx + ny + nz]);
+}
+
+template <int GEOM, typename RNG> struct LogicalDraw {
+    int op[2], xp[2], zp[2], nl;
+    // _apply_random_logical draw order: toric_model.py:228-253 (both layer operators first),
+    // planar_model.py:271-288, rotated_surface_model.py:331-346, xzzx_model.py:340-357
+    __device__ __forceinline__ void draw(RNG &rng, int L)
+    {
+        nl = GEOM == TORIC ? 2 : 1;
+        for (int l = 0; l < nl; l++) op[l] = (int)(rng.nb() * 4);
+        for (int l = 0; l < nl; l++) {
+            xp[l] = zp[l] = 0;
+            if (op[l] == 1 || op[l] == 2) xp[l] = (int)(rng.nb() * L);
+            if (op[l] == 3 || op[l] == 2) zp[l] = (int)(rng.nb() * L);
+        }
+    }
+    template <typename W, typename A> __device__ __forceinline__ int apply(const Geo &g, A &lat) const
+    {
+        int d = 0;
+        for (int l = 0; l < nl; l++) d += lat_apply_logical<GEOM, W>(g, lat, op[l], l, xp[l], zp[l]);
+        return d;
+    }
+};
+
+template <int GEOM, typename W, bool REPLAY, bool WEIGHTED>
+__global__ void __launch_bounds__(128) ladder_kernel(LadderParams p)
+{
+    typedef typename std::conditional<REPLAY, ReplayRng, NativeRng>::type RNG;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int T = blockDim.x, tid = threadIdx.x;
+    const Geo g = p.g;
+    W *tile = reinterpret_cast<W *>(smem);
+    unsigned char *sp = smem + (((size_t)g.nw * T * sizeof(W) + 15) & ~(size_t)15);
+    double *s_thrd = reinterpret_cast<double *>(sp);                       // [Nc][9]
+    uint32_t *s_thru = reinterpret_cast<uint32_t *>(s_thrd + p.Nc * 9);    // [Nc][9]
+    if (!WEIGHTED)
+        for (int i = tid; i < p.Nc * 9; i += T) { s_thrd[i] = p.thr_d[i]; s_thru[i] = p.thr_u[i]; }
+    __syncthreads();
+
+    const int G = p.G, Nc = p.Nc, L = g.L;
+    const int lane = tid & 31;
+    const int gl = lane & (G - 1);          // lane within the ladder's group
+    const int gbase = lane - gl;
+    const uint32_t gmask = G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1u);
+    const int64_t ladder = ((int64_t)blockIdx.x * T + tid) / G;   // within this launch
+    const bool valid = ladder < p.n_ladders && gl < Nc;
+    const int64_t gladder = p.ladder_offset + ladder;
+    constexpr int K = NumDraws<GEOM>::value;
+    constexpr int NU = NumUpd<GEOM>::value;
+    const int ns1 = g.nsites + 1;
+
+    SmemLat<W> lat{tile + tid, T};
+    int r = gl, flag = 0;
+    int n = 0, nx = 0, ny = 0, nz = 0, cls = 0;
+    int e_nz = 0, e_nxy = 0;  // rung-owned n_eff = e_nz + alpha * e_nxy (mcmc_alpha.py:22,56)
+    uint64_t h = 0;
+    bool dirty = true;
+    if (valid) {
+        const W *src = reinterpret_cast<const W *>(p.lat_in) + (p.init_broadcast ? ladder : ladder * Nc + gl) * g.nw;
+        for (int w = 0; w < g.nw; w++) lat.set(w, src[w]);
+        lat_count_xyz<W>(g, lat, nx, ny, nz);
+        n = nx + ny + nz;
+        e_nz = nz; e_nxy = nx + ny;
+        cls = class_raw_to_label(GEOM, lat_class<GEOM, W>(g, lat));
+        flag = (gl == Nc - 1) ? 1 : 0;
+        if (p.acct == ACCT_DC) h = lat_hash<W>(g, lat, p.hash_seed);
+    } else {
+        for (int w = 0; w < g.nw; w++) lat.set(w, (W)0);
+    }
+    RNG rng;
+    int base_nb = 0, base_py = 0;  // replay: group-uniform stream positions
+    if (REPLAY) {
+        ReplayRng *rr = reinterpret_cast<ReplayRng *>(&rng);
+        const int64_t lc = ladder < p.n_ladders ? ladder : 0;
+        rr->nb_base = p.u_nb + lc * p.n_nb;
+        rr->py_base = p.u_py + lc * p.n_py;
+        rr->n_nb = p.n_nb; rr->n_py = p.n_py;
+        rr->nbp = rr->pyp = 0;
+        rr->status = p.status;
+    } else {
+        reinterpret_cast<NativeRng *>(&rng)->init(p.seed, (uint64_t)gladder * 32u + (uint64_t)gl);
+    }
+    const bool top_logical = p.p_logical != 0.0;
+    unsigned long long *table = nullptr;
+    if (p.acct == ACCT_DC && ladder < p.n_ladders) table = p.tables + (uint64_t)(ladder / p.droplets) * (p.cap_mask + 1);
+
+    // group-uniform bookkeeping (every lane of the group carries the same values)
+    long long tops0 = 0, since_burn = 0, burn_in = 0, conv_start = 0, conv_streak = 0, steps_used = p.steps;
+    long long S2a = 0, S2b = 0, S4a = 0, S4b = 0;  // window sums of the n_err history (a: n or nz, b: nx+ny)
+    long long wA = 0, wB = 0, wC = 0, wl = 0;      // window bounds l/4, l/2, 3l/4 and history length l
+    int converged = 0;
+    bool done = !(ladder < p.n_ladders);
+    uint32_t nacc = 0, noff = 0;
+    uint32_t *hist = p.hist ? p.hist + (ladder < p.n_ladders ? ladder : 0) * p.steps : nullptr;
+    long long *eqc = p.eq_counts ? p.eq_counts + (ladder < p.n_ladders ? ladder : 0) * g.neq : nullptr;
+
+    for (long long step = 0; step < p.steps; step++) {
+        if (__all_sync(0xFFFFFFFFu, done)) break;
+        // ---------------- Ladder.update_ladder: every rung runs `iters` Metropolis steps ----------------
+        if (valid && !done) {
+            const bool is_top = (r == Nc - 1) && top_logical;
+            if (REPLAY) {
+                ReplayRng *rr = reinterpret_cast<ReplayRng *>(&rng);
+                rr->nbp = base_nb + r * K * p.iters;  // rungs below the top consume fixed amounts
+                rr->pyp = base_py + r * p.iters;
+            }
+            const double *wt = WEIGHTED ? p.wtab + (size_t)r * 4 * ns1 : nullptr;
+            double pb = 0.0;
+            if (WEIGHTED) pb = chain_weight(wt, ns1, nx, ny, nz);  // frozen for the block
+            for (int it = 0; it < p.iters; it++) {
+                bool logical = false;
+                if (is_top) logical = rng.py() < p.p_logical;
+                if (logical) {
+                    LogicalDraw<GEOM, RNG> ld;
+                    ld.draw(rng, L);
+                    int dE = ld.template apply<W>(g, lat);
+                    int dcls = 0;
+                    for (int l = 0; l < ld.nl; l++) dcls ^= p.cls_delta[l * 4 + ld.op[l]];
+                    bool acc;
+                    int mx = 0, my = 0, mz = 0;
+                    if (WEIGHTED) {
+                        lat_count_xyz<W>(g, lat, mx, my, mz);
+                        double pn = chain_weight(wt, ns1, mx, my, mz);
+                        acc = rng.py() < __ddiv_rn(pn, pb);
+                    } else {
+                        if (p.top_accept_all || dE <= 0) acc = true;
+                        else acc = rng.py() < p.thr_top_d[dE + 4 * L];
+                    }
+                    if (acc) {
+                        if (WEIGHTED) { nx = mx; ny = my; nz = mz; n = mx + my + mz; e_nz = mz; e_nxy = mx + my; }
+                        else n += dE;
+                        cls ^= dcls;
+                        nacc++;
+                    } else {
+                        ld.template apply<W>(g, lat);  // XOR is an involution: undo
+                    }
+                } else {
+                    int row, col, op, idx = 0;
+                    if (REPLAY) {
+                        ReplayRng *rr = reinterpret_cast<ReplayRng *>(&rng);
+                        double u[K];
+                        for (int k = 0; k < K; k++) u[k] = rr->nb();
+                        propose_replay<GEOM>(g, u, row, col, op);
+                        if (p.acct == ACCT_DC) idx = rco_to_idx<GEOM>(g, row, col, op);
+                    } else {
+                        idx = (int)__umulhi(reinterpret_cast<NativeRng *>(&rng)->next32(), (uint32_t)g.nstab);
+                        idx_to_rco<GEOM>(g, idx, row, col, op);
+                    }
+                    Upd<W> u;
+                    decode<GEOM, W>(g, row, col, op, u);
+                    W nv[NU];
+                    int dE = 0, dx = 0, dy = 0, dz = 0;
+#pragma unroll
+                    for (int i = 0; i < NU; i++) {
+                        W o = lat.get(u.w[i]);
+                        nv[i] = (W)(o ^ u.m[i]);
+                        if (WEIGHTED) {
+                            dx += popc(xmap(nv[i])) - popc(xmap(o));
+                            dy += popc(ymap(nv[i])) - popc(ymap(o));
+                            dz += popc(zmap(nv[i])) - popc(zmap(o));
+                        } else {
+                            dE += weight<W>(nv[i]) - weight<W>(o);
+                        }
+                    }
+                    bool acc;
+                    if (WEIGHTED) {
+                        double pn = chain_weight(wt, ns1, nx + dx, ny + dy, nz + dz);
+                        acc = rng.py() < __ddiv_rn(pn, pb);
+                    } else if (is_top) {
+                        if (p.top_accept_all || dE <= 0) acc = true;
+                        else acc = rng.py() < p.thr_top_d[dE + 4 * L];
+                    } else if (REPLAY) {
+                        acc = rng.py() < s_thrd[r * 9 + dE + QECMC_THR_OFF];
+                    } else {
+                        acc = reinterpret_cast<NativeRng *>(&rng)->next32() <= s_thru[r * 9 + dE + QECMC_THR_OFF];
+                    }
+                    if (acc) {
+#pragma unroll
+                        for (int i = 0; i < NU; i++) lat.set(u.w[i], nv[i]);
+                        if (WEIGHTED) { nx += dx; ny += dy; nz += dz; n = nx + ny + nz; e_nz = nz; e_nxy = nx + ny; }
+                        else n += dE;
+                        if (p.acct == ACCT_DC) h ^= p.stab_hash[idx];
+                        dirty = true;
+                        nacc++;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // ---------------- swap sweep, top to bottom (mcmc.py:96-103) ----------------
+        if (REPLAY) {
+            // the top rung ran last and consumed a data-dependent number of draws
+            ReplayRng *rr = reinterpret_cast<ReplayRng *>(&rng);
+            uint32_t bt = __ballot_sync(0xFFFFFFFFu, valid && r == Nc - 1);
+            int lt = __ffs((bt >> gbase) & gmask) - 1;
+            if (lt < 0) lt = 0;
+            base_nb = __shfl_sync(0xFFFFFFFFu, rr->nbp, lt, G);
+            base_py = __shfl_sync(0xFFFFFFFFu, rr->pyp, lt, G);
+            rr->nbp = base_nb;
+            rr->pyp = base_py;
+        }
+        double u_sw = 0.0;
+        if (!REPLAY) u_sw = rng.nb();  // lane i's draw decides pair (i, i+1)
+        for (int i = Nc - 2; i >= 0; i--) {
+            uint32_t b_lo = __ballot_sync(0xFFFFFFFFu, valid && r == i);
+            uint32_t b_hi = __ballot_sync(0xFFFFFFFFu, valid && r == i + 1);
+            int l_lo = __ffs((b_lo >> gbase) & gmask) - 1, l_hi = __ffs((b_hi >> gbase) & gmask) - 1;
+            if (l_lo < 0) l_lo = 0;
+            if (l_hi < 0) l_hi = 0;
+            bool swap;
+            if (p.kind == LK_ALPHA) {
+                // mcmc_alpha.py:117-123: PY draw always; float exponent n_eff_hi - n_eff_lo; n_eff stays with the rung
+                int lo_z = __shfl_sync(0xFFFFFFFFu, e_nz, l_lo, G), lo_xy = __shfl_sync(0xFFFFFFFFu, e_nxy, l_lo, G);
+                int hi_z = __shfl_sync(0xFFFFFFFFu, e_nz, l_hi, G), hi_xy = __shfl_sync(0xFFFFFFFFu, e_nxy, l_hi, G);
+                double ne_lo = __dadd_rn((double)lo_z, __dmul_rn(p.alpha, (double)lo_xy));
+                double ne_hi = __dadd_rn((double)hi_z, __dmul_rn(p.alpha, (double)hi_xy));
+                double u;
+                if (REPLAY) u = done ? 1.0 : rng.py();
+                else u = __shfl_sync(0xFFFFFFFFu, u_sw, i, G);
+                swap = u < pow(p.diff[i], __dadd_rn(ne_hi, -ne_lo));
+                if (swap) {  // the lanes trade rungs, so they trade the rung-owned n_eff too
+                    if (gl == l_lo) { e_nz = hi_z; e_nxy = hi_xy; }
+                    if (gl == l_hi) { e_nz = lo_z; e_nxy = lo_xy; }
+                }
+            } else {
+                int ne_lo = __shfl_sync(0xFFFFFFFFu, n, l_lo, G), ne_hi = __shfl_sync(0xFFFFFFFFu, n, l_hi, G);
+                double u = 0.0;
+                if (!REPLAY) u = __shfl_sync(0xFFFFFFFFu, u_sw, i, G);
+                if (p.kind == LK_DEPOL && ne_hi < ne_lo) {
+                    swap = true;  // mcmc.py:146-147: no draw
+                } else {
+                    if (REPLAY) u = done ? 1.0 : rng.nb();  // mcmc_biased.py:154-156 draws always
+                    swap = u < numba_pow_dev(p.diff[i], ne_hi - ne_lo);
+                }
+            }
+            if (swap && !done) {
+                if (gl == l_lo) r = i + 1;
+                else if (gl == l_hi) r = i;
+            }
+        }
+        if (REPLAY) {
+            ReplayRng *rr = reinterpret_cast<ReplayRng *>(&rng);
+            base_nb = rr->nbp;
+            base_py = rr->pyp;
+        }
+        if (valid && !done && r == Nc - 1) flag = 1;
+        const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, valid && r == 0);
+        int l0 = __ffs((b0 >> gbase) & gmask) - 1;
+        if (l0 < 0) l0 = 0;
+        const int flag0 = __shfl_sync(0xFFFFFFFFu, flag, l0, G);
+        if (!done && flag0 == 1) {
+            tops0++;
+            if (gl == l0) flag = 0;
+        }
+        // ---------------- snapshots (tests) ----------------
+        if (p.snap_lat && valid && !done) {
+            W *o = reinterpret_cast<W *>(p.snap_lat) + (((size_t)ladder * p.steps + step) * Nc + r) * g.nw;
+            for (int w = 0; w < g.nw; w++) o[w] = lat.get(w);
+            p.snap_flags[((size_t)ladder * p.steps + step) * Nc + r] = flag;
+            if (gl == 0) p.snap_tops0[(size_t)ladder * p.steps + step] = tops0;
+        }
+        // ---------------- accounting ----------------
+        if (p.acct == ACCT_PTEQ) {
+            // decoders.py:56-82 (PTEQ), decoders_biasednoise.py:196-215 (PTEQ_alpha records n_eff of the bottom rung)
+            const int cur = __shfl_sync(0xFFFFFFFFu, cls, l0, G);
+            const int h_a = __shfl_sync(0xFFFFFFFFu, p.kind == LK_ALPHA ? e_nz : n, l0, G);
+            const int h_b = __shfl_sync(0xFFFFFFFFu, p.kind == LK_ALPHA ? e_nxy : 0, l0, G);
+            if (!done) {
+                if (tops0 >= p.tops_burn) {
+                    since_burn = step - burn_in;
+                    if (gl == 0) {
+                        eqc[class_raw_to_label(GEOM, cur)]++;
+                        if (hist) hist[since_burn] = (uint32_t)h_a | ((uint32_t)h_b << 16);
+                    }
+                    // history windows [l/4, l/2) and [3l/4, l) of conv_crit_error_based_PT (decoders.py:93-105)
+                    wl = since_burn + 1;
+                    S4a += h_a; S4b += h_b;
+                    const long long nC = 3 * wl / 4, nB = wl / 2, nA = wl / 4;
+                    if (p.use_conv) {
+                        // entries written by the group's lane 0 in earlier steps (the __syncwarp above orders them)
+                        if (nC > wC) { uint32_t v = __ldcg(hist + wC); S4a -= v & 0xFFFF; S4b -= v >> 16; }
+                        if (nB > wB) { uint32_t v = __ldcg(hist + wB); S2a += v & 0xFFFF; S2b += v >> 16; }
+                        if (nA > wA) { uint32_t v = __ldcg(hist + wA); S2a -= v & 0xFFFF; S2b -= v >> 16; }
+                    }
+                    wC = nC; wB = nB; wA = nA;
+                } else {
+                    burn_in++;
+                }
+                if (p.use_conv && tops0 >= p.TOPS) {
+                    const long long l = since_burn + 1;
+                    double q2, q4;
+                    if (p.kind == LK_ALPHA) {
+                        q2 = ((double)S2a + p.alpha * (double)S2b) / (double)(l / 2 - l / 4);
+                        q4 = ((double)S4a + p.alpha * (double)S4b) / (double)(l - 3 * l / 4);
+                    } else {
+                        q2 = (double)S2a / (double)(l / 2 - l / 4);
+                        q4 = (double)S4a / (double)(l - 3 * l / 4);
+                    }
+                    const double err = fabs(q2 - q4);
+                    if (err < p.eps) {
+                        if (conv_streak >= p.SEQ) { done = true; converged = 1; steps_used = step + 1; }
+                        conv_streak = tops0 - conv_start;
+                    } else {
+                        conv_streak = 0;
+                        conv_start = tops0;
+                    }
+                }
+            }
+        } else if (p.acct == ACCT_DC) {
+            // PTDC_droplet (decoders.py:146-155) / STDC_droplet_alpha (decoders.py:521-531): every rung offers its
+            // state; a state unchanged since its last offer is already in the set
+            if (valid && !done && dirty) {
+                uint64_t aux = p.kind == LK_ALPHA ? ((uint64_t)nz | ((uint64_t)(nx + ny) << 11)) : (uint64_t)n;
+                uint64_t amask = (1ull << p.aux_bits) - 1ull;
+                uint64_t key = (h & ~amask) | aux | (1ull << 63);
+                uint64_t slot = (key >> p.aux_bits) & p.cap_mask;
+                while (true) {
+                    unsigned long long curk = __ldcg(table + slot);
+                    if (curk == key) break;
+                    if (curk == 0ull) {
+                        unsigned long long prev = atomicCAS(table + slot, 0ull, (unsigned long long)key);
+                        if (prev == 0ull || prev == key) break;
+                    }
+                    slot = (slot + 1) & p.cap_mask;
+                }
+                noff++;
+                dirty = false;
+            }
+        }
+    }
+    __syncwarp();
+    // ---------------- results ----------------
+    if (valid) {
+        if (p.lat_out) {
+            W *o = reinterpret_cast<W *>(p.lat_out) + ((size_t)ladder * Nc + r) * g.nw;
+            for (int w = 0; w < g.nw; w++) o[w] = lat.get(w);
+        }
+        if (p.flags_out) p.flags_out[(size_t)ladder * Nc + r] = flag;
+        if (p.neff_out) p.neff_out[(size_t)ladder * Nc + r] = make_int2(e_nz, e_nxy);
+        if (gl == 0) {
+            if (p.tops0_out) p.tops0_out[ladder] = tops0;
+            if (p.acct == ACCT_PTEQ) {
+                if (p.info) {
+                    p.info[4 * ladder] = steps_used;
+                    p.info[4 * ladder + 1] = since_burn;
+                    p.info[4 * ladder + 2] = tops0;
+                    p.info[4 * ladder + 3] = converged;
+                }
+                if (p.percent)  // decoders.py:89: (eq[since_burn] / (since_burn + 1) * 100).astype(np.uint8)
+                    for (int e = 0; e < g.neq; e++)
+                        p.percent[ladder * g.neq + e] = (uint8_t)(int)((double)eqc[e] / (double)(since_burn + 1) * 100);
+            }
+        }
+        if (p.counters) {
+            atomicAdd(p.counters + 0, (unsigned long long)nacc);
+            atomicAdd(p.counters + 1, (unsigned long long)noff);
+        }
+    }
+}
+
+// Z_E of a (syndrome, class) table whose keys carry (nz, nx+ny) in their low 22 bits:
+// sum over distinct chains of exp(-beta * (nz + alpha (nx+ny))) (decoders.py:568,577-578)
+static __global__ void table_sum_alpha_kernel(const unsigned long long *__restrict__ tables, uint64_t cap, double beta, double alpha,
+                                       double *__restrict__ Z, unsigned long long *distinct_out, unsigned long long *distinct_total)
+{
+    __shared__ double s_z[256];
+    __shared__ unsigned long long s_c[256];
+    const unsigned long long *tab = tables + (uint64_t)blockIdx.x * cap;
+    double z = 0;
+    unsigned long long cnt = 0;
+    for (uint64_t i = threadIdx.x; i < cap; i += blockDim.x) {
+        unsigned long long k = tab[i];
+        if (k) {
+            int nz = (int)(k & 0x7FF), nxy = (int)((k >> 11) & 0x7FF);
+            z += exp(-beta * ((double)nz + alpha * (double)nxy));
+            cnt++;
+        }
+    }
+    s_z[threadIdx.x] = z;
+    s_c[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { s_z[threadIdx.x] += s_z[threadIdx.x + s]; s_c[threadIdx.x] += s_c[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        Z[blockIdx.x] = s_z[0];
+        if (distinct_out) distinct_out[blockIdx.x] = s_c[0];
+        if (distinct_total) atomicAdd(distinct_total, s_c[0]);
+    }
+}
+
+}  // namespace qecmc

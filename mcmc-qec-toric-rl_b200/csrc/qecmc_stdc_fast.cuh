@@ -46,7 +46,7 @@ template <> __device__ __forceinline__ uint32_t gather_fields<uint64_t>(uint64_t
     return qa | (qb << 2) | (qc << 4) | (qd << 6);
 }
 
-template <int GEOM, typename W, bool REPLAY>
+template <int GEOM, typename W, bool REPLAY, int MODE>
 __global__ void __launch_bounds__(256) stdc_fast_kernel(StdcParams p, FastTables ft, PhiloxKeys keys)
 {
     static_assert(GEOM == TORIC || GEOM == PLANAR, "table-driven kernel covers the two-layer codes");
@@ -112,6 +112,9 @@ __global__ void __launch_bounds__(256) stdc_fast_kernel(StdcParams p, FastTables
     uint64_t keyA = 0, prevA = 0, keyB = 0, prevB = 0;
     uint32_t slotA = 0, slotB = 0;
     const uint32_t smask = (uint32_t)cap_mask;  // host guarantees cap <= 2^32 slots
+    const int imode = MODE == MODE_MEAN ? 3 : p.insert_mode;
+    SampleAcct<MODE> acct;
+    acct.init(p, tab);
     unsigned char *mybase = reinterpret_cast<unsigned char *>(tile + tid);
     const uint32_t wstride = (uint32_t)T * sizeof(W);
 
@@ -121,14 +124,6 @@ __global__ void __launch_bounds__(256) stdc_fast_kernel(StdcParams p, FastTables
         slot = (slot + 1u) & smask;                                                    \
         prev = atomicCAS(table + slot, 0ull, (unsigned long long)(key));               \
     } while (0)
-    // predicated atom.cas, output-only: when the predicate is false `prev` is undefined, which is fine because
-    // an entry's `prev` is only read one sample after that entry issued a CAS.  Written this way the result
-    // register is not copied after the atomic, so nothing waits on HBM until `prev` is read a sample later.
-#define QECMC_CAS_IF(pred, prev, slot, key)                                                                   \
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %4, 0;\n\t@q atom.global.cas.b64 %0, [%1], %2, %3;\n\t}" \
-                 : "=l"(prev)                                                                                  \
-                 : "l"(table + (slot)), "l"(0ull), "l"(key), "r"((uint32_t)(pred)))
-
     // one Metropolis step for stabilizer idx; r_acc / u_acc is the accept draw
     auto step = [&](int idx, uint32_t r_acc, double u_acc) {
         const uint2 d = s_desc[idx];
@@ -167,29 +162,28 @@ __global__ void __launch_bounds__(256) stdc_fast_kernel(StdcParams p, FastTables
         }
         if (--left == 0) {
             left = p.iters;
-            // branch-free bookkeeping: each entry issues at most one (predicated) CAS per sample
+            acct.sample(n);
             const uint64_t nkey = make_key(h, n);
             const uint32_t nslot = (uint32_t)(nkey >> QECMC_LEN_BITS) & smask;
-            const bool retryA = keyA != 0 && !QECMC_PROBE_DONE(prevA, keyA);
-            const bool retryB = keyB != 0 && !QECMC_PROBE_DONE(prevB, keyB);
-            if (dirty && retryA && retryB) {  // rare: both entries still colliding -> drain A in place
-                uint64_t pv = prevA;
-                uint32_t sl = slotA;
-                while (!QECMC_PROBE_DONE(pv, keyA)) QECMC_PROBE_NEXT(sl, pv, keyA);
-                keyA = nkey; slotA = nslot; prevA = nkey;  // placeholder "done" value until the CAS below lands
-                QECMC_CAS_IF(1, prevA, nslot, nkey);
-                QECMC_CAS_IF(1, prevB, (slotB + 1u) & smask, keyB);
-                slotB = (slotB + 1u) & smask;
-            } else {
-                const bool takeA = dirty && !retryA;
-                const bool takeB = dirty && retryA;   // then B is free (handled above otherwise)
-                const bool issueA = retryA || takeA, issueB = retryB || takeB;
-                slotA = takeA ? nslot : (slotA + 1u) & smask;
-                slotB = takeB ? nslot : (slotB + 1u) & smask;
-                keyA = issueA ? (takeA ? nkey : keyA) : 0ull;
-                keyB = issueB ? (takeB ? nkey : keyB) : 0ull;
-                QECMC_CAS_IF(issueA, prevA, slotA, keyA);
-                QECMC_CAS_IF(issueB, prevB, slotB, keyB);
+            if (imode == 2) {
+                if (keyA) {
+                    if (QECMC_PROBE_DONE(prevA, keyA)) keyA = 0;
+                    else QECMC_PROBE_NEXT(slotA, prevA, keyA);
+                }
+                if (keyB) {
+                    if (QECMC_PROBE_DONE(prevB, keyB)) keyB = 0;
+                    else QECMC_PROBE_NEXT(slotB, prevB, keyB);
+                }
+                if (dirty) {
+                    if (keyA && keyB) {  // rare: both entries still colliding
+                        while (!QECMC_PROBE_DONE(prevA, keyA)) QECMC_PROBE_NEXT(slotA, prevA, keyA);
+                        keyA = 0;
+                    }
+                    if (!keyA) { keyA = nkey; slotA = nslot; prevA = atomicCAS(table + nslot, 0ull, (unsigned long long)nkey); }
+                    else { keyB = nkey; slotB = nslot; prevB = atomicCAS(table + nslot, 0ull, (unsigned long long)nkey); }
+                }
+            } else if (imode == 0) {
+                if (dirty) table_insert(table, cap_mask, nkey);
             }
             noff += dirty;
             dirty = false;
@@ -218,11 +212,13 @@ __global__ void __launch_bounds__(256) stdc_fast_kernel(StdcParams p, FastTables
             step((int)__umulhi(r.x, nstab), r.y, 0.0);
         }
     }
-    if (keyA) while (!QECMC_PROBE_DONE(prevA, keyA)) QECMC_PROBE_NEXT(slotA, prevA, keyA);
-    if (keyB) while (!QECMC_PROBE_DONE(prevB, keyB)) QECMC_PROBE_NEXT(slotB, prevB, keyB);
+    if (imode == 2) {
+        if (keyA) while (!QECMC_PROBE_DONE(prevA, keyA)) QECMC_PROBE_NEXT(slotA, prevA, keyA);
+        if (keyB) while (!QECMC_PROBE_DONE(prevB, keyB)) QECMC_PROBE_NEXT(slotB, prevB, keyB);
+    }
 #undef QECMC_PROBE_DONE
 #undef QECMC_PROBE_NEXT
-#undef QECMC_CAS_IF
+    acct.finish(p, local);
     atomicAdd(p.counters + 0, (unsigned long long)nacc);
     atomicAdd(p.counters + 1, (unsigned long long)noff);
 }

@@ -139,6 +139,69 @@ def test_stdc_replay_matches_reference_golden(ctx, variant):
     assert n >= 2
 
 
+# ------------------------------------------------------------------ replay: STRC, single_temp
+@pytest.mark.parametrize("gcode,gchain,L,droplets,per_class", [
+    (O.TORIC, O.TORIC, 5, 1, False), (O.TORIC, O.TORIC, 5, 4, False), (O.TORIC, O.PLANAR, 5, 2, False),
+    (O.PLANAR, O.PLANAR, 5, 3, True), (O.PLANAR, O.PLANAR, 7, 2, False), (O.TORIC, O.TORIC, 17, 2, False),
+    (O.ROTATED, O.ROTATED, 5, 2, True)])
+def test_strc_replay_matches_oracle(ctx, gcode, gchain, L, droplets, per_class):
+    rng = np.random.default_rng(177 + L + droplets)
+    S, steps, iters = 3, 150, 5
+    n_eq = O.neq(gcode)
+    k = 3 if gchain in (O.TORIC, O.PLANAR) else 5
+    randomize = gcode in (O.TORIC, O.PLANAR) and not per_class
+    qs = [rand_lattice(rng, gcode, L, 0.1) for _ in range(S)]
+    qm = np.stack([O.all_classes(gcode, L, q) for q in qs]) if per_class else np.stack([q.reshape(-1) for q in qs])
+    n_chains = S * n_eq * droplets
+    u_nb, u_np = _stdc_streams(rng, n_chains, steps, iters, k, L)
+    out, st, mh, info = ctx.strc(gcode, gchain, L, qm, 0.1, 0.25, droplets, steps, iters=iters, per_class=per_class,
+                                 randomize=randomize, u_nb=u_nb, u_np=u_np, want_hist=True)
+    for s in range(S):
+        inits = qm[s] if per_class else O.all_classes(gcode, L, qs[s])
+        base = s * n_eq * droplets
+        nb = [O.Stream.replay(u_nb[base + i].reshape(-1)) for i in range(n_eq * droplets)]
+        np_ = [O.Stream.replay(u_np[base + i]) for i in range(n_eq * droplets)]
+        want, wmh, winfo = O.strc(gcode, gchain, L, inits, 0.1, 0.25, droplets, steps, nb, np_, iters=iters,
+                                  randomize=randomize, want_hist=True)
+        assert np.array_equal(mh[s].astype(np.int64), wmh), f"m(n) histogram differs for syndrome {s}"
+        assert np.array_equal(info[s].astype(np.int64), winfo), f"shortest / next-shortest bookkeeping differs ({s})"
+        np.testing.assert_allclose(out[s], want, rtol=1e-9)
+
+
+@pytest.mark.parametrize("variant", ["shipped", "toric"])
+def test_strc_replay_matches_reference_golden(ctx, variant):
+    n = 0
+    for c in golden(variant):
+        if c["kind"] != "strc" or c["conv_mult"] != 0:
+            continue
+        gcode, gchain, L = O.GEOM[c["geom"]], O.GEOM[c["chain_geom"]], c["L"]
+        n_eq, steps, iters = O.neq(gcode), c["steps"], 5
+        per_class = gcode != O.TORIC
+        u_nb = np.random.RandomState(c["nb_seed"]).random_sample(n_eq * steps * iters * 4).reshape(n_eq, steps * iters, 4)
+        u_np = np.random.RandomState(c["np_seed"]).random_sample(n_eq * 2 * L * L).reshape(n_eq, 2 * L * L)
+        qm = (c["inits"].reshape(1, n_eq, -1) if per_class else c["q"].reshape(1, -1)).copy()
+        out, st = ctx.strc(gcode, gchain, L, qm, c["p_error"], c["p_sampling"], 1, steps, iters=iters,
+                           per_class=per_class, randomize=bool(c["randomize"]), u_nb=u_nb, u_np=u_np)
+        np.testing.assert_allclose(out[0], c["out"], rtol=1e-9)
+        n += 1
+    assert n >= 1
+
+
+@pytest.mark.parametrize("g,L", [(O.TORIC, 5), (O.PLANAR, 7), (O.TORIC, 19)])
+def test_single_temp_replay_matches_oracle(ctx, g, L):
+    rng = np.random.default_rng(300 + L)
+    S, max_iters, iters = 4, 90, 5
+    n_eq = O.neq(g)
+    qs = [rand_lattice(rng, g, L, 0.1) for _ in range(S)]
+    qm = np.stack([q.reshape(-1) for q in qs])
+    u_nb = rng.random((S * n_eq, max_iters * iters, 4))
+    out, st = ctx.single_temp(g, g, L, qm, 0.2, max_iters, iters=iters, u_nb=u_nb)
+    for s in range(S):
+        nb = [O.Stream.replay(u_nb[s * n_eq + e].reshape(-1)) for e in range(n_eq)]
+        want = O.single_temp(g, g, L, O.all_classes(g, L, qs[s]), 0.2, max_iters, nb, iters=iters)
+        assert np.array_equal(out[s], want)
+
+
 # ------------------------------------------------------------------ native Philox
 def test_native_chain_statistics(ctx):
     """Native Philox chains: acceptance rate and mean weight agree with the oracle's MT19937 chains
@@ -193,3 +256,176 @@ def test_errors_are_loud(ctx):
         ctx.chain_update(O.TORIC, 5, bad, 0.1, 5)
     with pytest.raises(_lib.QecmcError):
         ctx.chain_update(O.ROTATED, 6, np.zeros((1, 36), np.uint8), 0.1, 5)
+
+
+# ------------------------------------------------------------------ replay: tempering ladders
+def _ladder_budget(g, Nc, iters, steps):
+    k = 3 if g in (O.TORIC, O.PLANAR) else 5
+    return steps * (Nc * k * iters + 6 * iters + Nc), steps * (Nc * iters + 2 * iters + Nc)
+
+
+LADDER_CASES = [
+    (0, O.TORIC, 5, 5, 0.5), (0, O.PLANAR, 5, 4, 0.5), (0, O.ROTATED, 7, 7, 0.5), (0, O.XZZX, 5, 5, 0.5),
+    (0, O.TORIC, 7, 1, 0.5), (0, O.ROTATED, 25, 25, 0.5), (0, O.TORIC, 5, 3, 0.0),
+    (1, O.TORIC, 5, 5, 0.5), (1, O.XZZX, 7, 6, 0.5), (1, O.PLANAR, 5, 1, 0.0), (1, O.ROTATED, 5, 5, 0.3),
+    (2, O.XZZX, 7, 7, 0.5), (2, O.TORIC, 5, 4, 0.5), (2, O.PLANAR, 7, 2, 0.0), (2, O.XZZX, 21, 21, 0.5),
+]
+
+
+@pytest.mark.parametrize("kind,g,L,Nc,p_logical", LADDER_CASES)
+def test_ladder_replay_matches_oracle(ctx, kind, g, L, Nc, p_logical):
+    """Ladder.step on the device == the oracle's, from the same NB / PY uniform streams: rung states, flags,
+    tops0 after every step and the rung-owned n_eff at the end, all bit-exact."""
+    rng = np.random.default_rng(9000 + 100 * kind + 10 * g + L + Nc)
+    S, steps, iters = 3, 12, 10
+    bottom = 0.12 if kind != 1 else 0.2
+    b = {0: 0.0, 1: 1.7, 2: 8.0}[kind]
+    qs = [rand_lattice(rng, g, L, 0.12) for _ in range(S)]
+    qm = np.stack([q.reshape(-1) for q in qs])
+    n_nb, n_py = _ladder_budget(g, Nc, iters, steps)
+    u_nb, u_py = rng.random((S, n_nb)), rng.random((S, n_py))
+    out = ctx.ladder_run(g, L, kind, qm, bottom, Nc, steps, iters=iters, param_b=b, p_logical=p_logical, u_nb=u_nb, u_py=u_py,
+                         snapshots=True)
+    for s in range(S):
+        lad = O.Ladder(kind, g, L, qs[s], bottom, Nc, p_logical, b)
+        nb, py = O.Stream.replay(u_nb[s]), O.Stream.replay(u_py[s])
+        for t in range(steps):
+            lad.step(iters, nb, py)
+            assert np.array_equal(out["snap_states"][s, t], lad.qm), f"rung states differ (ladder {s}, step {t})"
+            assert np.array_equal(out["snap_flags"][s, t], lad.flags), f"flags differ (ladder {s}, step {t})"
+            assert out["snap_tops0"][s, t] == lad.tops0.value
+        assert np.array_equal(out["rung_states"][s], lad.qm)
+        assert out["tops0"][s] == lad.tops0.value
+        if kind == 1:
+            assert np.array_equal(out["n_eff"][s], lad.n_eff)
+
+
+def _py_uniforms(seed, n):
+    import random
+    r = random.Random(seed)
+    return np.array([r.random() for _ in range(n)])
+
+
+def test_ladder_replay_matches_reference_golden(ctx):
+    """Ladder / Ladder_alpha / Ladder_biased of the seeded reference, from its own numba and CPython streams."""
+    n = 0
+    for c in golden("shipped"):
+        if c["kind"] != "ladder":
+            continue
+        kind = {"dep": 0, "alpha": 1, "biased": 2}[c["lkind"]]
+        g, L, Nc, iters = O.GEOM[c["geom"]], c["L"], c["Nc"], c["iters"]
+        steps = len(c["tops0"])
+        n_nb, n_py = _ladder_budget(g, Nc, iters, steps)
+        u_nb = np.random.RandomState(c["nb_seed"]).random_sample(n_nb).reshape(1, -1)
+        u_py = _py_uniforms(c["py_seed"], n_py).reshape(1, -1)
+        out = ctx.ladder_run(g, L, kind, c["q"].reshape(1, -1).copy(), c["bottom"], Nc, steps, iters=iters, param_b=c["b"],
+                             p_logical=c["p_logical"], u_nb=u_nb, u_py=u_py, snapshots=True)
+        for t in range(steps):
+            assert np.array_equal(out["snap_states"][0, t], c["states"][t].reshape(Nc, -1)), (c["geom"], c["lkind"], t)
+            assert list(out["snap_flags"][0, t]) == list(c["flags"][t])
+            assert out["snap_tops0"][0, t] == c["tops0"][t]
+        n += 1
+    assert n >= 12
+
+
+PTEQ_CASES = [(0, O.TORIC, 5, 0.1, 0.0), (0, O.ROTATED, 7, 0.12, 0.0), (0, O.PLANAR, 5, 0.1, 0.0), (0, O.XZZX, 5, 0.1, 0.0),
+              (1, O.XZZX, 5, 0.15, 2.0), (1, O.TORIC, 5, 0.15, 1.5), (2, O.XZZX, 7, 0.1, 10.0), (2, O.ROTATED, 5, 0.1, 3.0)]
+
+
+@pytest.mark.parametrize("kind,g,L,bottom,b", PTEQ_CASES)
+def test_pteq_replay_matches_oracle(ctx, kind, g, L, bottom, b):
+    """PTEQ with its convergence criterion: same class percentages, same number of steps, same tops0."""
+    rng = np.random.default_rng(500 + 10 * kind + g + L)
+    S, iters, cap = 3, 10, 3000
+    qs = [rand_lattice(rng, g, L, 0.1) for _ in range(S)]
+    qm = np.stack([q.reshape(-1) for q in qs])
+    n_nb, n_py = _ladder_budget(g, L, iters, cap)
+    u_nb, u_py = rng.random((S, n_nb)), rng.random((S, n_py))
+    pct, info = ctx.pteq(g, L, kind, qm, bottom, param_b=b, steps=cap, iters=iters, u_nb=u_nb, u_py=u_py)
+    for s in range(S):
+        want, winfo = O.pteq(kind, g, L, qs[s], bottom, O.Stream.replay(u_nb[s]), O.Stream.replay(u_py[s]), param_b=b,
+                             steps=cap, iters=iters)
+        assert info["steps"][s] == winfo["steps"], (info["steps"][s], winfo["steps"])
+        assert info["since_burn"][s] == winfo["since_burn"] and info["tops0"][s] == winfo["tops0"]
+        assert np.array_equal(info["counts"][s], winfo["counts"])
+        assert np.array_equal(pct[s], want)
+
+
+def test_pteq_replay_matches_reference_golden(ctx):
+    n = 0
+    for c in golden("shipped"):
+        if c["kind"] != "pteq":
+            continue
+        kind = {"dep": 0, "alpha": 1, "biased": 2}[c["lkind"]]
+        g, L = O.GEOM[c["geom"]], c["L"]
+        # the oracle (pinned to this very vector in test_oracle_golden) tells how many steps the reference ran
+        _, winfo = O.pteq(kind, g, L, c["q"], c["p"], O.Stream.mt(c["nb_seed"]), O.Stream.py(c["py_seed"]), param_b=c["b"],
+                          steps=c["steps"])
+        used = int(winfo["steps"])
+        n_nb, n_py = _ladder_budget(g, L, 10, used)
+        u_nb = np.random.RandomState(c["nb_seed"]).random_sample(n_nb).reshape(1, -1)
+        u_py = _py_uniforms(c["py_seed"], n_py).reshape(1, -1)
+        pct, info = ctx.pteq(g, L, kind, c["q"].reshape(1, -1).copy(), c["p"], param_b=c["b"], steps=used, u_nb=u_nb, u_py=u_py)
+        assert info["steps"][0] == used
+        assert np.array_equal(pct[0], c["out"]), (c["geom"], c["lkind"])
+        n += 1
+    assert n >= 12
+
+
+@pytest.mark.parametrize("g,L", [(O.PLANAR, 5), (O.ROTATED, 5), (O.XZZX, 7), (O.TORIC, 5)])
+def test_stdc_alpha_replay_matches_oracle(ctx, g, L):
+    """EWD-style STDC_Nall_n_alpha: distinct counts equal, class distribution to 1e-9."""
+    rng = np.random.default_rng(640 + g + L)
+    S, steps, iters, alpha = 2, 400, 5, 1.6
+    n_eq = O.neq(g)
+    k = 3 if g in (O.TORIC, O.PLANAR) else 5
+    qs = [rand_lattice(rng, g, L, 0.1) for _ in range(S)]
+    qm = np.stack([q.reshape(-1) for q in qs])
+    u_nb, u_py = rng.random((S * n_eq, steps * iters * k)), rng.random((S * n_eq, steps * iters))
+    out, distinct, st = ctx.stdc_alpha(g, L, qm, 0.25, alpha, 0.1, steps, iters=iters, u_nb=u_nb, u_py=u_py)
+    for s in range(S):
+        inits = O.all_classes(g, L, qs[s])
+        nb = O.Stream.replay(u_nb[s * n_eq:(s + 1) * n_eq].reshape(-1))
+        py = O.Stream.replay(u_py[s * n_eq:(s + 1) * n_eq].reshape(-1))
+        want, wdist = O.stdc_alpha(g, L, inits, 0.25, alpha, 0.1, steps, nb, py, iters=iters)
+        assert np.array_equal(distinct[s], wdist)
+        np.testing.assert_allclose(out[s], want, rtol=1e-9)
+
+
+def test_stdc_alpha_replay_matches_reference_golden(ctx):
+    n = 0
+    for c in golden("shipped"):
+        if c["kind"] != "stdc_alpha":
+            continue
+        g, L, steps = O.GEOM[c["geom"]], c["L"], c["steps"]
+        k = 3 if g in (O.TORIC, O.PLANAR) else 5
+        u_nb = np.random.RandomState(c["nb_seed"]).random_sample(4 * steps * 5 * k).reshape(4, -1)
+        u_py = _py_uniforms(c["py_seed"], 4 * steps * 5).reshape(4, -1)
+        out, distinct, st = ctx.stdc_alpha(g, L, c["q"].reshape(1, -1).copy(), c["pz_tilde_sampling"], c["alpha"], c["pz_tilde"],
+                                           steps, u_nb=u_nb, u_py=u_py)
+        np.testing.assert_allclose(out[0], c["out"], rtol=1e-9)
+        n += 1
+    assert n >= 3
+
+
+def test_native_pteq_agrees_with_oracle(ctx):
+    """Native Philox PTEQ (fixed number of steps): the class histogram of the bottom rung agrees with the
+    oracle's MT19937 run on the same syndromes -- same most likely class, percentages within sampling noise."""
+    g, L, p = O.ROTATED, 5, 0.1
+    rng = np.random.default_rng(21)
+    S, steps = 16, 20000
+    qs = [rand_lattice(rng, g, L, 0.1) for _ in range(S)]
+    qm = np.stack([q.reshape(-1) for q in qs])
+    pct, info = ctx.pteq(g, L, 0, qm, p, steps=steps, conv=False, seed=5)
+    agree, diffs = 0, []
+    for s in range(S):
+        want, _ = O.pteq(0, g, L, qs[s], p, O.Stream.mt(100 + s), O.Stream.py(200 + s), steps=steps, conv=False)
+        agree += int(pct[s].argmax() == want.argmax())
+        diffs.append(np.abs(pct[s].astype(int) - want.astype(int)))
+    diffs = np.array(diffs)
+    # two independent oracle runs of this configuration differ by up to ~15 points on near-degenerate syndromes
+    # (the class histogram of a 20000-step ladder has only a few hundred independent samples)
+    assert diffs.max() <= 25, diffs.max()
+    assert diffs.mean() <= 3.0, diffs.mean()
+    assert agree >= S - 2
+    assert (info["steps"] == steps).all()
