@@ -182,13 +182,25 @@ typedef struct qecmc_ladder_cfg {
     int64_t n_nb, n_py;
 } qecmc_ladder_cfg;
 
-/* `steps` calls of Ladder.step(iters) on S ladders, every rung starting from qm0[s] ([S][n_sites]).
- * Optional outputs in rung order (rung 0 = coldest): rung_states [S][Nc][n_sites], flags [S][Nc],
- * tops0 [S], n_eff [S][Nc] (alpha ladders), and the same after every step (tests):
- * snap_states [S][steps][Nc][n_sites], snap_flags [S][steps][Nc], snap_tops0 [S][steps]. */
-int qecmc_ladder_run(qecmc_ctx *ctx, const qecmc_ladder_cfg *cfg, const uint8_t *qm0, int64_t S, int64_t steps,
-                     uint8_t *rung_states, int32_t *flags, int64_t *tops0, double *n_eff, uint8_t *snap_states,
-                     int32_t *snap_flags, int64_t *snap_tops0, qecmc_stats *stats);
+/* `steps` calls of Ladder.step(iters) on S ladders.  Fresh start (resume == 0): every rung of ladder s
+ * starts from qm0[s] ([S][n_sites]), only the top rung flagged, tops0 = 0.  resume != 0: the ladders
+ * continue from rung_states / flags / tops0 (/ n_eff_parts), which are then in/out -- this is what the
+ * Python Ladder objects use between .step() calls.  All arrays are in rung order (rung 0 = coldest);
+ * every output is optional. */
+typedef struct qecmc_ladder_io {
+    const uint8_t *qm0;       /* [S][n_sites] */
+    int32_t resume, reserved;
+    uint8_t *rung_states;     /* [S][Nc][n_sites] */
+    int32_t *flags;           /* [S][Nc] */
+    int64_t *tops0;           /* [S] */
+    double  *n_eff;           /* [S][Nc] alpha ladders: the rung-owned n_eff = nz + alpha (nx + ny) (out only) */
+    int32_t *n_eff_parts;     /* [S][Nc][2] = (nz, nx + ny) of that n_eff, exact (in/out with resume) */
+    uint8_t *snap_states;     /* tests: [S][steps][Nc][n_sites] after every step */
+    int32_t *snap_flags;      /*        [S][steps][Nc] */
+    int64_t *snap_tops0;      /*        [S][steps] */
+} qecmc_ladder_io;
+int qecmc_ladder_run(qecmc_ctx *ctx, const qecmc_ladder_cfg *cfg, const qecmc_ladder_io *io, int64_t S, int64_t steps,
+                     qecmc_stats *stats);
 
 /* PTEQ / PTEQ_biased / PTEQ_alpha (decoders.py:25-105, decoders_biasednoise.py:28-90,175-237). */
 typedef struct qecmc_pteq_cfg {

@@ -49,6 +49,12 @@ class LadderCfg(C.Structure):
                 ("seed", C.c_uint64), ("u_nb", C.c_void_p), ("u_py", C.c_void_p), ("n_nb", C.c_int64), ("n_py", C.c_int64)]
 
 
+class LadderIO(C.Structure):
+    _fields_ = [("qm0", C.c_void_p), ("resume", C.c_int32), ("reserved", C.c_int32), ("rung_states", C.c_void_p),
+                ("flags", C.c_void_p), ("tops0", C.c_void_p), ("n_eff", C.c_void_p), ("n_eff_parts", C.c_void_p),
+                ("snap_states", C.c_void_p), ("snap_flags", C.c_void_p), ("snap_tops0", C.c_void_p)]
+
+
 class PteqCfg(C.Structure):
     _fields_ = [("ladder", LadderCfg), ("SEQ", C.c_int32), ("TOPS", C.c_int32), ("tops_burn", C.c_int32),
                 ("use_conv", C.c_int32), ("eps", C.c_double), ("steps", C.c_int64)]
@@ -94,8 +100,8 @@ def load():
     L.qecmc_strc.argtypes = [C.c_void_p, C.POINTER(StdcCfg), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                              C.POINTER(Stats)]
     L.qecmc_single_temp.argtypes = [C.c_void_p, C.POINTER(StdcCfg), C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(Stats)]
-    L.qecmc_ladder_run.argtypes = [C.c_void_p, C.POINTER(LadderCfg), C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 7 + \
-        [C.POINTER(Stats)]
+    L.qecmc_ladder_run.argtypes = [C.c_void_p, C.POINTER(LadderCfg), C.POINTER(LadderIO), C.c_int64, C.c_int64,
+                                   C.POINTER(Stats)]
     L.qecmc_pteq.argtypes = [C.c_void_p, C.POINTER(PteqCfg), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                              C.POINTER(Stats)]
     L.qecmc_pteq_dev.argtypes = [C.c_void_p, C.POINTER(PteqCfg), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
@@ -273,23 +279,34 @@ class Context:
         return LadderCfg(geom, L, kind, Nc, iters, 0, bottom, param_b, p_logical, seed, a, b, n_nb, n_py), keep
 
     def ladder_run(self, geom, L, kind, qm0, bottom, Nc, steps, iters=10, param_b=0.0, p_logical=0.0, seed=0, u_nb=None,
-                   u_py=None, snapshots=False):
-        """`steps` Ladder.step(iters) calls on S ladders (qm0 [S, n_sites]).  Returns a dict with rung_states
-        [S, Nc, n_sites], flags [S, Nc], tops0 [S], n_eff [S, Nc], stats (+ snap_* after every step)."""
-        _require_u8(qm0)
-        S, n = qm0.shape[0], nsites(geom, L)
-        assert qm0.size == S * n
+                   u_py=None, snapshots=False, resume=None):
+        """`steps` Ladder.step(iters) calls on S ladders.  Fresh start: qm0 [S, n_sites].  resume: a dict
+        returned by an earlier call (rung_states / flags / tops0 / n_eff_parts are continued in place).
+        Returns a dict with rung_states [S, Nc, n_sites], flags [S, Nc], tops0 [S], n_eff [S, Nc],
+        n_eff_parts [S, Nc, 2], stats (+ snap_* after every step)."""
+        n = nsites(geom, L)
+        if resume is None:
+            _require_u8(qm0)
+            S = qm0.shape[0]
+            assert qm0.size == S * n
+            out = dict(rung_states=np.zeros((S, Nc, n), np.uint8), flags=np.zeros((S, Nc), np.int32),
+                       tops0=np.zeros(S, np.int64), n_eff_parts=np.zeros((S, Nc, 2), np.int32))
+        else:
+            out = resume
+            S = out["rung_states"].shape[0]
+            _require_u8(out["rung_states"])
+        out["n_eff"] = np.zeros((S, Nc), np.float64)
         cfg, keep = self._ladder_cfg(geom, L, kind, Nc, iters, bottom, param_b, p_logical, seed, u_nb, u_py, S)
-        out = dict(rung_states=np.zeros((S, Nc, n), np.uint8), flags=np.zeros((S, Nc), np.int32), tops0=np.zeros(S, np.int64),
-                   n_eff=np.zeros((S, Nc), np.float64))
         snap = [None, None, None]
         if snapshots:
             snap = [np.zeros((S, steps, Nc, n), np.uint8), np.zeros((S, steps, Nc), np.int32), np.zeros((S, steps), np.int64)]
             out.update(snap_states=snap[0], snap_flags=snap[1], snap_tops0=snap[2])
+        io = LadderIO(qm0.ctypes.data if resume is None else None, 0 if resume is None else 1, 0,
+                      out["rung_states"].ctypes.data, out["flags"].ctypes.data, out["tops0"].ctypes.data,
+                      out["n_eff"].ctypes.data, out["n_eff_parts"].ctypes.data,
+                      *[x.ctypes.data if x is not None else None for x in snap])
         st = Stats()
-        _check(load().qecmc_ladder_run(self._h, C.byref(cfg), qm0.ctypes.data, S, steps, out["rung_states"].ctypes.data,
-                                       out["flags"].ctypes.data, out["tops0"].ctypes.data, out["n_eff"].ctypes.data,
-                                       *[x.ctypes.data if x is not None else None for x in snap], C.byref(st)))
+        _check(load().qecmc_ladder_run(self._h, C.byref(cfg), C.byref(io), S, steps, C.byref(st)))
         out["stats"] = st.as_dict()
         return out
 

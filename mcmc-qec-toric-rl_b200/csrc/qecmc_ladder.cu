@@ -294,47 +294,64 @@ void fill_stats(qecmc_ctx *c, qecmc_stats *stats, int64_t steps_total, const uns
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-extern "C" int qecmc_ladder_run(qecmc_ctx *c, const qecmc_ladder_cfg *cfg, const uint8_t *qm0, int64_t S, int64_t steps,
-                                uint8_t *rung_states, int32_t *flags, int64_t *tops0, double *n_eff, uint8_t *snap_states,
-                                int32_t *snap_flags, int64_t *snap_tops0, qecmc_stats *stats)
+extern "C" int qecmc_ladder_run(qecmc_ctx *c, const qecmc_ladder_cfg *cfg, const qecmc_ladder_io *io, int64_t S, int64_t steps,
+                                qecmc_stats *stats)
 {
-    if (!c || !qm0) return set_err(QECMC_ERR_ARG, "NULL argument");
+    if (!c || !io) return set_err(QECMC_ERR_ARG, "NULL argument");
     QTRY(check_ladder_cfg(cfg));
     if (S <= 0 || steps < 0) return set_err(QECMC_ERR_ARG, "S must be > 0 and steps >= 0");
-    if ((snap_states != nullptr) != (snap_flags != nullptr) || (snap_states != nullptr) != (snap_tops0 != nullptr))
+    if ((io->snap_states != nullptr) != (io->snap_flags != nullptr) || (io->snap_states != nullptr) != (io->snap_tops0 != nullptr))
         return set_err(QECMC_ERR_ARG, "snapshots need snap_states, snap_flags and snap_tops0 together");
+    if (io->resume && (!io->rung_states || !io->flags || !io->tops0))
+        return set_err(QECMC_ERR_ARG, "resume needs rung_states, flags and tops0 (in/out)");
+    if (!io->resume && !io->qm0) return set_err(QECMC_ERR_ARG, "qm0 is NULL");
     CUDA_OK(cudaSetDevice(c->device));
     c->launches = 0;
     const Geo g = make_geo(cfg->geom, cfg->L);
     const bool wide = cfg->L > 16;
     const size_t wb = wide ? 8 : 4;
     const int Nc = cfg->Nc;
+    const int64_t n_init = io->resume ? S * Nc : S;
     LadderDev d;
     LadderParams p;
     QTRY(setup_ladder(c, cfg, g, d, p));
     QTRY(stage_replay(c, cfg, S, d, p));
-    QTRY(d.qm.ensure((size_t)S * g.nsites));
-    QTRY(d.lat.ensure((size_t)S * g.nw * wb));
+    QTRY(d.qm.ensure((size_t)n_init * g.nsites));
+    QTRY(d.lat.ensure((size_t)n_init * g.nw * wb));
     QTRY(d.lat_out.ensure((size_t)S * Nc * g.nw * wb));
     QTRY(d.flags.ensure((size_t)S * Nc * sizeof(int)));
     QTRY(d.neff.ensure((size_t)S * Nc * sizeof(int2)));
     QTRY(d.tops0.ensure((size_t)S * sizeof(long long)));
     QTRY(c->counters.ensure(8 * sizeof(unsigned long long)));
     CUDA_OK(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(unsigned long long), c->stream));
-    CUDA_OK(cudaMemcpyAsync(d.qm.p, qm0, (size_t)S * g.nsites, cudaMemcpyHostToDevice, c->stream));
-    if (wide) QTRY(pack_lattices<uint64_t>(c, (const uint8_t *)d.qm.p, S, g, d.lat.p));
-    else QTRY(pack_lattices<uint32_t>(c, (const uint8_t *)d.qm.p, S, g, d.lat.p));
+    CUDA_OK(cudaMemcpyAsync(d.qm.p, io->resume ? io->rung_states : io->qm0, (size_t)n_init * g.nsites, cudaMemcpyHostToDevice, c->stream));
+    if (wide) QTRY(pack_lattices<uint64_t>(c, (const uint8_t *)d.qm.p, n_init, g, d.lat.p));
+    else QTRY(pack_lattices<uint32_t>(c, (const uint8_t *)d.qm.p, n_init, g, d.lat.p));
     p.acct = ACCT_NONE;
     p.n_ladders = S;
     p.steps = steps;
     p.lat_in = d.lat.p;
-    p.init_broadcast = 1;
+    p.init_broadcast = io->resume ? 0 : 1;
+    DevBuf flags_in, neff_in, tops0_in;
+    if (io->resume) {
+        QTRY(flags_in.ensure((size_t)S * Nc * sizeof(int)));
+        QTRY(tops0_in.ensure((size_t)S * sizeof(long long)));
+        CUDA_OK(cudaMemcpyAsync(flags_in.p, io->flags, (size_t)S * Nc * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CUDA_OK(cudaMemcpyAsync(tops0_in.p, io->tops0, (size_t)S * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+        p.flags_in = (const int *)flags_in.p;
+        p.tops0_in = (const long long *)tops0_in.p;
+        if (io->n_eff_parts) {
+            QTRY(neff_in.ensure((size_t)S * Nc * sizeof(int2)));
+            CUDA_OK(cudaMemcpyAsync(neff_in.p, io->n_eff_parts, (size_t)S * Nc * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+            p.neff_in = (const int2 *)neff_in.p;
+        }
+    }
     p.lat_out = d.lat_out.p;
     p.flags_out = (int *)d.flags.p;
     p.neff_out = (int2 *)d.neff.p;
     p.tops0_out = (long long *)d.tops0.p;
     p.counters = (unsigned long long *)c->counters.p;
-    if (snap_states) {
+    if (io->snap_states) {
         QTRY(d.snap_lat.ensure((size_t)S * steps * Nc * g.nw * wb + 8));
         QTRY(d.snap_flags.ensure((size_t)S * steps * Nc * sizeof(int) + 8));
         QTRY(d.snap_tops0.ensure((size_t)S * steps * sizeof(long long) + 8));
@@ -343,41 +360,46 @@ extern "C" int qecmc_ladder_run(qecmc_ctx *c, const qecmc_ladder_cfg *cfg, const
         p.snap_tops0 = (long long *)d.snap_tops0.p;
     }
     CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
-    QTRY(launch_ladder(c, p, cfg->u_nb != nullptr));
-    CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
-    QTRY(check_status(c, d));
+    int rc = launch_ladder(c, p, cfg->u_nb != nullptr);
+    if (rc == 0) rc = cudaEventRecord(c->ev[1], c->stream) == cudaSuccess ? 0 : set_err(QECMC_ERR_CUDA, "cudaEventRecord failed");
+    if (rc == 0) rc = check_status(c, d);
+    cudaStreamSynchronize(c->stream);
+    flags_in.release(); neff_in.release(); tops0_in.release();
+    if (rc) return rc;
     // results
     size_t out_bytes = (size_t)S * Nc * g.nsites;
-    size_t snap_bytes = snap_states ? (size_t)S * steps * Nc * g.nsites : 0;
+    size_t snap_bytes = io->snap_states ? (size_t)S * steps * Nc * g.nsites : 0;
     QTRY(d.bytes_out.ensure((out_bytes > snap_bytes ? out_bytes : snap_bytes) + 8));
-    if (rung_states) {
+    if (io->rung_states) {
         if (wide) unpack_async<uint64_t>(c, d.lat_out.p, (uint8_t *)d.bytes_out.p, S * Nc * g.nw, g.L);
         else unpack_async<uint32_t>(c, d.lat_out.p, (uint8_t *)d.bytes_out.p, S * Nc * g.nw, g.L);
-        CUDA_OK(cudaMemcpyAsync(rung_states, d.bytes_out.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaMemcpyAsync(io->rung_states, d.bytes_out.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
         CUDA_OK(cudaStreamSynchronize(c->stream));
     }
-    if (snap_states && steps > 0) {
+    if (io->snap_states && steps > 0) {
         if (wide) unpack_async<uint64_t>(c, d.snap_lat.p, (uint8_t *)d.bytes_out.p, S * steps * Nc * g.nw, g.L);
         else unpack_async<uint32_t>(c, d.snap_lat.p, (uint8_t *)d.bytes_out.p, S * steps * Nc * g.nw, g.L);
-        CUDA_OK(cudaMemcpyAsync(snap_states, d.bytes_out.p, snap_bytes, cudaMemcpyDeviceToHost, c->stream));
-        CUDA_OK(cudaMemcpyAsync(snap_flags, d.snap_flags.p, (size_t)S * steps * Nc * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        CUDA_OK(cudaMemcpyAsync(snap_tops0, d.snap_tops0.p, (size_t)S * steps * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaMemcpyAsync(io->snap_states, d.bytes_out.p, snap_bytes, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaMemcpyAsync(io->snap_flags, d.snap_flags.p, (size_t)S * steps * Nc * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaMemcpyAsync(io->snap_tops0, d.snap_tops0.p, (size_t)S * steps * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     }
-    if (flags) CUDA_OK(cudaMemcpyAsync(flags, d.flags.p, (size_t)S * Nc * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    if (tops0) CUDA_OK(cudaMemcpyAsync(tops0, d.tops0.p, (size_t)S * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    if (io->flags) CUDA_OK(cudaMemcpyAsync(io->flags, d.flags.p, (size_t)S * Nc * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (io->tops0) CUDA_OK(cudaMemcpyAsync(io->tops0, d.tops0.p, (size_t)S * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     std::vector<int2> ne;
-    if (n_eff) {
+    if (io->n_eff || io->n_eff_parts) {
         ne.resize((size_t)S * Nc);
         CUDA_OK(cudaMemcpyAsync(ne.data(), d.neff.p, ne.size() * sizeof(int2), cudaMemcpyDeviceToHost, c->stream));
     }
     unsigned long long cnt[8] = {0};
     CUDA_OK(cudaMemcpyAsync(cnt, c->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
-    if (n_eff)
-        for (size_t i = 0; i < ne.size(); i++) {
+    for (size_t i = 0; i < ne.size(); i++) {
+        if (io->n_eff) {
             volatile double t = cfg->param_b * (double)ne[i].y;  // zb + alpha * (xb + yb), mcmc_alpha.py:22
-            n_eff[i] = (double)ne[i].x + t;
+            io->n_eff[i] = (double)ne[i].x + t;
         }
+        if (io->n_eff_parts) { io->n_eff_parts[2 * i] = ne[i].x; io->n_eff_parts[2 * i + 1] = ne[i].y; }
+    }
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
     fill_stats(c, stats, S * Nc * steps * cfg->iters, cnt, ms, 1);

@@ -30,6 +30,9 @@ struct LadderParams {
     int64_t n_ladders, ladder_offset, steps;
     const void *lat_in;     // packed [n_ladders][nw] (init_broadcast) or [n_ladders][Nc][nw]
     int init_broadcast;
+    const int *flags_in;    // resume: [n_ladders][Nc] (optional; default: only the top rung is flagged)
+    const int2 *neff_in;    // resume: [n_ladders][Nc] rung-owned (nz, nx+ny) (optional; default: from the rung's state)
+    const long long *tops0_in;  // resume: [n_ladders] (optional)
     void *lat_out;          // packed [n_ladders][Nc][nw], rung order (optional)
     int *flags_out;         // [n_ladders][Nc] (optional)
     int2 *neff_out;         // [n_ladders][Nc] (nz, nx+ny) of the rung-owned n_eff (optional)
@@ -192,7 +195,8 @@ __global__ void __launch_bounds__(128) ladder_kernel(LadderParams p)
         n = nx + ny + nz;
         e_nz = nz; e_nxy = nx + ny;
         cls = class_raw_to_label(GEOM, lat_class<GEOM, W>(g, lat));
-        flag = (gl == Nc - 1) ? 1 : 0;
+        flag = p.flags_in ? p.flags_in[ladder * Nc + gl] : ((gl == Nc - 1) ? 1 : 0);
+        if (p.neff_in) { int2 e = p.neff_in[ladder * Nc + gl]; e_nz = e.x; e_nxy = e.y; }
         if (p.acct == ACCT_DC) h = lat_hash<W>(g, lat, p.hash_seed);
     } else {
         for (int w = 0; w < g.nw; w++) lat.set(w, (W)0);
@@ -215,7 +219,7 @@ __global__ void __launch_bounds__(128) ladder_kernel(LadderParams p)
     if (p.acct == ACCT_DC && ladder < p.n_ladders) table = p.tables + (uint64_t)(ladder / p.droplets) * (p.cap_mask + 1);
 
     // group-uniform bookkeeping (every lane of the group carries the same values)
-    long long tops0 = 0, since_burn = 0, burn_in = 0, conv_start = 0, conv_streak = 0, steps_used = p.steps;
+    long long tops0 = (p.tops0_in && ladder < p.n_ladders) ? p.tops0_in[ladder] : 0, since_burn = 0, burn_in = 0, conv_start = 0, conv_streak = 0, steps_used = p.steps;
     long long S2a = 0, S2b = 0, S4a = 0, S4b = 0;  // window sums of the n_err history (a: n or nz, b: nx+ny)
     long long wA = 0, wB = 0, wC = 0, wl = 0;      // window bounds l/4, l/2, 3l/4 and history length l
     int converged = 0;

@@ -8,6 +8,7 @@ built on it) proposes with:
 * ``"shipped"`` -- planar stabilizers on any (2, L, L) lattice, which is what the unmodified
   reference does (src/mcmc.py:6 imports planar_model._apply_random_stabilizer only).
 """
+import copy
 import itertools
 
 import numpy as np
@@ -20,9 +21,13 @@ SEED = 0x51ED2020
 
 
 def seed(value):
-    """Seed for the per-chain Philox streams of chains created afterwards."""
+    """Seed for the per-chain Philox streams of chains / ladders created afterwards."""
     global SEED
     SEED = int(value)
+
+
+def _new_stream():
+    return ((SEED & 0xFFFFFFFFFF) << 24) ^ next(_chain_ids)
 
 
 def fast_path_geometry(code):
@@ -42,7 +47,7 @@ class Chain:
         self.p_logical = 0
         self.flag = 0
         self.factor = ((self.p / 3.0) / (1.0 - self.p))
-        self._stream = (SEED << 20) ^ next(_chain_ids)
+        self._stream = _new_stream()
         self._steps = 0
 
     def _run(self, geom, iters, pow_kind):
@@ -58,8 +63,82 @@ class Chain:
         self._run(fast_path_geometry(self.code), iters, _lib.POW_NUMBA)
 
     def update_chain(self, iters):
-        """Chain.update_chain (src/mcmc.py:19-43).  The p_logical != 0 branch belongs to the top rung of a
-        Ladder and runs inside the ladder kernels; a free-standing chain has p_logical == 0."""
+        """Chain.update_chain (src/mcmc.py:19-43).  With p_logical != 0 this is a ladder's top rung (random logical
+        operators mixed in): it runs as a one-rung ladder block without swaps."""
         if self.p_logical != 0:
-            raise NotImplementedError("a chain with p_logical != 0 is a ladder's top rung: use Ladder.step / PTEQ")
-        self._run(self.code.geometry, iters, _lib.POW_LIBM)
+            _single_rung_block(self, _lib.LADDER_DEPOLARIZING, self.p, 0.0, iters)
+        else:
+            self._run(self.code.geometry, iters, _lib.POW_LIBM)
+
+
+def _single_rung_block(chain, kind, bottom, param_b, iters):
+    """`iters` slow-path steps of one chain = Ladder.step of a one-rung ladder (no swap partner)."""
+    q = np.ascontiguousarray(chain.code.qubit_matrix, dtype=np.uint8)
+    chain._steps += 1
+    out = _lib.default_context().ladder_run(chain.code.geometry, chain.code.system_size, kind, q.reshape(1, -1).copy(), bottom, 1,
+                                            1, iters=int(iters), param_b=param_b, p_logical=float(chain.p_logical),
+                                            seed=chain._stream + (chain._steps << 44))
+    chain.code.qubit_matrix = out["rung_states"][0, 0].reshape(q.shape)
+    return out
+
+
+class _LadderBase:
+    """Shared driver of Ladder / Ladder_alpha / Ladder_biased: the rung states live in numpy between .step() calls;
+    every .step(iters) is one device call that runs all rungs and the swap sweep (mcmc.py:94-103)."""
+    _kind = _lib.LADDER_DEPOLARIZING
+
+    def _setup(self, init_code, Nc, p_logical, bottom, param_b, ladder, chains):
+        self.init_code = init_code
+        self.Nc = Nc
+        self.p_logical = p_logical
+        self.chains = chains
+        self.chains[-1].flag = 1
+        self.chains[-1].p_logical = p_logical
+        self.tops0 = 0
+        self._bottom, self._param_b = bottom, param_b
+        self._stream = _new_stream()
+        self._calls = 0
+        self._parts = None
+
+    def _state(self):
+        n = self.chains[0].code.qubit_matrix.size
+        rs = np.stack([np.ascontiguousarray(c.code.qubit_matrix, dtype=np.uint8).reshape(-1) for c in self.chains])[None]
+        flags = np.array([[c.flag for c in self.chains]], np.int32)
+        if self._parts is None:  # Chain_alpha.__init__: n_eff from the initial state (mcmc_alpha.py:18-22)
+            self._parts = np.array([[[int((c.code.qubit_matrix == 3).sum()), int(((c.code.qubit_matrix == 1) |
+                                      (c.code.qubit_matrix == 2)).sum())] for c in self.chains]], np.int32)
+        return dict(rung_states=np.ascontiguousarray(rs), flags=flags, tops0=np.array([self.tops0], np.int64),
+                    n_eff_parts=np.ascontiguousarray(self._parts))
+
+    def update_ladder(self, iters):
+        for chain in self.chains:
+            chain.update_chain(iters)
+
+    def step(self, iters):
+        code0 = self.chains[0].code
+        self._calls += 1
+        out = _lib.default_context().ladder_run(code0.geometry, code0.system_size, self._kind, None, self._bottom, self.Nc, 1,
+                                                iters=int(iters), param_b=self._param_b, p_logical=float(self.p_logical),
+                                                seed=self._stream + (self._calls << 44), resume=self._state())
+        shape = code0.qubit_matrix.shape
+        for i, c in enumerate(self.chains):
+            c.code.qubit_matrix = out["rung_states"][0, i].reshape(shape).copy()
+            c.flag = int(out["flags"][0, i])
+            if hasattr(c, "n_eff"):
+                c.n_eff = float(out["n_eff"][0, i])
+        self._parts = out["n_eff_parts"]
+        self.tops0 = int(out["tops0"][0])
+
+
+class Ladder(_LadderBase):
+    """Ladder(p_bottom, init_code, Nc, p_logical=0): src/mcmc.py:49-103."""
+
+    def __init__(self, p_bottom, init_code, Nc, p_logical=0):
+        self.p_bottom = p_bottom
+        p_ladder = np.linspace(p_bottom, 0.75, Nc)
+        self.p_ladder = p_ladder
+        self.p_diff = (p_ladder[:-1] * (1 - p_ladder[1:])) / (p_ladder[1:] * (1 - p_ladder[:-1]))
+        self._setup(init_code, Nc, p_logical, p_bottom, 0.0, p_ladder, [Chain(p, copy.deepcopy(init_code)) for p in p_ladder])
+
+    def r_flip(self, ind_lo):
+        raise NotImplementedError("replica swaps run inside Ladder.step on the device")

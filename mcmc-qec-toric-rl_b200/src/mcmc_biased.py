@@ -1,0 +1,37 @@
+"""Chain_biased / Ladder_biased -- host mirror of the reference's src/mcmc_biased.py (Z-biased noise:
+pz = p eta/(eta+1), px = py = p/(2(eta+1))).  Frozen accept-ratio denominator per call."""
+import copy
+
+import numpy as np
+
+from .. import _lib
+from .mcmc import _LadderBase, _new_stream, _single_rung_block
+
+
+class Chain_biased:
+    def __init__(self, p, eta, code):
+        self.code = code
+        self.p = p
+        self.eta = eta
+        self.p_logical = 0
+        self.flag = 0
+        self._stream = _new_stream()
+        self._steps = 0
+
+    def update_chain(self, iters):
+        """mcmc_biased.py:21-59, `iters` steps on the GPU."""
+        _single_rung_block(self, _lib.LADDER_BIASED, self.p, self.eta, iters)
+
+
+class Ladder_biased(_LadderBase):
+    """Ladder_biased(p_bottom, init_code, eta, Nc, p_logical=0): src/mcmc_biased.py:66-124."""
+    _kind = _lib.LADDER_BIASED
+
+    def __init__(self, p_bottom, init_code, eta, Nc, p_logical=0):
+        self.eta = eta
+        p_top = (eta + 1) / (2 * eta + 1)
+        p_ladder = np.linspace(p_bottom, p_top, Nc)
+        self.p_ladder = p_ladder
+        self.p_diff = (p_ladder[:-1] * (1 - p_ladder[1:])) / (p_ladder[1:] * (1 - p_ladder[:-1]))
+        self._setup(init_code, Nc, p_logical, p_bottom, eta, p_ladder,
+                    [Chain_biased(p, eta, copy.deepcopy(init_code)) for p in p_ladder])
