@@ -283,7 +283,7 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "alu", "achieved": achieved_ops / 1e12, "peak": peak_ops / 1e12, "unit": "Tlaneop/s",
                      "frac": achieved_ops / peak_ops, "traffic": None,
-                     "kernel": "stdc_kernel<TORIC,u32,native>", "kernel_ms_per_launch": kern_ms / (args.steps * waves),
+                     "kernel": "stdc_fast_kernel<TORIC,u32,native,STDC>", "kernel_ms_per_launch": kern_ms / (args.steps * waves),
                      "units_per_launch": batch * steps_per_syndrome / waves, "algorithmic_laneops_per_step": W_INT,
                      "peak_source": f"{info['sm_count']} SMs x 128 int32 lanes x {sm_max_mhz:.0f} MHz ({peak_src} max SM clock)",
                      "note": "north_star: this path is integer-issue bound, not HBM or tensor bound (SURVEY.md 8d)",
@@ -300,9 +300,10 @@ def main():
         cores = host_cores()
         n_syn = max(1, min(cores, 64))
         cpu_port_rate(1, 1, 2000, 1)  # warm the library
-        rate, dt, steps = cpu_port_rate(n_syn, 1, samples, cores)
+        cpu_drop = 10   # sized for 10-30 s of host work
+        rate, dt, steps = cpu_port_rate(n_syn, cpu_drop, samples, cores)
         line["cpu_baseline"] = {"value": rate, "unit": "steps/s", "cores": cores, "kind": "port",
-                                "sample": f"{n_syn} syndromes x 16 classes x 1 chain x {samples} samples x {ITERS} steps "
+                                "sample": f"{n_syn} syndromes x 16 classes x {cpu_drop} chains x {samples} samples x {ITERS} steps "
                                           f"({steps:.3g} Metropolis steps, {dt:.1f} s) with oracle/qec_oracle.c"}
     print(json.dumps(line), flush=True)
     if world > 1:
