@@ -361,7 +361,10 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
     if (!(cfg->p_error > 0 && cfg->p_error < 1) || !(cfg->p_sampling > 0 && cfg->p_sampling < 1))
         return set_err(QECMC_ERR_ARG, "p_error / p_sampling outside (0,1)");
     if ((uint64_t)cfg->steps * (uint64_t)cfg->iters >= (1ull << 32)) return set_err(QECMC_ERR_UNSUPPORTED, "steps * iters must be < 2^32");
-    if (cfg->conv_mult != 0.0) return set_err(QECMC_ERR_UNSUPPORTED, "conv_mult != 0 is not implemented on the device path yet");
+    if (cfg->conv_mult != 0.0 && cfg->droplets != 1)
+        return set_err(QECMC_ERR_UNSUPPORTED, "conv_mult != 0 needs droplets == 1: the early-stop rule asks whether a chain is new "
+                                              "to its own droplet, and the droplets of a class share one distinct-chain set");
+    if (cfg->conv_mult < 0.0) return set_err(QECMC_ERR_ARG, "conv_mult must be >= 0");
     if (cfg->randomize && cfg->geom_code != TORIC && cfg->geom_code != PLANAR)
         return set_err(QECMC_ERR_ARG, "apply_stabilizers_uniform exists only for toric/planar codes");
     if (cfg->randomize && cfg->u_nb && !cfg->u_np) return set_err(QECMC_ERR_ARG, "replay with randomize needs u_np");
@@ -431,6 +434,8 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
     // diagnostic knob for roofline work (3 = chains without the distinct set: results are then meaningless)
     p.insert_mode = getenv("QECMC_DEBUG_INSERT_MODE") ? atoi(getenv("QECMC_DEBUG_INSERT_MODE")) : 2;
     p.max_length = 2 * cfg->L * cfg->L;  // decoders.py:747
+    p.conv_mult = mode == MODE_MEAN ? 0.0 : cfg->conv_mult;
+    p.steps_done = (unsigned long long *)c->counters.p + 4;
     p.short_out = (int *)c->shorts.p;
     p.sum_out = (unsigned long long *)c->sums.p;
     const double beta = -log((cfg->p_error / 3) / (1 - cfg->p_error));  // decoders.py:299
@@ -490,7 +495,7 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
         CUDA_OK(cudaMemcpyAsync(cnt, c->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
         CUDA_OK(cudaStreamSynchronize(c->stream));
         memset(stats, 0, sizeof(*stats));
-        stats->metropolis_steps = S * n_eq * (int64_t)cfg->droplets * cfg->steps * cfg->iters;
+        stats->metropolis_steps = (int64_t)cnt[4];
         stats->accepted = (int64_t)cnt[0];
         stats->samples = (int64_t)cnt[1];
         stats->distinct = (int64_t)cnt[3];

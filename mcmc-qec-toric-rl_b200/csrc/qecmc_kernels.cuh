@@ -184,6 +184,27 @@ struct StdcParams {
     int max_length;                // 2 * L * L (decoders.py:747)
     // single_temp (decoders.py:108-135): sum of the chain length over the first steps-1 samples
     unsigned long long *sum_out;   // [n_chains]
+    // early stop of decoders.py:257-263 / :795 (droplets == 1 only): a chain ends once no new chain of the shortest
+    // length has turned up for (conv_mult - 1) x as many samples as it took to find the last one
+    double conv_mult;
+    unsigned long long *steps_done;  // counters: Metropolis steps actually taken
+};
+
+// conv_mult bookkeeping of one chain; is_new = the sample was a chain this droplet had not seen before
+struct ConvStop {
+    int shortest;
+    double stop;
+    uint32_t sample;
+    bool fin;
+    __device__ __forceinline__ void init(const StdcParams &p) { shortest = p.max_length; stop = (double)p.steps; sample = 0; fin = false; }
+    __device__ __forceinline__ void after_sample(const StdcParams &p, bool is_new, int n)
+    {
+        if (p.conv_mult != 0.0) {
+            if (is_new && n <= shortest) { shortest = n; stop = (double)sample * p.conv_mult; }
+            if ((double)sample >= stop && (uint64_t)sample * 100ull >= (uint64_t)p.steps) fin = true;
+        }
+        sample++;
+    }
 };
 
 enum { MODE_STDC = 0, MODE_STRC = 1, MODE_MEAN = 2 };
@@ -286,6 +307,8 @@ __global__ void __launch_bounds__(256) stdc_kernel(StdcParams p)
     unsigned long long *table = p.tables + (uint64_t)tab * (p.cap_mask + 1);
     SampleAcct<MODE> acct;
     acct.init(p, tab);
+    ConvStop cs;
+    cs.init(p);
 
     unsigned long long nacc = 0, noff = 0, nins = 0;
     bool dirty = true;  // the first sample is always new to the chain
@@ -297,14 +320,16 @@ __global__ void __launch_bounds__(256) stdc_kernel(StdcParams p)
     if (--left == 0) {                                                      \
         left = p.iters;                                                     \
         acct.sample(n);                                                     \
-        if (MODE != MODE_MEAN && dirty) { noff++; nins += table_insert(table, p.cap_mask, make_key(h, n)); } \
+        bool is_new = false;                                                \
+        if (MODE != MODE_MEAN && dirty) { noff++; is_new = table_insert(table, p.cap_mask, make_key(h, n)); nins += is_new; } \
         dirty = false;                                                      \
+        cs.after_sample(p, is_new, n);                                      \
     }
 
     if (REPLAY) {
         constexpr int K = NumDraws<GEOM>::value;
         const double *u = p.u_nb + (uint64_t)gchain * tsteps * (K + 1);
-        for (uint64_t t = 0; t < tsteps; t++, u += K + 1) {
+        for (uint64_t t = 0; t < tsteps && !cs.fin; t++, u += K + 1) {
             int row, col, op, dE;
             propose_replay<GEOM>(g, u, row, col, op);
             int idx = rco_to_idx<GEOM>(g, row, col, op);
@@ -313,7 +338,7 @@ __global__ void __launch_bounds__(256) stdc_kernel(StdcParams p)
         }
     } else {
         uint32_t c0 = 0, c1 = 0;
-        for (uint64_t t = 0; t < tsteps; t += 2) {
+        for (uint64_t t = 0; t < tsteps && !cs.fin; t += 2) {
             uint4 r = philox4x32_10(c0, c1, cl, chh, k0, k1);
             if (++c0 == 0) ++c1;
             {
@@ -323,7 +348,7 @@ __global__ void __launch_bounds__(256) stdc_kernel(StdcParams p)
                 bool acc = metropolis<GEOM, W>(g, lat, row, col, op, dE, s_thr, r.y, s_thrd, 0.0, false);
                 QECMC_AFTER_STEP()
             }
-            if (t + 1 < tsteps) {
+            if (t + 1 < tsteps && !cs.fin) {
                 int row, col, op, dE;
                 int idx = (int)__umulhi(r.z, (uint32_t)g.nstab);
                 idx_to_rco<GEOM>(g, idx, row, col, op);
@@ -338,6 +363,7 @@ __global__ void __launch_bounds__(256) stdc_kernel(StdcParams p)
     atomicAdd(p.counters + 0, nacc);
     atomicAdd(p.counters + 1, noff);
     atomicAdd(p.counters + 2, nins);
+    atomicAdd(p.steps_done, (unsigned long long)cs.sample * (unsigned long long)p.iters);
 }
 
 // One block per (syndrome, class) table: N(n) histogram from the length field of the

@@ -112,7 +112,9 @@ __global__ void __launch_bounds__(256) stdc_fast_kernel(StdcParams p, FastTables
     uint64_t keyA = 0, prevA = 0, keyB = 0, prevB = 0;
     uint32_t slotA = 0, slotB = 0;
     const uint32_t smask = (uint32_t)cap_mask;  // host guarantees cap <= 2^32 slots
-    const int imode = MODE == MODE_MEAN ? 3 : p.insert_mode;
+    const int imode = MODE == MODE_MEAN ? 3 : (p.conv_mult != 0.0 ? 0 : p.insert_mode);  // the early stop needs the probe's answer now
+    ConvStop cs;
+    cs.init(p);
     SampleAcct<MODE> acct;
     acct.init(p, tab);
     unsigned char *mybase = reinterpret_cast<unsigned char *>(tile + tid);
@@ -163,6 +165,7 @@ __global__ void __launch_bounds__(256) stdc_fast_kernel(StdcParams p, FastTables
         if (--left == 0) {
             left = p.iters;
             acct.sample(n);
+            bool is_new = false;
             const uint64_t nkey = make_key(h, n);
             const uint32_t nslot = (uint32_t)(nkey >> QECMC_LEN_BITS) & smask;
             if (imode == 2) {
@@ -183,10 +186,11 @@ __global__ void __launch_bounds__(256) stdc_fast_kernel(StdcParams p, FastTables
                     else { keyB = nkey; slotB = nslot; prevB = atomicCAS(table + nslot, 0ull, (unsigned long long)nkey); }
                 }
             } else if (imode == 0) {
-                if (dirty) table_insert(table, cap_mask, nkey);
+                if (dirty) is_new = table_insert(table, cap_mask, nkey);
             }
             noff += dirty;
             dirty = false;
+            cs.after_sample(p, is_new, n);
         }
     };
 
@@ -194,7 +198,7 @@ __global__ void __launch_bounds__(256) stdc_fast_kernel(StdcParams p, FastTables
     if (REPLAY) {
         constexpr int K = NumDraws<GEOM>::value;
         const double *u = p.u_nb + (uint64_t)gchain * tsteps * (K + 1);
-        for (uint64_t t = 0; t < tsteps; t++, u += K + 1) {
+        for (uint64_t t = 0; t < tsteps && !cs.fin; t++, u += K + 1) {
             int row, col, op;
             propose_replay<GEOM>(g, u, row, col, op);
             step(rco_to_idx<GEOM>(g, row, col, op), 0u, u[K]);
@@ -202,12 +206,12 @@ __global__ void __launch_bounds__(256) stdc_fast_kernel(StdcParams p, FastTables
     } else {
         const uint32_t ncalls = (uint32_t)(tsteps >> 1);  // host guarantees tsteps < 2^32
         const uint32_t nstab = (uint32_t)g.nstab;
-        for (uint32_t c0 = 0; c0 < ncalls; c0++) {
+        for (uint32_t c0 = 0; c0 < ncalls && !cs.fin; c0++) {
             uint4 r = philox4x32_10(c0, 0u, cl, chh, keys);
             step((int)__umulhi(r.x, nstab), r.y, 0.0);
-            step((int)__umulhi(r.z, nstab), r.w, 0.0);
+            if (!cs.fin) step((int)__umulhi(r.z, nstab), r.w, 0.0);
         }
-        if (tsteps & 1) {
+        if ((tsteps & 1) && !cs.fin) {
             uint4 r = philox4x32_10(ncalls, 0u, cl, chh, keys);
             step((int)__umulhi(r.x, nstab), r.y, 0.0);
         }
@@ -221,6 +225,7 @@ __global__ void __launch_bounds__(256) stdc_fast_kernel(StdcParams p, FastTables
     acct.finish(p, local);
     atomicAdd(p.counters + 0, (unsigned long long)nacc);
     atomicAdd(p.counters + 1, (unsigned long long)noff);
+    atomicAdd(p.steps_done, (unsigned long long)cs.sample * (unsigned long long)p.iters);
 }
 
 }  // namespace qecmc

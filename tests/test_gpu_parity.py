@@ -118,25 +118,50 @@ def test_stdc_replay_matches_oracle(ctx, gcode, gchain, L, droplets, per_class):
     assert st["distinct"] == int(hist.sum())
 
 
-@pytest.mark.parametrize("variant", ["shipped", "toric"])
-def test_stdc_replay_matches_reference_golden(ctx, variant):
-    """STDC(droplets=1) of the seeded reference: same class distribution from its own draws."""
+def _golden_class_streams(fn, c):
+    """The reference ran its classes one after the other on ONE numba stream and ONE numpy stream (droplets=1).
+    With the conv_mult early stop a class consumes a data-dependent number of draws, so the start of every class's
+    slice is found by replaying the classes through the oracle (pinned to these very vectors) and reading the
+    stream positions."""
+    gcode, gchain, L = O.GEOM[c["geom"]], O.GEOM[c["chain_geom"]], c["L"]
+    n_eq, steps, iters = O.neq(gcode), c["steps"], 5
+    inits = c["inits"].reshape(n_eq, -1)
+    total = n_eq * steps * iters * 4
+    full_nb = np.random.RandomState(c["nb_seed"]).random_sample(total + steps * iters * 4)
+    full_np = np.random.RandomState(c["np_seed"]).random_sample((n_eq + 1) * 2 * L * L)
+    nb, np_ = O.Stream.replay(full_nb), O.Stream.replay(full_np)
+    u_nb = np.zeros((n_eq, steps * iters, 4))
+    u_np = np.zeros((n_eq, 2 * L * L))
+    for e in range(n_eq):
+        a, b = nb.drawn, np_.drawn
+        u_nb[e] = full_nb[a:a + steps * iters * 4].reshape(-1, 4)
+        u_np[e] = full_np[b:b + 2 * L * L]
+        getattr(O, fn)(gcode, gchain, L, inits[e:e + 1], c["p_error"], c["p_sampling"], 1, steps, [nb], [np_],
+                       randomize=bool(c["randomize"]), conv_mult=float(c["conv_mult"]))
+    return u_nb, u_np
+
+
+def _golden_driver(ctx, fn, variant):
     n = 0
     for c in golden(variant):
-        if c["kind"] != "stdc" or c["conv_mult"] != 0:
+        if c["kind"] != fn:
             continue
         gcode, gchain, L = O.GEOM[c["geom"]], O.GEOM[c["chain_geom"]], c["L"]
-        n_eq, steps, iters = O.neq(gcode), c["steps"], 5
+        n_eq, steps = O.neq(gcode), c["steps"]
         per_class = gcode != O.TORIC
-        # droplets=1 runs in-process: one global numba stream and one numpy stream, consumed class after class
-        u_nb = np.random.RandomState(c["nb_seed"]).random_sample(n_eq * steps * iters * 4).reshape(n_eq, steps * iters, 4)
-        u_np = np.random.RandomState(c["np_seed"]).random_sample(n_eq * 2 * L * L).reshape(n_eq, 2 * L * L)
+        u_nb, u_np = _golden_class_streams(fn, c)
         qm = (c["inits"].reshape(1, n_eq, -1) if per_class else c["q"].reshape(1, -1)).copy()
-        out, st = ctx.stdc(gcode, gchain, L, qm, c["p_error"], c["p_sampling"], 1, steps, iters=iters,
-                           per_class=per_class, randomize=bool(c["randomize"]), u_nb=u_nb, u_np=u_np)
+        out, st = getattr(ctx, fn)(gcode, gchain, L, qm, c["p_error"], c["p_sampling"], 1, steps, iters=5, per_class=per_class,
+                                   randomize=bool(c["randomize"]), conv_mult=float(c["conv_mult"]), u_nb=u_nb, u_np=u_np)
         np.testing.assert_allclose(out[0], c["out"], rtol=1e-9)
         n += 1
-    assert n >= 2
+    return n
+
+
+@pytest.mark.parametrize("variant", ["shipped", "toric"])
+def test_stdc_replay_matches_reference_golden(ctx, variant):
+    """STDC(droplets=1) of the seeded reference, with and without conv_mult: same class distribution from its own draws."""
+    assert _golden_driver(ctx, "stdc", variant) >= 4
 
 
 # ------------------------------------------------------------------ replay: STRC, single_temp
@@ -170,21 +195,22 @@ def test_strc_replay_matches_oracle(ctx, gcode, gchain, L, droplets, per_class):
 
 @pytest.mark.parametrize("variant", ["shipped", "toric"])
 def test_strc_replay_matches_reference_golden(ctx, variant):
+    assert _golden_driver(ctx, "strc", variant) >= 4
+
+
+@pytest.mark.parametrize("variant", ["shipped", "toric"])
+def test_single_temp_replay_matches_reference_golden(ctx, variant):
     n = 0
     for c in golden(variant):
-        if c["kind"] != "strc" or c["conv_mult"] != 0:
+        if c["kind"] != "single_temp":
             continue
         gcode, gchain, L = O.GEOM[c["geom"]], O.GEOM[c["chain_geom"]], c["L"]
-        n_eq, steps, iters = O.neq(gcode), c["steps"], 5
-        per_class = gcode != O.TORIC
-        u_nb = np.random.RandomState(c["nb_seed"]).random_sample(n_eq * steps * iters * 4).reshape(n_eq, steps * iters, 4)
-        u_np = np.random.RandomState(c["np_seed"]).random_sample(n_eq * 2 * L * L).reshape(n_eq, 2 * L * L)
-        qm = (c["inits"].reshape(1, n_eq, -1) if per_class else c["q"].reshape(1, -1)).copy()
-        out, st = ctx.strc(gcode, gchain, L, qm, c["p_error"], c["p_sampling"], 1, steps, iters=iters,
-                           per_class=per_class, randomize=bool(c["randomize"]), u_nb=u_nb, u_np=u_np)
-        np.testing.assert_allclose(out[0], c["out"], rtol=1e-9)
+        n_eq, m = O.neq(gcode), c["max_iters"]
+        u_nb = np.random.RandomState(c["nb_seed"]).random_sample(n_eq * m * 5 * 4).reshape(n_eq, m * 5, 4)
+        out, _ = ctx.single_temp(gcode, gchain, L, c["inits"].reshape(1, n_eq, -1).copy(), c["p"], m, per_class=True, u_nb=u_nb)
+        np.testing.assert_allclose(out[0], c["out"], rtol=1e-12)
         n += 1
-    assert n >= 1
+    assert n >= 2
 
 
 @pytest.mark.parametrize("g,L", [(O.TORIC, 5), (O.PLANAR, 7), (O.TORIC, 19)])
@@ -200,6 +226,34 @@ def test_single_temp_replay_matches_oracle(ctx, g, L):
         nb = [O.Stream.replay(u_nb[s * n_eq + e].reshape(-1)) for e in range(n_eq)]
         want = O.single_temp(g, g, L, O.all_classes(g, L, qs[s]), 0.2, max_iters, nb, iters=iters)
         assert np.array_equal(out[s], want)
+
+
+@pytest.mark.parametrize("fn", ["stdc", "strc"])
+@pytest.mark.parametrize("gcode,L", [(O.TORIC, 5), (O.PLANAR, 7), (O.ROTATED, 5)])
+def test_conv_mult_early_stop_matches_oracle(ctx, fn, gcode, L):
+    """conv_mult != 0 (decoders.py:257-263, :795), droplets = 1: chains stop at the same sample as the oracle's, so the
+    histograms of what they saw are identical."""
+    if fn == "strc" and gcode == O.ROTATED:
+        pytest.skip("covered by stdc")
+    rng = np.random.default_rng(4100 + L)
+    S, steps, iters, conv = 3, 400, 5, 2.0
+    n_eq = O.neq(gcode)
+    k = 3 if gcode in (O.TORIC, O.PLANAR) else 5
+    randomize = gcode in (O.TORIC, O.PLANAR)
+    qs = [rand_lattice(rng, gcode, L, 0.08) for _ in range(S)]
+    qm = np.stack([q.reshape(-1) for q in qs])
+    u_nb, u_np = _stdc_streams(rng, S * n_eq, steps, iters, k, L)
+    run = getattr(ctx, fn)
+    res = run(gcode, gcode, L, qm, 0.1, 0.25, 1, steps, iters=iters, randomize=randomize, conv_mult=conv, u_nb=u_nb, u_np=u_np,
+              want_hist=True)
+    assert res[1]["metropolis_steps"] < S * n_eq * steps * iters      # some chains did stop early
+    for s in range(S):
+        nb = [O.Stream.replay(u_nb[s * n_eq + i].reshape(-1)) for i in range(n_eq)]
+        np_ = [O.Stream.replay(u_np[s * n_eq + i]) for i in range(n_eq)]
+        want = getattr(O, fn)(gcode, gcode, L, O.all_classes(gcode, L, qs[s]), 0.1, 0.25, 1, steps, nb, np_, iters=iters,
+                              randomize=randomize, conv_mult=conv, want_hist=True)
+        assert np.array_equal(res[2][s].astype(np.int64), want[2 if fn == "stdc" else 1])
+        np.testing.assert_allclose(res[0][s], want[0], rtol=1e-9)
 
 
 # ------------------------------------------------------------------ native Philox
