@@ -74,6 +74,13 @@ def lib():
         L.qo_pteq.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _u8p, _f64p, _f64p, C.c_double, C.c_double,
                               C.c_int, C.c_int, C.c_int, C.c_double, C.c_int64, C.c_int64, C.c_int, _p, _p,
                               _i64p, _p, _p, _u8p]
+        L.qo_pteq_ex.restype = C.c_int64
+        L.qo_pteq_ex.argtypes = L.qo_pteq.argtypes + [_f64p, _i64p, _i64p]
+        L.qo_update_chain_fast_xyz.argtypes = [C.c_int, C.c_int, _u8p, _f64p, C.c_int64, _p]
+        L.qo_stdc_general_noise.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _u8p, _f64p, C.c_int, _f64p, C.c_double,
+                                            C.c_int, C.c_int64, C.c_int64, _p, _f64p, _f64p, _i64p]
+        L.qo_ptxc.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_double, C.c_double, C.c_int,
+                              C.c_int64, C.c_int64, _p, _p, _f64p, _p, _p]
         L.qo_stdc_batch.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, _u8p, C.c_double, C.c_double,
                                     C.c_int, C.c_int64, C.c_int64, C.c_uint32, C.c_int64, _f64p]
         _lib = L
@@ -301,6 +308,64 @@ def pteq(kind, geom, L, qm0, bottom, nb, py, Nc=None, param_b=0.0, SEQ=2, TOPS=1
                          param_b, p_logical, SEQ, TOPS, tops_burn, eps, steps, iters, int(conv), nb.h, py.h,
                          counts, C.addressof(sb), C.addressof(tops), pct)
     return pct, dict(steps=used, since_burn=sb.value, tops0=tops.value, counts=counts)
+
+
+def pteq_with_shortest(kind, geom, L, qm0, bottom, nb, py, Nc=None, param_b=0.0, SEQ=2, TOPS=10, tops_burn=2, eps=0.1,
+                       steps=50000000, iters=10, conv=True, p_logical=0.5):
+    """PTEQ_alpha_with_shortest (decoders_biasednoise.py:93-172): returns (percent uint8, eqdistr from the distinct
+    shortest chains, shortest_n percent, info)."""
+    Nc = Nc or L
+    lad = Ladder(kind, geom, L, qm0, bottom, Nc, p_logical, param_b)
+    n_eq = neq(geom)
+    counts = np.zeros(n_eq, np.int64)
+    sb, tops = C.c_int64(0), C.c_int64(0)
+    pct = np.zeros(n_eq, np.uint8)
+    slen, sn, su = np.zeros(n_eq), np.zeros(n_eq, np.int64), np.zeros(n_eq, np.int64)
+    used = lib().qo_pteq_ex(kind, geom, L, Nc, _flat(qm0), lad.ladder, lad.diff if lad.diff.size else np.zeros(1),
+                            param_b, p_logical, SEQ, TOPS, tops_burn, eps, steps, iters, int(conv), nb.h, py.h,
+                            counts, C.addressof(sb), C.addressof(tops), pct, slen, sn, su)
+    beta = -np.log(bottom)
+    z = su * np.exp(-beta * slen)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return pct, z / z.sum() * 100, sn / sn.sum() * 100, dict(steps=used, since_burn=sb.value, tops0=tops.value,
+                                                                 short_len=slen, short_n=sn, short_unique=su)
+
+
+def update_chain_fast_xyz(geom, L, qm, factors, iters, nb):
+    out = _flat(qm).copy()
+    lib().qo_update_chain_fast_xyz(geom, L, out, np.ascontiguousarray(factors, np.float64), iters, nb.h)
+    return out.reshape(np.shape(qm))
+
+
+def stdc_general_noise(geom_code, geom_chain, L, qm_classes, p_xyz, p_sampling, droplets, steps, nb, iters=5):
+    """STDC_general_noise_shortest (decoders.py:435-508); p_sampling: float (Chain) or array of 3 (Chain_xyz).
+    Returns (eqdistr, eqdistr_shortest, distinct)."""
+    n_eq = len(qm_classes)
+    n = nsites(geom_code, L)
+    q = np.ascontiguousarray(np.asarray(qm_classes, np.uint8).reshape(n_eq, n)).reshape(-1)
+    use_xyz = isinstance(p_sampling, np.ndarray)
+    ps_xyz = np.ascontiguousarray(p_sampling if use_xyz else np.zeros(3), np.float64)
+    out, out_s, distinct = np.zeros(n_eq), np.zeros(n_eq), np.zeros(n_eq, np.int64)
+    a = _stream_array(nb)
+    lib().qo_stdc_general_noise(geom_code, geom_chain, L, n_eq, q, np.ascontiguousarray(p_xyz, np.float64), int(use_xyz),
+                                ps_xyz, 0.0 if use_xyz else float(p_sampling), droplets, steps, iters, C.addressof(a),
+                                out, out_s, distinct)
+    return out, out_s, distinct
+
+
+def ptxc(mode, geom, L, qm_classes, p_error, p_sampling, droplets, Nc, steps, nb, py, iters=10, want_hist=False):
+    """mode 0: PTDC, mode 1: PTRC (decoders.py:138-233, 584-742); `steps` = per-ladder step count.
+    Returns class distribution in percent (float64)[, N_hist, m_hist [n_eq, Nc, n_sites+1] for PTRC]."""
+    n_eq = len(qm_classes)
+    n = nsites(geom, L)
+    q = np.ascontiguousarray(np.asarray(qm_classes, np.uint8).reshape(n_eq, n)).reshape(-1)
+    out = np.zeros(n_eq)
+    Nh = np.zeros((n_eq, Nc, n + 1), np.int64)
+    mh = np.zeros((n_eq, Nc, n + 1), np.int64)
+    a, b = _stream_array(nb), _stream_array(py)
+    lib().qo_ptxc(mode, geom, L, n_eq, Nc, q, p_error, p_sampling, droplets, steps, iters, C.addressof(a), C.addressof(b),
+                  out, Nh.ctypes.data, mh.ctypes.data)
+    return (out, Nh, mh) if want_hist else out
 
 
 def stdc_batch(geom_code, geom_chain, L, qm, p_error, p_sampling, droplets, steps, seed, iters=5, threads=1):

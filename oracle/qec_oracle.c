@@ -930,12 +930,19 @@ QO_EXPORT void qo_stdc_alpha(int geom, int L, int n_eq, const uint8_t *qm_init, 
  * qm0: single init state [n_sites] (deep-copied to every rung).
  * Returns steps executed; eq_counts[n_eq] = cumulative class counts at
  * since_burn; *since_burn_out; result percent = eq_counts/(since_burn+1)*100 -> uint8. */
-QO_EXPORT int64_t qo_pteq(int kind, int geom, int L, int Nc, const uint8_t *qm0, const double *ladder,
-                          const double *diff, double param_b, double p_logical, int SEQ, int TOPS,
-                          int tops_burn, double eps, int64_t steps, int64_t iters, int use_conv,
-                          qo_stream *nb, qo_stream *py, int64_t *eq_counts, int64_t *since_burn_out,
-                          int64_t *tops0_out, uint8_t *percent_out)
+/* qo_pteq_ex additionally keeps PTEQ_alpha_with_shortest's bookkeeping (decoders_biasednoise.py:114-146) when
+ * short_len != NULL: per class the smallest recorded bottom-rung value, how many samples hit it (short_n) and how
+ * many distinct bottom-rung states were seen at it (short_unique). */
+QO_EXPORT int64_t qo_pteq_ex(int kind, int geom, int L, int Nc, const uint8_t *qm0, const double *ladder,
+                             const double *diff, double param_b, double p_logical, int SEQ, int TOPS,
+                             int tops_burn, double eps, int64_t steps, int64_t iters, int use_conv,
+                             qo_stream *nb, qo_stream *py, int64_t *eq_counts, int64_t *since_burn_out,
+                             int64_t *tops0_out, uint8_t *percent_out, double *short_len, int64_t *short_n,
+                             int64_t *short_unique)
 {
+    qo_set *uniq[16] = {0};
+    if (short_len)
+        for (int e = 0; e < qo_neq(geom); e++) { short_len[e] = 100000; short_n[e] = 0; uniq[e] = qo_set_new(qo_nsites(geom, L)); }
     int n = qo_nsites(geom, L), n_eq = qo_neq(geom);
     uint8_t *qm = (uint8_t *)malloc((size_t)n * Nc);
     int32_t *flags = (int32_t *)calloc((size_t)Nc, sizeof(int32_t));
@@ -964,6 +971,20 @@ QO_EXPORT int64_t qo_pteq(int kind, int geom, int L, int Nc, const uint8_t *qm0,
                 hcap *= 2;
             }
             hist[since_burn] = (kind == 1) ? n_eff[0] : (double)qo_count_errors(qm, n);
+            if (short_len) {
+                double v = hist[since_burn];
+                int nw;
+                if (v < short_len[cur]) {
+                    short_n[cur] = 1;
+                    short_len[cur] = v;
+                    qo_set_free(uniq[cur]);
+                    uniq[cur] = qo_set_new(n);
+                    qo_set_add(uniq[cur], qm, &nw);
+                } else if (v == short_len[cur]) {
+                    short_n[cur]++;
+                    qo_set_add(uniq[cur], qm, &nw);
+                }
+            }
         } else {
             resulting_burn_in++;
         }
@@ -990,8 +1011,200 @@ QO_EXPORT int64_t qo_pteq(int kind, int geom, int L, int Nc, const uint8_t *qm0,
     if (percent_out)
         for (int e = 0; e < n_eq; e++)
             percent_out[e] = (uint8_t)((double)eq_counts[e] / (double)(since_burn + 1) * 100);
+    if (short_len)
+        for (int e = 0; e < n_eq; e++) { short_unique[e] = uniq[e]->cnt; qo_set_free(uniq[e]); }
     free(qm); free(flags); free(n_eff); free(hist);
     return step;
+}
+
+QO_EXPORT int64_t qo_pteq(int kind, int geom, int L, int Nc, const uint8_t *qm0, const double *ladder,
+                          const double *diff, double param_b, double p_logical, int SEQ, int TOPS,
+                          int tops_burn, double eps, int64_t steps, int64_t iters, int use_conv,
+                          qo_stream *nb, qo_stream *py, int64_t *eq_counts, int64_t *since_burn_out,
+                          int64_t *tops0_out, uint8_t *percent_out)
+{
+    return qo_pteq_ex(kind, geom, L, Nc, qm0, ladder, diff, param_b, p_logical, SEQ, TOPS, tops_burn, eps, steps, iters,
+                      use_conv, nb, py, eq_counts, since_burn_out, tops0_out, percent_out, NULL, NULL, NULL);
+}
+
+/* ------------------------------------------------------------------ */
+/* General (x, y, z) noise: Chain_xyz / _update_chain_fast_xyz          */
+/* (mcmc.py:106-114,162-173) and STDC_general_noise(_shortest)          */
+/* (decoders.py:325-508).                                               */
+/* ------------------------------------------------------------------ */
+/* accept iff u < (factors ** (n_new - n_old)).prod(): numpy power per element
+ * (libm pow), product accumulated from 1 in index order (numba's array.prod). */
+QO_EXPORT void qo_update_chain_fast_xyz(int geom, int L, uint8_t *qm, const double *factors, int64_t iters,
+                                        qo_stream *nb)
+{
+    int n = qo_nsites(geom, L);
+    int64_t c0[3], c1[3];
+    qo_count_xyz(qm, n, c0);
+    for (int64_t t = 0; t < iters; t++) {
+        int row, col, op;
+        qo_draw_stabilizer(geom, L, nb, &row, &col, &op);
+        qo_apply_stabilizer(geom, L, qm, row, col, op);
+        qo_count_xyz(qm, n, c1);
+        double r = 1.0;
+        for (int i = 0; i < 3; i++) r *= pow(factors[i], (double)(c1[i] - c0[i]));
+        if (qo_stream_next(nb) < r) { c0[0] = c1[0]; c0[1] = c1[1]; c0[2] = c1[2]; }
+        else qo_apply_stabilizer(geom, L, qm, row, col, op);
+    }
+}
+
+/* weighted length of decoders.py:406: sum of beta_i * n_i over the components with n_i > 0 */
+static double xyz_weight(const double *beta, const double *cnt)
+{
+    double w = 0.0;
+    for (int i = 0; i < 3; i++)
+        if (cnt[i] > 0) w += beta[i] * cnt[i];
+    return w;
+}
+
+/* use_xyz != 0: Chain_xyz(p_sampling array) ; else Chain(p_sampling scalar) -- both on the fast path with
+ * proposal geometry geom_chain; randomize is False in every branch of the reference (decoders.py:362,375).
+ * Outputs: eqdistr (all distinct chains), eqdistr_shortest (chains whose weighted length is np.isclose to the
+ * class minimum), both normalised to percent; distinct[n_eq] optional. */
+QO_EXPORT void qo_stdc_general_noise(int geom_code, int geom_chain, int L, int n_eq, const uint8_t *qm_init,
+                                     const double *p_xyz, int use_xyz, const double *p_sampling_xyz,
+                                     double p_sampling, int droplets, int64_t steps, int64_t iters, qo_stream **nb,
+                                     double *eqdistr, double *eqdistr_shortest, int64_t *distinct)
+{
+    int n = qo_nsites(geom_code, L);
+    double beta[3], factors[3] = {0, 0, 0};
+    for (int i = 0; i < 3; i++) beta[i] = -log((p_xyz[i] / 3) / (1 - p_xyz[i]));
+    if (use_xyz) {
+        double tot = p_sampling_xyz[0] + p_sampling_xyz[1] + p_sampling_xyz[2];
+        for (int i = 0; i < 3; i++) factors[i] = p_sampling_xyz[i] / (1.0 - tot);
+    }
+    double factor = (p_sampling / 3.0) / (1.0 - p_sampling);
+    uint8_t *qm = (uint8_t *)malloc((size_t)n);
+    double tot_all = 0, tot_short = 0;
+    for (int eq = 0; eq < n_eq; eq++) {
+        qo_set *all = qo_set_new(n);
+        for (int d = 0; d < droplets; d++) {
+            memcpy(qm, qm_init + (size_t)eq * n, (size_t)n);
+            for (int64_t s = 0; s < steps; s++) {
+                if (use_xyz) qo_update_chain_fast_xyz(geom_chain, L, qm, factors, iters, nb[eq * droplets + d]);
+                else qo_update_chain_fast(geom_chain, L, qm, factor, iters, nb[eq * droplets + d], NULL, NULL);
+                int nw;
+                int64_t e = qo_set_add(all, qm, &nw);
+                if (nw) {
+                    int64_t c[3];
+                    qo_count_xyz(qm, n, c);
+                    all->val[3 * e] = (double)c[0]; all->val[3 * e + 1] = (double)c[1]; all->val[3 * e + 2] = (double)c[2];
+                }
+            }
+        }
+        double wmin = INFINITY, z = 0, zs = 0;
+        for (int64_t e = 0; e < all->cnt; e++) {
+            double w = xyz_weight(beta, all->val + 3 * e);
+            if (w < wmin) wmin = w;
+            z += exp(-w);
+        }
+        for (int64_t e = 0; e < all->cnt; e++) {
+            double w = xyz_weight(beta, all->val + 3 * e);
+            if (fabs(w - wmin) <= 1e-8 + 1e-5 * fabs(wmin)) zs += exp(-w); /* np.isclose defaults */
+        }
+        eqdistr[eq] = z; eqdistr_shortest[eq] = zs;
+        tot_all += z; tot_short += zs;
+        if (distinct) distinct[eq] = all->cnt;
+        qo_set_free(all);
+    }
+    for (int eq = 0; eq < n_eq; eq++) {
+        eqdistr[eq] = eqdistr[eq] / tot_all * 100;
+        eqdistr_shortest[eq] = eqdistr_shortest[eq] / tot_short * 100;
+    }
+    free(qm);
+}
+
+/* ------------------------------------------------------------------ */
+/* PTDC / PTRC (decoders.py:138-233, 584-742) and                       */
+/* PTEQ_alpha_with_shortest (decoders_biasednoise.py:93-172)            */
+/* ------------------------------------------------------------------ */
+/* One class ladder per class (p_logical = 0), droplets ladders per class, each `steps` Ladder.step(iters)
+ * calls; after every step every rung's state is offered to the class's set (PTDC) or to the rung's own set with
+ * N(n) / m(n) counters (PTRC).  nb / py: per (class, droplet) streams.
+ * mode 0 = PTDC: out = Z_E = sum exp(-beta_error n) over the union, normalised percent (float; the reference
+ *                truncates to uint8).
+ * mode 1 = PTRC: out = sum over rungs i < Nc-1 of C_mean_i * sum_n m_i(n) exp(n d_beta_i - beta_i n0_i)
+ *                (decoders.py:721-739), droplet counters summed (decoders.py:699-718). */
+QO_EXPORT void qo_ptxc(int mode, int geom, int L, int n_eq, int Nc, const uint8_t *qm_init, double p_error,
+                       double p_sampling, int droplets, int64_t steps, int64_t iters, qo_stream **nb, qo_stream **py,
+                       double *out, int64_t *N_out /* mode 1: [n_eq][Nc][n+1] */, int64_t *m_out)
+{
+    int n = qo_nsites(geom, L);
+    double beta_error = -log((p_error / 3) / (1 - p_error));
+    double *ladder = (double *)malloc(sizeof(double) * (size_t)Nc);
+    double *diff = (double *)calloc((size_t)Nc, sizeof(double));
+    /* numpy.linspace(p_sampling, 0.75, Nc) */
+    if (Nc == 1) ladder[0] = p_sampling;
+    else {
+        double step = (0.75 - p_sampling) / (double)(Nc - 1);
+        for (int i = 0; i < Nc; i++) { volatile double t = (double)i * step; ladder[i] = t + p_sampling; }
+        ladder[Nc - 1] = 0.75;
+    }
+    for (int i = 0; i + 1 < Nc; i++) diff[i] = (ladder[i] * (1 - ladder[i + 1])) / (ladder[i + 1] * (1 - ladder[i]));
+    uint8_t *qm = (uint8_t *)malloc((size_t)n * Nc);
+    int32_t *flags = (int32_t *)malloc(sizeof(int32_t) * (size_t)Nc);
+    double *n_eff = (double *)calloc((size_t)Nc, sizeof(double));
+    int64_t *Nh = (int64_t *)malloc(sizeof(int64_t) * (size_t)Nc * (n + 1));
+    int64_t *mh = (int64_t *)malloc(sizeof(int64_t) * (size_t)Nc * (n + 1));
+    double total = 0;
+    for (int eq = 0; eq < n_eq; eq++) {
+        qo_set *all = qo_set_new(n);
+        memset(Nh, 0, sizeof(int64_t) * (size_t)Nc * (n + 1));
+        memset(mh, 0, sizeof(int64_t) * (size_t)Nc * (n + 1));
+        for (int d = 0; d < droplets; d++) {
+            qo_set **rung = (qo_set **)malloc(sizeof(qo_set *) * (size_t)Nc);
+            for (int i = 0; i < Nc; i++) { rung[i] = qo_set_new(n); memcpy(qm + (size_t)i * n, qm_init + (size_t)eq * n, (size_t)n); flags[i] = 0; }
+            flags[Nc - 1] = 1;
+            int64_t tops0 = 0;
+            for (int64_t s = 0; s < steps; s++) {
+                qo_ladder_step(0, geom, L, Nc, qm, ladder, diff, 0.0, 0.0, flags, n_eff, &tops0, iters,
+                               nb[eq * droplets + d], py[eq * droplets + d]);
+                for (int i = 0; i < Nc; i++) {
+                    int nw;
+                    const uint8_t *st = qm + (size_t)i * n;
+                    if (mode == 0) {
+                        int64_t e = qo_set_add(all, st, &nw);
+                        if (nw) all->val[3 * e] = qo_count_errors(st, n);
+                    } else {
+                        int64_t e = qo_set_add(rung[i], st, &nw);
+                        if (nw) { rung[i]->val[3 * e] = qo_count_errors(st, n); Nh[(size_t)i * (n + 1) + (int)rung[i]->val[3 * e]]++; }
+                        mh[(size_t)i * (n + 1) + (int)rung[i]->val[3 * e]]++;
+                    }
+                }
+            }
+            for (int i = 0; i < Nc; i++) qo_set_free(rung[i]);
+            free(rung);
+        }
+        double z = 0;
+        if (mode == 0) {
+            for (int64_t e = 0; e < all->cnt; e++) z += exp(-beta_error * all->val[3 * e]);
+        } else {
+            for (int i = 0; i < Nc - 1; i++) {
+                double beta_i = -log((ladder[i] / 3) / (1 - ladder[i])), d_beta = beta_i - beta_error;
+                const int64_t *N = Nh + (size_t)i * (n + 1), *m = mh + (size_t)i * (n + 1);
+                int l0 = -1, l1 = -1;
+                for (int l = 0; l <= n; l++)
+                    if (m[l]) { if (l0 < 0) l0 = l; else if (l1 < 0) l1 = l; }
+                double c_mean = (double)N[l0] / (double)m[l0] * exp(-beta_i * 0.0);
+                if (l1 >= 0) c_mean = (c_mean + (double)N[l1] / (double)m[l1] * exp(-beta_i * (double)(l1 - l0))) / 2.0;
+                double sum = 0;
+                for (int l = 0; l <= n; l++)
+                    if (m[l]) sum += (double)m[l] * exp((double)l * d_beta - beta_i * (double)l0);
+                z += c_mean * sum;
+            }
+            if (N_out) memcpy(N_out + (size_t)eq * Nc * (n + 1), Nh, sizeof(int64_t) * (size_t)Nc * (n + 1));
+            if (m_out) memcpy(m_out + (size_t)eq * Nc * (n + 1), mh, sizeof(int64_t) * (size_t)Nc * (n + 1));
+        }
+        out[eq] = z;
+        total += z;
+        qo_set_free(all);
+    }
+    for (int eq = 0; eq < n_eq; eq++) out[eq] = out[eq] / total * 100;
+    free(ladder); free(diff); free(qm); free(flags); free(n_eff); free(Nh); free(mh);
 }
 
 /* ------------------------------------------------------------------ */

@@ -252,6 +252,57 @@ def gen(variant):
             add("single_temp", geom=geom, chain_geom=chain_geom, L=L, q=q, inits=inits_arr, p=0.2, max_iters=200,
                 nb_seed=seed, out=out)
 
+    # ---- E. general noise, PTDC / PTRC, PTEQ_alpha_with_shortest (shipped variant only) ----
+    if variant == "shipped":
+        geom, L = "planar", 5
+        q = rand_lattice(rng, geom, L, 0.12)
+        inits_arr = np.array([c.qubit_matrix for c in class_inits(ref, geom, q)])
+        p_xyz = np.array([0.03, 0.02, 0.06])
+        # Chain_xyz trajectory (fast path, planar proposals)
+        seed = int(rng.integers(1, 2**31))
+        ref.seed_all(nb=seed)
+        ps = np.array([0.08, 0.06, 0.10])
+        ch = ref.mcmc.Chain_xyz(ps, make_code(ref, geom, q))
+        snaps = []
+        for _ in range(200):
+            ch.update_chain_fast(5)
+            snaps.append(ch.code.qubit_matrix.copy())
+        add("chain_fast_xyz", geom=geom, chain_geom="planar", L=L, q=q, p_sampling=ps, nb_seed=seed, iters=5, blocks=200,
+            out=np.array(snaps))
+        for ps in (None, np.array([0.08, 0.06, 0.10])):
+            seed = int(rng.integers(1, 2**31))
+            ref.seed_all(nb=seed)
+            out, out_s = ref.decoders.STDC_general_noise_shortest(class_inits(ref, geom, q), p_xyz, ps, droplets=1, steps=300)
+            add("stdc_general_noise", geom=geom, chain_geom="planar", L=L, q=q, inits=inits_arr, p_xyz=p_xyz,
+                p_sampling=(np.zeros(0) if ps is None else ps), steps=300, nb_seed=seed, out=out, out_shortest=out_s)
+        # PTDC / PTRC: one ladder per class, droplets = 1 (in process)
+        for g2 in ("toric", "planar"):
+            q2 = rand_lattice(rng, g2, 5, 0.1)
+            if g2 == "toric":
+                arr = np.array([ref.toric_model._to_class(e, q2) for e in range(16)])
+            else:
+                arr = np.array([c.qubit_matrix for c in class_inits(ref, g2, q2)])
+
+            def lst():
+                return [make_code(ref, g2, a) for a in arr]
+            seeds = [int(x) for x in rng.integers(1, 2**31, 2)]
+            ref.seed_all(py=seeds[0], nb=seeds[1])
+            out = ref.decoders.PTDC(lst(), 0.1, 0.25, droplets=1, Nc=4, steps=1200)
+            add("ptdc", geom=g2, L=5, q=q2, inits=arr, p_error=0.1, p_sampling=0.25, Nc=4, steps=1200, py_seed=seeds[0],
+                nb_seed=seeds[1], out=out)
+            seeds = [int(x) for x in rng.integers(1, 2**31, 2)]
+            ref.seed_all(py=seeds[0], nb=seeds[1])
+            out = ref.decoders.PTRC(lst(), 0.1, 0.25, droplets=1, Nc=4, steps=1200)
+            add("ptrc", geom=g2, L=5, q=q2, inits=arr, p_error=0.1, p_sampling=0.25, Nc=4, steps=1200, py_seed=seeds[0],
+                nb_seed=seeds[1], out=out)
+        for g2 in ("planar", "rotated", "xzzx"):
+            q2 = rand_lattice(rng, g2, 5, 0.1)
+            seeds = [int(x) for x in rng.integers(1, 2**31, 2)]
+            ref.seed_all(py=seeds[0], nb=seeds[1])
+            o1, o2, o3 = ref.decoders_biasednoise.PTEQ_alpha_with_shortest(make_code(ref, g2, q2), 0.15, alpha=2.0, steps=100000)
+            add("pteq_alpha_shortest", geom=g2, L=5, q=q2, p=0.15, b=2.0, py_seed=seeds[0], nb_seed=seeds[1], steps=100000,
+                out=o1, out_unique=o2, out_shortest_n=o3)
+
     arrays, manifest = {}, []
     for i, c in enumerate(cases):
         meta = {}

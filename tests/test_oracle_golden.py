@@ -125,5 +125,35 @@ def test_golden(variant, idx, c):
         cg = O.GEOM[c["chain_geom"]]
         out = O.single_temp(g, cg, L, c["inits"], c["p"], c["max_iters"], [nb] * O.neq(g))
         np.testing.assert_allclose(out, c["out"], rtol=1e-12)
+    elif kind == "chain_fast_xyz":
+        nb = O.Stream.mt(c["nb_seed"])
+        cg = O.GEOM[c["chain_geom"]]
+        ps = c["p_sampling"]
+        factors = ps / (1.0 - ps.sum())
+        cur = q.copy()
+        for want in c["out"]:
+            cur = O.update_chain_fast_xyz(cg, L, cur, factors, c["iters"], nb)
+            assert np.array_equal(cur, want)
+    elif kind == "stdc_general_noise":
+        nb = O.Stream.mt(c["nb_seed"])
+        cg = O.GEOM[c["chain_geom"]]
+        ps = c["p_sampling"] if c["p_sampling"].size else float(c["p_xyz"].sum())
+        out, out_s, _ = O.stdc_general_noise(g, cg, L, c["inits"], c["p_xyz"], ps, 1, c["steps"], [nb] * O.neq(g))
+        np.testing.assert_allclose(out, c["out"], rtol=1e-9)
+        np.testing.assert_allclose(out_s, c["out_shortest"], rtol=1e-9)
+    elif kind in ("ptdc", "ptrc"):
+        nb, py = O.Stream.mt(c["nb_seed"]), O.Stream.py(c["py_seed"])
+        n_eq = O.neq(g)
+        out = O.ptxc(0 if kind == "ptdc" else 1, g, L, c["inits"], c["p_error"], c["p_sampling"], 1, c["Nc"],
+                     c["steps"] // c["Nc"], [nb] * n_eq, [py] * n_eq)
+        # the reference truncates to uint8: allow the float result to sit within rounding of a truncation boundary
+        assert np.array_equal(np.floor(out + 1e-9).astype(np.uint8), c["out"]) or \
+            np.array_equal(out.astype(np.uint8), c["out"]), (out, c["out"])
+    elif kind == "pteq_alpha_shortest":
+        nb, py = O.Stream.mt(c["nb_seed"]), O.Stream.py(c["py_seed"])
+        pct, z, sn, info = O.pteq_with_shortest(1, g, L, q, c["p"], nb, py, param_b=c["b"], steps=c["steps"])
+        assert np.array_equal(pct, c["out"]), info
+        np.testing.assert_allclose(z, c["out_unique"], rtol=1e-9)
+        np.testing.assert_allclose(sn, c["out_shortest_n"], rtol=1e-12)
     else:
         raise AssertionError("unknown golden kind " + kind)
