@@ -232,6 +232,15 @@ typedef struct qecmc_ptdc_cfg {
 } qecmc_ptdc_cfg;
 int qecmc_ptdc(qecmc_ctx *ctx, const qecmc_ptdc_cfg *cfg, const uint8_t *qm, int64_t S, double *eqdistr, qecmc_stats *stats);
 
+/* PTRC / PTRC_droplet (decoders.py:584-742): the same ladders, but every rung keeps its own set of distinct
+ * chains with N(n) (distinct chains per length) and m(n) (visits per length), droplet counters summed
+ * (decoders.py:699-718); Z_E = sum over rungs i < Nc-1 of C_i * sum_n m_i(n) exp(n (beta_i - beta) - beta_i n0_i)
+ * with C_i the mean of N/m exp(-beta_i (n - n0)) over the two shortest lengths seen (decoders.py:721-739).
+ * conv_mult has no effect in the reference (its break is commented out) and is not a parameter here.
+ * N_hist, m_hist [S][n_eq][Nc][n_sites+1] optional. */
+int qecmc_ptrc(qecmc_ctx *ctx, const qecmc_ptdc_cfg *cfg, const uint8_t *qm, int64_t S, double *eqdistr,
+               int64_t *N_hist, int64_t *m_hist, qecmc_stats *stats);
+
 /* EWD-style STDC_Nall_n_alpha / STDC_droplet_alpha (decoders.py:510-581): one Chain_alpha per class,
  * `steps` samples of Chain_alpha.update_chain(iters), distinct chains weighted by
  * pz_tilde ** (nz + alpha (nx + ny)).  distinct [S][n_eq] optional. */

@@ -107,6 +107,8 @@ def load():
     L.qecmc_pteq_dev.argtypes = [C.c_void_p, C.POINTER(PteqCfg), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                  C.POINTER(Stats)]
     L.qecmc_ptdc.argtypes = [C.c_void_p, C.POINTER(PtdcCfg), C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(Stats)]
+    L.qecmc_ptrc.argtypes = [C.c_void_p, C.POINTER(PtdcCfg), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                             C.POINTER(Stats)]
     L.qecmc_stdc_alpha.argtypes = [C.c_void_p, C.POINTER(AlphaCfg), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.POINTER(Stats)]
     _lib = L
@@ -352,6 +354,24 @@ class Context:
         st = Stats()
         _check(load().qecmc_ptdc(self._h, C.byref(cfg), qm.ctypes.data, S, out.ctypes.data, C.byref(st)))
         return out, st.as_dict()
+
+    def ptrc(self, geom, L, qm, p_error, p_sampling, droplets, Nc, steps, iters=10, per_class=False, seed=0, u_nb=None,
+             u_py=None, want_hist=False):
+        """PTRC over a batch; `steps` is the per-ladder step count.  Returns (eqdistr float64 [S, n_eq], stats
+        [, N_hist, m_hist int64 [S, n_eq, Nc, n_sites+1]])."""
+        _require_u8(qm)
+        S, n, n_eq = qm.shape[0], nsites(geom, L), neq(geom)
+        assert qm.size == S * (n_eq if per_class else 1) * n
+        lc, keep = self._ladder_cfg(geom, L, LADDER_DEPOLARIZING, Nc, iters, p_sampling, 0.0, 0.0, seed, u_nb, u_py,
+                                    S * n_eq * droplets)
+        cfg = PtdcCfg(lc, droplets, int(per_class), int(steps), p_error)
+        out = np.zeros((S, n_eq), np.float64)
+        Nh = np.zeros((S, n_eq, Nc, n + 1), np.int64) if want_hist else None
+        mh = np.zeros((S, n_eq, Nc, n + 1), np.int64) if want_hist else None
+        st = Stats()
+        _check(load().qecmc_ptrc(self._h, C.byref(cfg), qm.ctypes.data, S, out.ctypes.data,
+                                 Nh.ctypes.data if want_hist else None, mh.ctypes.data if want_hist else None, C.byref(st)))
+        return (out, st.as_dict(), Nh, mh) if want_hist else (out, st.as_dict())
 
     def stdc_alpha(self, geom, L, qm, pz_tilde_sampling, alpha, pz_tilde, steps, iters=5, per_class=False, seed=0, u_nb=None,
                    u_py=None):

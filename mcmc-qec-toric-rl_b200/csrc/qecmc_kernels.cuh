@@ -387,7 +387,7 @@ static __global__ void table_hist_kernel(const unsigned long long *__restrict__ 
         unsigned long long cnt = 0;
         for (int n = 0; n <= nsites; n++)
             if (s_hist[n]) { z += (double)s_hist[n] * exp(-beta * (double)n); cnt += s_hist[n]; }
-        Z[blockIdx.x] = z;
+        if (Z) Z[blockIdx.x] = z;
         if (distinct) atomicAdd(distinct, cnt);
     }
 }

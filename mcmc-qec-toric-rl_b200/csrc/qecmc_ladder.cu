@@ -169,7 +169,7 @@ template <int GEOM, typename W> int launch_ladder_gw(qecmc_ctx *c, LadderParams 
 template <int GEOM> int launch_ladder_g(qecmc_ctx *c, LadderParams &p, bool replay, bool weighted)
 {
     class_deltas<GEOM>(p.g, p.cls_delta);
-    if (p.acct == ACCT_DC) {
+    if (p.acct >= ACCT_DC) {
         if (p.g.L > 16) QTRY((build_stab_hash<GEOM, uint64_t>(c, p.g, (uint64_t **)&p.stab_hash)));
         else QTRY((build_stab_hash<GEOM, uint32_t>(c, p.g, (uint64_t **)&p.stab_hash)));
     }
@@ -510,7 +510,8 @@ extern "C" int qecmc_pteq_dev(qecmc_ctx *c, const qecmc_pteq_cfg *cfg, const uin
 // Distinct-chain decoders on ladders: PTDC (decoders.py:138-233) and the EWD-style
 // STDC_Nall_n_alpha / STDC_droplet_alpha (decoders.py:510-581, a one-rung alpha "ladder").
 static int dc_common(qecmc_ctx *c, const qecmc_ladder_cfg *lc, int per_class_inits, int droplets, int64_t steps, double beta,
-                     const uint8_t *qm, int64_t S, double *eqdistr, int64_t *distinct, qecmc_stats *stats)
+                     const uint8_t *qm, int64_t S, double *eqdistr, int64_t *distinct, qecmc_stats *stats, bool rc = false,
+                     int64_t *N_hist = nullptr, int64_t *m_hist = nullptr)
 {
     if (!c || !qm || !eqdistr) return set_err(QECMC_ERR_ARG, "NULL argument");
     QTRY(check_ladder_cfg(lc));
@@ -525,13 +526,16 @@ static int dc_common(qecmc_ctx *c, const qecmc_ladder_cfg *lc, int per_class_ini
     LadderDev d;
     LadderParams p;
     QTRY(setup_ladder(c, lc, g, d, p));
-    uint64_t max_keys = (uint64_t)droplets * (uint64_t)steps * (uint64_t)lc->Nc;
+    // PTDC: one set per (syndrome, class); PTRC: one per (syndrome, class, droplet, rung)
+    uint64_t max_keys = rc ? (uint64_t)steps : (uint64_t)droplets * (uint64_t)steps * (uint64_t)lc->Nc;
     uint64_t cap = next_pow2(max_keys + max_keys / 4 + 1);
     if (cap < 1024) cap = 1024;
+    const int64_t tabs_per_class = rc ? (int64_t)droplets * lc->Nc : 1;
+    const int ns1 = g.nsites + 1;
     size_t fr = 0, tot = 0;
     CUDA_OK(cudaMemGetInfo(&fr, &tot));
     int64_t budget = c->table_budget ? c->table_budget : (int64_t)((double)(fr + c->tables.cap) * 0.85);
-    int64_t per_syndrome = (int64_t)n_eq * (int64_t)cap * 8;
+    int64_t per_syndrome = (int64_t)n_eq * tabs_per_class * ((int64_t)cap * 8 + (rc ? (int64_t)ns1 * 12 : 0));
     int64_t wave = budget / per_syndrome;
     if (wave < 1) return set_err(QECMC_ERR_NOMEM, "distinct-chain tables need %lld bytes per syndrome, budget is %lld",
                                  (long long)per_syndrome, (long long)budget);
@@ -563,8 +567,20 @@ static int dc_common(qecmc_ctx *c, const qecmc_ladder_cfg *lc, int per_class_ini
         CUDA_OK(cudaMemcpy2DAsync((char *)d.lat_out.p + (size_t)dr * g.nw * wb, (size_t)droplets * g.nw * wb, class_lat,
                                   (size_t)g.nw * wb, (size_t)g.nw * wb, (size_t)S * n_eq, cudaMemcpyDeviceToDevice, c->stream));
     QTRY(stage_replay(c, lc, S * n_eq * droplets, d, p));
-    p.acct = ACCT_DC;
+    p.acct = rc ? ACCT_RC : ACCT_DC;
     p.steps = steps;
+    DevBuf rc_m, rc_N, rc_Nout, rc_mout, lad_p;
+    if (rc) {
+        QTRY(rc_m.ensure((size_t)wave * n_eq * tabs_per_class * ns1 * sizeof(unsigned long long)));
+        QTRY(rc_N.ensure((size_t)wave * n_eq * tabs_per_class * ns1 * sizeof(uint32_t)));
+        QTRY(rc_Nout.ensure((size_t)S * n_eq * lc->Nc * ns1 * sizeof(long long)));
+        QTRY(rc_mout.ensure((size_t)S * n_eq * lc->Nc * ns1 * sizeof(long long)));
+        LadderTables lt;
+        make_ladder_tables(lc, g, lt);
+        QTRY(upload(c, lad_p, lt.ladder));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        p.rc_m_hist = (unsigned long long *)rc_m.p;
+    }
     p.init_broadcast = 1;
     p.droplets = droplets;
     p.aux_bits = lc->kind == LK_ALPHA ? 22 : QECMC_LEN_BITS;
@@ -576,7 +592,8 @@ static int dc_common(qecmc_ctx *c, const qecmc_ladder_cfg *lc, int per_class_ini
     int64_t waves = 0;
     for (int64_t s0 = 0; s0 < S; s0 += wave, waves++) {
         int64_t sw = S - s0 < wave ? S - s0 : wave;
-        CUDA_OK(cudaMemsetAsync(c->tables.p, 0, (size_t)sw * per_syndrome, c->stream));
+        CUDA_OK(cudaMemsetAsync(c->tables.p, 0, (size_t)sw * n_eq * tabs_per_class * cap * 8, c->stream));
+        if (rc) CUDA_OK(cudaMemsetAsync(rc_m.p, 0, (size_t)sw * n_eq * tabs_per_class * ns1 * sizeof(unsigned long long), c->stream));
         const int64_t l0 = s0 * n_eq * droplets;
         p.n_ladders = sw * n_eq * droplets;
         p.ladder_offset = l0;
@@ -584,7 +601,16 @@ static int dc_common(qecmc_ctx *c, const qecmc_ladder_cfg *lc, int per_class_ini
         if (u_nb0) { p.u_nb = u_nb0 + l0 * p.n_nb; p.u_py = u_py0 + l0 * p.n_py; }
         QTRY(launch_ladder(c, p, lc->u_nb != nullptr));
         const int64_t tabs = sw * n_eq;
-        if (lc->kind == LK_ALPHA) {
+        if (rc) {
+            table_hist_kernel<<<(unsigned)(tabs * tabs_per_class), 256, ns1 * sizeof(uint32_t), c->stream>>>(
+                (const unsigned long long *)c->tables.p, cap, g.nsites, 0.0, nullptr, (uint32_t *)rc_N.p,
+                (unsigned long long *)c->counters.p + 3);
+            c->launches++;
+            ptrc_finalize_kernel<<<(unsigned)((tabs + 63) / 64), 64, 0, c->stream>>>(
+                (const uint32_t *)rc_N.p, (const unsigned long long *)rc_m.p, tabs, droplets, lc->Nc, ns1, (const double *)lad_p.p,
+                beta, (double *)d.Zd.p + s0 * n_eq, (long long *)rc_Nout.p + (size_t)s0 * n_eq * lc->Nc * ns1,
+                (long long *)rc_mout.p + (size_t)s0 * n_eq * lc->Nc * ns1);
+        } else if (lc->kind == LK_ALPHA) {
             table_sum_alpha_kernel<<<(unsigned)tabs, 256, 0, c->stream>>>((const unsigned long long *)c->tables.p, cap, beta,
                                                                           lc->param_b, (double *)d.Zd.p + s0 * n_eq,
                                                                           (unsigned long long *)d.dist.p + s0 * n_eq,
@@ -606,10 +632,13 @@ static int dc_common(qecmc_ctx *c, const qecmc_ladder_cfg *lc, int per_class_ini
     CUDA_OK(cudaMemcpyAsync(eqdistr, c->out_f64.p, (size_t)S * n_eq * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (distinct && lc->kind == LK_ALPHA)
         CUDA_OK(cudaMemcpyAsync(distinct, d.dist.p, (size_t)S * n_eq * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    if (rc && N_hist) CUDA_OK(cudaMemcpyAsync(N_hist, rc_Nout.p, (size_t)S * n_eq * lc->Nc * ns1 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    if (rc && m_hist) CUDA_OK(cudaMemcpyAsync(m_hist, rc_mout.p, (size_t)S * n_eq * lc->Nc * ns1 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     unsigned long long cnt[8] = {0};
     CUDA_OK(cudaMemcpyAsync(cnt, c->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     cls_lat.release();
+    rc_m.release(); rc_N.release(); rc_Nout.release(); rc_mout.release(); lad_p.release();
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
     fill_stats(c, stats, S * n_eq * droplets * lc->Nc * steps * lc->iters, cnt, ms, waves);
@@ -649,4 +678,16 @@ extern "C" int qecmc_ptdc(qecmc_ctx *c, const qecmc_ptdc_cfg *cfg, const uint8_t
     if (!(cfg->p_error > 0 && cfg->p_error < 1)) return set_err(QECMC_ERR_ARG, "p_error outside (0,1)");
     const double beta = -log((cfg->p_error / 3) / (1 - cfg->p_error));  // decoders.py:205
     return dc_common(c, &cfg->ladder, cfg->per_class_inits, cfg->droplets, cfg->steps, beta, qm, S, eqdistr, nullptr, stats);
+}
+
+extern "C" int qecmc_ptrc(qecmc_ctx *c, const qecmc_ptdc_cfg *cfg, const uint8_t *qm, int64_t S, double *eqdistr,
+                          int64_t *N_hist, int64_t *m_hist, qecmc_stats *stats)
+{
+    if (!cfg) return set_err(QECMC_ERR_ARG, "cfg is NULL");
+    if (cfg->ladder.kind != LK_DEPOL) return set_err(QECMC_ERR_ARG, "PTRC runs depolarizing ladders");
+    if (!(cfg->p_error > 0 && cfg->p_error < 1)) return set_err(QECMC_ERR_ARG, "p_error outside (0,1)");
+    if (cfg->ladder.Nc < 2) return set_err(QECMC_ERR_ARG, "PTRC needs at least two rungs (the top rung is not used in the estimate)");
+    const double beta = -log((cfg->p_error / 3) / (1 - cfg->p_error));  // decoders.py:679
+    return dc_common(c, &cfg->ladder, cfg->per_class_inits, cfg->droplets, cfg->steps, beta, qm, S, eqdistr, nullptr, stats, true,
+                     N_hist, m_hist);
 }

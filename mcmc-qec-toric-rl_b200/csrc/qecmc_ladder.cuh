@@ -20,7 +20,7 @@
 namespace qecmc {
 
 enum { LK_DEPOL = 0, LK_ALPHA = 1, LK_BIASED = 2 };
-enum { ACCT_NONE = 0, ACCT_PTEQ = 1, ACCT_DC = 2 };
+enum { ACCT_NONE = 0, ACCT_PTEQ = 1, ACCT_DC = 2, ACCT_RC = 3 };
 
 struct LadderParams {
     Geo g;
@@ -64,6 +64,7 @@ struct LadderParams {
     int droplets, aux_bits;
     const uint64_t *stab_hash;
     uint64_t hash_seed;
+    unsigned long long *rc_m_hist; // ACCT_RC: [n_ladders][Nc][nsites+1] visits per length and rung (PTRC's m(n))
     unsigned long long *counters;  // [0] accepted [1] offered
     int *status;                   // != 0: a replay stream ran dry
 };
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(128) ladder_kernel(LadderParams p)
         cls = class_raw_to_label(GEOM, lat_class<GEOM, W>(g, lat));
         flag = p.flags_in ? p.flags_in[ladder * Nc + gl] : ((gl == Nc - 1) ? 1 : 0);
         if (p.neff_in) { int2 e = p.neff_in[ladder * Nc + gl]; e_nz = e.x; e_nxy = e.y; }
-        if (p.acct == ACCT_DC) h = lat_hash<W>(g, lat, p.hash_seed);
+        if (p.acct == ACCT_DC || p.acct == ACCT_RC) h = lat_hash<W>(g, lat, p.hash_seed);
     } else {
         for (int w = 0; w < g.nw; w++) lat.set(w, (W)0);
     }
@@ -217,6 +218,7 @@ __global__ void __launch_bounds__(128) ladder_kernel(LadderParams p)
     const bool top_logical = p.p_logical != 0.0;
     unsigned long long *table = nullptr;
     if (p.acct == ACCT_DC && ladder < p.n_ladders) table = p.tables + (uint64_t)(ladder / p.droplets) * (p.cap_mask + 1);
+    int last_r = -1;  // ACCT_RC: rung whose set saw this replica's current state
 
     // group-uniform bookkeeping (every lane of the group carries the same values)
     long long tops0 = (p.tops0_in && ladder < p.n_ladders) ? p.tops0_in[ladder] : 0, since_burn = 0, burn_in = 0, conv_start = 0, conv_streak = 0, steps_used = p.steps;
@@ -275,7 +277,7 @@ __global__ void __launch_bounds__(128) ladder_kernel(LadderParams p)
                         double u[K];
                         for (int k = 0; k < K; k++) u[k] = rr->nb();
                         propose_replay<GEOM>(g, u, row, col, op);
-                        if (p.acct == ACCT_DC) idx = rco_to_idx<GEOM>(g, row, col, op);
+                        if (p.acct >= ACCT_DC) idx = rco_to_idx<GEOM>(g, row, col, op);
                     } else {
                         idx = (int)__umulhi(reinterpret_cast<NativeRng *>(&rng)->next32(), (uint32_t)g.nstab);
                         idx_to_rco<GEOM>(g, idx, row, col, op);
@@ -313,7 +315,7 @@ __global__ void __launch_bounds__(128) ladder_kernel(LadderParams p)
                         for (int i = 0; i < NU; i++) lat.set(u.w[i], nv[i]);
                         if (WEIGHTED) { nx += dx; ny += dy; nz += dz; n = nx + ny + nz; e_nz = nz; e_nxy = nx + ny; }
                         else n += dE;
-                        if (p.acct == ACCT_DC) h ^= p.stab_hash[idx];
+                        if (p.acct >= ACCT_DC) h ^= p.stab_hash[idx];
                         dirty = true;
                         nacc++;
                     }
@@ -460,6 +462,29 @@ __global__ void __launch_bounds__(128) ladder_kernel(LadderParams p)
                 noff++;
                 dirty = false;
             }
+        } else if (p.acct == ACCT_RC) {
+            // PTRC_droplet (decoders.py:597-625): every rung keeps its own set of distinct chains and m(n)
+            if (valid && !done) {
+                const uint64_t t = (uint64_t)ladder * Nc + r;
+                atomicAdd(p.rc_m_hist + t * ns1 + n, 1ull);
+                if (dirty || r != last_r) {
+                    unsigned long long *tab = p.tables + t * (p.cap_mask + 1);
+                    uint64_t key = make_key(h, n);
+                    uint64_t slot = (key >> QECMC_LEN_BITS) & p.cap_mask;
+                    while (true) {
+                        unsigned long long curk = __ldcg(tab + slot);
+                        if (curk == key) break;
+                        if (curk == 0ull) {
+                            unsigned long long prev = atomicCAS(tab + slot, 0ull, (unsigned long long)key);
+                            if (prev == 0ull || prev == key) break;
+                        }
+                        slot = (slot + 1) & p.cap_mask;
+                    }
+                    noff++;
+                    dirty = false;
+                    last_r = r;
+                }
+            }
         }
     }
     __syncwarp();
@@ -490,6 +515,48 @@ __global__ void __launch_bounds__(128) ladder_kernel(LadderParams p)
             atomicAdd(p.counters + 1, (unsigned long long)noff);
         }
     }
+}
+
+// PTRC estimator (decoders.py:699-739) per (syndrome, class): N(n), m(n) of every rung summed over the droplets,
+// then for rungs i < Nc-1:  C_i = mean over the two shortest observed lengths of N/m * exp(-beta_i (n - n0)),
+// Z += C_i * sum_n m(n) exp(n (beta_i - beta_error) - beta_i n0).
+static __global__ void ptrc_finalize_kernel(const uint32_t *__restrict__ N_tab /* [tabs][droplets][Nc][ns1] */,
+                                            const unsigned long long *__restrict__ m_tab, int64_t tabs, int droplets, int Nc,
+                                            int ns1, const double *__restrict__ ladder_p, double beta_error,
+                                            double *__restrict__ Z, long long *__restrict__ N_out, long long *__restrict__ m_out)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= tabs) return;
+    double z = 0;
+    for (int i = 0; i < Nc; i++) {
+        const double beta_i = -log((ladder_p[i] / 3) / (1 - ladder_p[i])), d_beta = beta_i - beta_error;
+        int l0 = -1, l1 = -1;
+        double r0 = 0, r1 = 0, sum = 0;
+        // pass 1: two shortest lengths; pass 2 needs l0, so loop twice over the lengths
+        for (int pass = 0; pass < 2; pass++)
+            for (int l = 0; l < ns1; l++) {
+                long long N = 0, m = 0;
+                for (int d = 0; d < droplets; d++) {
+                    size_t o = (((size_t)t * droplets + d) * Nc + i) * ns1 + l;
+                    N += N_tab[o];
+                    m += (long long)m_tab[o];
+                }
+                if (pass == 0) {
+                    if (N_out) { N_out[((size_t)t * Nc + i) * ns1 + l] = N; m_out[((size_t)t * Nc + i) * ns1 + l] = m; }
+                    if (m) {
+                        if (l0 < 0) { l0 = l; r0 = (double)N / (double)m; }
+                        else if (l1 < 0) { l1 = l; r1 = (double)N / (double)m * exp(-beta_i * (double)(l1 - l0)); }
+                    }
+                } else if (m) {
+                    sum += (double)m * exp((double)l * d_beta - beta_i * (double)l0);
+                }
+            }
+        if (i < Nc - 1 && l0 >= 0) {
+            double c_mean = l1 >= 0 ? (r0 + r1) / 2.0 : r0;
+            z += c_mean * sum;
+        }
+    }
+    Z[t] = z;
 }
 
 // Z_E of a (syndrome, class) table whose keys carry (nz, nx+ny) in their low 22 bits:

@@ -483,3 +483,100 @@ def test_native_pteq_agrees_with_oracle(ctx):
     assert diffs.mean() <= 3.0, diffs.mean()
     assert agree >= S - 2
     assert (info["steps"] == steps).all()
+
+
+# ------------------------------------------------------------------ replay: PTDC
+def _ptxc_streams(rng, g, n_ladders, Nc, iters, steps):
+    n_nb, n_py = _ladder_budget(g, Nc, iters, steps)
+    return rng.random((n_ladders, n_nb)), rng.random((n_ladders, n_py))
+
+
+@pytest.mark.parametrize("g,L,Nc,droplets,per_class", [(O.TORIC, 5, 4, 1, False), (O.TORIC, 5, 3, 2, False),
+                                                        (O.PLANAR, 5, 5, 2, True), (O.ROTATED, 5, 4, 1, False),
+                                                        (O.XZZX, 7, 3, 2, True)])
+def test_ptdc_replay_matches_oracle(ctx, g, L, Nc, droplets, per_class):
+    rng = np.random.default_rng(7100 + g + L + Nc)
+    S, steps, iters = 2, 60, 10
+    n_eq = O.neq(g)
+    qs = [rand_lattice(rng, g, L, 0.1) for _ in range(S)]
+    qm = np.stack([O.all_classes(g, L, q) for q in qs]) if per_class else np.stack([q.reshape(-1) for q in qs])
+    u_nb, u_py = _ptxc_streams(rng, g, S * n_eq * droplets, Nc, iters, steps)
+    out, st = ctx.ptdc(g, L, qm, 0.1, 0.25, droplets, Nc, steps, iters=iters, per_class=per_class, u_nb=u_nb, u_py=u_py)
+    for s in range(S):
+        base = s * n_eq * droplets
+        nb = [O.Stream.replay(u_nb[base + i]) for i in range(n_eq * droplets)]
+        py = [O.Stream.replay(u_py[base + i]) for i in range(n_eq * droplets)]
+        want = O.ptxc(0, g, L, O.all_classes(g, L, qs[s]), 0.1, 0.25, droplets, Nc, steps, nb, py, iters=iters)
+        np.testing.assert_allclose(out[s], want, rtol=1e-9)
+
+
+def _golden_ladder_class_streams(c, n_eq, Nc, steps):
+    """PTDC / PTRC of the reference (droplets=1): the classes ran one after the other on ONE numba and ONE CPython
+    stream, each consuming a data-dependent amount (swap draws); the per-class slices start where the oracle,
+    pinned to these vectors, says the previous class stopped."""
+    g = O.GEOM[c["geom"]]
+    n_nb, n_py = _ladder_budget(g, Nc, 10, steps)
+    full_nb = np.random.RandomState(c["nb_seed"]).random_sample(n_nb * (n_eq + 1))
+    full_py = _py_uniforms(c["py_seed"], n_py * (n_eq + 1))
+    nb, py = O.Stream.replay(full_nb), O.Stream.replay(full_py)
+    u_nb, u_py = np.zeros((n_eq, n_nb)), np.zeros((n_eq, n_py))
+    inits = c["inits"].reshape(n_eq, -1)
+    for e in range(n_eq):
+        a, b = nb.drawn, py.drawn
+        u_nb[e], u_py[e] = full_nb[a:a + n_nb], full_py[b:b + n_py]
+        O.ptxc(0, g, c["L"], inits[e:e + 1], c["p_error"], c["p_sampling"], 1, Nc, steps, [nb], [py])
+    return u_nb, u_py
+
+
+def test_ptdc_replay_matches_reference_golden(ctx):
+    n = 0
+    for c in golden("shipped"):
+        if c["kind"] != "ptdc":
+            continue
+        g, L, Nc = O.GEOM[c["geom"]], c["L"], c["Nc"]
+        n_eq, steps = O.neq(g), c["steps"] // c["Nc"]
+        u_nb, u_py = _golden_ladder_class_streams(c, n_eq, Nc, steps)
+        out, _ = ctx.ptdc(g, L, c["inits"].reshape(1, n_eq, -1).copy(), c["p_error"], c["p_sampling"], 1, Nc, steps, per_class=True,
+                          u_nb=u_nb, u_py=u_py)
+        assert np.array_equal(out[0].astype(np.uint8), c["out"]) or np.array_equal(np.floor(out[0] + 1e-9).astype(np.uint8), c["out"])
+        n += 1
+    assert n >= 2
+
+
+# ------------------------------------------------------------------ replay: PTRC
+@pytest.mark.parametrize("g,L,Nc,droplets,per_class", [(O.TORIC, 5, 4, 1, False), (O.PLANAR, 5, 3, 2, True),
+                                                        (O.ROTATED, 5, 4, 2, False), (O.TORIC, 7, 2, 3, False)])
+def test_ptrc_replay_matches_oracle(ctx, g, L, Nc, droplets, per_class):
+    """Per-rung N(n) and m(n) (droplets summed) bit-exact, the class distribution to 1e-9."""
+    rng = np.random.default_rng(7300 + g + L + Nc)
+    S, steps, iters = 2, 60, 10
+    n_eq = O.neq(g)
+    qs = [rand_lattice(rng, g, L, 0.1) for _ in range(S)]
+    qm = np.stack([O.all_classes(g, L, q) for q in qs]) if per_class else np.stack([q.reshape(-1) for q in qs])
+    u_nb, u_py = _ptxc_streams(rng, g, S * n_eq * droplets, Nc, iters, steps)
+    out, st, Nh, mh = ctx.ptrc(g, L, qm, 0.1, 0.25, droplets, Nc, steps, iters=iters, per_class=per_class, u_nb=u_nb, u_py=u_py,
+                               want_hist=True)
+    for s in range(S):
+        base = s * n_eq * droplets
+        nb = [O.Stream.replay(u_nb[base + i]) for i in range(n_eq * droplets)]
+        py = [O.Stream.replay(u_py[base + i]) for i in range(n_eq * droplets)]
+        want, wN, wm = O.ptxc(1, g, L, O.all_classes(g, L, qs[s]), 0.1, 0.25, droplets, Nc, steps, nb, py, iters=iters,
+                              want_hist=True)
+        assert np.array_equal(mh[s], wm), "m(n) differs"
+        assert np.array_equal(Nh[s], wN), "N(n) differs"
+        np.testing.assert_allclose(out[s], want, rtol=1e-9)
+
+
+def test_ptrc_replay_matches_reference_golden(ctx):
+    n = 0
+    for c in golden("shipped"):
+        if c["kind"] != "ptrc":
+            continue
+        g, L, Nc = O.GEOM[c["geom"]], c["L"], c["Nc"]
+        n_eq, steps = O.neq(g), c["steps"] // c["Nc"]
+        u_nb, u_py = _golden_ladder_class_streams(c, n_eq, Nc, steps)
+        out, _ = ctx.ptrc(g, L, c["inits"].reshape(1, n_eq, -1).copy(), c["p_error"], c["p_sampling"], 1, Nc, steps, per_class=True,
+                          u_nb=u_nb, u_py=u_py)
+        assert np.array_equal(out[0].astype(np.uint8), c["out"]) or np.array_equal(np.floor(out[0] + 1e-9).astype(np.uint8), c["out"])
+        n += 1
+    assert n >= 2
