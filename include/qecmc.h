@@ -215,6 +215,13 @@ typedef struct qecmc_pteq_cfg {
  * eq_counts [S][n_eq] optional; info [S][4] = (steps used, since_burn, tops0, converged) optional. */
 int qecmc_pteq(qecmc_ctx *ctx, const qecmc_pteq_cfg *cfg, const uint8_t *qm, int64_t S, uint8_t *eqdistr,
                int64_t *eq_counts, int64_t *info, qecmc_stats *stats);
+/* PTEQ_alpha_with_shortest (decoders_biasednoise.py:93-172), for any ladder kind: PTEQ plus, per class, the
+ * smallest value recorded for the bottom rung (n_eff for alpha ladders, the chain length otherwise; 100000 when the
+ * class was never visited), the number of samples at that value and the number of distinct bottom-rung states seen
+ * at it.  All three [S][n_eq].  The reference's second and third return values follow as
+ * unique * exp(log(pz_tilde) * short_len) and short_n, each normalised to percent. */
+int qecmc_pteq_shortest(qecmc_ctx *ctx, const qecmc_pteq_cfg *cfg, const uint8_t *qm, int64_t S, uint8_t *eqdistr,
+                        double *short_len, int64_t *short_n, int64_t *short_unique, int64_t *info, qecmc_stats *stats);
 /* same with DEVICE qm / eqdistr; info stays a host pointer */
 int qecmc_pteq_dev(qecmc_ctx *ctx, const qecmc_pteq_cfg *cfg, const uint8_t *d_qm, int64_t S, uint8_t *d_eqdistr,
                    int64_t *info, qecmc_stats *stats);

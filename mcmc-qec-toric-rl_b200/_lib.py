@@ -104,6 +104,8 @@ def load():
                                    C.POINTER(Stats)]
     L.qecmc_pteq.argtypes = [C.c_void_p, C.POINTER(PteqCfg), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                              C.POINTER(Stats)]
+    L.qecmc_pteq_shortest.argtypes = [C.c_void_p, C.POINTER(PteqCfg), C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + \
+        [C.POINTER(Stats)]
     L.qecmc_pteq_dev.argtypes = [C.c_void_p, C.POINTER(PteqCfg), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                  C.POINTER(Stats)]
     L.qecmc_ptdc.argtypes = [C.c_void_p, C.POINTER(PtdcCfg), C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(Stats)]
@@ -329,6 +331,25 @@ class Context:
                                  info.ctypes.data, C.byref(st)))
         return pct, dict(steps=info[:, 0], since_burn=info[:, 1], tops0=info[:, 2], converged=info[:, 3], counts=counts,
                          stats=st.as_dict())
+
+    def pteq_shortest(self, geom, L, kind, qm, bottom, Nc=None, param_b=0.0, SEQ=2, TOPS=10, tops_burn=2, eps=0.1,
+                      steps=1000000, iters=10, conv=True, p_logical=0.5, seed=0, u_nb=None, u_py=None):
+        """PTEQ_alpha_with_shortest over a batch.  Returns (percent uint8 [S, n_eq], short_len, short_n, short_unique
+        [S, n_eq], info dict)."""
+        _require_u8(qm)
+        S, n, n_eq = qm.shape[0], nsites(geom, L), neq(geom)
+        assert qm.size == S * n
+        Nc = Nc or L
+        lc, keep = self._ladder_cfg(geom, L, kind, Nc, iters, bottom, param_b, p_logical, seed, u_nb, u_py, S)
+        cfg = PteqCfg(lc, SEQ, TOPS, tops_burn, int(bool(conv)), eps, int(steps))
+        pct = np.zeros((S, n_eq), np.uint8)
+        slen, sn, su = np.zeros((S, n_eq)), np.zeros((S, n_eq), np.int64), np.zeros((S, n_eq), np.int64)
+        info = np.zeros((S, 4), np.int64)
+        st = Stats()
+        _check(load().qecmc_pteq_shortest(self._h, C.byref(cfg), qm.ctypes.data, S, pct.ctypes.data, slen.ctypes.data,
+                                          sn.ctypes.data, su.ctypes.data, info.ctypes.data, C.byref(st)))
+        return pct, slen, sn, su, dict(steps=info[:, 0], since_burn=info[:, 1], tops0=info[:, 2], converged=info[:, 3],
+                                       stats=st.as_dict())
 
     def pteq_dev(self, geom, L, kind, d_qm_ptr, S, d_out_ptr, bottom, Nc=None, param_b=0.0, SEQ=2, TOPS=10, tops_burn=2,
                  eps=0.1, steps=1000000, iters=10, conv=True, p_logical=0.5, seed=0):

@@ -50,6 +50,7 @@ extern "C" void qecmc_destroy(qecmc_ctx *c)
     for (auto &kv : c->stab_hash) cudaFree(kv.second);
     for (auto &kv : c->stab_desc) cudaFree(kv.second);
     c->lut.release();
+    c->log_hash.release();
     for (auto &ev : c->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->own_stream);
     delete c;

@@ -27,6 +27,21 @@ template <int GEOM> void class_deltas(const Geo &g, int out[8])
         }
 }
 
+// fingerprints of the logical strings: [layer][X, Z][position] (the row-word layout does not depend on the word type)
+template <int GEOM> void logical_hashes(const Geo &g, uint64_t seed, std::vector<uint64_t> &out)
+{
+    out.assign(2 * 2 * 32, 0);
+    const int op_x = 1, op_z = (GEOM == TORIC || GEOM == XZZX) ? 3 : 2;  // the operator codes that act with X only / Z only
+    for (int l = 0; l < (GEOM == TORIC ? 2 : 1); l++)
+        for (int k = 0; k < 2; k++)
+            for (int pos = 0; pos < g.L; pos++) {
+                uint64_t buf[64] = {0};
+                HostLat<uint64_t> a{buf};
+                lat_apply_logical<GEOM, uint64_t>(g, a, k == 0 ? op_x : op_z, l, pos, pos);
+                out[(size_t)(l * 2 + k) * 32 + pos] = lat_hash<uint64_t>(g, a, seed);
+            }
+}
+
 // numpy.linspace(start, stop, num): arange(num) * step + start with the last point forced to stop
 std::vector<double> np_linspace(double start, double stop, int num)
 {
@@ -111,11 +126,12 @@ void make_ladder_tables(const qecmc_ladder_cfg *cfg, const Geo &g, LadderTables 
 }
 
 struct LadderDev {
+    DevBuf log_hash, short_v, short_n, short_u;
     DevBuf thr_d, thr_u, thr_top_d, diff, wtab, lat, lat_out, flags, neff, tops0, snap_lat, snap_flags, snap_tops0, hist, eqc,
         info, pct, status, u_nb, u_py, qm, bytes_out, Zd, dist;
     ~LadderDev()
     {
-        for (DevBuf *b : {&thr_d, &thr_u, &thr_top_d, &diff, &wtab, &lat, &lat_out, &flags, &neff, &tops0, &snap_lat,
+        for (DevBuf *b : {&log_hash, &short_v, &short_n, &short_u, &thr_d, &thr_u, &thr_top_d, &diff, &wtab, &lat, &lat_out, &flags, &neff, &tops0, &snap_lat,
                           &snap_flags, &snap_tops0, &hist, &eqc, &info, &pct, &status, &u_nb, &u_py, &qm, &bytes_out, &Zd, &dist})
             b->release();
     }
@@ -169,7 +185,15 @@ template <int GEOM, typename W> int launch_ladder_gw(qecmc_ctx *c, LadderParams 
 template <int GEOM> int launch_ladder_g(qecmc_ctx *c, LadderParams &p, bool replay, bool weighted)
 {
     class_deltas<GEOM>(p.g, p.cls_delta);
-    if (p.acct >= ACCT_DC) {
+    if (p.acct >= ACCT_DC || p.track_shortest) {
+        std::vector<uint64_t> lh;
+        logical_hashes<GEOM>(p.g, c->hash_seed, lh);
+        QTRY(c->log_hash.ensure(lh.size() * sizeof(uint64_t)));
+        CUDA_OK(cudaMemcpyAsync(c->log_hash.p, lh.data(), lh.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        p.log_hash = (const uint64_t *)c->log_hash.p;
+    }
+    if (p.acct >= ACCT_DC || p.track_shortest) {
         if (p.g.L > 16) QTRY((build_stab_hash<GEOM, uint64_t>(c, p.g, (uint64_t **)&p.stab_hash)));
         else QTRY((build_stab_hash<GEOM, uint32_t>(c, p.g, (uint64_t **)&p.stab_hash)));
     }
@@ -409,7 +433,8 @@ extern "C" int qecmc_ladder_run(qecmc_ctx *c, const qecmc_ladder_cfg *cfg, const
 // ------------------------------------------------------------------------------------------------
 // PTEQ / PTEQ_biased / PTEQ_alpha (decoders.py:25-89, decoders_biasednoise.py:28-75,175-222)
 static int pteq_common(qecmc_ctx *c, const qecmc_pteq_cfg *cfg, const uint8_t *qm, bool qm_on_device, int64_t S,
-                       uint8_t *eqdistr, int64_t *eq_counts, int64_t *info, bool out_on_device, qecmc_stats *stats)
+                       uint8_t *eqdistr, int64_t *eq_counts, int64_t *info, bool out_on_device, qecmc_stats *stats,
+                       double *short_len = nullptr, int64_t *short_n = nullptr, int64_t *short_unique = nullptr)
 {
     if (!c || !cfg || !qm || !eqdistr) return set_err(QECMC_ERR_ARG, "NULL argument");
     const qecmc_ladder_cfg *lc = &cfg->ladder;
@@ -426,15 +451,32 @@ static int pteq_common(qecmc_ctx *c, const qecmc_pteq_cfg *cfg, const uint8_t *q
     QTRY(setup_ladder(c, lc, g, d, p));
     // n_err history: 4 bytes per Ladder.step per ladder; ladders run in waves that fit the budget
     int64_t wave = S;
-    if (cfg->use_conv) {
+    const bool shortest = short_len != nullptr;
+    if (shortest && (!short_n || !short_unique)) return set_err(QECMC_ERR_ARG, "short_len, short_n and short_unique go together");
+    uint64_t scap = 0;
+    if (shortest) {
+        scap = next_pow2((uint64_t)cfg->steps + (uint64_t)cfg->steps / 4 + 1);
+        if (scap < 1024) scap = 1024;
+    }
+    if (cfg->use_conv || shortest) {
         size_t fr = 0, tot = 0;
         CUDA_OK(cudaMemGetInfo(&fr, &tot));
         int64_t budget = c->table_budget ? c->table_budget : (int64_t)((double)fr * 0.8);
-        wave = budget / (cfg->steps * 4);
+        wave = budget / ((cfg->use_conv ? cfg->steps * 4 : 0) + (int64_t)scap * 8);
         if (wave < 1) return set_err(QECMC_ERR_NOMEM, "the n_err history of one ladder needs %lld bytes, budget is %lld",
                                      (long long)cfg->steps * 4, (long long)budget);
         if (wave > S) wave = S;
-        QTRY(d.hist.ensure((size_t)wave * cfg->steps * 4));
+        if (cfg->use_conv) QTRY(d.hist.ensure((size_t)wave * cfg->steps * 4));
+        if (shortest) QTRY(c->tables.ensure((size_t)wave * scap * 8));
+    }
+    if (shortest) {
+        QTRY(d.short_v.ensure((size_t)S * g.neq * sizeof(double)));
+        QTRY(d.short_n.ensure((size_t)S * g.neq * sizeof(long long)));
+        QTRY(d.short_u.ensure((size_t)S * g.neq * sizeof(long long)));
+        std::vector<double> init((size_t)S * g.neq, 100000.0);  // decoders_biasednoise.py:116
+        CUDA_OK(cudaMemcpyAsync(d.short_v.p, init.data(), init.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CUDA_OK(cudaMemsetAsync(d.short_n.p, 0, (size_t)S * g.neq * sizeof(long long), c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
     }
     if (!qm_on_device) {
         QTRY(d.qm.ensure((size_t)S * g.nsites));
@@ -474,7 +516,22 @@ static int pteq_common(qecmc_ctx *c, const qecmc_pteq_cfg *cfg, const uint8_t *q
         p.info = (long long *)d.info.p + s0 * 4;
         p.percent = d_pct + s0 * g.neq;
         if (u_nb0) { p.u_nb = u_nb0 + s0 * p.n_nb; p.u_py = u_py0 + s0 * p.n_py; }
+        if (shortest) {
+            CUDA_OK(cudaMemsetAsync(c->tables.p, 0, (size_t)sw * scap * 8, c->stream));
+            p.track_shortest = 1;
+            p.tables = (unsigned long long *)c->tables.p;
+            p.cap_mask = scap - 1;
+            p.short_v = (double *)d.short_v.p + s0 * g.neq;
+            p.short_n = (long long *)d.short_n.p + s0 * g.neq;
+        }
         QTRY(launch_ladder(c, p, lc->u_nb != nullptr));
+        if (shortest) {
+            short_unique_kernel<<<(unsigned)sw, 256, 0, c->stream>>>((const unsigned long long *)c->tables.p, scap, g.neq,
+                                                                      lc->kind == LK_ALPHA, lc->param_b, p.short_v,
+                                                                      (long long *)d.short_u.p + s0 * g.neq);
+            c->launches++;
+            CUDA_OK(cudaGetLastError());
+        }
     }
     CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
     QTRY(check_status(c, d));
@@ -482,6 +539,11 @@ static int pteq_common(qecmc_ctx *c, const qecmc_pteq_cfg *cfg, const uint8_t *q
     CUDA_OK(cudaMemcpyAsync(h_info.data(), d.info.p, h_info.size() * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     if (!out_on_device) CUDA_OK(cudaMemcpyAsync(eqdistr, d.pct.p, (size_t)S * g.neq, cudaMemcpyDeviceToHost, c->stream));
     if (eq_counts) CUDA_OK(cudaMemcpyAsync(eq_counts, d.eqc.p, (size_t)S * g.neq * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    if (shortest) {
+        CUDA_OK(cudaMemcpyAsync(short_len, d.short_v.p, (size_t)S * g.neq * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaMemcpyAsync(short_n, d.short_n.p, (size_t)S * g.neq * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaMemcpyAsync(short_unique, d.short_u.p, (size_t)S * g.neq * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    }
     unsigned long long cnt[8] = {0};
     CUDA_OK(cudaMemcpyAsync(cnt, c->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -498,6 +560,13 @@ extern "C" int qecmc_pteq(qecmc_ctx *c, const qecmc_pteq_cfg *cfg, const uint8_t
                           int64_t *eq_counts, int64_t *info, qecmc_stats *stats)
 {
     return pteq_common(c, cfg, qm, false, S, eqdistr, eq_counts, info, false, stats);
+}
+
+extern "C" int qecmc_pteq_shortest(qecmc_ctx *c, const qecmc_pteq_cfg *cfg, const uint8_t *qm, int64_t S, uint8_t *eqdistr,
+                                   double *short_len, int64_t *short_n, int64_t *short_unique, int64_t *info, qecmc_stats *stats)
+{
+    if (!short_len || !short_n || !short_unique) return set_err(QECMC_ERR_ARG, "NULL argument");
+    return pteq_common(c, cfg, qm, false, S, eqdistr, nullptr, info, false, stats, short_len, short_n, short_unique);
 }
 
 extern "C" int qecmc_pteq_dev(qecmc_ctx *c, const qecmc_pteq_cfg *cfg, const uint8_t *d_qm, int64_t S, uint8_t *d_eqdistr,

@@ -64,6 +64,12 @@ struct LadderParams {
     int droplets, aux_bits;
     const uint64_t *stab_hash;
     uint64_t hash_seed;
+    const uint64_t *log_hash;      // [2 layers][X, Z][32 positions] fingerprints of the logical strings (when hashes are tracked
+                                   // on ladders whose top rung proposes logical operators)
+    // PTEQ_alpha_with_shortest (decoders_biasednoise.py:114-146); tables = one set per ladder, cap_mask slots
+    int track_shortest;
+    double *short_v;               // [n_ladders][n_eq] smallest recorded bottom-rung value per class (100000 = none)
+    long long *short_n;            // [n_ladders][n_eq] samples at that value
     unsigned long long *rc_m_hist; // ACCT_RC: [n_ladders][Nc][nsites+1] visits per length and rung (PTRC's m(n))
     unsigned long long *counters;  // [0] accepted [1] offered
     int *status;                   // != 0: a replay stream ran dry
@@ -148,6 +154,19 @@ template <int GEOM, typename RNG> struct LogicalDraw {
             if (op[l] == 3 || op[l] == 2) zp[l] = (int)(rng.nb() * L);
         }
     }
+    // fingerprint change of the drawn operator: XOR of the string fingerprints (the fingerprint is GF(2)-linear)
+    __device__ __forceinline__ uint64_t hash_delta(const uint64_t *lh) const
+    {
+        uint64_t d = 0;
+        for (int l = 0; l < nl; l++) {
+            const bool do_X = (GEOM == TORIC || GEOM == XZZX) ? (op[l] == 1 || op[l] == 2) : (op[l] == 1 || op[l] == 3);
+            const bool do_Z = op[l] == 2 || op[l] == 3;
+            const int px = GEOM == XZZX ? 0 : xp[l], pz = GEOM == XZZX ? 0 : zp[l];
+            if (do_X) d ^= lh[(l * 2 + 0) * 32 + px];
+            if (do_Z) d ^= lh[(l * 2 + 1) * 32 + pz];
+        }
+        return d;
+    }
     template <typename W, typename A> __device__ __forceinline__ int apply(const Geo &g, A &lat) const
     {
         int d = 0;
@@ -198,7 +217,7 @@ __global__ void __launch_bounds__(128) ladder_kernel(LadderParams p)
         cls = class_raw_to_label(GEOM, lat_class<GEOM, W>(g, lat));
         flag = p.flags_in ? p.flags_in[ladder * Nc + gl] : ((gl == Nc - 1) ? 1 : 0);
         if (p.neff_in) { int2 e = p.neff_in[ladder * Nc + gl]; e_nz = e.x; e_nxy = e.y; }
-        if (p.acct == ACCT_DC || p.acct == ACCT_RC) h = lat_hash<W>(g, lat, p.hash_seed);
+        if (p.acct >= ACCT_DC || p.track_shortest) h = lat_hash<W>(g, lat, p.hash_seed);
     } else {
         for (int w = 0; w < g.nw; w++) lat.set(w, (W)0);
     }
@@ -216,6 +235,7 @@ __global__ void __launch_bounds__(128) ladder_kernel(LadderParams p)
         reinterpret_cast<NativeRng *>(&rng)->init(p.seed, (uint64_t)gladder * 32u + (uint64_t)gl);
     }
     const bool top_logical = p.p_logical != 0.0;
+    const bool track_hash = p.acct >= ACCT_DC || p.track_shortest;
     unsigned long long *table = nullptr;
     if (p.acct == ACCT_DC && ladder < p.n_ladders) table = p.tables + (uint64_t)(ladder / p.droplets) * (p.cap_mask + 1);
     int last_r = -1;  // ACCT_RC: rung whose set saw this replica's current state
@@ -266,6 +286,8 @@ __global__ void __launch_bounds__(128) ladder_kernel(LadderParams p)
                         if (WEIGHTED) { nx = mx; ny = my; nz = mz; n = mx + my + mz; e_nz = mz; e_nxy = mx + my; }
                         else n += dE;
                         cls ^= dcls;
+                        if (track_hash) h ^= ld.hash_delta(p.log_hash);
+                        dirty = true;
                         nacc++;
                     } else {
                         ld.template apply<W>(g, lat);  // XOR is an involution: undo
@@ -277,7 +299,7 @@ __global__ void __launch_bounds__(128) ladder_kernel(LadderParams p)
                         double u[K];
                         for (int k = 0; k < K; k++) u[k] = rr->nb();
                         propose_replay<GEOM>(g, u, row, col, op);
-                        if (p.acct >= ACCT_DC) idx = rco_to_idx<GEOM>(g, row, col, op);
+                        if (track_hash) idx = rco_to_idx<GEOM>(g, row, col, op);
                     } else {
                         idx = (int)__umulhi(reinterpret_cast<NativeRng *>(&rng)->next32(), (uint32_t)g.nstab);
                         idx_to_rco<GEOM>(g, idx, row, col, op);
@@ -315,7 +337,7 @@ __global__ void __launch_bounds__(128) ladder_kernel(LadderParams p)
                         for (int i = 0; i < NU; i++) lat.set(u.w[i], nv[i]);
                         if (WEIGHTED) { nx += dx; ny += dy; nz += dz; n = nx + ny + nz; e_nz = nz; e_nxy = nx + ny; }
                         else n += dE;
-                        if (p.acct >= ACCT_DC) h ^= p.stab_hash[idx];
+                        if (track_hash) h ^= p.stab_hash[idx];
                         dirty = true;
                         nacc++;
                     }
@@ -407,6 +429,33 @@ __global__ void __launch_bounds__(128) ladder_kernel(LadderParams p)
                     if (gl == 0) {
                         eqc[class_raw_to_label(GEOM, cur)]++;
                         if (hist) hist[since_burn] = (uint32_t)h_a | ((uint32_t)h_b << 16);
+                    }
+                    if (p.track_shortest && gl == l0) {
+                        // the lane holding the bottom rung owns its class, recorded value and fingerprint
+                        const int lab = class_raw_to_label(GEOM, cur);
+                        volatile double *sv = p.short_v + (size_t)ladder * g.neq + lab;
+                        volatile long long *sn = p.short_n + (size_t)ladder * g.neq + lab;
+                        const double v = p.kind == LK_ALPHA ? __dadd_rn((double)h_a, __dmul_rn(p.alpha, (double)h_b)) : (double)h_a;
+                        const double cur_short = *sv;
+                        if (v <= cur_short) {
+                            if (v < cur_short) { *sv = v; *sn = 1; }
+                            else *sn = *sn + 1;
+                            // set of distinct bottom-rung states seen at the class's current shortest value: the key carries
+                            // class and value, so entries of a superseded (longer) shortest value simply stop matching
+                            const uint64_t aux = (uint64_t)h_a | ((uint64_t)h_b << 11) | ((uint64_t)lab << 22);
+                            const uint64_t key = (h & ~((1ull << 26) - 1ull)) | aux | (1ull << 63);
+                            unsigned long long *tab = p.tables + (uint64_t)ladder * (p.cap_mask + 1);
+                            uint64_t slot = (key >> 26) & p.cap_mask;
+                            while (true) {
+                                unsigned long long curk = __ldcg(tab + slot);
+                                if (curk == key) break;
+                                if (curk == 0ull) {
+                                    unsigned long long prev = atomicCAS(tab + slot, 0ull, (unsigned long long)key);
+                                    if (prev == 0ull || prev == key) break;
+                                }
+                                slot = (slot + 1) & p.cap_mask;
+                            }
+                        }
                     }
                     // history windows [l/4, l/2) and [3l/4, l) of conv_crit_error_based_PT (decoders.py:93-105)
                     wl = since_burn + 1;
@@ -557,6 +606,25 @@ static __global__ void ptrc_finalize_kernel(const uint32_t *__restrict__ N_tab /
         }
     }
     Z[t] = z;
+}
+
+// PTEQ_alpha_with_shortest: distinct bottom-rung states recorded at each class's final shortest value
+static __global__ void short_unique_kernel(const unsigned long long *__restrict__ tables, uint64_t cap, int n_eq, int alpha_kind,
+                                           double alpha, const double *__restrict__ short_v, long long *__restrict__ uniq)
+{
+    __shared__ unsigned int s_cnt[16];
+    if (threadIdx.x < 16) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned long long *tab = tables + (uint64_t)blockIdx.x * cap;
+    for (uint64_t i = threadIdx.x; i < cap; i += blockDim.x) {
+        unsigned long long k = tab[i];
+        if (!k) continue;
+        int a = (int)(k & 0x7FF), b = (int)((k >> 11) & 0x7FF), lab = (int)((k >> 22) & 0xF);
+        double v = alpha_kind ? __dadd_rn((double)a, __dmul_rn(alpha, (double)b)) : (double)a;
+        if (lab < n_eq && v == short_v[(size_t)blockIdx.x * n_eq + lab]) atomicAdd(&s_cnt[lab], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < n_eq) uniq[(size_t)blockIdx.x * n_eq + threadIdx.x] = s_cnt[threadIdx.x];
 }
 
 // Z_E of a (syndrome, class) table whose keys carry (nz, nx+ny) in their low 22 bits:

@@ -147,6 +147,24 @@ def PTDC(init_code, p_error, p_sampling=None, droplets=4, Nc=None, steps=20000, 
     return PTDC_batch([init_code], p_error, p_sampling, droplets, Nc, steps, conv_mult)[0]
 
 
+def PTRC_batch(init_codes, p_error, p_sampling=None, droplets=4, Nc=None, steps=20000, conv_mult=2.0, seed=None, device=0,
+               return_float=False):
+    """PTRC (decoders.py:638-742) -> uint8 [S, nbr_eq_classes] (truncated percent).  conv_mult is accepted and, as in
+    the reference (whose early-stop lines are commented out, decoders.py:628-631), has no effect.  A single code
+    object is accepted (classes reached with to_class); the reference raises TypeError there."""
+    p_sampling = p_sampling or p_error
+    code, qm, per_class = _batch(init_codes)
+    Nc = Nc or code.system_size
+    steps = int(steps) // Nc                       # decoders.py:666
+    out, _ = _lib.default_context(device).ptrc(code.geometry, code.system_size, qm, p_error, p_sampling, int(droplets), Nc,
+                                               steps, iters=10, per_class=per_class, seed=_next_seed(seed))
+    return out if return_float else out.astype(np.uint8)
+
+
+def PTRC(init_code, p_error, p_sampling=None, droplets=4, Nc=None, steps=20000, conv_mult=2.0):
+    return PTRC_batch([init_code], p_error, p_sampling, droplets, Nc, steps, conv_mult)[0]
+
+
 # ------------------------------------------------------------------------------------------------ EWD-style
 def STDC_Nall_n_alpha_batch(init_codes, pz_tilde_sampling=None, alpha=1, pz_tilde=0.1, steps=20000, seed=None, device=0):
     """STDC_Nall_n_alpha (decoders.py:537-581) -> float64 [S, nbr_eq_classes] (percent).  A single toric code is
@@ -170,6 +188,5 @@ def _not_yet(name, row):
     return f
 
 
-PTRC = _not_yet("PTRC", "decoders.py:638-742")
 STDC_general_noise = _not_yet("STDC_general_noise", "decoders.py:345-432")
 STDC_general_noise_shortest = _not_yet("STDC_general_noise_shortest", "decoders.py:435-508")

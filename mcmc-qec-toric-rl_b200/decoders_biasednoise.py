@@ -27,6 +27,31 @@ def PTEQ_alpha(init_code, pz_tilde, alpha=1, Nc=None, SEQ=2, TOPS=10, tops_burn=
     return PTEQ_alpha_batch([init_code], pz_tilde, alpha, Nc, SEQ, TOPS, tops_burn, eps, steps, iters, conv_criteria)[0]
 
 
-def PTEQ_alpha_with_shortest(*a, **k):
-    raise NotImplementedError("PTEQ_alpha_with_shortest (decoders_biasednoise.py:93-172) is not implemented on the device "
-                              "path yet (DESIGN.md section 8); there is no CPU fallback")
+def PTEQ_alpha_with_shortest_batch(init_codes, pz_tilde, alpha=1, Nc=None, SEQ=2, TOPS=10, tops_burn=2, eps=0.1,
+                                   steps=50000000, iters=10, conv_criteria='error_based', seed=None, device=0):
+    """PTEQ_alpha_with_shortest (decoders_biasednoise.py:93-172) over a batch.  Returns the reference's three arrays,
+    one row per syndrome: class percentages (uint8), the distribution from the distinct shortest chains
+    (float64 percent) and the share of samples at the shortest effective length (float64 percent)."""
+    import numpy as np
+    from .decoders import _batch, _next_seed
+    code, qm, per_class = _batch(init_codes)
+    if per_class:
+        raise TypeError("PTEQ_alpha_with_shortest takes a single code object per syndrome")
+    Nc = Nc or code.system_size
+    if tops_burn >= TOPS:
+        print('tops_burn has to be smaller than TOPS')
+    pct, slen, sn, su, info = _lib.default_context(device).pteq_shortest(
+        code.geometry, code.system_size, _lib.LADDER_ALPHA, qm, pz_tilde, Nc=Nc, param_b=float(alpha), SEQ=SEQ, TOPS=TOPS,
+        tops_burn=tops_burn, eps=eps, steps=int(steps), iters=int(iters), conv=(conv_criteria == 'error_based'), p_logical=0.5,
+        seed=_next_seed(seed))
+    beta = -np.log(pz_tilde)
+    z = su * np.exp(-beta * slen)                    # every stored chain has the class's shortest effective length
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return pct, z / z.sum(1, keepdims=True) * 100, sn / sn.sum(1, keepdims=True) * 100
+
+
+def PTEQ_alpha_with_shortest(init_code, pz_tilde, alpha=1, Nc=None, SEQ=2, TOPS=10, tops_burn=2, eps=0.1, steps=50000000,
+                             iters=10, conv_criteria='error_based'):
+    a, b, c = PTEQ_alpha_with_shortest_batch([init_code], pz_tilde, alpha, Nc, SEQ, TOPS, tops_burn, eps, steps, iters,
+                                             conv_criteria)
+    return a[0], b[0], c[0]

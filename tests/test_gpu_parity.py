@@ -580,3 +580,46 @@ def test_ptrc_replay_matches_reference_golden(ctx):
         assert np.array_equal(out[0].astype(np.uint8), c["out"]) or np.array_equal(np.floor(out[0] + 1e-9).astype(np.uint8), c["out"])
         n += 1
     assert n >= 2
+
+
+# ------------------------------------------------------------------ replay: PTEQ_alpha_with_shortest
+@pytest.mark.parametrize("kind,g,L,bottom,b", [(1, O.PLANAR, 5, 0.15, 2.0), (1, O.XZZX, 5, 0.2, 1.5), (1, O.TORIC, 5, 0.15, 2.0),
+                                               (0, O.ROTATED, 5, 0.1, 0.0), (2, O.XZZX, 7, 0.1, 6.0)])
+def test_pteq_shortest_replay_matches_oracle(ctx, kind, g, L, bottom, b):
+    rng = np.random.default_rng(800 + 10 * kind + g + L)
+    S, iters, cap = 3, 10, 2500
+    qs = [rand_lattice(rng, g, L, 0.1) for _ in range(S)]
+    qm = np.stack([q.reshape(-1) for q in qs])
+    n_nb, n_py = _ladder_budget(g, L, iters, cap)
+    u_nb, u_py = rng.random((S, n_nb)), rng.random((S, n_py))
+    pct, slen, sn, su, info = ctx.pteq_shortest(g, L, kind, qm, bottom, param_b=b, steps=cap, iters=iters, u_nb=u_nb, u_py=u_py)
+    for s in range(S):
+        want, _, _, winfo = O.pteq_with_shortest(kind, g, L, qs[s], bottom, O.Stream.replay(u_nb[s]), O.Stream.replay(u_py[s]),
+                                                 param_b=b, steps=cap, iters=iters)
+        assert info["steps"][s] == winfo["steps"]
+        assert np.array_equal(pct[s], want)
+        assert np.array_equal(slen[s], winfo["short_len"]), (slen[s], winfo["short_len"])
+        assert np.array_equal(sn[s], winfo["short_n"])
+        assert np.array_equal(su[s], winfo["short_unique"]), (su[s], winfo["short_unique"])
+
+
+def test_pteq_shortest_replay_matches_reference_golden(ctx):
+    n = 0
+    for c in golden("shipped"):
+        if c["kind"] != "pteq_alpha_shortest":
+            continue
+        g, L = O.GEOM[c["geom"]], c["L"]
+        _, _, _, winfo = O.pteq_with_shortest(1, g, L, c["q"], c["p"], O.Stream.mt(c["nb_seed"]), O.Stream.py(c["py_seed"]),
+                                              param_b=c["b"], steps=c["steps"])
+        used = int(winfo["steps"])
+        n_nb, n_py = _ladder_budget(g, L, 10, used)
+        u_nb = np.random.RandomState(c["nb_seed"]).random_sample(n_nb).reshape(1, -1)
+        u_py = _py_uniforms(c["py_seed"], n_py).reshape(1, -1)
+        pct, slen, sn, su, info = ctx.pteq_shortest(g, L, 1, c["q"].reshape(1, -1).copy(), c["p"], param_b=c["b"], steps=used,
+                                                    u_nb=u_nb, u_py=u_py)
+        assert np.array_equal(pct[0], c["out"])
+        z = su[0] * np.exp(np.log(c["p"]) * slen[0])          # decoders_biasednoise.py:163-169
+        np.testing.assert_allclose(z / z.sum() * 100, c["out_unique"], rtol=1e-9)
+        np.testing.assert_allclose(sn[0] / sn[0].sum() * 100, c["out_shortest_n"], rtol=1e-12)
+        n += 1
+    assert n >= 3
