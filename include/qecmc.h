@@ -264,6 +264,37 @@ typedef struct qecmc_alpha_cfg {
 int qecmc_stdc_alpha(qecmc_ctx *ctx, const qecmc_alpha_cfg *cfg, const uint8_t *qm, int64_t S, double *eqdistr,
                      int64_t *distinct, qecmc_stats *stats);
 
+/* ------------------------------------------------------------------------------
+ * General (x, y, z) noise: STDC_general_noise / STDC_general_noise_shortest / STDC_droplet_general_noise
+ * (decoders.py:325-508) over Chain_xyz.update_chain_fast (_update_chain_fast_xyz, src/mcmc.py:106-114,162-173) when
+ * the sampling rate is a triple, or over Chain.update_chain_fast when it is a scalar.  No rain (randomize is False in
+ * every branch of the reference).  Weight of a distinct chain = exp(-sum_{i: n_i > 0} beta_i n_i),
+ * beta_i = -log((p_i / 3) / (1 - p_i)).
+ *   eqdistr          [S][n_eq] percent over all distinct chains
+ *   eqdistr_shortest [S][n_eq] percent over the chains whose weighted length is np.isclose to the class minimum (optional)
+ *   distinct         [S][n_eq] optional
+ * ------------------------------------------------------------------------------ */
+typedef struct qecmc_xyz_cfg {
+    int32_t geom_code, geom_chain, L, droplets;
+    int32_t iters;             /* 5 in the reference (decoders.py:336) */
+    int32_t per_class_inits;
+    int32_t use_xyz_sampling;  /* 1: Chain_xyz(p_sampling_xyz); 0: Chain(p_sampling) */
+    int32_t reserved;
+    int64_t steps;
+    double  p_xyz[3];          /* error model (p_x, p_y, p_z) */
+    double  p_sampling_xyz[3];
+    double  p_sampling;
+    uint64_t seed;
+    const double *u_nb;        /* replay: [S*n_eq*droplets][steps*iters][k+1] numba-stream draws */
+} qecmc_xyz_cfg;
+/* Chain_xyz.update_chain_fast (src/mcmc.py:113-114): `iters` steps on `chains` lattices in place, accept iff
+ * u < prod_i (p_i / (1 - sum p))^(dn_i).  cfg->p is ignored; p_xyz = the chain's (p_x, p_y, p_z).
+ * u != NULL: replay, [chains][iters][k+1] numba-stream draws. */
+int qecmc_chain_update_xyz(qecmc_ctx *ctx, const qecmc_chain_cfg *cfg, const double *p_xyz, const double *u, uint8_t *qm,
+                           int64_t chains, int64_t iters, qecmc_stats *stats);
+int qecmc_stdc_general_noise(qecmc_ctx *ctx, const qecmc_xyz_cfg *cfg, const uint8_t *qm, int64_t S, double *eqdistr,
+                             double *eqdistr_shortest, int64_t *distinct, qecmc_stats *stats);
+
 #ifdef __cplusplus
 }
 #endif

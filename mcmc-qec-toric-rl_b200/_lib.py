@@ -71,6 +71,13 @@ class AlphaCfg(C.Structure):
                 ("seed", C.c_uint64), ("u_nb", C.c_void_p), ("u_py", C.c_void_p), ("n_nb", C.c_int64), ("n_py", C.c_int64)]
 
 
+class XyzCfg(C.Structure):
+    _fields_ = [("geom_code", C.c_int32), ("geom_chain", C.c_int32), ("L", C.c_int32), ("droplets", C.c_int32),
+                ("iters", C.c_int32), ("per_class_inits", C.c_int32), ("use_xyz_sampling", C.c_int32), ("reserved", C.c_int32),
+                ("steps", C.c_int64), ("p_xyz", C.c_double * 3), ("p_sampling_xyz", C.c_double * 3), ("p_sampling", C.c_double),
+                ("seed", C.c_uint64), ("u_nb", C.c_void_p)]
+
+
 LADDER_DEPOLARIZING, LADDER_ALPHA, LADDER_BIASED = 0, 1, 2
 
 _lib = None
@@ -111,6 +118,10 @@ def load():
     L.qecmc_ptdc.argtypes = [C.c_void_p, C.POINTER(PtdcCfg), C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(Stats)]
     L.qecmc_ptrc.argtypes = [C.c_void_p, C.POINTER(PtdcCfg), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                              C.POINTER(Stats)]
+    L.qecmc_chain_update_xyz.argtypes = [C.c_void_p, C.POINTER(ChainCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                         C.c_int64, C.POINTER(Stats)]
+    L.qecmc_stdc_general_noise.argtypes = [C.c_void_p, C.POINTER(XyzCfg), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.POINTER(Stats)]
     L.qecmc_stdc_alpha.argtypes = [C.c_void_p, C.POINTER(AlphaCfg), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.POINTER(Stats)]
     _lib = L
@@ -413,6 +424,45 @@ class Context:
         _check(load().qecmc_stdc_alpha(self._h, C.byref(cfg), qm.ctypes.data, S, out.ctypes.data, distinct.ctypes.data,
                                        C.byref(st)))
         return out, distinct, st.as_dict()
+
+    def chain_update_xyz(self, geom_chain, L, qm, p_xyz, iters, seed=0, stream_offset=0, u=None):
+        """Chain_xyz.update_chain_fast on qm [chains, n_sites] in place; u: replay draws [chains, iters, k+1]."""
+        _require_u8(qm)
+        chains = qm.shape[0]
+        cfg = ChainCfg(geom_chain, L, POW_NUMBA, 0, 0.5, seed, stream_offset)
+        pp = (C.c_double * 3)(*[float(x) for x in p_xyz])
+        if u is not None:
+            u = np.ascontiguousarray(u, np.float64)
+            assert u.size == chains * iters * (ndraws(geom_chain) + 1)
+        st = Stats()
+        _check(load().qecmc_chain_update_xyz(self._h, C.byref(cfg), pp, u.ctypes.data if u is not None else None,
+                                             qm.ctypes.data, chains, iters, C.byref(st)))
+        return st.as_dict()
+
+    def stdc_general_noise(self, geom_code, geom_chain, L, qm, p_xyz, p_sampling, droplets, steps, iters=5, per_class=False,
+                           seed=0, u_nb=None):
+        """STDC_general_noise(_shortest) over a batch; p_sampling: float (Chain) or array of 3 (Chain_xyz).
+        Returns (eqdistr, eqdistr_shortest [S, n_eq] float64, distinct [S, n_eq], stats)."""
+        _require_u8(qm)
+        S, n, n_eq = qm.shape[0], nsites(geom_code, L), neq(geom_code)
+        assert qm.size == S * (n_eq if per_class else 1) * n
+        use_xyz = isinstance(p_sampling, np.ndarray)
+        keep, a = [], None
+        if u_nb is not None:
+            u_nb = np.ascontiguousarray(u_nb, np.float64)
+            assert u_nb.size == S * n_eq * droplets * steps * iters * (ndraws(geom_chain) + 1)
+            keep.append(u_nb)
+            a = u_nb.ctypes.data
+        cfg = XyzCfg(geom_code, geom_chain, L, droplets, iters, int(per_class), int(use_xyz), 0, int(steps),
+                     (C.c_double * 3)(*[float(x) for x in p_xyz]),
+                     (C.c_double * 3)(*([float(x) for x in p_sampling] if use_xyz else [0.0, 0.0, 0.0])),
+                     0.0 if use_xyz else float(p_sampling), seed, a)
+        out, out_s = np.zeros((S, n_eq)), np.zeros((S, n_eq))
+        distinct = np.zeros((S, n_eq), np.int64)
+        st = Stats()
+        _check(load().qecmc_stdc_general_noise(self._h, C.byref(cfg), qm.ctypes.data, S, out.ctypes.data, out_s.ctypes.data,
+                                               distinct.ctypes.data, C.byref(st)))
+        return out, out_s, distinct, st.as_dict()
 
     def stdc_dev(self, geom_code, geom_chain, L, d_qm_ptr, S, d_out_ptr, p_error, p_sampling, droplets, steps, iters=5,
                  per_class=False, randomize=True, seed=0, want_stats=True):

@@ -15,7 +15,7 @@ from .src.toric_model import Toric_code            # noqa: F401  (re-exported li
 from .src.planar_model import Planar_code          # noqa: F401
 from .src.rotated_surface_model import RotSurCode  # noqa: F401
 from .src.xzzx_model import xzzx_code              # noqa: F401
-from .src.mcmc import Chain, Ladder                # noqa: F401
+from .src.mcmc import Chain, Ladder, Chain_xyz     # noqa: F401
 from .src.mcmc_alpha import Chain_alpha, Ladder_alpha      # noqa: F401
 from .src.mcmc_biased import Chain_biased, Ladder_biased   # noqa: F401
 
@@ -179,14 +179,27 @@ def STDC_Nall_n_alpha(init_code, pz_tilde_sampling=None, alpha=1, pz_tilde=0.1, 
     return STDC_Nall_n_alpha_batch([init_code], pz_tilde_sampling, alpha, pz_tilde, steps)[0]
 
 
-# ------------------------------------------------------------------------------------------------ not on the device yet
-def _not_yet(name, row):
-    def f(*a, **k):
-        raise NotImplementedError(f"{name} ({row}) is not implemented on the device path yet (DESIGN.md section 8); "
-                                  "there is no CPU fallback")
-    f.__name__ = name
-    return f
+# ------------------------------------------------------------------------------------------------ general noise
+def STDC_general_noise_shortest_batch(init_codes, p_xyz, p_sampling=None, droplets=10, steps=20000, seed=None, device=0):
+    """STDC_general_noise_shortest (decoders.py:435-508) over a batch -> (eqdistr, eqdistr_shortest), float64 [S, n_eq]."""
+    p_xyz = np.asarray(p_xyz, dtype=np.float64)
+    if p_sampling is None:
+        p_sampling = float(p_xyz.sum())            # decoders.py:438-439: a scalar, so the sampling chain is a plain Chain
+    code, qm, per_class = _batch(init_codes)
+    _fast_path_check(code, per_class)
+    out, out_s, _, _ = _lib.default_context(device).stdc_general_noise(
+        code.geometry, _mcmc.fast_path_geometry(code), code.system_size, qm, p_xyz,
+        np.asarray(p_sampling, dtype=np.float64) if type(p_sampling) == np.ndarray else float(p_sampling), int(droplets), int(steps),
+        iters=5, per_class=per_class, seed=_next_seed(seed))
+    return out, out_s
 
 
-STDC_general_noise = _not_yet("STDC_general_noise", "decoders.py:345-432")
-STDC_general_noise_shortest = _not_yet("STDC_general_noise_shortest", "decoders.py:435-508")
+def STDC_general_noise_shortest(init_code, p_xyz, p_sampling=None, droplets=10, steps=20000):
+    a, b = STDC_general_noise_shortest_batch([init_code], p_xyz, p_sampling, droplets, steps)
+    return a[0], b[0]
+
+
+def STDC_general_noise(init_code, p_xyz, p_sampling=None, droplets=10, steps=20000, shortest_only=False):
+    """decoders.py:345-432; shortest_only keeps only the chains whose weighted length is np.isclose to the minimum."""
+    a, b = STDC_general_noise_shortest_batch([init_code], p_xyz, p_sampling, droplets, steps)
+    return b[0] if shortest_only else a[0]

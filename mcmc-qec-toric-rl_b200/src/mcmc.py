@@ -71,6 +71,27 @@ class Chain:
             self._run(self.code.geometry, iters, _lib.POW_LIBM)
 
 
+class Chain_xyz:
+    """Chain_xyz(p_xyz, code): fast-path chain for general (p_x, p_y, p_z) noise (src/mcmc.py:106-114)."""
+
+    def __init__(self, p_xyz, code):
+        self.code = code
+        self.p_xyz = np.asarray(p_xyz, dtype=np.float64)
+        self.factors = self.p_xyz / (1.0 - self.p_xyz.sum())
+        self.qubit_errors = code.count_errors_xyz()
+        self._stream = _new_stream()
+        self._steps = 0
+
+    def update_chain_fast(self, iters):
+        q = np.ascontiguousarray(self.code.qubit_matrix, dtype=np.uint8)
+        flat = q.reshape(1, -1).copy()
+        _lib.default_context().chain_update_xyz(fast_path_geometry(self.code), self.code.system_size, flat, self.p_xyz, int(iters),
+                                                seed=self._stream, stream_offset=self._steps)
+        self._steps += int(iters)
+        self.code.qubit_matrix = flat.reshape(q.shape)
+        self.qubit_errors = self.code.count_errors_xyz()
+
+
 def _single_rung_block(chain, kind, bottom, param_b, iters):
     """`iters` slow-path steps of one chain = Ladder.step of a one-rung ladder (no swap partner)."""
     q = np.ascontiguousarray(chain.code.qubit_matrix, dtype=np.uint8)

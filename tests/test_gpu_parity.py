@@ -623,3 +623,71 @@ def test_pteq_shortest_replay_matches_reference_golden(ctx):
         np.testing.assert_allclose(sn[0] / sn[0].sum() * 100, c["out_shortest_n"], rtol=1e-12)
         n += 1
     assert n >= 3
+
+
+# ------------------------------------------------------------------ replay: general (x, y, z) noise
+@pytest.mark.parametrize("gcode,gchain,L,droplets,xyz", [(O.PLANAR, O.PLANAR, 5, 1, True), (O.PLANAR, O.PLANAR, 7, 3, True),
+                                                         (O.PLANAR, O.PLANAR, 5, 2, False), (O.TORIC, O.TORIC, 5, 2, True),
+                                                         (O.TORIC, O.PLANAR, 5, 1, False)])
+def test_stdc_general_noise_replay_matches_oracle(ctx, gcode, gchain, L, droplets, xyz):
+    rng = np.random.default_rng(8800 + gcode + L + droplets)
+    S, steps, iters = 2, 150, 5
+    n_eq = O.neq(gcode)
+    p_xyz = np.array([0.03, 0.02, 0.07])
+    ps = np.array([0.09, 0.05, 0.12]) if xyz else float(p_xyz.sum())
+    qs = [rand_lattice(rng, gcode, L, 0.1) for _ in range(S)]
+    qm = np.stack([O.all_classes(gcode, L, q) for q in qs])
+    u_nb = rng.random((S * n_eq * droplets, steps * iters, 4))
+    out, out_s, distinct, st = ctx.stdc_general_noise(gcode, gchain, L, qm, p_xyz, ps, droplets, steps, iters=iters, per_class=True,
+                                                      u_nb=u_nb)
+    for s in range(S):
+        base = s * n_eq * droplets
+        nb = [O.Stream.replay(u_nb[base + i].reshape(-1)) for i in range(n_eq * droplets)]
+        want, want_s, wd = O.stdc_general_noise(gcode, gchain, L, qm[s], p_xyz, ps, droplets, steps, nb, iters=iters)
+        assert np.array_equal(distinct[s], wd)
+        np.testing.assert_allclose(out[s], want, rtol=1e-9)
+        np.testing.assert_allclose(out_s[s], want_s, rtol=1e-9)
+
+
+def test_stdc_general_noise_replay_matches_reference_golden(ctx):
+    n = 0
+    for c in golden("shipped"):
+        if c["kind"] != "stdc_general_noise":
+            continue
+        g, cg, L, steps = O.GEOM[c["geom"]], O.GEOM[c["chain_geom"]], c["L"], c["steps"]
+        n_eq = O.neq(g)
+        ps = c["p_sampling"] if c["p_sampling"].size else float(c["p_xyz"].sum())
+        u_nb = np.random.RandomState(c["nb_seed"]).random_sample(n_eq * steps * 5 * 4).reshape(n_eq, steps * 5, 4)
+        out, out_s, _, _ = ctx.stdc_general_noise(g, cg, L, c["inits"].reshape(1, n_eq, -1).copy(), c["p_xyz"], ps, 1, steps,
+                                                  per_class=True, u_nb=u_nb)
+        np.testing.assert_allclose(out[0], c["out"], rtol=1e-9)
+        np.testing.assert_allclose(out_s[0], c["out_shortest"], rtol=1e-9)
+        n += 1
+    assert n >= 2
+
+
+def test_chain_xyz_replay_matches_reference_golden_and_oracle(ctx):
+    """Chain_xyz.update_chain_fast: the reference's own trajectory from its numba draws, and the oracle on random draws."""
+    n = 0
+    for c in golden("shipped"):
+        if c["kind"] != "chain_fast_xyz":
+            continue
+        g, L, iters, blocks = O.GEOM[c["chain_geom"]], c["L"], c["iters"], c["blocks"]
+        u = np.random.RandomState(c["nb_seed"]).random_sample(iters * blocks * 4).reshape(blocks, iters, 4)
+        cur = c["q"].reshape(1, -1).copy()
+        for b in range(blocks):
+            ctx.chain_update_xyz(g, L, cur, c["p_sampling"], iters, u=u[b:b + 1])
+            assert np.array_equal(cur[0], c["out"][b].reshape(-1)), b
+        n += 1
+    assert n >= 1
+    rng = np.random.default_rng(99)
+    for g, L in ((O.TORIC, 7), (O.PLANAR, 19), (O.ROTATED, 9), (O.XZZX, 5)):
+        k = 3 if g in (O.TORIC, O.PLANAR) else 5
+        ps = np.array([0.07, 0.11, 0.05])
+        qm = np.stack([rand_lattice(rng, g, L, 0.15).reshape(-1) for _ in range(20)])
+        u = rng.random((20, 200, k + 1))
+        got = qm.copy()
+        ctx.chain_update_xyz(g, L, got, ps, 200, u=u)
+        for i in range(20):
+            want = O.update_chain_fast_xyz(g, L, qm[i], ps / (1 - ps.sum()), 200, O.Stream.replay(u[i].reshape(-1)))
+            assert np.array_equal(got[i], want)
