@@ -174,6 +174,12 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # NCCL (and anything else native) may print to stdout; the contract is ONE JSON line there, so fd 1 points at
+    # stderr until the line is ready
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from mcmc_qec_toric_rl_b200 import _lib
@@ -253,8 +259,12 @@ def main():
     f1.record(stream)
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    per_rank = None
     if world > 1:
         t = torch.tensor([ms, ms_e2e, kern_ms], dtype=torch.float64, device="cuda")
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = [[round(float(x), 3) for x in a.tolist()] for a in allt]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e, kern_ms = [float(x) for x in t.tolist()]
     if rank != 0:
@@ -296,6 +306,8 @@ def main():
                         "waves_per_step": waves},
         "device": info["name"],
     }
+    if per_rank:
+        line["per_rank_ms"] = {"what": "[timed region, e2e region, chain kernels] per rank", "values": per_rank}
     if not args.no_cpu_baseline and world == 1:
         cores = host_cores()
         n_syn = max(1, min(cores, 64))
@@ -305,6 +317,8 @@ def main():
         line["cpu_baseline"] = {"value": rate, "unit": "steps/s", "cores": cores, "kind": "port",
                                 "sample": f"{n_syn} syndromes x 16 classes x {cpu_drop} chains x {samples} samples x {ITERS} steps "
                                           f"({steps:.3g} Metropolis steps, {dt:.1f} s) with oracle/qec_oracle.c"}
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

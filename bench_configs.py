@@ -1,0 +1,181 @@
+#!/usr/bin/env python
+"""Secondary measurements: the BASELINE.json configs other than the headline one (which bench.py times).
+
+    python bench_configs.py [--config toric5|rotated25|xzzx21|planar_sweep|all] [--out profiles/xxx.jsonl]
+
+One JSON line per configuration: Metropolis steps/s and syndromes/s on one GPU through the host-buffer C ABI
+(H2D + kernels + D2H inside the timed region), the logical failure rate of the decoded batch, and the oracle port
+timed on the host cores on a bounded sample of the same workload.  These lines are evidence for DESIGN.md; the
+driver's contract line comes from bench.py."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def synth(shape, p, rng, px=None, py=None, pz=None):
+    """i.i.d. Pauli errors: depolarizing rate p, or (px, py, pz)."""
+    r = rng.random(shape)
+    q = np.zeros(shape, np.uint8)
+    if px is None:
+        px = py = pz = p / 3.0
+    q[r < pz] = 3
+    q[(r >= pz) & (r < pz + px)] = 1
+    q[(r >= pz + px) & (r < pz + px + py)] = 2
+    return q
+
+
+def hide_class(O, g, L, qs, rng):
+    """generate_data.py:122-131: remember the class, then apply a random logical operator."""
+    truth = np.array([O.eq_class(g, L, q) for q in qs])
+    out = []
+    for q in qs:
+        nb = O.Stream.mt(int(rng.integers(1, 2**31)))
+        out.append(O.apply_random_logical(g, L, q, nb)[0])
+    return np.stack(out), truth
+
+
+def timed(fn):
+    import torch
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = fn()
+    torch.cuda.synchronize()
+    return out, time.perf_counter() - t0
+
+
+def run_toric5(ctx, O):
+    g, L, S, p = O.TORIC, 5, 100, 0.10
+    rng = np.random.default_rng(1)
+    qs, truth = hide_class(O, g, L, synth((S, 2, L, L), p, rng), rng)
+    qm = np.ascontiguousarray(qs.reshape(S, -1))
+    drop, steps = 10, 5 * L ** 4
+    res = {}
+    for name, fn in (("STDC", ctx.stdc), ("STRC", ctx.strc)):
+        fn(g, g, L, qm, p, 0.25, drop, steps, seed=1)     # warm-up at full size (allocations, module load)
+        (out, st), dt = timed(lambda: fn(g, g, L, qm, p, 0.25, drop, steps, seed=7))
+        res[name] = {"steps_per_s": st["metropolis_steps"] / dt, "syndromes_per_s": S / dt, "seconds": dt,
+                     "logical_failure_rate": float((out.argmax(1) != truth).mean())}
+    t0 = time.perf_counter()
+    ref = O.stdc_batch(g, g, L, qm, p, 0.25, drop, steps, seed=3, threads=cores())
+    dt = time.perf_counter() - t0
+    res["cpu_baseline"] = {"value": S * 16 * drop * steps * 5 / dt, "unit": "steps/s", "cores": cores(), "kind": "port",
+                           "sample": f"all {S} syndromes, STDC", "logical_failure_rate": float((ref.argmax(1) != truth).mean())}
+    return {"config": "toric d=5, depolarizing p=0.10, STDC/STRC of 100 syndromes, droplets=10, steps=3125, p_sampling=0.25",
+            **res}
+
+
+def _pteq_config(ctx, O, name, g, L, kind, bottom, b, S, steps, qs, truth, cpu_ladders, cpu_steps):
+    qm = np.ascontiguousarray(qs.reshape(S, -1))
+    ctx.pteq(g, L, kind, qm[:8], bottom, param_b=b, steps=50, conv=False, seed=1)
+    (pct, info), dt = timed(lambda: ctx.pteq(g, L, kind, qm, bottom, param_b=b, steps=steps, conv=False, seed=11))
+    msteps = info["stats"]["metropolis_steps"]
+    res = {"config": name, "ladders": S, "Nc": L, "ladder_steps": steps, "steps_per_s": msteps / dt, "syndromes_per_s": S / dt,
+           "seconds": dt, "kernel_ms": info["stats"]["chain_kernel_ms"], "kernel_steps_per_s": msteps / (info["stats"]["chain_kernel_ms"] * 1e-3),
+           "accept_rate": info["stats"]["accepted"] / msteps, "logical_failure_rate": float((pct.argmax(1) != truth).mean()),
+           "tops0_mean": float(info["tops0"].mean())}
+    # with the reference's convergence criterion
+    (pct2, info2), dt2 = timed(lambda: ctx.pteq(g, L, kind, qm, bottom, param_b=b, steps=steps, conv=True, seed=12))
+    res["with_convergence"] = {"seconds": dt2, "syndromes_per_s": S / dt2, "converged": float(info2["converged"].mean()),
+                               "mean_steps": float(info2["steps"].mean()),
+                               "logical_failure_rate": float((pct2.argmax(1) != truth).mean())}
+    import concurrent.futures as cf
+
+    def one(i):
+        return O.pteq(kind, g, L, qs[i], bottom, O.Stream.mt(100 + i), O.Stream.py(200 + i), param_b=b, steps=cpu_steps, conv=False)[0]
+    t0 = time.perf_counter()
+    with cf.ThreadPoolExecutor(cores()) as ex:
+        outs = list(ex.map(one, range(cpu_ladders)))
+    dtc = time.perf_counter() - t0
+    res["cpu_baseline"] = {"value": cpu_ladders * L * 10 * cpu_steps / dtc, "unit": "steps/s", "cores": cores(), "kind": "port",
+                           "sample": f"{cpu_ladders} ladders x {cpu_steps} ladder steps ({dtc:.1f} s)"}
+    return res
+
+
+def run_rotated25(ctx, O, S=4736, steps=2000):
+    g, L, p = O.ROTATED, 25, 0.15
+    rng = np.random.default_rng(3)
+    qs, truth = hide_class(O, g, L, synth((S, L, L), p, rng), rng)
+    return _pteq_config(ctx, O, "rotated surface code d=25, depolarizing p=0.15, PTEQ Nc=25 iters=10 p_logical=0.5",
+                        g, L, 0, p, 0.0, S, steps, qs, truth, 2 * cores(), 12000)
+
+
+def run_xzzx21(ctx, O, S=4736, steps=2000):
+    g, L, p, eta = O.XZZX, 21, 0.15, 100.0
+    rng = np.random.default_rng(4)
+    pz, px = p * eta / (eta + 1), p / (2 * (eta + 1))
+    qs, truth = hide_class(O, g, L, synth((S, L, L), p, rng, px, px, pz), rng)
+    out = {"biased": _pteq_config(ctx, O, "XZZX d=21, Z-biased eta=100 p=0.15, PTEQ_biased Nc=21", g, L, 2, p, eta, S, steps, qs, truth,
+                                  2 * cores(), 1500)}
+    pz_tilde = (p / (1 + 1 / eta)) / (1 - p)
+    alpha = float(np.log(pz_tilde / (2 * eta)) / np.log(pz_tilde))
+    out["alpha"] = _pteq_config(ctx, O, f"XZZX d=21, pz_tilde={pz_tilde:.5f} alpha={alpha:.4f}, PTEQ_alpha Nc=21", g, L, 1, pz_tilde,
+                                alpha, S, steps, qs, truth, 2 * cores(), 1500)
+    return out
+
+
+def run_planar_sweep(ctx, O, ps=(0.10, 0.15, 0.20), ds=(7, 11, 15, 21), droplets=16):
+    """Threshold sweep: STDC, classes reached on device, steps = d^4, one GPU-filling batch per (d, p)."""
+    g = O.PLANAR
+    info = ctx.device_info()
+    rows = []
+    for d in ds:
+        steps = d ** 4
+        cap = 1
+        while cap < droplets * steps * 1.25 + 1:
+            cap *= 2
+        fit = int(info["free_mem"] * 0.8) // (4 * cap * 8)
+        S = max(8, min(fit, (info["sm_count"] * 1280) // (4 * droplets)))
+        for p in ps:
+            rng = np.random.default_rng(50 + d)
+            raw = synth((S, 2, d, d), p, rng)
+            raw[:, 1, -1, :] = 0
+            raw[:, 1, :, -1] = 0
+            qs, truth = hide_class(O, g, d, raw, rng)
+            qm = np.ascontiguousarray(qs.reshape(S, -1))
+            (out, st), dt = timed(lambda: ctx.stdc(g, g, d, qm, p, 0.25, droplets, steps, seed=5))
+            rows.append({"d": d, "p": p, "syndromes": S, "steps_per_s": st["metropolis_steps"] / dt, "syndromes_per_s": S / dt,
+                         "seconds": dt, "logical_failure_rate": float((out.argmax(1) != truth).mean()),
+                         "distinct_per_sample": st["distinct"] / (S * 4 * droplets * steps)})
+    return {"config": "planar code threshold sweep, STDC, 4 classes x 16 chains, steps = d^4, p_sampling = 0.25", "points": rows}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="all")
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+    from mcmc_qec_toric_rl_b200 import _lib
+    from oracle import oracle as O
+    O.lib()
+    ctx = _lib.Context(0)
+    runs = {"toric5": run_toric5, "rotated25": run_rotated25, "xzzx21": run_xzzx21, "planar_sweep": run_planar_sweep}
+    todo = list(runs) if args.config == "all" else [args.config]
+    lines = []
+    for name in todo:
+        res = runs[name](ctx, O)
+        res["name"] = name
+        res["device"] = ctx.device_info()["name"]
+        line = json.dumps(res)
+        print(line, flush=True)
+        lines.append(line)
+    if args.out:
+        with open(args.out, "w") as f:
+            f.write("\n".join(lines) + "\n")
+
+
+if __name__ == "__main__":
+    main()

@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "csrc", "libqecmc.so")
+SO = os.environ.get("QECMC_LIB") or os.path.join(HERE, "csrc", "libqecmc.so")
 
 TORIC, PLANAR, ROTATED, XZZX = 0, 1, 2, 3
 GEOM_NAMES = {"toric": TORIC, "planar": PLANAR, "rotated": ROTATED, "xzzx": XZZX}
