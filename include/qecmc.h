@@ -295,6 +295,54 @@ int qecmc_chain_update_xyz(qecmc_ctx *ctx, const qecmc_chain_cfg *cfg, const dou
 int qecmc_stdc_general_noise(qecmc_ctx *ctx, const qecmc_xyz_cfg *cfg, const uint8_t *qm, int64_t S, double *eqdistr,
                              double *eqdistr_shortest, int64_t *distinct, qecmc_stats *stats);
 
+/* ---- The workload loop around the decoders: generate_data.py:53-261 ---------------------------------------------
+ * A batch of syndromes is drawn, labelled, hidden, decoded and scored without leaving the GPU.
+ *
+ * generate_random_error.  toric_form = 1: Toric_code.generate_random_error(p_error) (toric_model.py:15-24): a qubit
+ * errs iff u < p_error and then carries np.random.randint(3) + 1.  toric_form = 0: generate_random_error(p_x, p_y, p_z)
+ * of Planar_code (planar_model.py:18-37; layer 1 loses its last row and column), RotSurCode
+ * (rotated_surface_model.py:25-38) and xzzx_code (xzzx_model.py:16-29): r < p_z -> Z, p_z < r < p_z + p_x -> X,
+ * p_z + p_x < r < p_z + p_x + p_y -> Y.
+ *   u      replay: [S][n_sites] the reference's uniforms in lattice order (NULL: native Philox keyed by seed)
+ *   pauli  replay, toric form only: [S][n_sites] the randint(3) + 1 draws
+ *   qm     out [S][n_sites]; eq_true out [S] = define_equivalence_class() of each lattice (optional)
+ * _dev variants: every pointer (including cfg->u / cfg->pauli) is a device pointer. */
+typedef struct qecmc_noise_cfg {
+    int32_t geom, L;
+    int32_t toric_form, reserved;
+    double  p_error;            /* toric form */
+    double  p_x, p_y, p_z;      /* xyz form */
+    uint64_t seed;
+    const double  *u;
+    const uint8_t *pauli;
+} qecmc_noise_cfg;
+int qecmc_generate_errors(qecmc_ctx *ctx, const qecmc_noise_cfg *cfg, int64_t S, uint8_t *qm, int32_t *eq_true);
+int qecmc_generate_errors_dev(qecmc_ctx *ctx, const qecmc_noise_cfg *cfg, int64_t S, uint8_t *d_qm, int32_t *d_eq_true);
+
+/* define_equivalence_class of S lattices (toric_model.py:317-351, planar_model.py:379-390,
+ * rotated_surface_model.py:411-420, xzzx_model.py:455-486): cls[S] in [0, 16) (toric) or [0, 4). */
+int qecmc_define_equivalence_class(qecmc_ctx *ctx, int32_t geom, int32_t L, const uint8_t *qm, int64_t S, int32_t *cls);
+int qecmc_define_equivalence_class_dev(qecmc_ctx *ctx, int32_t geom, int32_t L, const uint8_t *d_qm, int64_t S, int32_t *d_cls);
+
+/* apply_random_logical in place on S lattices (toric_model.py:228-253, planar_model.py:271-288,
+ * rotated_surface_model.py:331-346, xzzx_model.py:340-357) -- generate_data.py:131 hides the true class this way.
+ *   u    replay: [S][6] numba-stream uniforms in draw order (toric: op0, op1, then X_pos / Z_pos per layer as drawn;
+ *        others: op, X_pos, Z_pos as drawn); NULL: native Philox keyed by seed
+ *   ops  out, optional: [S][2] the operator drawn per layer (second entry 0 for the one-layer codes) */
+int qecmc_apply_random_logical(qecmc_ctx *ctx, int32_t geom, int32_t L, uint8_t *qm, int64_t S, uint64_t seed, const double *u,
+                               int32_t *ops);
+int qecmc_apply_random_logical_dev(qecmc_ctx *ctx, int32_t geom, int32_t L, uint8_t *d_qm, int64_t S, uint64_t seed,
+                                   const double *d_u, int32_t *d_ops);
+
+/* Failure count of generate_data.py:137-201: choice = np.argmax(distr) (use_argmin = 1: np.argmin, the single_temp
+ * rule of :199-201), failure iff choice != eq_true.  distr is [S][n_eq] float64 (QECMC_DISTR_F64) or uint8
+ * (QECMC_DISTR_U8, the PT decoders).  choice [S] is optional; *failures is a host int64 in both variants. */
+enum qecmc_distr_dtype { QECMC_DISTR_F64 = 0, QECMC_DISTR_U8 = 1 };
+int qecmc_count_failures(qecmc_ctx *ctx, const void *distr, int32_t dtype, int32_t use_argmin, int32_t n_eq, int64_t S,
+                         const int32_t *eq_true, int32_t *choice, int64_t *failures);
+int qecmc_count_failures_dev(qecmc_ctx *ctx, const void *d_distr, int32_t dtype, int32_t use_argmin, int32_t n_eq, int64_t S,
+                             const int32_t *d_eq_true, int32_t *d_choice, int64_t *failures);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,7 +78,14 @@ class XyzCfg(C.Structure):
                 ("seed", C.c_uint64), ("u_nb", C.c_void_p)]
 
 
+class NoiseCfg(C.Structure):
+    _fields_ = [("geom", C.c_int32), ("L", C.c_int32), ("toric_form", C.c_int32), ("reserved", C.c_int32),
+                ("p_error", C.c_double), ("p_x", C.c_double), ("p_y", C.c_double), ("p_z", C.c_double),
+                ("seed", C.c_uint64), ("u", C.c_void_p), ("pauli", C.c_void_p)]
+
+
 LADDER_DEPOLARIZING, LADDER_ALPHA, LADDER_BIASED = 0, 1, 2
+DISTR_F64, DISTR_U8 = 0, 1
 
 _lib = None
 
@@ -124,6 +131,16 @@ def load():
                                            C.c_void_p, C.POINTER(Stats)]
     L.qecmc_stdc_alpha.argtypes = [C.c_void_p, C.POINTER(AlphaCfg), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.POINTER(Stats)]
+    L.qecmc_generate_errors.argtypes = [C.c_void_p, C.POINTER(NoiseCfg), C.c_int64, C.c_void_p, C.c_void_p]
+    L.qecmc_generate_errors_dev.argtypes = L.qecmc_generate_errors.argtypes
+    L.qecmc_define_equivalence_class.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
+    L.qecmc_define_equivalence_class_dev.argtypes = L.qecmc_define_equivalence_class.argtypes
+    L.qecmc_apply_random_logical.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p,
+                                             C.c_void_p]
+    L.qecmc_apply_random_logical_dev.argtypes = L.qecmc_apply_random_logical.argtypes
+    L.qecmc_count_failures.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
+                                       C.c_void_p, C.POINTER(C.c_int64)]
+    L.qecmc_count_failures_dev.argtypes = L.qecmc_count_failures.argtypes
     _lib = L
     return L
 
@@ -473,6 +490,85 @@ class Context:
         _check(load().qecmc_stdc_dev(self._h, C.byref(cfg), C.c_void_p(d_qm_ptr), S, C.c_void_p(d_out_ptr), None,
                                      C.byref(st) if want_stats else None))
         return st.as_dict() if want_stats else None
+
+
+    # ---- the workload loop around the decoders (generate_data.py:53-261) ----
+    @staticmethod
+    def _noise_cfg(geom, L, p_error, p_xyz, seed, u, pauli):
+        toric_form = p_xyz is None
+        px, py, pz = (0.0, 0.0, 0.0) if toric_form else [float(x) for x in p_xyz]
+        return NoiseCfg(geom, L, int(toric_form), 0, float(p_error or 0.0), px, py, pz, seed, u, pauli)
+
+    def generate_errors(self, geom, L, S, p_error=None, p_xyz=None, seed=0, u=None, pauli=None, want_class=True):
+        """generate_random_error on the device: p_error = the toric form (toric_model.py:15-24), p_xyz = (p_x, p_y, p_z)
+        (planar_model.py:18-37 and friends).  u / pauli replay the reference's own draws.  -> (qm [S, n_sites], eq_true [S])"""
+        n = nsites(geom, L)
+        if u is not None:
+            u = np.ascontiguousarray(u, dtype=np.float64)
+            assert u.size == S * n, "u must hold S * n_sites uniforms"
+        if pauli is not None:
+            pauli = np.ascontiguousarray(pauli, dtype=np.uint8)
+            assert pauli.size == S * n
+        cfg = self._noise_cfg(geom, L, p_error, p_xyz, seed, u.ctypes.data if u is not None else None,
+                              pauli.ctypes.data if pauli is not None else None)
+        qm = np.zeros((S, n), np.uint8)
+        cls = np.zeros(S, np.int32)
+        _check(load().qecmc_generate_errors(self._h, C.byref(cfg), S, qm.ctypes.data, cls.ctypes.data if want_class else None))
+        return qm, (cls if want_class else None)
+
+    def generate_errors_dev(self, geom, L, S, d_qm_ptr, d_eq_true_ptr, p_error=None, p_xyz=None, seed=0):
+        cfg = self._noise_cfg(geom, L, p_error, p_xyz, seed, None, None)
+        _check(load().qecmc_generate_errors_dev(self._h, C.byref(cfg), S, C.c_void_p(d_qm_ptr),
+                                                C.c_void_p(d_eq_true_ptr) if d_eq_true_ptr else None))
+
+    def define_equivalence_class(self, geom, L, qm):
+        qm = np.ascontiguousarray(qm)
+        _require_u8(qm)
+        S = qm.size // nsites(geom, L)
+        cls = np.zeros(S, np.int32)
+        _check(load().qecmc_define_equivalence_class(self._h, geom, L, qm.ctypes.data, S, cls.ctypes.data))
+        return cls
+
+    def define_equivalence_class_dev(self, geom, L, d_qm_ptr, S, d_cls_ptr):
+        _check(load().qecmc_define_equivalence_class_dev(self._h, geom, L, C.c_void_p(d_qm_ptr), S, C.c_void_p(d_cls_ptr)))
+
+    def apply_random_logical(self, geom, L, qm, seed=0, u=None):
+        """apply_random_logical on every lattice of the batch -> (new qm, ops [S, 2])"""
+        qm = np.array(qm, dtype=np.uint8, order="C", copy=True)
+        S = qm.size // nsites(geom, L)
+        if u is not None:
+            u = np.ascontiguousarray(u, dtype=np.float64)
+            assert u.shape == (S, 6), "u must be [S, 6] (unused trailing entries are ignored)"
+        ops = np.zeros((S, 2), np.int32)
+        _check(load().qecmc_apply_random_logical(self._h, geom, L, qm.ctypes.data, S, seed, u.ctypes.data if u is not None else None,
+                                                 ops.ctypes.data))
+        return qm, ops
+
+    def apply_random_logical_dev(self, geom, L, d_qm_ptr, S, seed=0):
+        _check(load().qecmc_apply_random_logical_dev(self._h, geom, L, C.c_void_p(d_qm_ptr), S, seed, None, None))
+
+    def count_failures(self, distr, eq_true, use_argmin=False):
+        """np.argmax(distr) != eq_true per syndrome (np.argmin for single_temp) -> (failures, choice [S])"""
+        distr = np.ascontiguousarray(distr)
+        if distr.dtype == np.uint8:
+            dt = DISTR_U8
+        else:
+            distr = np.ascontiguousarray(distr, dtype=np.float64)
+            dt = DISTR_F64
+        S, n_eq = distr.shape
+        eq_true = np.ascontiguousarray(eq_true, dtype=np.int32)
+        choice = np.zeros(S, np.int32)
+        fails = C.c_int64(0)
+        _check(load().qecmc_count_failures(self._h, distr.ctypes.data, dt, int(use_argmin), n_eq, S, eq_true.ctypes.data,
+                                           choice.ctypes.data, C.byref(fails)))
+        return int(fails.value), choice
+
+    def count_failures_dev(self, d_distr_ptr, dtype, n_eq, S, d_eq_true_ptr, d_choice_ptr=None, use_argmin=False):
+        fails = C.c_int64(0)
+        _check(load().qecmc_count_failures_dev(self._h, C.c_void_p(d_distr_ptr), dtype, int(use_argmin), n_eq, S,
+                                               C.c_void_p(d_eq_true_ptr), C.c_void_p(d_choice_ptr) if d_choice_ptr else None,
+                                               C.byref(fails)))
+        return int(fails.value)
 
 
 def _require_u8(a):

@@ -35,6 +35,13 @@ extern "C" int qecmc_create(int device, qecmc_ctx **out)
     CUDA_OK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     for (auto &ev : c->ev) CUDA_OK(cudaEventCreate(&ev));
+    // The distinct-chain probes touch one random 8-byte slot each: ask L2 for the smallest DRAM fetch (a hint; 32/64/128).
+    {
+        const char *e = getenv("QECMC_L2_FETCH");
+        size_t gran = e ? (size_t)atoi(e) : 32;
+        if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+        cudaGetLastError();
+    }
     *out = c;
     return 0;
 }
@@ -298,9 +305,14 @@ static int launch_stdc_fast(qecmc_ctx *c, StdcParams &p)
     size_t fixed = (size_t)p.gchain.nstab * 16 + 512 * 5 + 16;
     QTRY(pick_threads(per_chain, fixed + 256, c->prop, &T, &nb));
     size_t smem = ((per_chain * T + 15) & ~(size_t)15) + fixed;
-    CUDA_OK(cudaFuncSetAttribute(stdc_fast_kernel<GEOM, W, REPLAY, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned grid = (unsigned)((p.n_chains + T - 1) / T);
-    stdc_fast_kernel<GEOM, W, REPLAY, MODE><<<grid, T, smem, c->stream>>>(p, ft, keys);
+    if (REPLAY || p.conv_mult != 0.0) {
+        CUDA_OK(cudaFuncSetAttribute(stdc_fast_kernel<GEOM, W, REPLAY, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stdc_fast_kernel<GEOM, W, REPLAY, MODE, true><<<grid, T, smem, c->stream>>>(p, ft, keys);
+    } else {
+        CUDA_OK(cudaFuncSetAttribute(stdc_fast_kernel<GEOM, W, false, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stdc_fast_kernel<GEOM, W, false, MODE, false><<<grid, T, smem, c->stream>>>(p, ft, keys);
+    }
     c->launches++;
     CUDA_OK(cudaGetLastError());
     return 0;

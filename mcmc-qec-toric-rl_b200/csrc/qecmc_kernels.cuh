@@ -207,6 +207,17 @@ struct ConvStop {
     }
 };
 
+// ConvStopT<false>: conv_mult == 0 is known on the host, nothing to track
+template <bool CONV> struct ConvStopT : ConvStop {
+    __device__ __forceinline__ uint32_t samples() const { return sample; }
+};
+template <> struct ConvStopT<false> {
+    static constexpr bool fin = false;
+    __device__ __forceinline__ void init(const StdcParams &) {}
+    __device__ __forceinline__ void after_sample(const StdcParams &, bool, int) {}
+    __device__ __forceinline__ uint32_t samples() const { return 0; }
+};
+
 enum { MODE_STDC = 0, MODE_STRC = 1, MODE_MEAN = 2 };
 
 // Per-sample bookkeeping beyond the distinct set.

@@ -46,8 +46,10 @@ template <> __device__ __forceinline__ uint32_t gather_fields<uint64_t>(uint64_t
     return qa | (qb << 2) | (qc << 4) | (qd << 6);
 }
 
-template <int GEOM, typename W, bool REPLAY, int MODE>
-__global__ void __launch_bounds__(256) stdc_fast_kernel(StdcParams p, FastTables ft, PhiloxKeys keys)
+// CONV = false drops the conv_mult early-stop state (ConvStop) from the loop: the headline configuration
+// (conv_mult == 0) then fits the register budget of five 256-thread CTAs per SM.
+template <int GEOM, typename W, bool REPLAY, int MODE, bool CONV>
+__global__ void __launch_bounds__(256, CONV ? (sizeof(W) == 4 ? 4 : 2) : (sizeof(W) == 4 ? 5 : 3)) stdc_fast_kernel(StdcParams p, FastTables ft, PhiloxKeys keys)
 {
     static_assert(GEOM == TORIC || GEOM == PLANAR, "table-driven kernel covers the two-layer codes");
     extern __shared__ __align__(16) unsigned char smem[];
@@ -112,8 +114,8 @@ __global__ void __launch_bounds__(256) stdc_fast_kernel(StdcParams p, FastTables
     uint64_t keyA = 0, prevA = 0, keyB = 0, prevB = 0;
     uint32_t slotA = 0, slotB = 0;
     const uint32_t smask = (uint32_t)cap_mask;  // host guarantees cap <= 2^32 slots
-    const int imode = MODE == MODE_MEAN ? 3 : (p.conv_mult != 0.0 ? 0 : p.insert_mode);  // the early stop needs the probe's answer now
-    ConvStop cs;
+    const int imode = MODE == MODE_MEAN ? 3 : (CONV && p.conv_mult != 0.0 ? 0 : p.insert_mode);  // the early stop needs the probe's answer now
+    ConvStopT<CONV> cs;
     cs.init(p);
     SampleAcct<MODE> acct;
     acct.init(p, tab);
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(256) stdc_fast_kernel(StdcParams p, FastTables
     acct.finish(p, local);
     atomicAdd(p.counters + 0, (unsigned long long)nacc);
     atomicAdd(p.counters + 1, (unsigned long long)noff);
-    atomicAdd(p.steps_done, (unsigned long long)cs.sample * (unsigned long long)p.iters);
+    atomicAdd(p.steps_done, CONV ? (unsigned long long)cs.samples() * (unsigned long long)p.iters : (unsigned long long)tsteps);
 }
 
 }  // namespace qecmc

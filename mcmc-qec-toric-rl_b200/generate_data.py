@@ -1,0 +1,202 @@
+"""The reference's workload loop (generate_data.py:19-261) as batches on the GPU.
+
+``generate(file_path, params, nbr_datapoints, fixed_errors)`` keeps the reference's signature, parameter dictionary
+and on-disk format: a pandas DataFrame indexed by (data_nr, type) with one 'data' column -- row (-1, 0) holds
+``params``, row (i, 0) the uint8 error lattice of data point i *before* its class was hidden, row (i, 1) the decoder's
+class distribution (generate_data.py:232-255) -- so ``MCMCDataReader`` (src/mcmc.py) and downstream consumers read
+GPU-generated files unchanged.
+
+Per batch the device draws the errors (generate_random_error), labels them (define_equivalence_class -> eq_true),
+hides the class (apply_random_logical), decodes, and counts ``argmax != eq_true`` (argmin for "ST"); lattices stay in
+HBM between those steps for the decoders that have a device-pointer entry (STDC, PTEQ family), the others take the
+hidden lattices through their host-buffer ``*_batch`` entry.  MWPM initialisation and the MWPM / eMWPM methods need
+the external blossom5 solver and are out of scope.
+"""
+import numpy as np
+
+from . import _lib
+from . import decoders as _dec
+from . import decoders_biasednoise as _decb
+from .src import mcmc as _mcmc
+from .src.toric_model import Toric_code
+from .src.planar_model import Planar_code
+from .src.rotated_surface_model import RotSurCode
+from .src.xzzx_model import xzzx_code
+
+_CODES = {'toric': Toric_code, 'planar': Planar_code, 'rotated': RotSurCode, 'xzzx': xzzx_code}
+
+
+def noise_probabilities(params):
+    """(p_error, None) for the toric form or (None, (p_x, p_y, p_z)) -- generate_data.py:57-118."""
+    code, noise = params['code'], params.get('noise', 'depolarizing')
+    if code == 'toric':
+        assert noise == 'depolarizing'
+        return params['p_error'], None
+    if code == 'planar':
+        assert noise in ['depolarizing', 'alpha']
+    if noise == 'depolarizing':
+        p = params['p_error'] / 3
+        return None, (p, p, p)
+    if noise == 'biased':
+        eta, p = params['eta'], params['p_error']
+        p_x = p / (2 * (eta + 1))
+        return None, (p_x, p_x, p * eta / (eta + 1))
+    if noise == 'alpha':
+        pz_tilde, alpha = params['p_error'], params['alpha']
+        p_tilde = pz_tilde + 2 * pz_tilde**alpha
+        p = p_tilde / (1 + p_tilde)
+        p_x = pz_tilde**alpha * (1 - p)
+        return None, (p_x, p_x, pz_tilde * (1 - p))
+    raise ValueError(f"unknown noise model {noise!r}")
+
+
+def _wrap(code_cls, size, qm):
+    out = []
+    for q in qm:
+        c = code_cls(size)
+        c.qubit_matrix = q.reshape(c.qubit_matrix.shape).copy()
+        out.append(c)
+    return out
+
+
+def decode_batch(params, hidden, seed=None, device=0):
+    """Decoder dispatch of generate_data.py:137-201 on a batch of hidden lattices (numpy [S, n_sites]).
+    -> (distributions [S, n_eq], use_argmin)"""
+    method, noise = params['method'], params.get('noise', 'depolarizing')
+    code_cls, size = _CODES[params['code']], params['size']
+    codes = _wrap(code_cls, size, hidden)
+    kw = dict(seed=seed, device=device)
+    if method == 'PTEQ':
+        if noise == 'depolarizing':
+            return _dec.PTEQ_batch(codes, params['p_error'], steps=params.get('pt_steps', 1000000), **kw), False
+        if noise == 'biased':
+            p, eta = params['p_error'], params['eta']
+            pz_tilde = (p / (1 + 1 / eta)) / (1 - p)
+            alpha = np.log(pz_tilde / (2 * eta)) / np.log(pz_tilde)
+            return _decb.PTEQ_alpha_batch(codes, pz_tilde, alpha=alpha, steps=params.get('pt_steps', 1000000), **kw), False
+        if noise == 'alpha':
+            return _decb.PTEQ_alpha_batch(codes, params['p_error'], alpha=params['alpha'], Nc=params.get('Nc'),
+                                          SEQ=params.get('SEQ', 2), TOPS=params.get('TOPS', 10), eps=params.get('eps', 0.1),
+                                          iters=params.get('iters', 10), conv_criteria=params.get('conv_criteria', 'error_based'),
+                                          steps=params.get('pt_steps', 1000000), **kw), False
+    if method == 'PTEQ_with_shortest':
+        assert noise == 'alpha'
+        out = _decb.PTEQ_alpha_with_shortest_batch(codes, params['p_error'], alpha=params['alpha'],
+                                                   steps=params.get('pt_steps', 1000000), **kw)
+        return np.concatenate([np.asarray(o, dtype=np.float64) for o in out], axis=1), False
+    if method == 'PTDC':
+        return _dec.PTDC_batch(codes, params['p_error'], params['p_sampling'], **kw), False
+    if method == 'PTRC':
+        return _dec.PTRC_batch(codes, params['p_error'], params['p_sampling'], **kw), False
+    if method == 'STDC':
+        return _dec.STDC_batch(codes, params['p_error'], params['p_sampling'], steps=params['steps'],
+                               droplets=params['droplets'], **kw), False
+    if method == 'STDC_N_n':
+        assert noise == 'alpha'
+        return _dec.STDC_Nall_n_alpha_batch(codes, params['p_sampling'], params['alpha'], params['p_error'],
+                                            steps=params['steps'], **kw), False
+    if method == 'ST':
+        return _dec.single_temp_batch(codes, params['p_error'], params['steps'], **kw), True
+    if method == 'STRC':
+        return _dec.STRC_batch(codes, params['p_error'], p_sampling=params['p_sampling'], steps=params['steps'],
+                               droplets=params['droplets'], **kw), False
+    if method in ('MWPM', 'eMWPM'):
+        raise NotImplementedError("MWPM needs the external blossom5 solver (src/mwpm.py:391); out of scope")
+    raise ValueError(f"unknown method {method!r}")
+
+
+def generate_batch(params, S, seed=0, device=0):
+    """One batch of the workload loop -> dict(qubit=[S, n_sites] uint8, eq_true=[S], distr=[S, n_eq], choice=[S],
+    failures=int).  The STDC and depolarizing-PTEQ paths keep the lattices on the device from error generation to
+    failure counting; the others stage the hidden lattices through the host-buffer decoder entry."""
+    import torch
+    if params.get('mwpm_init'):
+        raise NotImplementedError("mwpm_init needs the external blossom5 solver (src/mwpm.py:391); out of scope")
+    ctx = _lib.default_context(device)
+    geom = _lib.GEOM_NAMES[params['code']]
+    L = params['size']
+    n, n_eq = _lib.nsites(geom, L), _lib.neq(geom)
+    p_error, p_xyz = noise_probabilities(params)
+    dev = torch.device('cuda', device)
+    with torch.cuda.device(dev):
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        d_q = torch.empty((S, n), dtype=torch.uint8, device=dev)
+        d_true = torch.empty(S, dtype=torch.int32, device=dev)
+        ctx.generate_errors_dev(geom, L, S, d_q.data_ptr(), d_true.data_ptr(), p_error=p_error, p_xyz=p_xyz, seed=seed)
+        d_hidden = d_q.clone()                                                    # df_qubit keeps the unhidden error
+        ctx.apply_random_logical_dev(geom, L, d_hidden.data_ptr(), S, seed=seed ^ 0x5A5A5A5A)
+        method, noise = params['method'], params.get('noise', 'depolarizing')
+        use_argmin = False
+        d_choice = torch.empty(S, dtype=torch.int32, device=dev)
+        if method == 'STDC' and geom in (_lib.TORIC, _lib.PLANAR):
+            d_out = torch.empty((S, n_eq), dtype=torch.float64, device=dev)
+            code0 = _CODES[params['code']](L)
+            ctx.stdc_dev(geom, _mcmc.fast_path_geometry(code0), L, d_hidden.data_ptr(), S, d_out.data_ptr(), params['p_error'],
+                         params['p_sampling'] or params['p_error'], int(params['droplets']), int(params['steps']), iters=5,
+                         per_class=False, randomize=True, seed=seed + 1, want_stats=False)
+            failures = ctx.count_failures_dev(d_out.data_ptr(), _lib.DISTR_F64, n_eq, S, d_true.data_ptr(), d_choice.data_ptr())
+            distr = d_out.cpu().numpy()
+        elif method == 'PTEQ' and noise == 'depolarizing':
+            d_out = torch.empty((S, n_eq), dtype=torch.uint8, device=dev)
+            ctx.pteq_dev(geom, L, _lib.LADDER_DEPOLARIZING, d_hidden.data_ptr(), S, d_out.data_ptr(), params['p_error'],
+                         Nc=params.get('Nc'), SEQ=params.get('SEQ', 2), TOPS=params.get('TOPS', 10), eps=params.get('eps', 0.1),
+                         steps=params.get('pt_steps', 1000000), iters=params.get('iters', 10), seed=seed + 1)
+            failures = ctx.count_failures_dev(d_out.data_ptr(), _lib.DISTR_U8, n_eq, S, d_true.data_ptr(), d_choice.data_ptr())
+            distr = d_out.cpu().numpy()
+        else:
+            distr, use_argmin = decode_batch(params, d_hidden.cpu().numpy(), seed=seed + 1, device=device)
+            ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+            # PTEQ_with_shortest scores on the first four entries only (generate_data.py:170)
+            scored = np.ascontiguousarray(distr[:, :n_eq])
+            d_scored = torch.from_numpy(scored).to(dev)
+            failures = ctx.count_failures_dev(d_scored.data_ptr(), _lib.DISTR_U8 if scored.dtype == np.uint8 else _lib.DISTR_F64,
+                                              n_eq, S, d_true.data_ptr(), d_choice.data_ptr(), use_argmin=use_argmin)
+        out = dict(qubit=d_q.cpu().numpy(), eq_true=d_true.cpu().numpy(), distr=distr, choice=d_choice.cpu().numpy(),
+                   failures=int(failures))
+        ctx.set_stream(None)
+    return out
+
+
+def generate(file_path, params, nbr_datapoints=10**6, fixed_errors=None, batch=256, seed=None, device=0, verbose=True):
+    """generate_data.py:19-261.  Extra keyword arguments (batch, seed, device) have no reference counterpart: the
+    reference decodes one syndrome at a time, unseeded."""
+    import pandas as pd
+    names = ['data_nr', 'type']
+    frames = [pd.DataFrame([[params]], index=pd.MultiIndex.from_product([[-1], np.arange(1)], names=names), columns=['data'])]
+    if verbose:
+        print('\nDataFrame with opened at: ' + str(file_path))
+    if fixed_errors is not None:
+        nbr_datapoints = 10000000
+    failed_syndroms = 0
+    seed = _dec._next_seed(seed)
+    shape = (2, params['size'], params['size']) if params['code'] in ('toric', 'planar') else (params['size'], params['size'])
+    i = 0
+    while i < nbr_datapoints:
+        S = min(batch, nbr_datapoints - i)
+        res = generate_batch(params, S, seed=seed + 7919 * i, device=device)
+        rows, idx = [], []
+        for s in range(S):
+            rows.append([res['qubit'][s].reshape(shape).astype(np.uint8)])
+            idx.append((i + s, 0))
+            rows.append([np.array(res['distr'][s])])
+            idx.append((i + s, 1))
+            failed_syndroms += int(res['choice'][s] != res['eq_true'][s])
+            if fixed_errors is not None and failed_syndroms == fixed_errors:
+                S = s + 1
+                break
+        rows, idx = rows[:2 * S], idx[:2 * S]
+        frames.append(pd.DataFrame(rows, index=pd.MultiIndex.from_tuples(idx, names=names), columns=['data']))
+        i += S
+        df = pd.concat(frames)
+        df.to_pickle(file_path)                       # intermediate save point (writing over), generate_data.py:244-248
+        if verbose:
+            print('Failed so far:', failed_syndroms, 'of', i)
+        if fixed_errors is not None and failed_syndroms == fixed_errors:
+            if verbose:
+                print('Desired amount of failes syndroms achieved, breaking loop.')
+            break
+    df = pd.concat(frames)
+    df.to_pickle(file_path)
+    if verbose:
+        print('\nCompleted')
+    return failed_syndroms, i

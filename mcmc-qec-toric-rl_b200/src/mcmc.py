@@ -163,3 +163,30 @@ class Ladder(_LadderBase):
 
     def r_flip(self, ind_lo):
         raise NotImplementedError("replica swaps run inside Ladder.step on the device")
+
+
+class MCMCDataReader:
+    """Reader of the workload loop's pickle (src/mcmc.py:118-141): a DataFrame indexed by (data_nr, type)."""
+
+    def __init__(self, file_path, size):
+        import pandas as pd
+        self.__file_path = file_path
+        self.__size = size
+        try:
+            self.__df = pd.read_pickle(file_path)
+            self.__capacity = self.__df.index[-1][0] + 1   # number of data samples in the dataset
+        except Exception:
+            print('No input file for MCMCDataReader')
+        self.__current_index = 0
+
+    def full(self):
+        return self.__df.to_numpy().ravel()
+
+    def has_next(self):
+        return self.__current_index < self.__capacity
+
+    def current_index(self):
+        return self.__current_index
+
+    def get_capacity(self):
+        return self.__capacity

@@ -165,6 +165,31 @@ def apply_random_logical(geom, L, qm, nb):
     return out.reshape(np.shape(qm)), d
 
 
+def generate_errors(geom, L, u, p_error=None, p_xyz=None, pauli=None):
+    """generate_random_error from explicit uniforms (toric form when p_xyz is None)."""
+    u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1)
+    out = np.zeros(nsites(geom, L), np.uint8)
+    toric_form = p_xyz is None
+    px, py, pz = (0.0, 0.0, 0.0) if toric_form else [float(x) for x in p_xyz]
+    pa = np.ascontiguousarray(pauli, dtype=np.uint8).reshape(-1) if pauli is not None else np.zeros(1, np.uint8)
+    f = lib().qo_generate_errors
+    f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    f.restype = None
+    f(geom, L, int(toric_form), float(p_error or 0.0), px, py, pz, u.ctypes.data, pa.ctypes.data, out.ctypes.data)
+    return out
+
+
+def count_failures(distr, eq_true, use_argmin=False):
+    distr = np.ascontiguousarray(distr, dtype=np.float64)
+    eq_true = np.ascontiguousarray(eq_true, dtype=np.int32)
+    S, n_eq = distr.shape
+    choice = np.zeros(S, np.int32)
+    f = lib().qo_count_failures
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+    f.restype = C.c_int64
+    return int(f(distr.ctypes.data, n_eq, S, int(use_argmin), eq_true.ctypes.data, choice.ctypes.data)), choice
+
+
 def eq_class(geom, L, qm):
     return lib().qo_class(geom, L, _flat(qm))
 

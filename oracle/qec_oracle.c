@@ -335,6 +335,47 @@ QO_EXPORT int qo_apply_random_logical(int geom, int L, uint8_t *qm, qo_stream *n
     return qo_apply_logical(geom, L, qm, op, 0, X_pos, Z_pos);
 }
 
+/* generate_random_error from explicit uniforms (the workload step before the path, generate_data.py:57-118).
+ * toric_form: Toric_code.generate_random_error(p_error), toric_model.py:15-24 -- u is np.random.uniform per layer,
+ * pauli is np.random.randint(3) + 1; `error = qubits > p_error -> 0`, `no_error = qubits < p_error -> 1`, times pauli.
+ * otherwise: generate_random_error(p_x, p_y, p_z) of planar_model.py:18-37 (layer 1 loses its last row and column),
+ * rotated_surface_model.py:25-38, xzzx_model.py:16-29 -- one rand.random() per site, strict chained comparisons. */
+QO_EXPORT void qo_generate_errors(int geom, int L, int toric_form, double p_error, double p_x, double p_y, double p_z,
+                                  const double *u, const uint8_t *pauli, uint8_t *qm)
+{
+    int n = qo_nsites(geom, L);
+    for (int i = 0; i < n; i++) {
+        double r = u[i];
+        int q = 0;
+        if (toric_form) q = r < p_error ? pauli[i] : 0;
+        else if (r < p_z) q = 3;
+        else if (p_z < r && r < (p_z + p_x)) q = 1;
+        else if ((p_z + p_x) < r && r < (p_z + p_x + p_y)) q = 2;
+        qm[i] = (uint8_t)q;
+    }
+    if (geom == QO_PLANAR)
+        for (int k = 0; k < L; k++) {
+            qm[L * L + (L - 1) * L + k] = 0; /* qubit_matrix[1, -1, :] = 0 */
+            qm[L * L + k * L + (L - 1)] = 0; /* qubit_matrix[1, :, -1] = 0 */
+        }
+}
+
+/* failure rule of generate_data.py:137-201: np.argmax (np.argmin for single_temp) != eq_true; first extremum, NaN wins */
+QO_EXPORT int64_t qo_count_failures(const double *distr, int n_eq, int64_t S, int use_argmin, const int32_t *eq_true, int32_t *choice)
+{
+    int64_t fails = 0;
+    for (int64_t s = 0; s < S; s++) {
+        const double *d = distr + s * n_eq;
+        int best = 0;
+        double bv = d[0];
+        for (int e = 1; e < n_eq && bv == bv; e++)
+            if (d[e] != d[e] || (use_argmin ? d[e] < bv : d[e] > bv)) { best = e; bv = d[e]; }
+        if (choice) choice[s] = best;
+        fails += best != eq_true[s];
+    }
+    return fails;
+}
+
 /* _define_equivalence_class.  toric_model.py:317-351, planar_model.py:379-390,
  * rotated_surface_model.py:411-420, xzzx_model.py:455-486. */
 QO_EXPORT int qo_class(int geom, int L, const uint8_t *qm)
