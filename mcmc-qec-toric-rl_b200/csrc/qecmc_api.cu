@@ -2,6 +2,7 @@
 // memory, wave scheduling of the distinct-chain tables, host<->device staging.
 #include "qecmc_internal.h"
 #include "qecmc_stdc_fast.cuh"
+#include "qecmc_dedupe.cuh"
 
 using namespace qecmc;
 
@@ -35,13 +36,6 @@ extern "C" int qecmc_create(int device, qecmc_ctx **out)
     CUDA_OK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     for (auto &ev : c->ev) CUDA_OK(cudaEventCreate(&ev));
-    // The distinct-chain probes touch one random 8-byte slot each: ask L2 for the smallest DRAM fetch (a hint; 32/64/128).
-    {
-        const char *e = getenv("QECMC_L2_FETCH");
-        size_t gran = e ? (size_t)atoi(e) : 32;
-        if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
-        cudaGetLastError();
-    }
     *out = c;
     return 0;
 }
@@ -58,6 +52,8 @@ extern "C" void qecmc_destroy(qecmc_ctx *c)
     for (auto &kv : c->stab_desc) cudaFree(kv.second);
     c->lut.release();
     c->log_hash.release();
+    c->log_counts.release();
+    c->dd_scratch.release();
     for (auto &ev : c->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->own_stream);
     delete c;
@@ -302,9 +298,14 @@ static int launch_stdc_fast(qecmc_ctx *c, StdcParams &p)
     make_philox_keys(p.seed, keys);
     int T = 0, nb = 0;
     size_t per_chain = (size_t)p.gchain.nw * sizeof(W);
-    size_t fixed = (size_t)p.gchain.nstab * 16 + 512 * 5 + 16;
-    QTRY(pick_threads(per_chain, fixed + 256, c->prop, &T, &nb));
-    size_t smem = ((per_chain * T + 15) & ~(size_t)15) + fixed;
+    // static part: LUTs (512 * 5 + 72 B) and, for 32-bit row words, descriptor + fingerprint arrays of 512 entries;
+    // wider lattices keep descriptors and fingerprints behind the tile in dynamic shared memory
+    const bool static_tab = sizeof(W) == 4;
+    if (static_tab && p.gchain.nstab > QECMC_FAST_STATIC_NSTAB) return set_err(QECMC_ERR_UNSUPPORTED, "internal: %d stabilizers exceed the static tables", p.gchain.nstab);
+    size_t stat = 512 * 5 + 128 + (static_tab ? (size_t)QECMC_FAST_STATIC_NSTAB * 16 : 0);
+    size_t dyn_fixed = static_tab ? 0 : (size_t)p.gchain.nstab * 16 + 16;
+    QTRY(pick_threads(per_chain, stat + dyn_fixed + 256, c->prop, &T, &nb));
+    size_t smem = ((per_chain * T + 15) & ~(size_t)15) + dyn_fixed;
     unsigned grid = (unsigned)((p.n_chains + T - 1) / T);
     if (REPLAY || p.conv_mult != 0.0) {
         CUDA_OK(cudaFuncSetAttribute(stdc_fast_kernel<GEOM, W, REPLAY, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -389,23 +390,45 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
     const int n_eq = gcode.neq;
     const int nh = gcode.nsites + 1;
 
-    // distinct-chain tables: capacity covers the worst case (every sample distinct) at load <= 0.8
+    // Distinct-chain accounting.  Default: per-chain key logs counted afterwards by log_dedupe_kernel (streams through
+    // HBM).  The open-addressing tables in HBM remain for the early stop (it needs "new or not" at once) and for key
+    // counts beyond what the dedupe kernel's bucket fan-out covers.
+    const int forced_mode = getenv("QECMC_DEBUG_INSERT_MODE") ? atoi(getenv("QECMC_DEBUG_INSERT_MODE")) : -1;
+    const uint64_t max_keys = (uint64_t)cfg->droplets * (uint64_t)cfg->steps;
+    const bool use_logs = mode != MODE_MEAN && cfg->conv_mult == 0.0 && (forced_mode < 0 || forced_mode == 4) &&
+                          max_keys <= (uint64_t)QECMC_DD_MAX_BUCKETS * QECMC_DD_BUCKET_TARGET && (uint64_t)cfg->steps < (1ull << 32);
+    const int64_t log_cap = (cfg->steps + 1) & ~(int64_t)1;
+    int dd_grid = c->prop.multiProcessorCount;
     uint64_t cap = 0;
     int64_t per_syndrome = 0, wave = S;
     if (mode != MODE_MEAN) {
-        uint64_t max_keys = (uint64_t)cfg->droplets * (uint64_t)cfg->steps;
-        cap = next_pow2(max_keys + max_keys / 4 + 1);
-        if (cap < 1024) cap = 1024;
-        if (cap > (1ull << 32)) return set_err(QECMC_ERR_UNSUPPORTED, "more than 2^32 slots per distinct-chain table");
         size_t fr = 0, tot = 0;
         CUDA_OK(cudaMemGetInfo(&fr, &tot));
-        int64_t budget = c->table_budget ? c->table_budget : (int64_t)((double)(fr + c->tables.cap) * 0.85);
-        per_syndrome = (int64_t)n_eq * (int64_t)cap * 8;
-        wave = budget / per_syndrome;
-        if (wave < 1)
-            return set_err(QECMC_ERR_NOMEM, "distinct-chain tables need %lld bytes per syndrome, budget is %lld",
-                           (long long)per_syndrome, (long long)budget);
-        if (wave > S) wave = S;
+        int64_t budget = c->table_budget ? c->table_budget : (int64_t)((double)(fr + c->tables.cap + c->dd_scratch.cap) * 0.85);
+        if (use_logs) {
+            if ((int64_t)S * n_eq < dd_grid) dd_grid = (int)(S * n_eq);
+            const int64_t scratch_bytes = (int64_t)dd_grid * cfg->droplets * log_cap * 8;
+            per_syndrome = (int64_t)n_eq * cfg->droplets * log_cap * 8;
+            wave = (budget - scratch_bytes) / per_syndrome;
+            if (wave < 1)
+                return set_err(QECMC_ERR_NOMEM, "key logs need %lld bytes per syndrome plus %lld bytes of scratch, budget is %lld",
+                               (long long)per_syndrome, (long long)scratch_bytes, (long long)budget);
+            if (wave > S) wave = S;
+            QTRY(c->dd_scratch.ensure((size_t)scratch_bytes));
+            QTRY(c->log_counts.ensure((size_t)wave * n_eq * cfg->droplets * sizeof(uint32_t)));
+            QTRY(c->scratch.ensure(2 * sizeof(int)));
+        } else {
+            // capacity covers the worst case (every sample distinct) at load <= 0.8
+            cap = next_pow2(max_keys + max_keys / 4 + 1);
+            if (cap < 1024) cap = 1024;
+            if (cap > (1ull << 32)) return set_err(QECMC_ERR_UNSUPPORTED, "more than 2^32 slots per distinct-chain table");
+            per_syndrome = (int64_t)n_eq * (int64_t)cap * 8;
+            wave = budget / per_syndrome;
+            if (wave < 1)
+                return set_err(QECMC_ERR_NOMEM, "distinct-chain tables need %lld bytes per syndrome, budget is %lld",
+                               (long long)per_syndrome, (long long)budget);
+            if (wave > S) wave = S;
+        }
         QTRY(c->tables.ensure((size_t)wave * per_syndrome));
     }
     int64_t n_lat = cfg->per_class_inits ? S * n_eq : S;
@@ -445,7 +468,10 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
     p.u_np = cfg->u_np;
     p.counters = (unsigned long long *)c->counters.p;
     // diagnostic knob for roofline work (3 = chains without the distinct set: results are then meaningless)
-    p.insert_mode = getenv("QECMC_DEBUG_INSERT_MODE") ? atoi(getenv("QECMC_DEBUG_INSERT_MODE")) : 2;
+    p.insert_mode = use_logs ? 4 : (forced_mode >= 0 && forced_mode != 4 ? forced_mode : 2);
+    p.logs = (unsigned long long *)c->tables.p;
+    p.log_counts = (uint32_t *)c->log_counts.p;
+    p.log_cap = log_cap;
     p.max_length = 2 * cfg->L * cfg->L;  // decoders.py:747
     p.conv_mult = mode == MODE_MEAN ? 0.0 : cfg->conv_mult;
     p.steps_done = (unsigned long long *)c->counters.p + 4;
@@ -458,7 +484,7 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
     int64_t waves = 0;
     for (int64_t s0 = 0; s0 < S; s0 += wave, waves++) {
         int64_t sw = S - s0 < wave ? S - s0 : wave;
-        if (mode != MODE_MEAN) CUDA_OK(cudaMemsetAsync(c->tables.p, 0, (size_t)sw * per_syndrome, c->stream));
+        if (mode != MODE_MEAN && !use_logs) CUDA_OK(cudaMemsetAsync(c->tables.p, 0, (size_t)sw * per_syndrome, c->stream));
         p.lat0 = (const char *)c->packed.p + (size_t)(cfg->per_class_inits ? s0 * n_eq : s0) * gcode.nw * wbytes;
         p.n_chains = sw * n_eq * cfg->droplets;
         p.chain_offset = s0 * n_eq * cfg->droplets;
@@ -469,7 +495,32 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
         else QTRY(launch_stdc_mode<MODE_MEAN>(c, p, wide, cfg->u_nb != nullptr));
         CUDA_OK(cudaEventRecord(c->ev[3], c->stream));
         const int64_t tabs = sw * n_eq;
-        if (mode != MODE_MEAN) {
+        if (mode != MODE_MEAN && use_logs) {
+            DedupeParams dp;
+            dp.logs = (const unsigned long long *)c->tables.p;
+            dp.log_counts = (const uint32_t *)c->log_counts.p;
+            dp.log_cap = log_cap;
+            dp.droplets = cfg->droplets;
+            dp.tabs = tabs;
+            dp.scratch = (unsigned long long *)c->dd_scratch.p;
+            dp.scratch_cap = (int64_t)cfg->droplets * log_cap;
+            dp.nsites = gcode.nsites;
+            dp.beta = beta;
+            dp.Z = (double *)c->Z.p + s0 * n_eq;
+            dp.N_hist = d_nh ? d_nh + (size_t)s0 * n_eq * nh : nullptr;
+            dp.distinct = (unsigned long long *)c->counters.p + 3;
+            dp.err = (int *)c->scratch.p + 1;
+            const size_t dsm = (size_t)QECMC_DD_HASH_SLOTS * 8 + 4096 * 4 + (size_t)QECMC_DD_MAX_BUCKETS * 8;
+            CUDA_OK(cudaFuncSetAttribute(log_dedupe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+            CUDA_OK(cudaMemsetAsync(dp.err, 0, sizeof(int), c->stream));
+            log_dedupe_kernel<<<(unsigned)(tabs < dd_grid ? tabs : dd_grid), QECMC_DD_THREADS, dsm, c->stream>>>(dp);
+            c->launches++;
+            CUDA_OK(cudaGetLastError());
+            int derr = 0;
+            CUDA_OK(cudaMemcpyAsync(&derr, dp.err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_OK(cudaStreamSynchronize(c->stream));
+            if (derr) return set_err(QECMC_ERR_UNSUPPORTED, "internal: key-log dedupe overflow (%d)", derr);
+        } else if (mode != MODE_MEAN) {
             table_hist_kernel<<<(unsigned)tabs, 512, nh * sizeof(uint32_t), c->stream>>>(
                 (const unsigned long long *)c->tables.p, cap, gcode.nsites, beta, (double *)c->Z.p + s0 * n_eq,
                 d_nh ? d_nh + (size_t)s0 * n_eq * nh : nullptr, (unsigned long long *)c->counters.p + 3);

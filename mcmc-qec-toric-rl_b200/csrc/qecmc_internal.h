@@ -58,7 +58,7 @@ struct qecmc_ctx {
         shorts, sums;
     std::map<std::tuple<int, int, int>, uint64_t *> stab_hash;  // (geom, L, wide) -> device table
     std::map<std::tuple<int, int, int>, uint2 *> stab_desc;     // (geom, L, wide) -> descriptor table
-    DevBuf lut, log_hash;
+    DevBuf lut, log_hash, log_counts, dd_scratch;
     cudaEvent_t ev[4];
     uint64_t hash_seed = 0x5EEDC0DE2020ull;
     int64_t launches = 0;

@@ -177,7 +177,11 @@ struct StdcParams {
     Thr thr;
     const double *u_nb, *u_np;
     unsigned long long *counters;  // [0] accepted [1] offered [2] inserted
-    int insert_mode;               // 2 asynchronous CAS (default); diagnostics: 0 synchronous probe, 3 no inserts
+    int insert_mode;               // 4 per-chain key logs + log_dedupe_kernel (default when applicable); 2 prefetch + deferred
+                                   // probe of the HBM set; 1 asynchronous CAS; diagnostics: 0 synchronous probe, 3 no inserts
+    unsigned long long *logs;      // insert_mode 4: [n_chains][log_cap] offered keys, in order
+    uint32_t *log_counts;          // [n_chains]
+    int64_t log_cap;
     // STRC (decoders.py:745-832): visits per length m(n), per droplet shortest / next-shortest visited length
     unsigned long long *m_hist;    // [S_wave * n_eq][nsites + 1]
     int *short_out;                // [n_chains][2]
@@ -315,7 +319,8 @@ __global__ void __launch_bounds__(256) stdc_kernel(StdcParams p)
     }
     int n = lat_weight<W>(g, lat);
     uint64_t h = lat_hash<W>(g, lat, p.hash_seed);
-    unsigned long long *table = p.tables + (uint64_t)tab * (p.cap_mask + 1);
+    const bool log_mode = MODE != MODE_MEAN && p.insert_mode == 4 && p.conv_mult == 0.0;
+    unsigned long long *table = log_mode ? p.logs + (uint64_t)local * (uint64_t)p.log_cap : p.tables + (uint64_t)tab * (p.cap_mask + 1);
     SampleAcct<MODE> acct;
     acct.init(p, tab);
     ConvStop cs;
@@ -332,7 +337,10 @@ __global__ void __launch_bounds__(256) stdc_kernel(StdcParams p)
         left = p.iters;                                                     \
         acct.sample(n);                                                     \
         bool is_new = false;                                                \
-        if (MODE != MODE_MEAN && dirty) { noff++; is_new = table_insert(table, p.cap_mask, make_key(h, n)); nins += is_new; } \
+        if (MODE != MODE_MEAN && dirty) {                                   \
+            if (log_mode) table[noff++] = make_key(h, n);                   \
+            else { noff++; is_new = table_insert(table, p.cap_mask, make_key(h, n)); nins += is_new; } \
+        }                                                                   \
         dirty = false;                                                      \
         cs.after_sample(p, is_new, n);                                      \
     }
@@ -369,6 +377,7 @@ __global__ void __launch_bounds__(256) stdc_kernel(StdcParams p)
         }
     }
 #undef QECMC_AFTER_STEP
+    if (log_mode) p.log_counts[local] = (uint32_t)noff;
     acct.finish(p, local);
     // statistics: three atomics per chain at the very end (negligible)
     atomicAdd(p.counters + 0, nacc);

@@ -17,6 +17,8 @@ namespace qecmc {
 
 // descriptor words:  x = sh | w0<<8 | w1<<16 | w2<<24
 //                    y = sh2 | f_and<<8 | f_or<<16 | (v==3)<<24
+#define QECMC_FAST_STATIC_NSTAB 512   // 2 * 16 * 16: every two-layer code with 32-bit row words
+
 struct FastTables {
     const uint2 *desc;       // [nstab]
     const uint32_t *thr;     // [512] native thresholds by (v==3)*256 + f
@@ -46,22 +48,41 @@ template <> __device__ __forceinline__ uint32_t gather_fields<uint64_t>(uint64_t
     return qa | (qb << 2) | (qc << 4) | (qd << 6);
 }
 
+// One asynchronous probe of the distinct set: atom.cas with the old word landing in `prev`, which is read a sample
+// later.  Inline PTX pins `prev` as the destination register: with the atomicCAS intrinsic and more than one
+// call site the compiler returned the word in a scratch pair and copied it out right behind the atom, which
+// parks the warp on the memory scoreboard for the whole HBM round trip.
+__device__ __forceinline__ void cas_async(unsigned long long &prev, unsigned long long *addr, unsigned long long key)
+{
+    asm volatile("atom.global.cas.b64 %0, [%1], %2, %3;" : "=l"(prev) : "l"(addr), "l"(0ull), "l"(key));
+}
+
+__device__ __forceinline__ void prefetch_l2(const void *addr)
+{
+    asm volatile("prefetch.global.L2 [%0];" : : "l"(addr));
+}
+
 // CONV = false drops the conv_mult early-stop state (ConvStop) from the loop: the headline configuration
 // (conv_mult == 0) then fits the register budget of five 256-thread CTAs per SM.
+// Shared memory: the LUTs are static arrays, and for 32-bit row words (L <= 16, at most 512 stabilizers) so are the
+// descriptors and fingerprints, which makes every table address an immediate; the lattice tile is the dynamic part.
 template <int GEOM, typename W, bool REPLAY, int MODE, bool CONV>
 __global__ void __launch_bounds__(256, CONV ? (sizeof(W) == 4 ? 4 : 2) : (sizeof(W) == 4 ? 5 : 3)) stdc_fast_kernel(StdcParams p, FastTables ft, PhiloxKeys keys)
 {
     static_assert(GEOM == TORIC || GEOM == PLANAR, "table-driven kernel covers the two-layer codes");
+    constexpr bool STATIC_TAB = sizeof(W) == 4;
+    constexpr int NTAB = STATIC_TAB ? QECMC_FAST_STATIC_NSTAB : 1;
     extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint32_t s_thr[512];
+    __shared__ int8_t s_dE[512];
+    __shared__ double s_thrd[QECMC_THR_N];
+    __shared__ uint64_t s_hs_st[NTAB];
+    __shared__ uint2 s_desc_st[NTAB];
     const int T = blockDim.x, tid = threadIdx.x;
     const Geo g = p.gchain;
     W *tile = reinterpret_cast<W *>(smem);
-    unsigned char *sp = smem + (((size_t)g.nw * T * sizeof(W) + 15) & ~(size_t)15);
-    uint64_t *s_hs = reinterpret_cast<uint64_t *>(sp);
-    uint2 *s_desc = reinterpret_cast<uint2 *>(s_hs + g.nstab);
-    uint32_t *s_thr = reinterpret_cast<uint32_t *>(s_desc + g.nstab);
-    int8_t *s_dE = reinterpret_cast<int8_t *>(s_thr + 512);
-    __shared__ double s_thrd[QECMC_THR_N];
+    uint64_t *s_hs = STATIC_TAB ? s_hs_st : reinterpret_cast<uint64_t *>(smem + (((size_t)g.nw * T * sizeof(W) + 15) & ~(size_t)15));
+    uint2 *s_desc = STATIC_TAB ? s_desc_st : reinterpret_cast<uint2 *>(s_hs + g.nstab);
     for (int i = tid; i < g.nstab; i += T) { s_hs[i] = p.stab_hash[i]; s_desc[i] = ft.desc[i]; }
     for (int i = tid; i < 512; i += T) { s_thr[i] = ft.thr[i]; s_dE[i] = ft.dE[i]; }
     if (tid < QECMC_THR_N) s_thrd[tid] = p.thr.d[tid];
@@ -101,20 +122,20 @@ __global__ void __launch_bounds__(256, CONV ? (sizeof(W) == 4 ? 4 : 2) : (sizeof
     }
     int n = lat_weight<W>(g, lat);
     uint64_t h = lat_hash<W>(g, lat, p.hash_seed);
-    unsigned long long *table = p.tables + (uint64_t)tab * (p.cap_mask + 1);
     const uint64_t cap_mask = p.cap_mask;
+    const int imode = MODE == MODE_MEAN ? 3 : (CONV && p.conv_mult != 0.0 ? 0 : p.insert_mode);  // the early stop needs the probe's answer now
+    // log mode: `table` is this chain's key log
+    unsigned long long *table = imode == 4 ? p.logs + (uint64_t)local * (uint64_t)p.log_cap : p.tables + (uint64_t)tab * (cap_mask + 1);
 
     uint32_t nacc = 0, noff = 0;
     bool dirty = true;  // the first sample is always new to the chain
     int left = p.iters;
-    // Asynchronous distinct-set inserts: a sample's key goes straight to atomicCAS(slot, 0, key) and the
-    // returned word is only looked at one sample (>= iters Metropolis steps) later, so the chain never
-    // waits on HBM.  A collision re-issues the CAS on the next slot and stays pending.  Two entries in
-    // flight per chain; only if both are still colliding when a third key arrives is one drained in place.
-    uint64_t keyA = 0, prevA = 0, keyB = 0, prevB = 0;
-    uint32_t slotA = 0, slotB = 0;
+    // Distinct-chain accounting by insert mode: 4 (default) appends the key to this chain's log and leaves the counting to
+    // log_dedupe_kernel; 2 prefetches the set's slot at one sample and probes it at the next; 1 issues atom.cas at once
+    // and reads the returned word a sample later (the table modes serve conv_mult and oversized key counts).
+    unsigned long long key = 0, prev = 0;   // key != 0: `key` is waiting for / looking at `slot`; `prev`: mode 1's answer
+    uint32_t slot = 0;
     const uint32_t smask = (uint32_t)cap_mask;  // host guarantees cap <= 2^32 slots
-    const int imode = MODE == MODE_MEAN ? 3 : (CONV && p.conv_mult != 0.0 ? 0 : p.insert_mode);  // the early stop needs the probe's answer now
     ConvStopT<CONV> cs;
     cs.init(p);
     SampleAcct<MODE> acct;
@@ -122,12 +143,6 @@ __global__ void __launch_bounds__(256, CONV ? (sizeof(W) == 4 ? 4 : 2) : (sizeof
     unsigned char *mybase = reinterpret_cast<unsigned char *>(tile + tid);
     const uint32_t wstride = (uint32_t)T * sizeof(W);
 
-#define QECMC_PROBE_DONE(prev, key) ((prev) == 0ull || (prev) == (key))
-#define QECMC_PROBE_NEXT(slot, prev, key)                                              \
-    do {                                                                               \
-        slot = (slot + 1u) & smask;                                                    \
-        prev = atomicCAS(table + slot, 0ull, (unsigned long long)(key));               \
-    } while (0)
     // one Metropolis step for stabilizer idx; r_acc / u_acc is the accept draw
     auto step = [&](int idx, uint32_t r_acc, double u_acc) {
         const uint2 d = s_desc[idx];
@@ -168,27 +183,46 @@ __global__ void __launch_bounds__(256, CONV ? (sizeof(W) == 4 ? 4 : 2) : (sizeof
             left = p.iters;
             acct.sample(n);
             bool is_new = false;
-            const uint64_t nkey = make_key(h, n);
-            const uint32_t nslot = (uint32_t)(nkey >> QECMC_LEN_BITS) & smask;
-            if (imode == 2) {
-                if (keyA) {
-                    if (QECMC_PROBE_DONE(prevA, keyA)) keyA = 0;
-                    else QECMC_PROBE_NEXT(slotA, prevA, keyA);
-                }
-                if (keyB) {
-                    if (QECMC_PROBE_DONE(prevB, keyB)) keyB = 0;
-                    else QECMC_PROBE_NEXT(slotB, prevB, keyB);
+            if (imode == 4) {
+                if (dirty) table[noff] = make_key(h, n);   // fire-and-forget store; log_dedupe_kernel counts later
+            } else if (imode == 2) {
+                // Two-phase insert: the sample that produces a key only prefetches its slot's sector into L2 (no
+                // destination register, so nothing to wait for); the probe itself runs one sample later against a
+                // line that is by then L2-resident, and a collision walks on within the same sector 3 times in 4.
+                if (key) {
+                    unsigned long long q;
+                    do {
+                        q = atomicCAS(table + slot, 0ull, key);
+                        slot = (slot + 1u) & smask;
+                    } while (q != 0ull && q != key);
+                    key = 0;
                 }
                 if (dirty) {
-                    if (keyA && keyB) {  // rare: both entries still colliding
-                        while (!QECMC_PROBE_DONE(prevA, keyA)) QECMC_PROBE_NEXT(slotA, prevA, keyA);
-                        keyA = 0;
-                    }
-                    if (!keyA) { keyA = nkey; slotA = nslot; prevA = atomicCAS(table + nslot, 0ull, (unsigned long long)nkey); }
-                    else { keyB = nkey; slotB = nslot; prevB = atomicCAS(table + nslot, 0ull, (unsigned long long)nkey); }
+                    key = make_key(h, n);
+                    slot = (uint32_t)(key >> QECMC_LEN_BITS) & smask;
+                    prefetch_l2(table + slot);
                 }
+            } else if (imode == 1) {
+                bool fire = false;
+                if (key) {
+                    if (prev == 0ull || prev == key) key = 0;
+                    else { slot = (slot + 1u) & smask; fire = true; }
+                }
+                if (dirty) {
+                    if (key) {  // the previous key is still looking for its slot: finish it here
+                        unsigned long long q;
+                        do {
+                            q = atomicCAS(table + slot, 0ull, key);
+                            slot = (slot + 1u) & smask;
+                        } while (q != 0ull && q != key);
+                    }
+                    key = make_key(h, n);
+                    slot = (uint32_t)(key >> QECMC_LEN_BITS) & smask;
+                    fire = true;
+                }
+                if (fire) cas_async(prev, table + slot, key);
             } else if (imode == 0) {
-                if (dirty) is_new = table_insert(table, cap_mask, nkey);
+                if (dirty) is_new = table_insert(table, cap_mask, make_key(h, n));
             }
             noff += dirty;
             dirty = false;
@@ -218,12 +252,20 @@ __global__ void __launch_bounds__(256, CONV ? (sizeof(W) == 4 ? 4 : 2) : (sizeof
             step((int)__umulhi(r.x, nstab), r.y, 0.0);
         }
     }
-    if (imode == 2) {
-        if (keyA) while (!QECMC_PROBE_DONE(prevA, keyA)) QECMC_PROBE_NEXT(slotA, prevA, keyA);
-        if (keyB) while (!QECMC_PROBE_DONE(prevB, keyB)) QECMC_PROBE_NEXT(slotB, prevB, keyB);
+    if (imode == 1 && key) {
+        while (prev != 0ull && prev != key) {
+            slot = (slot + 1u) & smask;
+            prev = atomicCAS(table + slot, 0ull, key);
+        }
     }
-#undef QECMC_PROBE_DONE
-#undef QECMC_PROBE_NEXT
+    if (imode == 2 && key) {
+        unsigned long long q;
+        do {
+            q = atomicCAS(table + slot, 0ull, key);
+            slot = (slot + 1u) & smask;
+        } while (q != 0ull && q != key);
+    }
+    if (imode == 4) p.log_counts[local] = noff;
     acct.finish(p, local);
     atomicAdd(p.counters + 0, (unsigned long long)nacc);
     atomicAdd(p.counters + 1, (unsigned long long)noff);

@@ -1,0 +1,21 @@
+"""Small driver for ncu captures of the tempering-ladder kernel: one GPU-filling PTEQ launch of a given config."""
+import sys, os
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from mcmc_qec_toric_rl_b200 import _lib
+
+which = sys.argv[1] if len(sys.argv) > 1 else "rotated25"
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+S = int(sys.argv[3]) if len(sys.argv) > 3 else 4736
+ctx = _lib.Context(0)
+rng = np.random.default_rng(3)
+if which == "rotated25":
+    g, L, kind, bottom, b = _lib.ROTATED, 25, _lib.LADDER_DEPOLARIZING, 0.15, 0.0
+elif which == "xzzx21_biased":
+    g, L, kind, bottom, b = _lib.XZZX, 21, _lib.LADDER_BIASED, 0.15, 100.0
+else:
+    g, L, kind, bottom, b = _lib.XZZX, 21, _lib.LADDER_ALPHA, 0.17474, 0.6447
+q = ((rng.random((S, L * L)) < 0.15) * rng.integers(1, 4, (S, L * L))).astype(np.uint8)
+pct, info = ctx.pteq(g, L, kind, q, bottom, param_b=b, steps=steps, conv=False, seed=11)
+st = info["stats"]
+print(which, "S", S, "steps", steps, "kernel_ms", st["chain_kernel_ms"], "metropolis steps/s", st["metropolis_steps"] / (st["chain_kernel_ms"] * 1e-3))

@@ -691,3 +691,27 @@ def test_chain_xyz_replay_matches_reference_golden_and_oracle(ctx):
         for i in range(20):
             want = O.update_chain_fast_xyz(g, L, qm[i], ps / (1 - ps.sum()), 200, O.Stream.replay(u[i].reshape(-1)))
             assert np.array_equal(got[i], want)
+
+
+# ------------------------------------------------------------------ key logs + dedupe kernel vs the HBM set
+@pytest.mark.parametrize("g,L,droplets,steps", [(O.TORIC, 7, 16, 20000), (O.PLANAR, 9, 64, 6000), (O.TORIC, 15, 7, 9001),
+                                                (O.TORIC, 5, 1, 333)])
+def test_log_dedupe_equals_table_set(ctx, g, L, droplets, steps, monkeypatch):
+    """The same native chains counted two ways: per-chain key logs reduced by log_dedupe_kernel (bucketed shared-memory
+    sets; default) and the open-addressing set in HBM.  N(n), the class distributions' inputs, must agree exactly --
+    this exercises the multi-bucket path (tens of thousands of keys per table) that the small replay cases do not."""
+    rng = np.random.default_rng(4000 + L)
+    S = 5
+    qm = np.stack([rand_lattice(rng, g, L, 0.12).reshape(-1) for _ in range(S)])
+    outs = {}
+    for mode in ("4", "2", "0"):
+        monkeypatch.setenv("QECMC_DEBUG_INSERT_MODE", mode)
+        out, st, hist = ctx.stdc(g, g, L, qm, 0.12, 0.3, droplets, steps, seed=99, want_hist=True)
+        outs[mode] = (out, st, hist)
+    monkeypatch.delenv("QECMC_DEBUG_INSERT_MODE")
+    assert outs["4"][1]["table_slots"] == 0 and outs["2"][1]["table_slots"] > 0      # really two different paths
+    for mode in ("2", "0"):
+        assert np.array_equal(outs["4"][2], outs[mode][2])
+        assert outs["4"][1]["distinct"] == outs[mode][1]["distinct"]
+        assert np.allclose(outs["4"][0], outs[mode][0], rtol=1e-12)
+    assert outs["4"][1]["distinct"] > 0.1 * S * O.neq(g) * droplets * steps * 0.1
