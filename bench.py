@@ -33,7 +33,10 @@ SAMPLES = L ** 4
 ITERS = 5
 N_EQ = 16
 W_INT = 170.0      # int32 lane-ops per toric/planar depolarizing Metropolis step (agreed figure)
-W_HBM = 16.0 / 5   # bytes of distinct-set traffic per Metropolis step (8 B probe + 8 B insert per 5-step sample)
+W_LOG = 8.0        # bytes a chain appends to its key log per offered sample (the chain kernel's only steady HBM traffic)
+# ncu, full-size launch of this exact command (profiles/r01_ncu_fullsize_stdc_v6.csv): warp instructions and DRAM bytes
+NCU_CHAIN = {"file": "profiles/r01_ncu_fullsize_stdc_v6.csv", "warp_inst_per_launch": 148783220588, "dram_bytes_per_launch": 6104559104 + 27513273088,
+             "issue_active_pct": 67.10, "steps_per_launch": 185 * 16 * 64 * 50625 * 5}
 
 
 def synth_syndromes(n, seed, L=L, p=P_ERROR):
@@ -153,7 +156,7 @@ def run_reference(args, rank, world):
 def workload_config(batch, n_gpus):
     return {"workload": "toric d=15 depolarizing p=0.15, STDC: 16 classes x 64 chains x 15^4 samples x 5 steps, p_sampling=0.25",
             "syndromes_per_step_per_gpu": batch, "parallelism": f"syndrome-sharded x{n_gpus}, no collective",
-            "l2": "working set = distinct-chain tables (tens of GB, re-zeroed every step) >> 126 MB L2"}
+            "l2": "working set = per-chain key logs (tens of GB, rewritten every step) >> 126 MB L2"}
 
 
 def main():
@@ -198,10 +201,9 @@ def main():
     steps_per_syndrome = N_EQ * DROPLETS * samples * ITERS
     # table arena: leave room for torch + staging
     ctx.set_table_budget(int(info["free_mem"] * 0.88))
-    cap = 1
-    while cap < DROPLETS * samples * 1.25 + 1:
-        cap *= 2
-    fit = int(info["free_mem"] * 0.88) // (N_EQ * cap * 8)
+    log_cap = (samples + 1) & ~1                               # key-log entries per chain
+    scratch = info["sm_count"] * DROPLETS * log_cap * 8        # dedupe kernel: one table's keys per CTA
+    fit = (int(info["free_mem"] * 0.88) - scratch) // (N_EQ * DROPLETS * log_cap * 8)
     fill = (info["sm_count"] * 1280) // (N_EQ * DROPLETS)  # chains resident per wave at 1280 threads/SM
     batch = args.syndromes or max(1, min(fit, fill))
     n_steps = args.steps + args.warmup
@@ -236,9 +238,11 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     kern_ms, launches, accepted, offered, distinct = 0.0, 0, 0, 0, 0
+    call_ms = []
     for k in range(args.warmup, n_steps):
         st = step_dev(k)
         kern_ms += st["chain_kernel_ms"]
+        call_ms.append(round(st["total_ms"], 2))
         launches += st["kernel_launches"]
         accepted += st["accepted"]
         offered += st["samples"]
@@ -280,7 +284,8 @@ def main():
     peak_ops = info["sm_count"] * 128 * sm_max_mhz * 1e6            # int32 lane-ops/s, one GPU
     kern_steps_per_s = batch * steps_per_syndrome * args.steps / (kern_ms * 1e-3)   # per GPU, chain kernel only
     achieved_ops = kern_steps_per_s * W_INT
-    hbm_alg = (offered / args.steps) * 16.0 / ((kern_ms / args.steps) * 1e-3) / 1e9  # GB/s, rank 0
+    hbm_alg = (offered / args.steps) * W_LOG / ((kern_ms / args.steps) * 1e-3) / 1e9  # GB/s, rank 0
+    full_size = samples == SAMPLES and batch * steps_per_syndrome == NCU_CHAIN["steps_per_launch"]
     line = {
         "metric": "metropolis_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -292,14 +297,24 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "alu", "achieved": achieved_ops / 1e12, "peak": peak_ops / 1e12, "unit": "Tlaneop/s",
-                     "frac": achieved_ops / peak_ops, "traffic": None,
+                     "frac": achieved_ops / peak_ops,
+                     "traffic": NCU_CHAIN["dram_bytes_per_launch"] if full_size else None,
+                     "issue": {"what": "issue slots the kernel really spends (ncu smsp__inst_executed x 32 lanes / steps) and the share of "
+                                       "issue cycles used; the agreed 170 lane-ops per step of SURVEY.md 8d is an estimate made before "
+                                       "the kernel existed",
+                               "lane_slots_per_step": NCU_CHAIN["warp_inst_per_launch"] * 32 / NCU_CHAIN["steps_per_launch"],
+                               "issue_active_pct_ncu": NCU_CHAIN["issue_active_pct"],
+                               "frac_at_measured_slots": kern_steps_per_s * (NCU_CHAIN["warp_inst_per_launch"] * 32 / NCU_CHAIN["steps_per_launch"]) / peak_ops,
+                               "source": NCU_CHAIN["file"]},
                      "kernel": "stdc_fast_kernel<TORIC,u32,native,STDC>", "kernel_ms_per_launch": kern_ms / (args.steps * waves),
                      "units_per_launch": batch * steps_per_syndrome / waves, "algorithmic_laneops_per_step": W_INT,
                      "peak_source": f"{info['sm_count']} SMs x 128 int32 lanes x {sm_max_mhz:.0f} MHz ({peak_src} max SM clock)",
                      "note": "north_star: this path is integer-issue bound, not HBM or tensor bound (SURVEY.md 8d)",
                      "hbm": {"achieved": hbm_alg, "peak": float(peaks.get("hbm_gbs", 6650.0)), "unit": "GB/s",
                              "frac": hbm_alg / float(peaks.get("hbm_gbs", 6650.0)),
-                             "what": "distinct-set probes+inserts, 16 B per offered sample", "peak_source": peak_src}},
+                             "what": "key-log appends, 8 B per offered sample (the dedupe kernel streams them afterwards)",
+                             "peak_source": peak_src},
+                     "other_kernels_ms_per_step": (ms - kern_ms) / args.steps, "call_ms": call_ms},
         "chain_stats": {"accept_rate": accepted / (batch * steps_per_syndrome * args.steps),
                         "offered_per_sample": offered / (batch * N_EQ * DROPLETS * samples * args.steps),
                         "distinct_per_sample": distinct / (batch * N_EQ * DROPLETS * samples * args.steps),

@@ -304,10 +304,11 @@ static int launch_stdc_fast(qecmc_ctx *c, StdcParams &p)
     if (static_tab && p.gchain.nstab > QECMC_FAST_STATIC_NSTAB) return set_err(QECMC_ERR_UNSUPPORTED, "internal: %d stabilizers exceed the static tables", p.gchain.nstab);
     size_t stat = 512 * 5 + 128 + (static_tab ? (size_t)QECMC_FAST_STATIC_NSTAB * 16 : 0);
     size_t dyn_fixed = static_tab ? 0 : (size_t)p.gchain.nstab * 16 + 16;
-    QTRY(pick_threads(per_chain, stat + dyn_fixed + 256, c->prop, &T, &nb));
+    const bool conv = REPLAY || p.conv_mult != 0.0;
+    QTRY(pick_threads(per_chain, stat + dyn_fixed + 256, c->prop, &T, &nb, static_tab && !conv, conv ? 56 : 48));
     size_t smem = ((per_chain * T + 15) & ~(size_t)15) + dyn_fixed;
     unsigned grid = (unsigned)((p.n_chains + T - 1) / T);
-    if (REPLAY || p.conv_mult != 0.0) {
+    if (conv) {
         CUDA_OK(cudaFuncSetAttribute(stdc_fast_kernel<GEOM, W, REPLAY, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         stdc_fast_kernel<GEOM, W, REPLAY, MODE, true><<<grid, T, smem, c->stream>>>(p, ft, keys);
     } else {
@@ -510,7 +511,7 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
             dp.N_hist = d_nh ? d_nh + (size_t)s0 * n_eq * nh : nullptr;
             dp.distinct = (unsigned long long *)c->counters.p + 3;
             dp.err = (int *)c->scratch.p + 1;
-            const size_t dsm = (size_t)QECMC_DD_HASH_SLOTS * 8 + 4096 * 4 + (size_t)QECMC_DD_MAX_BUCKETS * 8;
+            const size_t dsm = (size_t)QECMC_DD_HASH_SLOTS * QECMC_DD_GROUPS * 8 + 4096 * 4 + (size_t)QECMC_DD_MAX_BUCKETS * 8 + QECMC_DD_MAX_CNT * 4;
             CUDA_OK(cudaFuncSetAttribute(log_dedupe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
             CUDA_OK(cudaMemsetAsync(dp.err, 0, sizeof(int), c->stream));
             log_dedupe_kernel<<<(unsigned)(tabs < dd_grid ? tabs : dd_grid), QECMC_DD_THREADS, dsm, c->stream>>>(dp);

@@ -8,6 +8,7 @@
 //   A  bucket histogram of the table's keys (low fingerprint bits)
 //   B  scatter into the CTA's scratch area, bucket by bucket
 //   C  per bucket: insert into a shared-memory hash set; a key new to the set bumps N(len)
+// Buckets take ~1024 logged keys; the set of a bucket has 4096 slots.
 // One CTA owns one table at a time, so there is no inter-CTA synchronisation.  Same semantics as the global set:
 // the distinct keys of all droplets of the class (STDC_droplet / STDC, decoders.py:236-322).
 #pragma once
@@ -16,9 +17,13 @@
 namespace qecmc {
 
 #define QECMC_DD_THREADS 1024
-#define QECMC_DD_HASH_SLOTS 16384   // 128 KiB of shared memory
+#define QECMC_DD_GROUPS 4           // independent groups of 256 threads in step C, one bucket each at a time
+#define QECMC_DD_HASH_SLOTS 4096    // per group; four sets = 128 KiB of shared memory
 #define QECMC_DD_MAX_BUCKETS 4096
-#define QECMC_DD_BUCKET_TARGET 6144 // keys per bucket aimed for: load <= 0.5 with room for fluctuation
+#define QECMC_DD_BUCKET_TARGET 1024 // logged keys per bucket aimed for (distinct keys load the set to <= 0.25 on average)
+#define QECMC_DD_KPT 4              // keys per thread held in registers: one chunk = 1024 keys per group
+#define QECMC_DD_SEG_PAIRS 512      // a warp streams a chain's log in segments of 512 16-byte pairs
+#define QECMC_DD_MAX_CNT 1024       // chain counts staged in shared memory up to this many droplets
 
 struct DedupeParams {
     const unsigned long long *logs;  // [chains][log_cap]
@@ -33,87 +38,107 @@ struct DedupeParams {
     double *Z;                       // [tabs]
     uint32_t *N_hist;                // [tabs][nsites + 1], optional
     unsigned long long *distinct;    // += distinct keys
-    int *err;                        // set if a bucket cannot fit the shared-memory set
+    int *err;                        // 1: a shared-memory set filled up, 2: scratch too small
 };
 
-__device__ __forceinline__ void dd_insert(unsigned long long *hash, uint32_t mask, int shift, unsigned long long key, uint32_t *hist)
+// insert into a shared-memory set of mask + 1 slots; a key new to the set bumps N(len)
+__device__ __forceinline__ void dd_insert(unsigned long long *hash, uint32_t mask, int shift, unsigned long long key, uint32_t *hist, int *err)
 {
     uint32_t slot = (uint32_t)(key >> shift) & mask;
-    while (true) {
+    for (uint32_t tries = 0; tries <= mask; tries++) {
         unsigned long long prev = atomicCAS(hash + slot, 0ull, key);
         if (prev == 0ull) { atomicAdd(hist + (uint32_t)(key & QECMC_LEN_MASK), 1u); return; }
         if (prev == key) return;
         slot = (slot + 1u) & mask;
     }
+    *err = 1;
 }
 
-// visit every logged key of table `tab`: chains one after the other, 16-byte loads, two per thread in flight
-template <typename F> __device__ __forceinline__ void dd_for_each_key(const DedupeParams &p, int64_t tab, F f)
+// Visit every logged key of table `tab`.  Work items are (chain, segment of 512 pairs), dealt to the warps round-robin;
+// a lane keeps four 16-byte loads in flight.  s_cnt: the chains' key counts (shared memory), max_cnt their maximum.
+template <typename F>
+__device__ __forceinline__ void dd_for_each_key(const DedupeParams &p, int64_t tab, const uint32_t *s_cnt, uint32_t max_cnt, F f)
 {
-    const int tid = threadIdx.x;
-    for (int d = 0; d < p.droplets; d++) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t segs = (max_cnt / 2 + QECMC_DD_SEG_PAIRS - 1) / QECMC_DD_SEG_PAIRS + 1;   // +1: the odd tail item
+    const uint32_t items = (uint32_t)p.droplets * segs;
+    for (uint32_t t = warp; t < items; t += QECMC_DD_THREADS / 32) {
+        const uint32_t d = t / segs, sg = t - d * segs;
         const int64_t chain = tab * p.droplets + d;
-        const uint32_t c = p.log_counts[chain];
-        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(p.logs + chain * p.log_cap);
+        const uint32_t c = d < QECMC_DD_MAX_CNT ? s_cnt[d] : p.log_counts[chain];
         const uint32_t pairs = c >> 1;
-        uint32_t i = tid;
-        for (; i + QECMC_DD_THREADS < pairs; i += 2 * QECMC_DD_THREADS) {
-            ulonglong2 a = __ldcs(src + i), b = __ldcs(src + i + QECMC_DD_THREADS);
-            f(a.x); f(a.y); f(b.x); f(b.y);
+        if (sg == segs - 1) {   // tail item: the last key of an odd-length log
+            if ((c & 1u) && lane == 0) f(p.logs[chain * p.log_cap + c - 1]);
+            continue;
         }
-        for (; i < pairs; i += QECMC_DD_THREADS) {
+        const uint32_t lo = sg * QECMC_DD_SEG_PAIRS;
+        if (lo >= pairs) continue;
+        const uint32_t hi = min(pairs, lo + QECMC_DD_SEG_PAIRS);
+        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(p.logs + chain * p.log_cap);
+        uint32_t i = lo + lane;
+        for (; i + 96 < hi; i += 128) {
+            ulonglong2 a0 = __ldcs(src + i), a1 = __ldcs(src + i + 32), a2 = __ldcs(src + i + 64), a3 = __ldcs(src + i + 96);
+            f(a0.x); f(a0.y); f(a1.x); f(a1.y); f(a2.x); f(a2.y); f(a3.x); f(a3.y);
+        }
+        for (; i < hi; i += 32) {
             ulonglong2 a = __ldcs(src + i);
             f(a.x); f(a.y);
         }
-        if ((c & 1u) && tid == 0) f(p.logs[chain * p.log_cap + c - 1]);
     }
 }
 
 __global__ void __launch_bounds__(QECMC_DD_THREADS, 1) log_dedupe_kernel(DedupeParams p)
 {
+    constexpr int T = QECMC_DD_THREADS, HS = QECMC_DD_HASH_SLOTS, KPT = QECMC_DD_KPT, GT = QECMC_DD_THREADS / QECMC_DD_GROUPS;
     extern __shared__ __align__(16) unsigned char dsm[];
-    unsigned long long *hash = reinterpret_cast<unsigned long long *>(dsm);
-    uint32_t *hist = reinterpret_cast<uint32_t *>(hash + QECMC_DD_HASH_SLOTS);
+    unsigned long long *hash = reinterpret_cast<unsigned long long *>(dsm);   // one set of HS slots per group
+    uint32_t *hist = reinterpret_cast<uint32_t *>(hash + QECMC_DD_GROUPS * HS);   // [4096] N(len)
     uint32_t *bcnt = hist + 4096;                     // keys per bucket
-    uint32_t *boff = bcnt + QECMC_DD_MAX_BUCKETS;     // exclusive prefix, then scatter cursor
+    uint32_t *boff = bcnt + QECMC_DD_MAX_BUCKETS;     // exclusive prefix, then scatter cursor (= bucket end afterwards)
+    uint32_t *s_cnt = boff + QECMC_DD_MAX_BUCKETS;    // [QECMC_DD_MAX_CNT] keys per chain
     __shared__ unsigned long long s_total;
+    __shared__ uint32_t s_max;
     __shared__ uint32_t s_warp[32];
     const int tid = threadIdx.x;
     unsigned long long *scratch = p.scratch + (uint64_t)blockIdx.x * p.scratch_cap;
     const int nh = p.nsites + 1;
 
     for (int64_t tab = blockIdx.x; tab < p.tabs; tab += gridDim.x) {
-        if (tid == 0) s_total = 0;
-        for (int i = tid; i < nh; i += QECMC_DD_THREADS) hist[i] = 0;
+        if (tid == 0) { s_total = 0; s_max = 0; }
+        for (int i = tid; i < nh; i += T) hist[i] = 0;
+        for (int i = tid; i < HS; i += T) hash[i] = 0ull;   // the single-set path below uses group 0's set
         __syncthreads();
         {
             unsigned long long loc = 0;
-            for (int d = tid; d < p.droplets; d += QECMC_DD_THREADS) loc += p.log_counts[tab * p.droplets + d];
-            if (loc) atomicAdd(&s_total, loc);
+            uint32_t mx = 0;
+            for (int d = tid; d < p.droplets; d += T) {
+                uint32_t c = p.log_counts[tab * p.droplets + d];
+                if (d < QECMC_DD_MAX_CNT) s_cnt[d] = c;
+                loc += c;
+                mx = max(mx, c);
+            }
+            if (loc) { atomicAdd(&s_total, loc); atomicMax(&s_max, mx); }
         }
         __syncthreads();
         const uint64_t total = s_total;
+        const uint32_t max_cnt = s_max;
         int lg = 0;
         while (lg < 12 && ((uint64_t)QECMC_DD_BUCKET_TARGET << lg) < total) lg++;
         const uint32_t NB = 1u << lg;
         const int shift = QECMC_LEN_BITS + lg;       // set slots come from the fingerprint bits above the bucket bits
         if (lg == 0) {
             // everything fits one shared-memory set: insert straight from the logs
-            uint32_t cap = 64;
-            while (cap < 2 * total && cap < QECMC_DD_HASH_SLOTS) cap <<= 1;
-            if (total > (uint64_t)(QECMC_DD_HASH_SLOTS * 0.85)) { if (tid == 0) *p.err = 1; }
-            else {
-                for (uint32_t i = tid; i < cap; i += QECMC_DD_THREADS) hash[i] = 0ull;
-                __syncthreads();
-                dd_for_each_key(p, tab, [&](unsigned long long k) { dd_insert(hash, cap - 1, shift, k, hist); });
-            }
+            dd_for_each_key(p, tab, s_cnt, max_cnt, [&](unsigned long long k) { dd_insert(hash, HS - 1, shift, k, hist, p.err); });
+        } else if (total > (uint64_t)p.scratch_cap) {
+            if (tid == 0) *p.err = 2;
         } else {
-            for (uint32_t i = tid; i < NB; i += QECMC_DD_THREADS) bcnt[i] = 0;
+            for (uint32_t i = tid; i < NB; i += T) bcnt[i] = 0;
             __syncthreads();
-            dd_for_each_key(p, tab, [&](unsigned long long k) { atomicAdd(&bcnt[(uint32_t)(k >> QECMC_LEN_BITS) & (NB - 1)], 1u); });
+            // A: bucket histogram
+            dd_for_each_key(p, tab, s_cnt, max_cnt, [&](unsigned long long k) { atomicAdd(&bcnt[(uint32_t)(k >> QECMC_LEN_BITS) & (NB - 1)], 1u); });
             __syncthreads();
             {   // exclusive scan of bcnt -> boff (NB <= 4096 = 4 per thread)
-                const uint32_t per = (NB + QECMC_DD_THREADS - 1) / QECMC_DD_THREADS;   // 1..4
+                const uint32_t per = (NB + T - 1) / T;   // 1..4
                 uint32_t v[4], sum = 0;
                 for (uint32_t j = 0; j < per; j++) { uint32_t idx = tid * per + j; v[j] = idx < NB ? bcnt[idx] : 0; sum += v[j]; }
                 uint32_t inc = sum;
@@ -130,28 +155,49 @@ __global__ void __launch_bounds__(QECMC_DD_THREADS, 1) log_dedupe_kernel(DedupeP
                 for (uint32_t j = 0; j < per; j++) { uint32_t idx = tid * per + j; if (idx < NB) boff[idx] = run; run += v[j]; }
             }
             __syncthreads();
-            if (total > (uint64_t)p.scratch_cap) { if (tid == 0) *p.err = 2; __syncthreads(); continue; }
-            dd_for_each_key(p, tab, [&](unsigned long long k) {
+            // B: scatter into the CTA's scratch area, bucket by bucket
+            dd_for_each_key(p, tab, s_cnt, max_cnt, [&](unsigned long long k) {
                 uint32_t pos = atomicAdd(&boff[(uint32_t)(k >> QECMC_LEN_BITS) & (NB - 1)], 1u);
                 scratch[pos] = k;
             });
             __syncthreads();   // boff[b] is now the END of bucket b; its keys are visible to the whole CTA
-            for (uint32_t b = 0; b < NB; b++) {
-                const uint32_t nb = bcnt[b], end = boff[b];
-                if (nb == 0) continue;
-                if (nb > (uint32_t)(QECMC_DD_HASH_SLOTS * 0.85)) { if (tid == 0) *p.err = 1; continue; }
-                uint32_t cap = 64;
-                while (cap < 2 * nb && cap < QECMC_DD_HASH_SLOTS) cap <<= 1;
-                for (uint32_t i = tid; i < cap; i += QECMC_DD_THREADS) hash[i] = 0ull;
-                __syncthreads();
-                const unsigned long long *src = scratch + (end - nb);
-                for (uint32_t i = tid; i < nb; i += QECMC_DD_THREADS) dd_insert(hash, cap - 1, shift, src[i], hist);
-                __syncthreads();
+            // C: four groups of 256 threads work on a bucket each (named barriers, so a group waiting for its slowest
+            // warp leaves the issue slots to the others); a group loads its next bucket's first chunk into registers
+            // before it inserts the current one
+            const int grp = tid / GT, gt = tid % GT;
+            unsigned long long *hb = hash + grp * HS;
+            unsigned long long k[KPT], kn[KPT];
+            if ((uint32_t)grp < NB) {
+                const uint32_t nb0 = bcnt[grp];
+                const unsigned long long *src0 = scratch + (boff[grp] - nb0);
+#pragma unroll
+                for (int j = 0; j < KPT; j++) { uint32_t idx = j * GT + gt; k[j] = idx < nb0 ? src0[idx] : 0ull; }
+            }
+            for (uint32_t b = grp; b < NB; b += QECMC_DD_GROUPS) {
+                const uint32_t nb = bcnt[b];
+                const unsigned long long *src = scratch + (boff[b] - nb);
+                uint32_t cap = 256;                         // set sized to the bucket: load <= 0.5, fewer slots to clear
+                while (cap < 2 * nb && cap < (uint32_t)HS) cap <<= 1;
+                for (uint32_t i = gt; i < cap; i += GT) hb[i] = 0ull;
+                if (b + QECMC_DD_GROUPS < NB) {
+                    const uint32_t nb1 = bcnt[b + QECMC_DD_GROUPS];
+                    const unsigned long long *src1 = scratch + (boff[b + QECMC_DD_GROUPS] - nb1);
+#pragma unroll
+                    for (int j = 0; j < KPT; j++) { uint32_t idx = j * GT + gt; kn[j] = idx < nb1 ? src1[idx] : 0ull; }
+                }
+                asm volatile("bar.sync %0, %1;" : : "r"(1 + grp), "r"(GT) : "memory");
+#pragma unroll
+                for (int j = 0; j < KPT; j++)
+                    if (k[j]) dd_insert(hb, cap - 1, shift, k[j], hist, p.err);
+                for (uint32_t idx = KPT * GT + gt; idx < nb; idx += GT) dd_insert(hb, cap - 1, shift, src[idx], hist, p.err);   // long lists of repeats
+#pragma unroll
+                for (int j = 0; j < KPT; j++) k[j] = kn[j];
+                asm volatile("bar.sync %0, %1;" : : "r"(1 + grp), "r"(GT) : "memory");
             }
         }
         __syncthreads();
         if (p.N_hist)
-            for (int i = tid; i < nh; i += QECMC_DD_THREADS) p.N_hist[(uint64_t)tab * nh + i] = hist[i];
+            for (int i = tid; i < nh; i += T) p.N_hist[(uint64_t)tab * nh + i] = hist[i];
         if (tid == 0) {
             double z = 0;
             unsigned long long cnt = 0;

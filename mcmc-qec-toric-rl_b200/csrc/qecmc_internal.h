@@ -49,6 +49,20 @@ struct DevBuf {
     }
 };
 
+// device buffers of the tempering-ladder drivers (qecmc_ladder.cu); they live in the context so that repeated calls
+// reuse them
+struct LadderDev {
+    DevBuf log_hash, short_v, short_n, short_u;
+    DevBuf thr_d, thr_u, thr_top_d, diff, wtab, lat, lat_out, flags, neff, tops0, snap_lat, snap_flags, snap_tops0, hist, eqc,
+        info, pct, status, u_nb, u_py, qm, bytes_out, Zd, dist;
+    ~LadderDev()
+    {
+        for (DevBuf *b : {&log_hash, &short_v, &short_n, &short_u, &thr_d, &thr_u, &thr_top_d, &diff, &wtab, &lat, &lat_out, &flags, &neff, &tops0, &snap_lat,
+                          &snap_flags, &snap_tops0, &hist, &eqc, &info, &pct, &status, &u_nb, &u_py, &qm, &bytes_out, &Zd, &dist})
+            b->release();
+    }
+};
+
 struct qecmc_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -59,6 +73,7 @@ struct qecmc_ctx {
     std::map<std::tuple<int, int, int>, uint64_t *> stab_hash;  // (geom, L, wide) -> device table
     std::map<std::tuple<int, int, int>, uint2 *> stab_desc;     // (geom, L, wide) -> descriptor table
     DevBuf lut, log_hash, log_counts, dd_scratch;
+    LadderDev ld;
     cudaEvent_t ev[4];
     uint64_t hash_seed = 0x5EEDC0DE2020ull;
     int64_t launches = 0;
@@ -138,17 +153,21 @@ template <int GEOM, typename W> static int build_stab_hash(qecmc_ctx *c, const G
     return 0;
 }
 
-static inline int pick_threads(size_t bytes_per_chain, size_t fixed, const cudaDeviceProp &prop, int *threads, int *blocks_per_sm)
+static inline int pick_threads(size_t bytes_per_chain, size_t fixed, const cudaDeviceProp &prop, int *threads, int *blocks_per_sm,
+                               bool allow640 = false, int regs_per_thread = 0)
 {
     // largest resident chain count per SM within the shared-memory budget, 256-thread CTAs preferred
     size_t budget = prop.sharedMemPerMultiprocessor;
     int best_T = 0, best_res = 0;
-    for (int T : {256, 128, 64}) {
+    // candidates in order of preference: a later one wins only with strictly more resident chains
+    for (int T : {640, 256, 128, 64}) {
+        if (T == 640 && !allow640) continue;
         size_t per_block = bytes_per_chain * T + fixed + 1024;  // +1 KiB reserved per CTA
         if (bytes_per_chain * T + fixed > prop.sharedMemPerBlockOptin) continue;
         int nb = (int)(budget / per_block);
         int max_thr = prop.maxThreadsPerMultiProcessor;
         if (nb * T > max_thr) nb = max_thr / T;
+        if (regs_per_thread > 0 && nb * T * regs_per_thread > prop.regsPerMultiprocessor) nb = prop.regsPerMultiprocessor / (T * regs_per_thread);
         if (nb * T > best_res) { best_res = nb * T; best_T = T; *blocks_per_sm = nb; }
     }
     if (!best_T) return set_err(QECMC_ERR_UNSUPPORTED, "lattice does not fit in shared memory");

@@ -125,17 +125,6 @@ void make_ladder_tables(const qecmc_ladder_cfg *cfg, const Geo &g, LadderTables 
     }
 }
 
-struct LadderDev {
-    DevBuf log_hash, short_v, short_n, short_u;
-    DevBuf thr_d, thr_u, thr_top_d, diff, wtab, lat, lat_out, flags, neff, tops0, snap_lat, snap_flags, snap_tops0, hist, eqc,
-        info, pct, status, u_nb, u_py, qm, bytes_out, Zd, dist;
-    ~LadderDev()
-    {
-        for (DevBuf *b : {&log_hash, &short_v, &short_n, &short_u, &thr_d, &thr_u, &thr_top_d, &diff, &wtab, &lat, &lat_out, &flags, &neff, &tops0, &snap_lat,
-                          &snap_flags, &snap_tops0, &hist, &eqc, &info, &pct, &status, &u_nb, &u_py, &qm, &bytes_out, &Zd, &dist})
-            b->release();
-    }
-};
 
 template <typename T> int upload(qecmc_ctx *c, DevBuf &b, const std::vector<T> &v)
 {
@@ -336,7 +325,7 @@ extern "C" int qecmc_ladder_run(qecmc_ctx *c, const qecmc_ladder_cfg *cfg, const
     const size_t wb = wide ? 8 : 4;
     const int Nc = cfg->Nc;
     const int64_t n_init = io->resume ? S * Nc : S;
-    LadderDev d;
+    LadderDev &d = c->ld;   // device buffers persist in the context: no cudaMalloc / cudaFree per call
     LadderParams p;
     QTRY(setup_ladder(c, cfg, g, d, p));
     QTRY(stage_replay(c, cfg, S, d, p));
@@ -446,7 +435,7 @@ static int pteq_common(qecmc_ctx *c, const qecmc_pteq_cfg *cfg, const uint8_t *q
     const Geo g = make_geo(lc->geom, lc->L);
     const bool wide = lc->L > 16;
     const size_t wb = wide ? 8 : 4;
-    LadderDev d;
+    LadderDev &d = c->ld;   // device buffers persist in the context: no cudaMalloc / cudaFree per call
     LadderParams p;
     QTRY(setup_ladder(c, lc, g, d, p));
     // n_err history: 4 bytes per Ladder.step per ladder; ladders run in waves that fit the budget
@@ -592,7 +581,7 @@ static int dc_common(qecmc_ctx *c, const qecmc_ladder_cfg *lc, int per_class_ini
     const bool wide = lc->L > 16;
     const size_t wb = wide ? 8 : 4;
     const int n_eq = g.neq;
-    LadderDev d;
+    LadderDev &d = c->ld;   // device buffers persist in the context: no cudaMalloc / cudaFree per call
     LadderParams p;
     QTRY(setup_ladder(c, lc, g, d, p));
     // PTDC: one set per (syndrome, class); PTRC: one per (syndrome, class, droplet, rung)

@@ -64,10 +64,13 @@ __device__ __forceinline__ void prefetch_l2(const void *addr)
 
 // CONV = false drops the conv_mult early-stop state (ConvStop) from the loop: the headline configuration
 // (conv_mult == 0) then fits the register budget of five 256-thread CTAs per SM.
+// That variant is launched as two 640-thread CTAs per SM: same 1280 resident chains as five 256-thread CTAs, measured
+// 7 % faster (177 vs 190 ms per launch at the headline configuration); a CTA-wide barrier every few hundred steps, tried
+// against warps drifting apart under oldest-first scheduling, changed nothing.
 // Shared memory: the LUTs are static arrays, and for 32-bit row words (L <= 16, at most 512 stabilizers) so are the
 // descriptors and fingerprints, which makes every table address an immediate; the lattice tile is the dynamic part.
 template <int GEOM, typename W, bool REPLAY, int MODE, bool CONV>
-__global__ void __launch_bounds__(256, CONV ? (sizeof(W) == 4 ? 4 : 2) : (sizeof(W) == 4 ? 5 : 3)) stdc_fast_kernel(StdcParams p, FastTables ft, PhiloxKeys keys)
+__global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 640 : 256, CONV ? (sizeof(W) == 4 ? 4 : 2) : (sizeof(W) == 4 ? 2 : 3)) stdc_fast_kernel(StdcParams p, FastTables ft, PhiloxKeys keys)
 {
     static_assert(GEOM == TORIC || GEOM == PLANAR, "table-driven kernel covers the two-layer codes");
     constexpr bool STATIC_TAB = sizeof(W) == 4;
