@@ -298,14 +298,14 @@ static int launch_stdc_fast(qecmc_ctx *c, StdcParams &p)
     make_philox_keys(p.seed, keys);
     int T = 0, nb = 0;
     size_t per_chain = (size_t)p.gchain.nw * sizeof(W);
-    // static part: LUTs (512 * 5 + 72 B) and, for 32-bit row words, descriptor + fingerprint arrays of 512 entries;
+    // static part: LUTs (512 * 5 + 72 B) and, for 32-bit row words, expanded descriptor (2 x 16 B) + fingerprint arrays of 512 entries;
     // wider lattices keep descriptors and fingerprints behind the tile in dynamic shared memory
     const bool static_tab = sizeof(W) == 4;
     if (static_tab && p.gchain.nstab > QECMC_FAST_STATIC_NSTAB) return set_err(QECMC_ERR_UNSUPPORTED, "internal: %d stabilizers exceed the static tables", p.gchain.nstab);
-    size_t stat = 512 * 5 + 128 + (static_tab ? (size_t)QECMC_FAST_STATIC_NSTAB * 16 : 0);
+    size_t stat = 512 * 5 + 128 + (static_tab ? (size_t)QECMC_FAST_STATIC_NSTAB * 40 : 0);
     size_t dyn_fixed = static_tab ? 0 : (size_t)p.gchain.nstab * 16 + 16;
     const bool conv = REPLAY || p.conv_mult != 0.0;
-    QTRY(pick_threads(per_chain, stat + dyn_fixed + 256, c->prop, &T, &nb, static_tab && !conv, conv ? 56 : 48));
+    QTRY(pick_threads(per_chain, stat + dyn_fixed + 256, c->prop, &T, &nb, static_tab && !conv, conv ? 56 : 64));
     size_t smem = ((per_chain * T + 15) & ~(size_t)15) + dyn_fixed;
     unsigned grid = (unsigned)((p.n_chains + T - 1) / T);
     if (conv) {

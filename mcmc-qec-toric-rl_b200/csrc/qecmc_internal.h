@@ -154,14 +154,14 @@ template <int GEOM, typename W> static int build_stab_hash(qecmc_ctx *c, const G
 }
 
 static inline int pick_threads(size_t bytes_per_chain, size_t fixed, const cudaDeviceProp &prop, int *threads, int *blocks_per_sm,
-                               bool allow640 = false, int regs_per_thread = 0)
+                               bool allow1024 = false, int regs_per_thread = 0)
 {
     // largest resident chain count per SM within the shared-memory budget, 256-thread CTAs preferred
     size_t budget = prop.sharedMemPerMultiprocessor;
     int best_T = 0, best_res = 0;
     // candidates in order of preference: a later one wins only with strictly more resident chains
-    for (int T : {640, 256, 128, 64}) {
-        if (T == 640 && !allow640) continue;
+    for (int T : {1024, 256, 128, 64}) {
+        if (T == 1024 && !allow1024) continue;
         size_t per_block = bytes_per_chain * T + fixed + 1024;  // +1 KiB reserved per CTA
         if (bytes_per_chain * T + fixed > prop.sharedMemPerBlockOptin) continue;
         int nb = (int)(budget / per_block);

@@ -57,6 +57,41 @@ __device__ __forceinline__ void cas_async(unsigned long long &prev, unsigned lon
     asm volatile("atom.global.cas.b64 %0, [%1], %2, %3;" : "=l"(prev) : "l"(addr), "l"(0ull), "l"(key));
 }
 
+// The static tables of the 32-bit-word variant live in one struct and are read through ld.shared with an explicit
+// 32-bit base + immediate offset: left to itself the compiler re-derives every table's shared-window address (three
+// instructions each, CTA rank in the cluster included) at every use instead of keeping five bases in registers.
+struct FastTabs {
+    uint4 A[QECMC_FAST_STATIC_NSTAB];       // {byte offset of word 0, 1, 2 in the thread's tile column, packed shifts / masks}
+    uint4 B[QECMC_FAST_STATIC_NSTAB];       // {XOR mask of word 0, 1, 2}: read on accept only
+    uint64_t hs[QECMC_FAST_STATIC_NSTAB];   // fingerprint change per stabilizer
+    uint32_t thr[512];                      // threshold by (Pauli, gathered fields)
+    int8_t dE[512];                         // weight change by (Pauli, gathered fields)
+};
+template <int OFF> __device__ __forceinline__ uint4 lds_v4(uint32_t a)
+{
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a), "n"(OFF));
+    return v;
+}
+template <int OFF> __device__ __forceinline__ uint2 lds_v2(uint32_t a)
+{
+    uint2 v;
+    asm("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(a), "n"(OFF));
+    return v;
+}
+template <int OFF> __device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
+    return v;
+}
+template <int OFF> __device__ __forceinline__ int lds_s8(uint32_t a)
+{
+    int v;
+    asm("ld.shared.s8 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
+    return v;
+}
+
 __device__ __forceinline__ void prefetch_l2(const void *addr)
 {
     asm volatile("prefetch.global.L2 [%0];" : : "l"(addr));
@@ -64,29 +99,54 @@ __device__ __forceinline__ void prefetch_l2(const void *addr)
 
 // CONV = false drops the conv_mult early-stop state (ConvStop) from the loop: the headline configuration
 // (conv_mult == 0) then fits the register budget of five 256-thread CTAs per SM.
-// That variant is launched as two 640-thread CTAs per SM: same 1280 resident chains as five 256-thread CTAs, measured
-// 7 % faster (177 vs 190 ms per launch at the headline configuration); a CTA-wide barrier every few hundred steps, tried
-// against warps drifting apart under oldest-first scheduling, changed nothing.
+// That variant runs as ONE 1024-thread CTA per SM with up to 64 registers.  Measured at the headline configuration, per
+// syndrome: five 256-thread CTAs (48 registers, 1280 chains per SM) 1.03 ms, two 640-thread CTAs 0.96 ms, one
+// 1024-thread CTA 0.92 ms -- fewer rematerialised addresses (95.8 instead of 98.8 issue slots per step) and 74 % instead
+// of 72 % of the issue cycles used.  With several CTAs per SM the oldest-first warp scheduler lets one CTA finish long
+// before the others (ncu: 31.8 of 40 warps active on average); pacing the CTAs against each other through a grid-wide
+// epoch counter brought that to 39.98 of 40 but did not raise the issue rate, so it was dropped.
 // Shared memory: the LUTs are static arrays, and for 32-bit row words (L <= 16, at most 512 stabilizers) so are the
 // descriptors and fingerprints, which makes every table address an immediate; the lattice tile is the dynamic part.
 template <int GEOM, typename W, bool REPLAY, int MODE, bool CONV>
-__global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 640 : 256, CONV ? (sizeof(W) == 4 ? 4 : 2) : (sizeof(W) == 4 ? 2 : 3)) stdc_fast_kernel(StdcParams p, FastTables ft, PhiloxKeys keys)
+__global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ? (sizeof(W) == 4 ? 4 : 2) : (sizeof(W) == 4 ? 1 : 3)) stdc_fast_kernel(StdcParams p, FastTables ft, PhiloxKeys keys)
 {
     static_assert(GEOM == TORIC || GEOM == PLANAR, "table-driven kernel covers the two-layer codes");
     constexpr bool STATIC_TAB = sizeof(W) == 4;
-    constexpr int NTAB = STATIC_TAB ? QECMC_FAST_STATIC_NSTAB : 1;
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ uint32_t s_thr[512];
-    __shared__ int8_t s_dE[512];
+    __shared__ __align__(16) unsigned char s_tabs_raw[STATIC_TAB ? sizeof(FastTabs) : 16];
+    __shared__ uint32_t s_thr_dyn[STATIC_TAB ? 1 : 512];
+    __shared__ int8_t s_dE_dyn[STATIC_TAB ? 4 : 512];
     __shared__ double s_thrd[QECMC_THR_N];
-    __shared__ uint64_t s_hs_st[NTAB];
-    __shared__ uint2 s_desc_st[NTAB];
+    FastTabs &tb = *reinterpret_cast<FastTabs *>(s_tabs_raw);
+    uint32_t *s_thr = STATIC_TAB ? tb.thr : s_thr_dyn;
+    int8_t *s_dE = STATIC_TAB ? tb.dE : s_dE_dyn;
+    const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(s_tabs_raw);
     const int T = blockDim.x, tid = threadIdx.x;
     const Geo g = p.gchain;
     W *tile = reinterpret_cast<W *>(smem);
-    uint64_t *s_hs = STATIC_TAB ? s_hs_st : reinterpret_cast<uint64_t *>(smem + (((size_t)g.nw * T * sizeof(W) + 15) & ~(size_t)15));
-    uint2 *s_desc = STATIC_TAB ? s_desc_st : reinterpret_cast<uint2 *>(s_hs + g.nstab);
-    for (int i = tid; i < g.nstab; i += T) { s_hs[i] = p.stab_hash[i]; s_desc[i] = ft.desc[i]; }
+    uint64_t *s_hs = STATIC_TAB ? tb.hs : reinterpret_cast<uint64_t *>(smem + (((size_t)g.nw * T * sizeof(W) + 15) & ~(size_t)15));
+    uint2 *s_desc = STATIC_TAB ? nullptr : reinterpret_cast<uint2 *>(s_hs + g.nstab);
+    for (int i = tid; i < g.nstab; i += T) {
+        s_hs[i] = p.stab_hash[i];
+        const uint2 d = ft.desc[i];
+        if (STATIC_TAB) {
+            const uint32_t ws = (uint32_t)T * sizeof(W);
+            const uint32_t sh = d.x & 63u, sh2 = d.y & 63u, fa = (d.y >> 8) & 0xFFu, f_or9 = d.y >> 16;
+            const uint32_t v = (d.y & 0x01000000u) ? 3u : 1u;
+            uint32_t m0, m1, m2;
+            if (GEOM == TORIC) { m1 = m2 = v << sh; m0 = m1 | (v << sh2); }
+            else {
+                m0 = ((fa & 1u) ? v << sh : 0u) | ((fa & 4u) ? v << sh2 : 0u);
+                m1 = (fa & 16u) ? v << sh : 0u;
+                m2 = (fa & 64u) ? v << sh : 0u;
+            }
+            tb.A[i] = make_uint4(((d.x >> 8) & 0xFFu) * ws, ((d.x >> 16) & 0xFFu) * ws, (d.x >> 24) * ws,
+                                 sh | (((sh2 - 2u) & 31u) << 8) | (f_or9 << 13) | (GEOM == PLANAR ? fa << 22 : 0u));
+            tb.B[i] = make_uint4(m0, m1, m2, 0u);
+        } else {
+            s_desc[i] = d;
+        }
+    }
     for (int i = tid; i < 512; i += T) { s_thr[i] = ft.thr[i]; s_dE[i] = ft.dE[i]; }
     if (tid < QECMC_THR_N) s_thrd[tid] = p.thr.d[tid];
     __syncthreads();
@@ -148,37 +208,73 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 640 : 256, CONV ? 
 
     // one Metropolis step for stabilizer idx; r_acc / u_acc is the accept draw
     auto step = [&](int idx, uint32_t r_acc, double u_acc) {
-        const uint2 d = s_desc[idx];
-        W *p0 = reinterpret_cast<W *>(mybase + ((d.x >> 8) & 0xFFu) * wstride);
-        W *p1 = reinterpret_cast<W *>(mybase + ((d.x >> 16) & 0xFFu) * wstride);
-        W *p2 = reinterpret_cast<W *>(mybase + (d.x >> 24) * wstride);
-        const W o0 = *p0, o1 = *p1, o2 = *p2;
-        uint32_t f = gather_fields<W>(o0, o1, o2, d.x, d.y);
-        uint32_t li;
-        if (GEOM == TORIC) li = (f & 0xFFu) | (d.y >> 16);                            // f_or carries (v==3) at bit 8
-        else li = (f & ((d.y >> 8) & 0xFFu)) | (d.y >> 16);
+        W *p0, *p1, *p2;
+        W o0, o1, o2;
+        uint32_t li, dx = 0, dy = 0;
+        if (STATIC_TAB) {
+            const uint4 A = lds_v4<offsetof(FastTabs, A)>(tbase + (uint32_t)idx * 16u);
+            p0 = reinterpret_cast<W *>(mybase + A.x);
+            p1 = reinterpret_cast<W *>(mybase + A.y);
+            p2 = reinterpret_cast<W *>(mybase + A.z);
+            o0 = *p0; o1 = *p1; o2 = *p2;
+            // the funnel shift reads the low five bits of its shift operand, so the packed word serves as it is
+            const uint32_t a0 = (uint32_t)o0, a1 = (uint32_t)o1, a2 = (uint32_t)o2;
+            const uint32_t ta = __funnelshift_r(a0, a0, A.w);
+            const uint32_t tb = __funnelshift_r(a0, a0, A.w >> 8);
+            const uint32_t tc = __funnelshift_r(a1, a1, A.w - 4u);
+            const uint32_t td = __funnelshift_r(a2, a2, A.w - 6u);
+            const uint32_t s1 = (ta & 0x03u) | (tb & ~0x03u);
+            const uint32_t s2 = (tc & 0x30u) | (td & ~0x30u);
+            const uint32_t f = (s1 & 0x0Fu) | (s2 & ~0x0Fu);
+            if (GEOM == TORIC) li = (f & 0xFFu) | (A.w >> 13);
+            else li = (f & (A.w >> 22)) | ((A.w >> 13) & 0x1FFu);
+        } else {
+            const uint2 d = s_desc[idx];
+            dx = d.x; dy = d.y;
+            p0 = reinterpret_cast<W *>(mybase + ((d.x >> 8) & 0xFFu) * wstride);
+            p1 = reinterpret_cast<W *>(mybase + ((d.x >> 16) & 0xFFu) * wstride);
+            p2 = reinterpret_cast<W *>(mybase + (d.x >> 24) * wstride);
+            o0 = *p0; o1 = *p1; o2 = *p2;
+            uint32_t f = gather_fields<W>(o0, o1, o2, d.x, d.y);
+            if (GEOM == TORIC) li = (f & 0xFFu) | (d.y >> 16);                            // f_or carries (v==3) at bit 8
+            else li = (f & ((d.y >> 8) & 0xFFu)) | (d.y >> 16);
+        }
         bool acc;
         if (REPLAY) acc = u_acc < s_thrd[(int)s_dE[li] + QECMC_THR_OFF];
+        else if (STATIC_TAB) acc = r_acc <= lds_u32<offsetof(FastTabs, thr)>(tbase + li * 4u);
         else acc = r_acc <= s_thr[li];
         if (acc) {
-            const uint32_t sh = d.x & 63u, sh2 = d.y & 63u;
-            const W v = (d.y & 0x01000000u) ? (W)3 : (W)1;
-            W m0, m1, m2;
-            if (GEOM == TORIC) {
-                m1 = (W)(v << sh);
-                m2 = m1;
-                m0 = (W)(m1 | (W)(v << sh2));
+            if (STATIC_TAB) {
+                const uint4 B = lds_v4<offsetof(FastTabs, B)>(tbase + (uint32_t)idx * 16u);
+                *p0 = (W)(o0 ^ (W)B.x);
+                *p1 = (W)(o1 ^ (W)B.y);
+                *p2 = (W)(o2 ^ (W)B.z);
             } else {
-                const uint32_t fa = d.y >> 8;
-                m0 = (W)(((fa & 1u) ? (W)(v << sh) : (W)0) | ((fa & 4u) ? (W)(v << sh2) : (W)0));
-                m1 = (fa & 16u) ? (W)(v << sh) : (W)0;
-                m2 = (fa & 64u) ? (W)(v << sh) : (W)0;
+                const uint32_t sh = dx & 63u, sh2 = dy & 63u;
+                const W v = (dy & 0x01000000u) ? (W)3 : (W)1;
+                W m0, m1, m2;
+                if (GEOM == TORIC) {
+                    m1 = (W)(v << sh);
+                    m2 = m1;
+                    m0 = (W)(m1 | (W)(v << sh2));
+                } else {
+                    const uint32_t fa = dy >> 8;
+                    m0 = (W)(((fa & 1u) ? (W)(v << sh) : (W)0) | ((fa & 4u) ? (W)(v << sh2) : (W)0));
+                    m1 = (fa & 16u) ? (W)(v << sh) : (W)0;
+                    m2 = (fa & 64u) ? (W)(v << sh) : (W)0;
+                }
+                *p0 = (W)(o0 ^ m0);
+                *p1 = (W)(o1 ^ m1);
+                *p2 = (W)(o2 ^ m2);
             }
-            *p0 = (W)(o0 ^ m0);
-            *p1 = (W)(o1 ^ m1);
-            *p2 = (W)(o2 ^ m2);
-            n += (int)s_dE[li];
-            h ^= s_hs[idx];
+            if (STATIC_TAB) {
+                n += lds_s8<offsetof(FastTabs, dE)>(tbase + li);
+                const uint2 hv = lds_v2<offsetof(FastTabs, hs)>(tbase + (uint32_t)idx * 8u);
+                h ^= (uint64_t)hv.x | ((uint64_t)hv.y << 32);
+            } else {
+                n += (int)s_dE[li];
+                h ^= s_hs[idx];
+            }
             dirty = true;
             nacc++;
         }
