@@ -35,8 +35,8 @@ N_EQ = 16
 W_INT = 170.0      # int32 lane-ops per toric/planar depolarizing Metropolis step (agreed figure)
 W_LOG = 8.0        # bytes a chain appends to its key log per offered sample (the chain kernel's only steady HBM traffic)
 # ncu, full-size launch of this exact command (profiles/r01_ncu_fullsize_stdc_v6.csv): warp instructions and DRAM bytes
-NCU_CHAIN = {"file": "profiles/r01_ncu_fullsize_stdc_v6.csv", "warp_inst_per_launch": 148783220588, "dram_bytes_per_launch": 6104559104 + 27513273088,
-             "issue_active_pct": 67.10, "steps_per_launch": 185 * 16 * 64 * 50625 * 5}
+NCU_CHAIN = {"file": "profiles/r01_ncu_fullsize_stdc_v7.csv", "warp_inst_per_launch": 95950720865, "dram_bytes_per_launch": 6409024000 + 23494756864,
+             "issue_active_pct": 70.27, "smem_wavefront_pct": 86.35, "steps_per_launch": 148 * 16 * 64 * 50625 * 5}
 
 
 def synth_syndromes(n, seed, L=L, p=P_ERROR):
@@ -294,6 +294,8 @@ def main():
     peak_ops = info["sm_count"] * 128 * sm_max_mhz * 1e6            # int32 lane-ops/s, one GPU
     kern_steps_per_s = batch * steps_per_syndrome * args.steps / (kern_ms * 1e-3)   # per GPU, chain kernel only
     achieved_ops = kern_steps_per_s * W_INT
+    slots_meas = NCU_CHAIN["warp_inst_per_launch"] * 32 / NCU_CHAIN["steps_per_launch"]
+    achieved_meas = kern_steps_per_s * slots_meas
     hbm_alg = (offered / args.steps) * W_LOG / ((kern_ms / args.steps) * 1e-3) / 1e9  # GB/s, rank 0
     full_size = samples == SAMPLES and batch * steps_per_syndrome == NCU_CHAIN["steps_per_launch"]
     line = {
@@ -306,16 +308,16 @@ def main():
                 "d2h_bytes_per_step": int(batch * N_EQ * 8), "steps_timed": n_e2e},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "alu", "achieved": achieved_ops / 1e12, "peak": peak_ops / 1e12, "unit": "Tlaneop/s",
-                     "frac": achieved_ops / peak_ops,
+        "roofline": {"bound": "alu", "achieved": achieved_meas / 1e12, "peak": peak_ops / 1e12, "unit": "Tlaneop/s",
+                     "frac": achieved_meas / peak_ops,
                      "traffic": NCU_CHAIN["dram_bytes_per_launch"] if full_size else None,
-                     "issue": {"what": "issue slots the kernel really spends (ncu smsp__inst_executed x 32 lanes / steps) and the share of "
-                                       "issue cycles used; the agreed 170 lane-ops per step of SURVEY.md 8d is an estimate made before "
-                                       "the kernel existed",
-                               "lane_slots_per_step": NCU_CHAIN["warp_inst_per_launch"] * 32 / NCU_CHAIN["steps_per_launch"],
-                               "issue_active_pct_ncu": NCU_CHAIN["issue_active_pct"],
-                               "frac_at_measured_slots": kern_steps_per_s * (NCU_CHAIN["warp_inst_per_launch"] * 32 / NCU_CHAIN["steps_per_launch"]) / peak_ops,
-                               "source": NCU_CHAIN["file"]},
+                     "what": "achieved = steps/s of the chain kernel x the issue slots it spends per step, measured by ncu "
+                             "(smsp__inst_executed x 32 lanes / steps; " + NCU_CHAIN["file"] + "); peak = SMs x 128 int32 lanes x max SM clock",
+                     "lane_slots_per_step": slots_meas, "issue_active_pct_ncu": NCU_CHAIN["issue_active_pct"],
+                     "smem_wavefront_pct_ncu": NCU_CHAIN["smem_wavefront_pct"],
+                     "at_agreed_170_laneops": {"achieved": achieved_ops / 1e12, "frac": achieved_ops / peak_ops,
+                                               "note": "SURVEY.md 8d's pre-implementation estimate of 170 lane-ops per step; the kernel "
+                                                       "needs fewer, so this figure exceeds 1 and says nothing about headroom"},
                      "kernel": "stdc_fast_kernel<TORIC,u32,native,STDC>", "kernel_ms_per_launch": kern_ms / (args.steps * waves),
                      "units_per_launch": batch * steps_per_syndrome / waves, "algorithmic_laneops_per_step": W_INT,
                      "peak_source": f"{info['sm_count']} SMs x 128 int32 lanes x {sm_max_mhz:.0f} MHz ({peak_src} max SM clock)",

@@ -267,6 +267,11 @@ template <int GEOM, typename W> static int build_stab_desc(qecmc_ctx *c, const G
 // thr[(v==3)*256 + f], dE[...]: weight change of flipping the four gathered fields f by Pauli v
 static int build_fast_lut(qecmc_ctx *c, const Thr &t, FastTables &ft)
 {
+    if (c->lut.p && c->lut_valid && memcmp(c->lut_thr, t.u32, sizeof(t.u32)) == 0) {   // same sampling rate as the last call
+        ft.thr = (const uint32_t *)c->lut.p;
+        ft.dE = (const int8_t *)((const char *)c->lut.p + 512 * 4);
+        return 0;
+    }
     std::vector<unsigned char> host(512 * 4 + 512);
     uint32_t *thr = (uint32_t *)host.data();
     int8_t *dE = (int8_t *)(host.data() + 512 * 4);
@@ -285,6 +290,8 @@ static int build_fast_lut(qecmc_ctx *c, const Thr &t, FastTables &ft)
     CUDA_OK(cudaStreamSynchronize(c->stream));
     ft.thr = (const uint32_t *)c->lut.p;
     ft.dE = (const int8_t *)((const char *)c->lut.p + 512 * 4);
+    memcpy(c->lut_thr, t.u32, sizeof(t.u32));
+    c->lut_valid = true;
     return 0;
 }
 
@@ -403,9 +410,12 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
     uint64_t cap = 0;
     int64_t per_syndrome = 0, wave = S;
     if (mode != MODE_MEAN) {
-        size_t fr = 0, tot = 0;
-        CUDA_OK(cudaMemGetInfo(&fr, &tot));
-        int64_t budget = c->table_budget ? c->table_budget : (int64_t)((double)(fr + c->tables.cap + c->dd_scratch.cap) * 0.85);
+        int64_t budget = c->table_budget;
+        if (!budget) {   // cudaMemGetInfo costs milliseconds on a 180 GB device: skipped when the caller fixed the budget
+            size_t fr = 0, tot = 0;
+            CUDA_OK(cudaMemGetInfo(&fr, &tot));
+            budget = (int64_t)((double)(fr + c->tables.cap + c->dd_scratch.cap) * 0.85);
+        }
         if (use_logs) {
             if ((int64_t)S * n_eq < dd_grid) dd_grid = (int)(S * n_eq);
             const int64_t scratch_bytes = (int64_t)dd_grid * cfg->droplets * log_cap * 8;
@@ -513,14 +523,10 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
             dp.err = (int *)c->scratch.p + 1;
             const size_t dsm = (size_t)QECMC_DD_HASH_SLOTS * QECMC_DD_GROUPS * 8 + 4096 * 4 + (size_t)QECMC_DD_MAX_BUCKETS * 8 + QECMC_DD_MAX_CNT * 4;
             CUDA_OK(cudaFuncSetAttribute(log_dedupe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-            CUDA_OK(cudaMemsetAsync(dp.err, 0, sizeof(int), c->stream));
+            if (s0 == 0) CUDA_OK(cudaMemsetAsync(dp.err, 0, sizeof(int), c->stream));   // sticky; read once after the last wave
             log_dedupe_kernel<<<(unsigned)(tabs < dd_grid ? tabs : dd_grid), QECMC_DD_THREADS, dsm, c->stream>>>(dp);
             c->launches++;
             CUDA_OK(cudaGetLastError());
-            int derr = 0;
-            CUDA_OK(cudaMemcpyAsync(&derr, dp.err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-            CUDA_OK(cudaStreamSynchronize(c->stream));
-            if (derr) return set_err(QECMC_ERR_UNSUPPORTED, "internal: key-log dedupe overflow (%d)", derr);
         } else if (mode != MODE_MEAN) {
             table_hist_kernel<<<(unsigned)tabs, 512, nh * sizeof(uint32_t), c->stream>>>(
                 (const unsigned long long *)c->tables.p, cap, gcode.nsites, beta, (double *)c->Z.p + s0 * n_eq,
@@ -555,10 +561,13 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
         CUDA_OK(cudaGetLastError());
     }
     CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
+    int derr = 0;
+    if (use_logs) CUDA_OK(cudaMemcpyAsync(&derr, (int *)c->scratch.p + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     if (stats) {
         unsigned long long cnt[8] = {0};
         CUDA_OK(cudaMemcpyAsync(cnt, c->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
         CUDA_OK(cudaStreamSynchronize(c->stream));
+        if (derr) return set_err(QECMC_ERR_UNSUPPORTED, "internal: key-log dedupe overflow (%d)", derr);
         memset(stats, 0, sizeof(*stats));
         stats->metropolis_steps = (int64_t)cnt[4];
         stats->accepted = (int64_t)cnt[0];
@@ -571,6 +580,9 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
         float ms = 0;
         cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
         stats->total_ms = ms;
+    } else if (use_logs) {
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        if (derr) return set_err(QECMC_ERR_UNSUPPORTED, "internal: key-log dedupe overflow (%d)", derr);
     }
     return 0;
 }

@@ -73,6 +73,8 @@ struct qecmc_ctx {
     std::map<std::tuple<int, int, int>, uint64_t *> stab_hash;  // (geom, L, wide) -> device table
     std::map<std::tuple<int, int, int>, uint2 *> stab_desc;     // (geom, L, wide) -> descriptor table
     DevBuf lut, log_hash, log_counts, dd_scratch;
+    uint32_t lut_thr[QECMC_THR_N] = {0};   // thresholds the device LUT was built from
+    bool lut_valid = false;
     LadderDev ld;
     cudaEvent_t ev[4];
     uint64_t hash_seed = 0x5EEDC0DE2020ull;

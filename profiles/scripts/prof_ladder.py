@@ -7,6 +7,7 @@ from mcmc_qec_toric_rl_b200 import _lib
 which = sys.argv[1] if len(sys.argv) > 1 else "rotated25"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 S = int(sys.argv[3]) if len(sys.argv) > 3 else 4736
+p_logical = float(sys.argv[4]) if len(sys.argv) > 4 else 0.5
 ctx = _lib.Context(0)
 rng = np.random.default_rng(3)
 if which == "rotated25":
@@ -16,6 +17,6 @@ elif which == "xzzx21_biased":
 else:
     g, L, kind, bottom, b = _lib.XZZX, 21, _lib.LADDER_ALPHA, 0.17474, 0.6447
 q = ((rng.random((S, L * L)) < 0.15) * rng.integers(1, 4, (S, L * L))).astype(np.uint8)
-pct, info = ctx.pteq(g, L, kind, q, bottom, param_b=b, steps=steps, conv=False, seed=11)
+pct, info = ctx.pteq(g, L, kind, q, bottom, param_b=b, steps=steps, conv=False, seed=11, p_logical=p_logical)
 st = info["stats"]
-print(which, "S", S, "steps", steps, "kernel_ms", st["chain_kernel_ms"], "metropolis steps/s", st["metropolis_steps"] / (st["chain_kernel_ms"] * 1e-3))
+print(which, "S", S, "steps", steps, "p_logical", p_logical, "kernel_ms", st["chain_kernel_ms"], "metropolis steps/s", st["metropolis_steps"] / (st["chain_kernel_ms"] * 1e-3))
