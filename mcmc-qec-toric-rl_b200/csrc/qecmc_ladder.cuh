@@ -253,45 +253,98 @@ __global__ void __launch_bounds__(128) ladder_kernel(LadderParams p)
     for (long long step = 0; step < p.steps; step++) {
         if (__all_sync(0xFFFFFFFFu, done)) break;
         // ---------------- Ladder.update_ladder: every rung runs `iters` Metropolis steps ----------------
-        if (valid && !done) {
-            const bool is_top = (r == Nc - 1) && top_logical;
-            if (REPLAY) {
+        const bool active = valid && !done;
+        {
+            const bool is_top = active && (r == Nc - 1) && top_logical;
+            if (REPLAY && active) {
                 ReplayRng *rr = reinterpret_cast<ReplayRng *>(&rng);
                 rr->nbp = base_nb + r * K * p.iters;  // rungs below the top consume fixed amounts
                 rr->pyp = base_py + r * p.iters;
             }
-            const double *wt = WEIGHTED ? p.wtab + (size_t)r * 4 * ns1 : nullptr;
+            const double *wt = WEIGHTED ? p.wtab + (size_t)(active ? r : 0) * 4 * ns1 : nullptr;
             double pb = 0.0;
-            if (WEIGHTED) pb = chain_weight(wt, ns1, nx, ny, nz);  // frozen for the block
+            if (WEIGHTED && active) pb = chain_weight(wt, ns1, nx, ny, nz);  // frozen for the block
             for (int it = 0; it < p.iters; it++) {
+                // A logical operator touches O(L) row words.  Only the top rung proposes one (with probability p_logical),
+                // so instead of one lane working through the rows while the others wait, the WARP evaluates it: the owner
+                // draws the operator and broadcasts it, lane j forms the new value of row word j (and j + 32) of the
+                // owner's lattice, the weight change is a warp reduction, the owner decides, and on accept the lanes commit
+                // their words.  Same draws in the same order, same arithmetic as _apply_random_logical + update_chain.
                 bool logical = false;
-                if (is_top) logical = rng.py() < p.p_logical;
-                if (logical) {
-                    LogicalDraw<GEOM, RNG> ld;
-                    ld.draw(rng, L);
-                    int dE = ld.template apply<W>(g, lat);
-                    int dcls = 0;
-                    for (int l = 0; l < ld.nl; l++) dcls ^= p.cls_delta[l * 4 + ld.op[l]];
-                    bool acc;
-                    int mx = 0, my = 0, mz = 0;
+                LogicalDraw<GEOM, RNG> ld;
+                ld.op[0] = ld.op[1] = ld.xp[0] = ld.xp[1] = ld.zp[0] = ld.zp[1] = 0;
+                ld.nl = GEOM == TORIC ? 2 : 1;
+                if (is_top) {
+                    logical = rng.py() < p.p_logical;
+                    if (logical) ld.draw(rng, L);
+                }
+                uint32_t lm = __ballot_sync(0xFFFFFFFFu, logical);
+                while (lm) {
+                    const int src = __ffs(lm) - 1;
+                    lm &= lm - 1;
+                    const int packed = ld.op[0] | (ld.op[1] << 2) | (ld.xp[0] << 4) | (ld.zp[0] << 9) | (ld.xp[1] << 14) | (ld.zp[1] << 19);
+                    const int pk = __shfl_sync(0xFFFFFFFFu, packed, src);
+                    const int o0 = pk & 3, o1 = (pk >> 2) & 3, x0 = (pk >> 4) & 31, z0 = (pk >> 9) & 31, x1 = (pk >> 14) & 31, z1 = (pk >> 19) & 31;
+                    W *col = tile + ((tid & ~31) + src);   // the owner's column of the tile
+                    W nv[2] = {0, 0};
+                    bool touched[2] = {false, false};
+                    int dE = 0, dx = 0, dy = 0, dz = 0;
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        const int w = lane + 32 * k;
+                        if (w < g.nw) {
+                            const W m = logical_mask<GEOM, W>(g, w, o0, o1, x0, z0, x1, z1);
+                            if (m) {
+                                const W o = col[w * T];
+                                nv[k] = (W)(o ^ m);
+                                touched[k] = true;
+                                if (WEIGHTED) {
+                                    dx += popc(xmap(nv[k])) - popc(xmap(o));
+                                    dy += popc(ymap(nv[k])) - popc(ymap(o));
+                                    dz += popc(zmap(nv[k])) - popc(zmap(o));
+                                } else {
+                                    dE += weight<W>(nv[k]) - weight<W>(o);
+                                }
+                            }
+                        }
+                    }
                     if (WEIGHTED) {
-                        lat_count_xyz<W>(g, lat, mx, my, mz);
-                        double pn = chain_weight(wt, ns1, mx, my, mz);
-                        acc = rng.py() < __ddiv_rn(pn, pb);
+                        dx = __reduce_add_sync(0xFFFFFFFFu, dx);
+                        dy = __reduce_add_sync(0xFFFFFFFFu, dy);
+                        dz = __reduce_add_sync(0xFFFFFFFFu, dz);
                     } else {
-                        if (p.top_accept_all || dE <= 0) acc = true;
-                        else acc = rng.py() < p.thr_top_d[dE + 4 * L];
+                        dE = __reduce_add_sync(0xFFFFFFFFu, dE);
                     }
+                    bool acc = false;
+                    if (lane == src) {
+                        if (WEIGHTED) {
+                            double pn = chain_weight(wt, ns1, nx + dx, ny + dy, nz + dz);
+                            acc = rng.py() < __ddiv_rn(pn, pb);
+                        } else {
+                            if (p.top_accept_all || dE <= 0) acc = true;
+                            else acc = rng.py() < p.thr_top_d[dE + 4 * L];
+                        }
+                        if (acc) {
+                            int dcls = 0;
+                            for (int l = 0; l < ld.nl; l++) dcls ^= p.cls_delta[l * 4 + ld.op[l]];
+                            if (WEIGHTED) { nx += dx; ny += dy; nz += dz; n = nx + ny + nz; e_nz = nz; e_nxy = nx + ny; }
+                            else n += dE;
+                            cls ^= dcls;
+                            if (track_hash) h ^= ld.hash_delta(p.log_hash);
+                            dirty = true;
+                            nacc++;
+                        }
+                    }
+                    acc = __shfl_sync(0xFFFFFFFFu, (int)acc, src) != 0;
                     if (acc) {
-                        if (WEIGHTED) { nx = mx; ny = my; nz = mz; n = mx + my + mz; e_nz = mz; e_nxy = mx + my; }
-                        else n += dE;
-                        cls ^= dcls;
-                        if (track_hash) h ^= ld.hash_delta(p.log_hash);
-                        dirty = true;
-                        nacc++;
-                    } else {
-                        ld.template apply<W>(g, lat);  // XOR is an involution: undo
+#pragma unroll
+                        for (int k = 0; k < 2; k++)
+                            if (touched[k]) col[(lane + 32 * k) * T] = nv[k];
                     }
+                    __syncwarp();
+                }
+                if (!active || logical) {
+                    // nothing more this iteration (idle lane, or the logical move was this rung's step)
                 } else {
                     int row, col, op, idx = 0;
                     if (REPLAY) {

@@ -348,6 +348,37 @@ QHD int lat_apply_logical(const Geo &g, A &a, int op, int layer, int X_pos, int 
     return d;
 }
 
+// The same operators as XOR masks per row word: mask of word w for the operator(s) of _apply_random_logical
+// (op0 / X0 / Z0 on layer 0 -- the only layer of the one-layer codes --, op1 / X1 / Z1 on the toric code's layer 1).
+// Applying the masks to every word equals lat_apply_logical layer by layer (XOR commutes; X ^ Z = Y on a shared qubit).
+template <int GEOM, typename W> QHD W logical_mask(const Geo &g, int w, int op0, int op1, int X0, int Z0, int X1, int Z1)
+{
+    const int L = g.L;
+    W m = 0;
+    if (GEOM == TORIC) {
+        if (w < L) {
+            if ((op0 == 1 || op0 == 2) && w == X0) m ^= rowmask<W>(1, L);
+            if (op0 == 3 || op0 == 2) m ^= fld<W>(3, Z0);
+        } else {
+            const int i = w - L;
+            if (op1 == 1 || op1 == 2) m ^= fld<W>(1, X1);
+            if ((op1 == 3 || op1 == 2) && i == Z1) m ^= rowmask<W>(3, L);
+        }
+    } else if (GEOM == PLANAR) {
+        if (w < L) {
+            if ((op0 == 1 || op0 == 3) && w == X0) m ^= rowmask<W>(1, L);
+            if (op0 == 2 || op0 == 3) m ^= fld<W>(3, Z0);
+        }
+    } else if (GEOM == ROTATED) {
+        if (op0 == 1 || op0 == 3) m ^= fld<W>(1, X0);
+        if ((op0 == 2 || op0 == 3) && w == Z0) m ^= rowmask<W>(3, L);
+    } else {
+        if (op0 == 1 || op0 == 2) m ^= fld<W>(1, L - 1 - w);
+        if (op0 == 3 || op0 == 2) m ^= fld<W>(3, w);
+    }
+    return m;
+}
+
 // Move into class eq keeping the syndrome.  Toric: _to_class, toric_model.py:354-377;
 // others: apply_logical(define_equivalence_class() ^ eq), decoders.py:556-560.
 template <int GEOM, typename W, typename A> QHD void lat_to_class(const Geo &g, A &a, int eq)

@@ -17,6 +17,7 @@ elif which == "xzzx21_biased":
 else:
     g, L, kind, bottom, b = _lib.XZZX, 21, _lib.LADDER_ALPHA, 0.17474, 0.6447
 q = ((rng.random((S, L * L)) < 0.15) * rng.integers(1, 4, (S, L * L))).astype(np.uint8)
+ctx.pteq(g, L, kind, q[:64], bottom, param_b=b, steps=3, conv=False, seed=1, p_logical=p_logical)      # module load, allocations
 pct, info = ctx.pteq(g, L, kind, q, bottom, param_b=b, steps=steps, conv=False, seed=11, p_logical=p_logical)
 st = info["stats"]
 print(which, "S", S, "steps", steps, "p_logical", p_logical, "kernel_ms", st["chain_kernel_ms"], "metropolis steps/s", st["metropolis_steps"] / (st["chain_kernel_ms"] * 1e-3))
