@@ -20,6 +20,7 @@
 namespace qecmc {
 
 enum { LK_DEPOL = 0, LK_ALPHA = 1, LK_BIASED = 2 };
+#define QECMC_PW_K 31   // swap-sweep power table covers weight differences of up to 31 between neighbouring rungs
 enum { ACCT_NONE = 0, ACCT_PTEQ = 1, ACCT_DC = 2, ACCT_RC = 3 };
 
 struct LadderParams {
@@ -141,13 +142,15 @@ __device__ __forceinline__ double chain_weight(const double *wt, int ns1, int nx
 }
 
 template <int GEOM, typename RNG> struct LogicalDraw {
-    int op[2], xp[2], zp[2], nl;
+    static constexpr int nl = GEOM == TORIC ? 2 : 1;   // compile-time: the small arrays stay in registers
+    int op[2], xp[2], zp[2];
     // _apply_random_logical draw order: toric_model.py:228-253 (both layer operators first),
     // planar_model.py:271-288, rotated_surface_model.py:331-346, xzzx_model.py:340-357
     __device__ __forceinline__ void draw(RNG &rng, int L)
     {
-        nl = GEOM == TORIC ? 2 : 1;
+#pragma unroll
         for (int l = 0; l < nl; l++) op[l] = (int)(rng.nb() * 4);
+#pragma unroll
         for (int l = 0; l < nl; l++) {
             xp[l] = zp[l] = 0;
             if (op[l] == 1 || op[l] == 2) xp[l] = (int)(rng.nb() * L);
@@ -158,6 +161,7 @@ template <int GEOM, typename RNG> struct LogicalDraw {
     __device__ __forceinline__ uint64_t hash_delta(const uint64_t *lh) const
     {
         uint64_t d = 0;
+#pragma unroll
         for (int l = 0; l < nl; l++) {
             const bool do_X = (GEOM == TORIC || GEOM == XZZX) ? (op[l] == 1 || op[l] == 2) : (op[l] == 1 || op[l] == 3);
             const bool do_Z = op[l] == 2 || op[l] == 3;
@@ -176,7 +180,7 @@ template <int GEOM, typename RNG> struct LogicalDraw {
 };
 
 template <int GEOM, typename W, bool REPLAY, bool WEIGHTED>
-__global__ void __launch_bounds__(128) ladder_kernel(LadderParams p)
+__global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
 {
     typedef typename std::conditional<REPLAY, ReplayRng, NativeRng>::type RNG;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -188,6 +192,76 @@ __global__ void __launch_bounds__(128) ladder_kernel(LadderParams p)
     uint32_t *s_thru = reinterpret_cast<uint32_t *>(s_thrd + p.Nc * 9);    // [Nc][9]
     if (!WEIGHTED)
         for (int i = tid; i < p.Nc * 9; i += T) { s_thrd[i] = p.thr_d[i]; s_thru[i] = p.thr_u[i]; }
+    // One-layer codes (rotated, XZZX): a stabilizer touches at most two adjacent qubits in each of two row words, so the
+    // step is table driven.  Per stabilizer: the two word indices, the bit position of each word's lower touched field and
+    // the Paulis applied to the four slots (a nibble per word); the weight changes (dx, dy, dz and their sum) come from a
+    // LUT indexed by (Pauli pattern, the four touched fields).  Both tables are built here from decode<GEOM>().
+    constexpr bool TABLE = GEOM == ROTATED || GEOM == XZZX;
+    uint2 *s_ld = reinterpret_cast<uint2 *>(s_thru + p.Nc * 9 + ((p.Nc * 9) & 1));   // [nstab], 8-byte aligned
+    uint16_t *s_ll = reinterpret_cast<uint16_t *>(s_ld + (TABLE ? g.nstab : 0));                    // [patterns <= 16][256]
+    __shared__ uint32_t s_patmask[8];
+    // swap sweep: diff[i]^k for |k| <= QECMC_PW_K, made with the same square-and-multiply routine the sweep would call
+    // (bit-identical), so a pair costs one table read instead of a multiply loop and, for k < 0, a division
+    double *s_pw = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(s_ll) + (TABLE ? 16 * 256 * 2 : 0));
+    const bool use_pw = p.kind != LK_ALPHA && p.Nc > 1;
+    if (use_pw)
+        for (int e = tid; e < (p.Nc - 1) * (2 * QECMC_PW_K + 1); e += T)
+            s_pw[e] = numba_pow_dev(p.diff[e / (2 * QECMC_PW_K + 1)], e % (2 * QECMC_PW_K + 1) - QECMC_PW_K);
+    if (TABLE) {
+        if (tid < 8) s_patmask[tid] = 0;
+        __syncthreads();
+        for (int i = tid; i < g.nstab; i += T) {
+            int row, col, op;
+            idx_to_rco<GEOM>(g, i, row, col, op);
+            Upd<W> u;
+            decode<GEOM, W>(g, row, col, op, u);
+            uint32_t pos[2], nib[2];
+            for (int k = 0; k < 2; k++) {
+                int b = 0;
+                while (b < 2 * g.L && !((u.m[k] >> b) & 3)) b += 2;
+                pos[k] = u.m[k] ? (uint32_t)b : 0u;
+                nib[k] = (uint32_t)(u.m[k] >> pos[k]) & 0xFu;
+            }
+            const uint32_t pat = nib[0] | (nib[1] << 4);
+            s_ld[i] = make_uint2((uint32_t)u.w[0] | ((uint32_t)u.w[1] << 8) | (pos[0] << 16) | (pos[1] << 24), pat);
+            atomicOr(&s_patmask[pat >> 5], 1u << (pat & 31));
+        }
+        __syncthreads();
+        // pattern id = rank of the pattern among those present
+        for (int i = tid; i < g.nstab; i += T) {
+            const uint32_t pat = s_ld[i].y & 0xFFu;
+            uint32_t id = __popc(s_patmask[pat >> 5] & ((1u << (pat & 31)) - 1u));
+            for (uint32_t wq = 0; wq < (pat >> 5); wq++) id += __popc(s_patmask[wq]);
+            s_ld[i].y = pat | (id << 8);
+        }
+        for (int e = tid; e < 16 * 256; e += T) {
+            // the pattern with rank e >> 8
+            int want = e >> 8, pat = -1;
+            for (int wq = 0; wq < 8 && pat < 0; wq++) {
+                uint32_t mbits = s_patmask[wq];
+                const int c = __popc(mbits);
+                if (want >= c) { want -= c; continue; }
+                while (want--) mbits &= mbits - 1;
+                pat = wq * 32 + __ffs(mbits) - 1;
+            }
+            uint32_t packed = 0;
+            if (pat >= 0) {
+                const int f = e & 255;
+                int dx = 0, dy = 0, dz = 0;
+                for (int sl = 0; sl < 4; sl++) {
+                    const int v = (pat >> (2 * sl)) & 3, q = (f >> (2 * sl)) & 3;
+                    if (v) {
+                        const int nq = q ^ v;
+                        dx += (nq == 1) - (q == 1);
+                        dy += (nq == 2) - (q == 2);
+                        dz += (nq == 3) - (q == 3);
+                    }
+                }
+                packed = (uint32_t)(dx + 4) | ((uint32_t)(dy + 4) << 4) | ((uint32_t)(dz + 4) << 8) | ((uint32_t)(dx + dy + dz + 4) << 12);
+            }
+            s_ll[e] = (uint16_t)packed;
+        }
+    }
     __syncthreads();
 
     const int G = p.G, Nc = p.Nc, L = g.L;
@@ -273,7 +347,6 @@ __global__ void __launch_bounds__(128) ladder_kernel(LadderParams p)
                 bool logical = false;
                 LogicalDraw<GEOM, RNG> ld;
                 ld.op[0] = ld.op[1] = ld.xp[0] = ld.xp[1] = ld.zp[0] = ld.zp[1] = 0;
-                ld.nl = GEOM == TORIC ? 2 : 1;
                 if (is_top) {
                     logical = rng.py() < p.p_logical;
                     if (logical) ld.draw(rng, L);
@@ -326,6 +399,7 @@ __global__ void __launch_bounds__(128) ladder_kernel(LadderParams p)
                         }
                         if (acc) {
                             int dcls = 0;
+#pragma unroll
                             for (int l = 0; l < ld.nl; l++) dcls ^= p.cls_delta[l * 4 + ld.op[l]];
                             if (WEIGHTED) { nx += dx; ny += dy; nz += dz; n = nx + ny + nz; e_nz = nz; e_nxy = nx + ny; }
                             else n += dE;
@@ -355,22 +429,37 @@ __global__ void __launch_bounds__(128) ladder_kernel(LadderParams p)
                         if (track_hash) idx = rco_to_idx<GEOM>(g, row, col, op);
                     } else {
                         idx = (int)__umulhi(reinterpret_cast<NativeRng *>(&rng)->next32(), (uint32_t)g.nstab);
-                        idx_to_rco<GEOM>(g, idx, row, col, op);
+                        if (!TABLE) idx_to_rco<GEOM>(g, idx, row, col, op);
                     }
                     Upd<W> u;
-                    decode<GEOM, W>(g, row, col, op, u);
                     W nv[NU];
                     int dE = 0, dx = 0, dy = 0, dz = 0;
+                    if (TABLE) {
+                        if (REPLAY && !track_hash) idx = rco_to_idx<GEOM>(g, row, col, op);
+                        const uint2 D = s_ld[idx];
+                        u.w[0] = (int)(D.x & 0xFFu);
+                        u.w[1] = (int)((D.x >> 8) & 0xFFu);
+                        const uint32_t p0 = (D.x >> 16) & 0xFFu, p1 = D.x >> 24;
+                        const W o0 = lat.get(u.w[0]), o1 = lat.get(u.w[1]);
+                        const uint32_t f = ((uint32_t)(o0 >> p0) & 0xFu) | (((uint32_t)(o1 >> p1) & 0xFu) << 4);
+                        const uint32_t pk = s_ll[((D.y >> 8) << 8) + f];
+                        nv[0] = (W)(o0 ^ ((W)(D.y & 0xFu) << p0));
+                        nv[1] = (W)(o1 ^ ((W)((D.y >> 4) & 0xFu) << p1));
+                        if (WEIGHTED) { dx = (int)(pk & 15u) - 4; dy = (int)((pk >> 4) & 15u) - 4; dz = (int)((pk >> 8) & 15u) - 4; }
+                        else dE = (int)(pk >> 12) - 4;
+                    } else {
+                        decode<GEOM, W>(g, row, col, op, u);
 #pragma unroll
-                    for (int i = 0; i < NU; i++) {
-                        W o = lat.get(u.w[i]);
-                        nv[i] = (W)(o ^ u.m[i]);
-                        if (WEIGHTED) {
-                            dx += popc(xmap(nv[i])) - popc(xmap(o));
-                            dy += popc(ymap(nv[i])) - popc(ymap(o));
-                            dz += popc(zmap(nv[i])) - popc(zmap(o));
-                        } else {
-                            dE += weight<W>(nv[i]) - weight<W>(o);
+                        for (int i = 0; i < NU; i++) {
+                            W o = lat.get(u.w[i]);
+                            nv[i] = (W)(o ^ u.m[i]);
+                            if (WEIGHTED) {
+                                dx += popc(xmap(nv[i])) - popc(xmap(o));
+                                dy += popc(ymap(nv[i])) - popc(ymap(o));
+                                dz += popc(zmap(nv[i])) - popc(zmap(o));
+                            } else {
+                                dE += weight<W>(nv[i]) - weight<W>(o);
+                            }
                         }
                     }
                     bool acc;
@@ -441,7 +530,10 @@ __global__ void __launch_bounds__(128) ladder_kernel(LadderParams p)
                     swap = true;  // mcmc.py:146-147: no draw
                 } else {
                     if (REPLAY) u = done ? 1.0 : rng.nb();  // mcmc_biased.py:154-156 draws always
-                    swap = u < numba_pow_dev(p.diff[i], ne_hi - ne_lo);
+                    const int k = ne_hi - ne_lo;
+                    const double pw = (use_pw && k >= -QECMC_PW_K && k <= QECMC_PW_K) ? s_pw[i * (2 * QECMC_PW_K + 1) + k + QECMC_PW_K]
+                                                                                       : numba_pow_dev(p.diff[i], k);
+                    swap = u < pw;
                 }
             }
             if (swap && !done) {
