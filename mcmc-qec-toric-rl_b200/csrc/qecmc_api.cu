@@ -313,6 +313,8 @@ static int launch_stdc_fast(qecmc_ctx *c, StdcParams &p)
     size_t dyn_fixed = static_tab ? 0 : (size_t)p.gchain.nstab * 16 + 16;
     const bool conv = REPLAY || p.conv_mult != 0.0;
     QTRY(pick_threads(per_chain, stat + dyn_fixed + 256, c->prop, &T, &nb, static_tab && !conv, conv ? 56 : 64));
+    // a small batch is spread over the SMs rather than packed into a few large CTAs
+    while (T > 64 && (p.n_chains + T - 1) / T < c->prop.multiProcessorCount) T /= 2;
     size_t smem = ((per_chain * T + 15) & ~(size_t)15) + dyn_fixed;
     unsigned grid = (unsigned)((p.n_chains + T - 1) / T);
     if (conv) {
@@ -383,9 +385,6 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
     if (!(cfg->p_error > 0 && cfg->p_error < 1) || !(cfg->p_sampling > 0 && cfg->p_sampling < 1))
         return set_err(QECMC_ERR_ARG, "p_error / p_sampling outside (0,1)");
     if ((uint64_t)cfg->steps * (uint64_t)cfg->iters >= (1ull << 32)) return set_err(QECMC_ERR_UNSUPPORTED, "steps * iters must be < 2^32");
-    if (cfg->conv_mult != 0.0 && cfg->droplets != 1)
-        return set_err(QECMC_ERR_UNSUPPORTED, "conv_mult != 0 needs droplets == 1: the early-stop rule asks whether a chain is new "
-                                              "to its own droplet, and the droplets of a class share one distinct-chain set");
     if (cfg->conv_mult < 0.0) return set_err(QECMC_ERR_ARG, "conv_mult must be >= 0");
     if (cfg->randomize && cfg->geom_code != TORIC && cfg->geom_code != PLANAR)
         return set_err(QECMC_ERR_ARG, "apply_stabilizers_uniform exists only for toric/planar codes");
@@ -403,8 +402,16 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
     // counts beyond what the dedupe kernel's bucket fan-out covers.
     const int forced_mode = getenv("QECMC_DEBUG_INSERT_MODE") ? atoi(getenv("QECMC_DEBUG_INSERT_MODE")) : -1;
     const uint64_t max_keys = (uint64_t)cfg->droplets * (uint64_t)cfg->steps;
-    const bool use_logs = mode != MODE_MEAN && cfg->conv_mult == 0.0 && (forced_mode < 0 || forced_mode == 4) &&
-                          max_keys <= (uint64_t)QECMC_DD_MAX_BUCKETS * QECMC_DD_BUCKET_TARGET && (uint64_t)cfg->steps < (1ull << 32);
+    const bool fits_dedupe = max_keys <= (uint64_t)QECMC_DD_MAX_BUCKETS * QECMC_DD_BUCKET_TARGET && (uint64_t)cfg->steps < (1ull << 32);
+    // conv_mult != 0 (early stop, decoders.py:257-263): "new" means new to the DROPLET, so every chain probes a set of
+    // its own (synchronously: the rule needs the answer at once) and logs only the keys new to it; the union over the
+    // droplets of a class is then the same dedupe as without early stop.
+    const bool conv = mode != MODE_MEAN && cfg->conv_mult != 0.0;
+    const bool conv_logs = conv && fits_dedupe && forced_mode != 0;
+    if (conv && !conv_logs && cfg->droplets != 1)
+        return set_err(QECMC_ERR_UNSUPPORTED, "conv_mult != 0 with droplets > 1 needs droplets * steps <= %llu",
+                       (unsigned long long)QECMC_DD_MAX_BUCKETS * QECMC_DD_BUCKET_TARGET);
+    const bool use_logs = conv_logs || (mode != MODE_MEAN && !conv && (forced_mode < 0 || forced_mode == 4) && fits_dedupe);
     const int64_t log_cap = (cfg->steps + 1) & ~(int64_t)1;
     int dd_grid = c->prop.multiProcessorCount;
     uint64_t cap = 0;
@@ -419,7 +426,11 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
         if (use_logs) {
             if ((int64_t)S * n_eq < dd_grid) dd_grid = (int)(S * n_eq);
             const int64_t scratch_bytes = (int64_t)dd_grid * cfg->droplets * log_cap * 8;
-            per_syndrome = (int64_t)n_eq * cfg->droplets * log_cap * 8;
+            if (conv_logs) {   // one set per chain: capacity covers every sample distinct at load <= 0.8
+                cap = next_pow2((uint64_t)cfg->steps + (uint64_t)cfg->steps / 4 + 1);
+                if (cap < 1024) cap = 1024;
+            }
+            per_syndrome = (int64_t)n_eq * cfg->droplets * (log_cap + (int64_t)cap) * 8;
             wave = (budget - scratch_bytes) / per_syndrome;
             if (wave < 1)
                 return set_err(QECMC_ERR_NOMEM, "key logs need %lld bytes per syndrome plus %lld bytes of scratch, budget is %lld",
@@ -479,8 +490,10 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
     p.u_np = cfg->u_np;
     p.counters = (unsigned long long *)c->counters.p;
     // diagnostic knob for roofline work (3 = chains without the distinct set: results are then meaningless)
-    p.insert_mode = use_logs ? 4 : (forced_mode >= 0 && forced_mode != 4 ? forced_mode : 2);
-    p.logs = (unsigned long long *)c->tables.p;
+    p.insert_mode = conv_logs ? 5 : use_logs ? 4 : (forced_mode >= 0 && forced_mode != 4 ? forced_mode : 2);
+    // conv_logs: [per-chain sets of the wave | per-chain logs of the wave]; logs only: the logs start the buffer
+    const size_t chain_sets_bytes = conv_logs ? (size_t)wave * n_eq * cfg->droplets * (size_t)cap * 8 : 0;
+    p.logs = (unsigned long long *)((char *)c->tables.p + chain_sets_bytes);
     p.log_counts = (uint32_t *)c->log_counts.p;
     p.log_cap = log_cap;
     p.max_length = 2 * cfg->L * cfg->L;  // decoders.py:747
@@ -496,6 +509,7 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
     for (int64_t s0 = 0; s0 < S; s0 += wave, waves++) {
         int64_t sw = S - s0 < wave ? S - s0 : wave;
         if (mode != MODE_MEAN && !use_logs) CUDA_OK(cudaMemsetAsync(c->tables.p, 0, (size_t)sw * per_syndrome, c->stream));
+        if (conv_logs) CUDA_OK(cudaMemsetAsync(c->tables.p, 0, (size_t)sw * n_eq * cfg->droplets * (size_t)cap * 8, c->stream));
         p.lat0 = (const char *)c->packed.p + (size_t)(cfg->per_class_inits ? s0 * n_eq : s0) * gcode.nw * wbytes;
         p.n_chains = sw * n_eq * cfg->droplets;
         p.chain_offset = s0 * n_eq * cfg->droplets;
@@ -508,7 +522,7 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
         const int64_t tabs = sw * n_eq;
         if (mode != MODE_MEAN && use_logs) {
             DedupeParams dp;
-            dp.logs = (const unsigned long long *)c->tables.p;
+            dp.logs = p.logs;
             dp.log_counts = (const uint32_t *)c->log_counts.p;
             dp.log_cap = log_cap;
             dp.droplets = cfg->droplets;

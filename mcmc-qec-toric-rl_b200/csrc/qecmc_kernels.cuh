@@ -177,7 +177,8 @@ struct StdcParams {
     Thr thr;
     const double *u_nb, *u_np;
     unsigned long long *counters;  // [0] accepted [1] offered [2] inserted
-    int insert_mode;               // 4 per-chain key logs + log_dedupe_kernel (default when applicable); 2 prefetch + deferred
+    int insert_mode;               // 4 per-chain key logs + log_dedupe_kernel (default when applicable); 5 early stop: a set per
+                                   // chain (probed at once) + a log of the keys new to the chain + dedupe; 2 prefetch + deferred
                                    // probe of the HBM set; 1 asynchronous CAS; diagnostics: 0 synchronous probe, 3 no inserts
     unsigned long long *logs;      // insert_mode 4: [n_chains][log_cap] offered keys, in order
     uint32_t *log_counts;          // [n_chains]
@@ -320,7 +321,11 @@ __global__ void __launch_bounds__(256) stdc_kernel(StdcParams p)
     int n = lat_weight<W>(g, lat);
     uint64_t h = lat_hash<W>(g, lat, p.hash_seed);
     const bool log_mode = MODE != MODE_MEAN && p.insert_mode == 4 && p.conv_mult == 0.0;
-    unsigned long long *table = log_mode ? p.logs + (uint64_t)local * (uint64_t)p.log_cap : p.tables + (uint64_t)tab * (p.cap_mask + 1);
+    const bool conv_log = MODE != MODE_MEAN && p.insert_mode == 5;   // early stop: a set per chain + a log of the keys new to it
+    unsigned long long *table = log_mode ? p.logs + (uint64_t)local * (uint64_t)p.log_cap
+                                         : p.tables + (uint64_t)(conv_log ? local : tab) * (p.cap_mask + 1);
+    unsigned long long *clog = p.logs + (uint64_t)local * (uint64_t)p.log_cap;
+    uint32_t nlog = 0;
     SampleAcct<MODE> acct;
     acct.init(p, tab);
     ConvStop cs;
@@ -339,7 +344,8 @@ __global__ void __launch_bounds__(256) stdc_kernel(StdcParams p)
         bool is_new = false;                                                \
         if (MODE != MODE_MEAN && dirty) {                                   \
             if (log_mode) table[noff++] = make_key(h, n);                   \
-            else { noff++; is_new = table_insert(table, p.cap_mask, make_key(h, n)); nins += is_new; } \
+            else { noff++; is_new = table_insert(table, p.cap_mask, make_key(h, n)); nins += is_new;  \
+                   if (conv_log && is_new) clog[nlog++] = make_key(h, n); }        \
         }                                                                   \
         dirty = false;                                                      \
         cs.after_sample(p, is_new, n);                                      \
@@ -378,6 +384,7 @@ __global__ void __launch_bounds__(256) stdc_kernel(StdcParams p)
     }
 #undef QECMC_AFTER_STEP
     if (log_mode) p.log_counts[local] = (uint32_t)noff;
+    if (conv_log) p.log_counts[local] = nlog;
     acct.finish(p, local);
     // statistics: three atomics per chain at the very end (negligible)
     atomicAdd(p.counters + 0, nacc);

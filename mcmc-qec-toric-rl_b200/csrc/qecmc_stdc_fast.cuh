@@ -186,9 +186,12 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ?
     int n = lat_weight<W>(g, lat);
     uint64_t h = lat_hash<W>(g, lat, p.hash_seed);
     const uint64_t cap_mask = p.cap_mask;
-    const int imode = MODE == MODE_MEAN ? 3 : (CONV && p.conv_mult != 0.0 ? 0 : p.insert_mode);  // the early stop needs the probe's answer now
-    // log mode: `table` is this chain's key log
-    unsigned long long *table = imode == 4 ? p.logs + (uint64_t)local * (uint64_t)p.log_cap : p.tables + (uint64_t)tab * (cap_mask + 1);
+    // the early stop needs the probe's answer at once: mode 5 (a set per chain + a log of the keys new to it) or 0 (the class's set)
+    const int imode = MODE == MODE_MEAN ? 3 : (CONV && p.conv_mult != 0.0 ? (p.insert_mode == 5 ? 5 : 0) : p.insert_mode);
+    // mode 4: `table` is this chain's key log; mode 5: this chain's own set
+    unsigned long long *table = imode == 4 ? p.logs + (uint64_t)local * (uint64_t)p.log_cap
+                              : p.tables + (uint64_t)(imode == 5 ? local : tab) * (cap_mask + 1);
+    uint32_t nlog = 0;
 
     uint32_t nacc = 0, noff = 0;
     bool dirty = true;  // the first sample is always new to the chain
@@ -322,6 +325,12 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ?
                 if (fire) cas_async(prev, table + slot, key);
             } else if (imode == 0) {
                 if (dirty) is_new = table_insert(table, cap_mask, make_key(h, n));
+            } else if (CONV && imode == 5) {
+                if (dirty) {
+                    const uint64_t k = make_key(h, n);
+                    is_new = table_insert(table, cap_mask, k);
+                    if (is_new) p.logs[(uint64_t)local * (uint64_t)p.log_cap + nlog++] = k;
+                }
             }
             noff += dirty;
             dirty = false;
@@ -365,6 +374,7 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ?
         } while (q != 0ull && q != key);
     }
     if (imode == 4) p.log_counts[local] = noff;
+    if (imode == 5) p.log_counts[local] = nlog;
     acct.finish(p, local);
     atomicAdd(p.counters + 0, (unsigned long long)nacc);
     atomicAdd(p.counters + 1, (unsigned long long)noff);

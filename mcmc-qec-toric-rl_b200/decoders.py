@@ -60,7 +60,7 @@ def _fast_path_check(code, per_class):
 def STDC_batch(init_codes, p_error, p_sampling=None, droplets=10, steps=20000, conv_mult=0, seed=None, device=0,
                return_stats=False):
     """STDC (decoders.py:268-322) for a list of init_code arguments -> float64 [S, nbr_eq_classes] (percent).
-    conv_mult != 0 (the early stop of decoders.py:257-263) is exact for droplets == 1 and rejected otherwise."""
+    conv_mult != 0 is the early stop of decoders.py:257-263 ("new" = new to the droplet: a set per chain on the device)."""
     p_sampling = p_sampling or p_error
     code, qm, per_class = _batch(init_codes)
     _fast_path_check(code, per_class)

@@ -228,29 +228,32 @@ def test_single_temp_replay_matches_oracle(ctx, g, L):
         assert np.array_equal(out[s], want)
 
 
+@pytest.mark.parametrize("droplets", [1, 3])
 @pytest.mark.parametrize("fn", ["stdc", "strc"])
 @pytest.mark.parametrize("gcode,L", [(O.TORIC, 5), (O.PLANAR, 7), (O.ROTATED, 5)])
-def test_conv_mult_early_stop_matches_oracle(ctx, fn, gcode, L):
-    """conv_mult != 0 (decoders.py:257-263, :795), droplets = 1: chains stop at the same sample as the oracle's, so the
-    histograms of what they saw are identical."""
+def test_conv_mult_early_stop_matches_oracle(ctx, fn, gcode, L, droplets):
+    """conv_mult != 0 (decoders.py:257-263, :795): "new" is new to the droplet, so every chain stops at the same sample
+    as the oracle's and the union of what the droplets of a class saw gives identical histograms -- also with several
+    droplets per class (a set per chain + a log of the keys new to it, then the dedupe kernel)."""
     if fn == "strc" and gcode == O.ROTATED:
         pytest.skip("covered by stdc")
-    rng = np.random.default_rng(4100 + L)
+    rng = np.random.default_rng(4100 + L + droplets)
     S, steps, iters, conv = 3, 400, 5, 2.0
     n_eq = O.neq(gcode)
     k = 3 if gcode in (O.TORIC, O.PLANAR) else 5
     randomize = gcode in (O.TORIC, O.PLANAR)
     qs = [rand_lattice(rng, gcode, L, 0.08) for _ in range(S)]
     qm = np.stack([q.reshape(-1) for q in qs])
-    u_nb, u_np = _stdc_streams(rng, S * n_eq, steps, iters, k, L)
+    u_nb, u_np = _stdc_streams(rng, S * n_eq * droplets, steps, iters, k, L)
     run = getattr(ctx, fn)
-    res = run(gcode, gcode, L, qm, 0.1, 0.25, 1, steps, iters=iters, randomize=randomize, conv_mult=conv, u_nb=u_nb, u_np=u_np,
-              want_hist=True)
-    assert res[1]["metropolis_steps"] < S * n_eq * steps * iters      # some chains did stop early
+    res = run(gcode, gcode, L, qm, 0.1, 0.25, droplets, steps, iters=iters, randomize=randomize, conv_mult=conv, u_nb=u_nb,
+              u_np=u_np, want_hist=True)
+    assert res[1]["metropolis_steps"] < S * n_eq * droplets * steps * iters      # some chains did stop early
     for s in range(S):
-        nb = [O.Stream.replay(u_nb[s * n_eq + i].reshape(-1)) for i in range(n_eq)]
-        np_ = [O.Stream.replay(u_np[s * n_eq + i]) for i in range(n_eq)]
-        want = getattr(O, fn)(gcode, gcode, L, O.all_classes(gcode, L, qs[s]), 0.1, 0.25, 1, steps, nb, np_, iters=iters,
+        base = s * n_eq * droplets
+        nb = [O.Stream.replay(u_nb[base + i].reshape(-1)) for i in range(n_eq * droplets)]
+        np_ = [O.Stream.replay(u_np[base + i]) for i in range(n_eq * droplets)]
+        want = getattr(O, fn)(gcode, gcode, L, O.all_classes(gcode, L, qs[s]), 0.1, 0.25, droplets, steps, nb, np_, iters=iters,
                               randomize=randomize, conv_mult=conv, want_hist=True)
         assert np.array_equal(res[2][s].astype(np.int64), want[2 if fn == "stdc" else 1])
         np.testing.assert_allclose(res[0][s], want[0], rtol=1e-9)
