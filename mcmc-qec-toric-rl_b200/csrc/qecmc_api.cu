@@ -309,9 +309,12 @@ static int launch_stdc_fast(qecmc_ctx *c, StdcParams &p)
     // wider lattices keep descriptors and fingerprints behind the tile in dynamic shared memory
     const bool static_tab = sizeof(W) == 4;
     if (static_tab && p.gchain.nstab > QECMC_FAST_STATIC_NSTAB) return set_err(QECMC_ERR_UNSUPPORTED, "internal: %d stabilizers exceed the static tables", p.gchain.nstab);
-    size_t stat = 512 * 5 + 128 + (static_tab ? (size_t)QECMC_FAST_STATIC_NSTAB * 40 : 0);
-    size_t dyn_fixed = static_tab ? 0 : (size_t)p.gchain.nstab * 16 + 16;
     const bool conv = REPLAY || p.conv_mult != 0.0;
+    // 32-bit row words: the table struct opens the dynamic shared memory (8 interleaved copies of the two hot tables in
+    // the one-CTA-per-SM variant), the tile follows; wider lattices keep plain tables behind the tile
+    const size_t tabs_bytes = !static_tab ? 0 : conv ? ((sizeof(FastTabs<1>) + 15) & ~(size_t)15) : ((sizeof(FastTabs<8>) + 15) & ~(size_t)15);
+    size_t stat = 512 * 5 + 128;
+    size_t dyn_fixed = static_tab ? tabs_bytes : (size_t)p.gchain.nstab * 16 + 16;
     QTRY(pick_threads(per_chain, stat + dyn_fixed + 256, c->prop, &T, &nb, static_tab && !conv, conv ? 56 : 64));
     // a small batch is spread over the SMs rather than packed into a few large CTAs
     while (T > 64 && (p.n_chains + T - 1) / T < c->prop.multiProcessorCount) T /= 2;

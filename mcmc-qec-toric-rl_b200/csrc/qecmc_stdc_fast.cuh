@@ -60,11 +60,16 @@ __device__ __forceinline__ void cas_async(unsigned long long &prev, unsigned lon
 // The static tables of the 32-bit-word variant live in one struct and are read through ld.shared with an explicit
 // 32-bit base + immediate offset: left to itself the compiler re-derives every table's shared-window address (three
 // instructions each, CTA rank in the cluster included) at every use instead of keeping five bases in registers.
-struct FastTabs {
-    uint4 A[QECMC_FAST_STATIC_NSTAB];       // {byte offset of word 0, 1, 2 in the thread's tile column, packed shifts / masks}
+// A and thr are looked up with a random index by every lane at every step; stored once, those reads cost ~10 and ~3.5
+// shared-memory wavefronts through bank conflicts.  They are therefore kept in REP copies interleaved per
+// entry, lane j reading copy j & 7: the eight lanes of a quarter-warp then hit eight different 16-byte bank groups
+// whatever their indices are, i.e. the 16-byte read is conflict-free (4 wavefronts) and the 4-byte read nearly so.
+// (Only the one-CTA-per-SM variant replicates, REP = 8; the early-stop / replay variants share the SM among four CTAs.)
+template <int REP> struct FastTabs {
+    uint4 A[QECMC_FAST_STATIC_NSTAB * REP];   // [stabilizer][copy] {byte offset of word 0, 1, 2 in the thread's tile column, packed shifts / masks}
+    uint32_t thr[512 * REP];                  // [(Pauli, gathered fields)][copy] threshold
     uint4 B[QECMC_FAST_STATIC_NSTAB];       // {XOR mask of word 0, 1, 2}: read on accept only
     uint64_t hs[QECMC_FAST_STATIC_NSTAB];   // fingerprint change per stabilizer
-    uint32_t thr[512];                      // threshold by (Pauli, gathered fields)
     int8_t dE[512];                         // weight change by (Pauli, gathered fields)
 };
 template <int OFF> __device__ __forceinline__ uint4 lds_v4(uint32_t a)
@@ -112,15 +117,20 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ?
 {
     static_assert(GEOM == TORIC || GEOM == PLANAR, "table-driven kernel covers the two-layer codes");
     constexpr bool STATIC_TAB = sizeof(W) == 4;
-    extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ __align__(16) unsigned char s_tabs_raw[STATIC_TAB ? sizeof(FastTabs) : 16];
+    constexpr int REP = (STATIC_TAB && !CONV) ? 8 : 1;
+    typedef FastTabs<REP> Tabs;
+    constexpr size_t TABS_BYTES = STATIC_TAB ? ((sizeof(Tabs) + 15) & ~(size_t)15) : 0;   // the tables open the dynamic shared memory
+    extern __shared__ __align__(16) unsigned char smem_all[];
+    unsigned char *smem = smem_all + TABS_BYTES;                                         // tile (and, for 64-bit words, the plain tables)
     __shared__ uint32_t s_thr_dyn[STATIC_TAB ? 1 : 512];
     __shared__ int8_t s_dE_dyn[STATIC_TAB ? 4 : 512];
     __shared__ double s_thrd[QECMC_THR_N];
-    FastTabs &tb = *reinterpret_cast<FastTabs *>(s_tabs_raw);
-    uint32_t *s_thr = STATIC_TAB ? tb.thr : s_thr_dyn;
+    Tabs &tb = *reinterpret_cast<Tabs *>(smem_all);
+    uint32_t *s_thr = s_thr_dyn;
     int8_t *s_dE = STATIC_TAB ? tb.dE : s_dE_dyn;
-    const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(s_tabs_raw);
+    const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(smem_all);
+    const uint32_t tbaseA = tbase + (threadIdx.x & (REP - 1)) * 16u;   // this lane's copy of A
+    const uint32_t tbaseT = tbase + (threadIdx.x & (REP - 1)) * 4u;    // ... and of thr
     const int T = blockDim.x, tid = threadIdx.x;
     const Geo g = p.gchain;
     W *tile = reinterpret_cast<W *>(smem);
@@ -140,14 +150,19 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ?
                 m1 = (fa & 16u) ? v << sh : 0u;
                 m2 = (fa & 64u) ? v << sh : 0u;
             }
-            tb.A[i] = make_uint4(((d.x >> 8) & 0xFFu) * ws, ((d.x >> 16) & 0xFFu) * ws, (d.x >> 24) * ws,
-                                 sh | (((sh2 - 2u) & 31u) << 8) | (f_or9 << 13) | (GEOM == PLANAR ? fa << 22 : 0u));
+            const uint4 a = make_uint4(((d.x >> 8) & 0xFFu) * ws, ((d.x >> 16) & 0xFFu) * ws, (d.x >> 24) * ws,
+                                       sh | (((sh2 - 2u) & 31u) << 8) | (f_or9 << 13) | (GEOM == PLANAR ? fa << 22 : 0u));
+            for (int r = 0; r < REP; r++) tb.A[i * REP + r] = a;
             tb.B[i] = make_uint4(m0, m1, m2, 0u);
         } else {
             s_desc[i] = d;
         }
     }
-    for (int i = tid; i < 512; i += T) { s_thr[i] = ft.thr[i]; s_dE[i] = ft.dE[i]; }
+    for (int i = tid; i < 512; i += T) {
+        s_dE[i] = ft.dE[i];
+        if (STATIC_TAB) for (int r = 0; r < REP; r++) tb.thr[i * REP + r] = ft.thr[i];
+        else s_thr[i] = ft.thr[i];
+    }
     if (tid < QECMC_THR_N) s_thrd[tid] = p.thr.d[tid];
     __syncthreads();
     const int64_t local = (int64_t)blockIdx.x * T + tid;
@@ -215,7 +230,7 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ?
         W o0, o1, o2;
         uint32_t li, dx = 0, dy = 0;
         if (STATIC_TAB) {
-            const uint4 A = lds_v4<offsetof(FastTabs, A)>(tbase + (uint32_t)idx * 16u);
+            const uint4 A = lds_v4<offsetof(Tabs, A)>(tbaseA + (uint32_t)idx * (16u * REP));
             p0 = reinterpret_cast<W *>(mybase + A.x);
             p1 = reinterpret_cast<W *>(mybase + A.y);
             p2 = reinterpret_cast<W *>(mybase + A.z);
@@ -244,11 +259,11 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ?
         }
         bool acc;
         if (REPLAY) acc = u_acc < s_thrd[(int)s_dE[li] + QECMC_THR_OFF];
-        else if (STATIC_TAB) acc = r_acc <= lds_u32<offsetof(FastTabs, thr)>(tbase + li * 4u);
+        else if (STATIC_TAB) acc = r_acc <= lds_u32<offsetof(Tabs, thr)>(tbaseT + li * (4u * REP));
         else acc = r_acc <= s_thr[li];
         if (acc) {
             if (STATIC_TAB) {
-                const uint4 B = lds_v4<offsetof(FastTabs, B)>(tbase + (uint32_t)idx * 16u);
+                const uint4 B = lds_v4<offsetof(Tabs, B)>(tbase + (uint32_t)idx * 16u);
                 *p0 = (W)(o0 ^ (W)B.x);
                 *p1 = (W)(o1 ^ (W)B.y);
                 *p2 = (W)(o2 ^ (W)B.z);
@@ -271,8 +286,8 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ?
                 *p2 = (W)(o2 ^ m2);
             }
             if (STATIC_TAB) {
-                n += lds_s8<offsetof(FastTabs, dE)>(tbase + li);
-                const uint2 hv = lds_v2<offsetof(FastTabs, hs)>(tbase + (uint32_t)idx * 8u);
+                n += lds_s8<offsetof(Tabs, dE)>(tbase + li);
+                const uint2 hv = lds_v2<offsetof(Tabs, hs)>(tbase + (uint32_t)idx * 8u);
                 h ^= (uint64_t)hv.x | ((uint64_t)hv.y << 32);
             } else {
                 n += (int)s_dE[li];
