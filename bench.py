@@ -207,9 +207,9 @@ def main():
     steps_per_syndrome = N_EQ * DROPLETS * samples * ITERS
     # table arena: leave room for torch + staging
     ctx.set_table_budget(int(info["free_mem"] * 0.88))
-    log_cap = (samples + 1) & ~1                               # key-log entries per chain
-    scratch = info["sm_count"] * DROPLETS * log_cap * 8        # dedupe kernel: one table's keys per CTA
-    fit = (int(info["free_mem"] * 0.88) - scratch) // (N_EQ * DROPLETS * log_cap * 8)
+    keys_max = DROPLETS * samples                              # worst case: every sample of every droplet logs a key
+    per_table = (128 * ((keys_max + 127) // 128 + 66) + max(1024, keys_max // 16)) * 8   # bucket logs + overflow log
+    fit = int(info["free_mem"] * 0.88) // (N_EQ * per_table)
     fill = (info["sm_count"] * 1024) // (N_EQ * DROPLETS)  # chains resident per wave: one 1024-thread CTA per SM
     batch = args.syndromes or max(1, min(fit, fill))
     n_steps = args.steps + args.warmup

@@ -319,10 +319,22 @@ static int launch_stdc_fast(qecmc_ctx *c, StdcParams &p)
     // a small batch is spread over the SMs rather than packed into a few large CTAs
     while (T > 64 && (p.n_chains + T - 1) / T < c->prop.multiProcessorCount) T /= 2;
     size_t smem = ((per_chain * T + 15) & ~(size_t)15) + dyn_fixed;
+    if (p.insert_mode == 6) {   // per-CTA cursors into the bucket logs, behind the tile
+        if (conv || !static_tab || T % p.droplets != 0 || p.n_chains % T != 0) return set_err(QECMC_ERR_UNSUPPORTED, "internal: bucket-log mode misconfigured");
+        p.tables_per_cta = T / p.droplets;
+        smem += (size_t)p.tables_per_cta * QECMC_NBC * 4;
+    }
     unsigned grid = (unsigned)((p.n_chains + T - 1) / T);
     if (conv) {
         CUDA_OK(cudaFuncSetAttribute(stdc_fast_kernel<GEOM, W, REPLAY, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         stdc_fast_kernel<GEOM, W, REPLAY, MODE, true><<<grid, T, smem, c->stream>>>(p, ft, keys);
+    } else if (p.insert_mode == 6) {
+        if constexpr (sizeof(W) == 4 && MODE != MODE_MEAN) {
+            CUDA_OK(cudaFuncSetAttribute(stdc_fast_kernel<GEOM, W, false, MODE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            stdc_fast_kernel<GEOM, W, false, MODE, false, true><<<grid, T, smem, c->stream>>>(p, ft, keys);
+        } else {
+            return set_err(QECMC_ERR_UNSUPPORTED, "internal: bucket-log mode misconfigured");
+        }
     } else {
         CUDA_OK(cudaFuncSetAttribute(stdc_fast_kernel<GEOM, W, false, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         stdc_fast_kernel<GEOM, W, false, MODE, false><<<grid, T, smem, c->stream>>>(p, ft, keys);
@@ -376,7 +388,7 @@ struct StdcOut {
 };
 
 static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uint8_t *d_qm, int64_t S, const StdcOut &out,
-                    qecmc_stats *stats)
+                    qecmc_stats *stats, bool allow_bucket_logs = true)
 {
     if (!c || !cfg || !d_qm || !out.eqdistr) return set_err(QECMC_ERR_ARG, "NULL argument");
     if (S <= 0) return set_err(QECMC_ERR_ARG, "S must be > 0");
@@ -416,6 +428,20 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
                        (unsigned long long)QECMC_DD_MAX_BUCKETS * QECMC_DD_BUCKET_TARGET);
     const bool use_logs = conv_logs || (mode != MODE_MEAN && !conv && (forced_mode < 0 || forced_mode == 4) && fits_dedupe);
     const int64_t log_cap = (cfg->steps + 1) & ~(int64_t)1;
+    // Insert mode 6: the table-driven kernel (toric / planar, 32-bit row words, native draws, no early stop) splits the
+    // keys of a table into QECMC_NBC coarse bucket logs as it produces them, when a syndrome's chains fill whole CTAs and
+    // the per-CTA cursors fit beside the tile; the reduction is then one pass (bucket_dedupe_kernel).
+    const int per_syn_chains = n_eq * cfg->droplets;
+    const bool fast_u32 = (cfg->geom_chain == TORIC || cfg->geom_chain == PLANAR) && cfg->L <= 16;
+    bool use_blogs = allow_bucket_logs && use_logs && !conv && !cfg->u_nb && fast_u32 && (forced_mode < 0 || forced_mode == 6) &&
+                     per_syn_chains % 1024 == 0 && 64 % cfg->droplets == 0 && cfg->droplets <= 64;
+    if (use_blogs) {
+        // the largest CTA the launch will use is 1024 threads: its cursors must fit next to tile and tables
+        const size_t used = (size_t)gchain.nw * 4 * 1024 + ((sizeof(FastTabs<8>) + 15) & ~(size_t)15) + 2048;
+        const size_t cursors = (size_t)(1024 / cfg->droplets) * QECMC_NBC * 4;
+        if (used + cursors > c->prop.sharedMemPerBlockOptin) use_blogs = false;
+    }
+    uint64_t bcap = 0, ovf_cap = 0;
     int dd_grid = c->prop.multiProcessorCount;
     uint64_t cap = 0;
     int64_t per_syndrome = 0, wave = S;
@@ -426,7 +452,17 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
             CUDA_OK(cudaMemGetInfo(&fr, &tot));
             budget = (int64_t)((double)(fr + c->tables.cap + c->dd_scratch.cap) * 0.85);
         }
-        if (use_logs) {
+        if (use_blogs) {
+            bcap = ((max_keys + QECMC_NBC - 1) / QECMC_NBC + 64 + 1) & ~(uint64_t)1;
+            ovf_cap = max_keys / 16 < 1024 ? 1024 : max_keys / 16;
+            per_syndrome = (int64_t)n_eq * (int64_t)(QECMC_NBC * bcap + ovf_cap) * 8;
+            wave = budget / per_syndrome;
+            if (wave < 1)
+                return set_err(QECMC_ERR_NOMEM, "bucket logs need %lld bytes per syndrome, budget is %lld", (long long)per_syndrome, (long long)budget);
+            if (wave > S) wave = S;
+            QTRY(c->log_counts.ensure((size_t)wave * n_eq * (QECMC_NBC + 1) * sizeof(uint32_t)));
+            QTRY(c->scratch.ensure(2 * sizeof(int)));
+        } else if (use_logs) {
             if ((int64_t)S * n_eq < dd_grid) dd_grid = (int)(S * n_eq);
             const int64_t scratch_bytes = (int64_t)dd_grid * cfg->droplets * log_cap * 8;
             if (conv_logs) {   // one set per chain: capacity covers every sample distinct at load <= 0.8
@@ -493,7 +529,16 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
     p.u_np = cfg->u_np;
     p.counters = (unsigned long long *)c->counters.p;
     // diagnostic knob for roofline work (3 = chains without the distinct set: results are then meaningless)
-    p.insert_mode = conv_logs ? 5 : use_logs ? 4 : (forced_mode >= 0 && forced_mode != 4 ? forced_mode : 2);
+    p.insert_mode = use_blogs ? 6 : conv_logs ? 5 : use_logs ? 4 : (forced_mode >= 0 && forced_mode != 4 && forced_mode != 6 ? forced_mode : 2);
+    if (use_blogs) {   // [bucket logs of the wave | overflow logs of the wave]; counts: [tables][NBC] then [tables]
+        p.blogs = (unsigned long long *)c->tables.p;
+        p.bcap = (uint32_t)bcap;
+        p.ovf = p.blogs + (size_t)wave * n_eq * QECMC_NBC * bcap;
+        p.ovf_cap = (uint32_t)ovf_cap;
+        p.bcounts = (uint32_t *)c->log_counts.p;
+        p.ovf_cnt = p.bcounts + (size_t)wave * n_eq * QECMC_NBC;
+        p.log_err = (int *)c->scratch.p + 1;
+    }
     // conv_logs: [per-chain sets of the wave | per-chain logs of the wave]; logs only: the logs start the buffer
     const size_t chain_sets_bytes = conv_logs ? (size_t)wave * n_eq * cfg->droplets * (size_t)cap * 8 : 0;
     p.logs = (unsigned long long *)((char *)c->tables.p + chain_sets_bytes);
@@ -513,6 +558,10 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
         int64_t sw = S - s0 < wave ? S - s0 : wave;
         if (mode != MODE_MEAN && !use_logs) CUDA_OK(cudaMemsetAsync(c->tables.p, 0, (size_t)sw * per_syndrome, c->stream));
         if (conv_logs) CUDA_OK(cudaMemsetAsync(c->tables.p, 0, (size_t)sw * n_eq * cfg->droplets * (size_t)cap * 8, c->stream));
+        if (use_blogs) {
+            CUDA_OK(cudaMemsetAsync(p.ovf_cnt, 0, (size_t)wave * n_eq * sizeof(uint32_t), c->stream));
+            if (s0 == 0) CUDA_OK(cudaMemsetAsync(p.log_err, 0, sizeof(int), c->stream));
+        }
         p.lat0 = (const char *)c->packed.p + (size_t)(cfg->per_class_inits ? s0 * n_eq : s0) * gcode.nw * wbytes;
         p.n_chains = sw * n_eq * cfg->droplets;
         p.chain_offset = s0 * n_eq * cfg->droplets;
@@ -523,7 +572,28 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
         else QTRY(launch_stdc_mode<MODE_MEAN>(c, p, wide, cfg->u_nb != nullptr));
         CUDA_OK(cudaEventRecord(c->ev[3], c->stream));
         const int64_t tabs = sw * n_eq;
-        if (mode != MODE_MEAN && use_logs) {
+        if (use_blogs) {
+            BucketDedupeParams bp;
+            bp.blogs = p.blogs;
+            bp.bcounts = p.bcounts;
+            bp.bcap = p.bcap;
+            bp.ovf = p.ovf;
+            bp.ovf_cnt = p.ovf_cnt;
+            bp.ovf_cap = p.ovf_cap;
+            bp.tabs = tabs;
+            bp.nsites = gcode.nsites;
+            bp.beta = beta;
+            bp.Z = (double *)c->Z.p + s0 * n_eq;
+            bp.N_hist = d_nh ? d_nh + (size_t)s0 * n_eq * nh : nullptr;
+            bp.distinct = (unsigned long long *)c->counters.p + 3;
+            bp.err = p.log_err;
+            const size_t dsm = (size_t)QECMC_BD_SLOTS * 8 + 4096 * 4;
+            CUDA_OK(cudaFuncSetAttribute(bucket_dedupe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+            const int64_t sms = c->prop.multiProcessorCount;
+            bucket_dedupe_kernel<<<(unsigned)(tabs < sms ? tabs : sms), QECMC_BD_THREADS, dsm, c->stream>>>(bp);
+            c->launches++;
+            CUDA_OK(cudaGetLastError());
+        } else if (mode != MODE_MEAN && use_logs) {
             DedupeParams dp;
             dp.logs = p.logs;
             dp.log_counts = (const uint32_t *)c->log_counts.p;
@@ -584,6 +654,7 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
         unsigned long long cnt[8] = {0};
         CUDA_OK(cudaMemcpyAsync(cnt, c->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
         CUDA_OK(cudaStreamSynchronize(c->stream));
+        if (derr && use_blogs) return stdc_run(c, cfg, mode, d_qm, S, out, stats, false);   // a bucket overflowed: redo with per-chain logs
         if (derr) return set_err(QECMC_ERR_UNSUPPORTED, "internal: key-log dedupe overflow (%d)", derr);
         memset(stats, 0, sizeof(*stats));
         stats->metropolis_steps = (int64_t)cnt[4];
@@ -599,6 +670,7 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
         stats->total_ms = ms;
     } else if (use_logs) {
         CUDA_OK(cudaStreamSynchronize(c->stream));
+        if (derr && use_blogs) return stdc_run(c, cfg, mode, d_qm, S, out, stats, false);
         if (derr) return set_err(QECMC_ERR_UNSUPPORTED, "internal: key-log dedupe overflow (%d)", derr);
     }
     return 0;

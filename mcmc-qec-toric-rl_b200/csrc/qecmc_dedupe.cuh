@@ -210,4 +210,92 @@ __global__ void __launch_bounds__(QECMC_DD_THREADS, 1) log_dedupe_kernel(DedupeP
     }
 }
 
+// ---- insert mode 6: the chain kernel already split every table's keys into QECMC_NBC coarse bucket logs, so the
+// reduction is a single pass: one CTA per table, bucket after bucket into one shared-memory set of 16384 slots; the next
+// bucket's keys are loaded into registers while the current one is inserted.  Keys that found their bucket log full sit in
+// the table's overflow log and are picked up by scanning it for every bucket (rare, bounded by the overflow capacity).
+#define QECMC_BD_THREADS 1024
+#define QECMC_BD_SLOTS 16384
+#define QECMC_BD_KPT 8
+
+struct BucketDedupeParams {
+    const unsigned long long *blogs;   // [tabs][QECMC_NBC][bcap]
+    const uint32_t *bcounts;           // [tabs][QECMC_NBC]
+    uint32_t bcap;
+    const unsigned long long *ovf;     // [tabs][ovf_cap]
+    const uint32_t *ovf_cnt;           // [tabs]
+    uint32_t ovf_cap;
+    int64_t tabs;
+    int nsites;
+    double beta;
+    double *Z;
+    uint32_t *N_hist;
+    unsigned long long *distinct;
+    int *err;
+};
+
+__global__ void __launch_bounds__(QECMC_BD_THREADS, 1) bucket_dedupe_kernel(BucketDedupeParams p)
+{
+    constexpr int T = QECMC_BD_THREADS, HS = QECMC_BD_SLOTS, KPT = QECMC_BD_KPT;
+    extern __shared__ __align__(16) unsigned char dsm[];
+    unsigned long long *hash = reinterpret_cast<unsigned long long *>(dsm);
+    uint32_t *hist = reinterpret_cast<uint32_t *>(hash + HS);   // [4096]
+    const int tid = threadIdx.x;
+    const int nh = p.nsites + 1;
+    const int shift = QECMC_LEN_BITS + 7;   // set slots from the fingerprint bits above the 7 coarse-bucket bits
+    for (int64_t tab = blockIdx.x; tab < p.tabs; tab += gridDim.x) {
+        for (int i = tid; i < nh; i += T) hist[i] = 0;
+        const uint32_t *cnt = p.bcounts + tab * QECMC_NBC;
+        const unsigned long long *logs = p.blogs + (uint64_t)tab * QECMC_NBC * p.bcap;
+        const uint32_t novf = min(p.ovf_cnt[tab], p.ovf_cap);
+        const unsigned long long *ovf = p.ovf + (uint64_t)tab * p.ovf_cap;
+        unsigned long long k[KPT], kn[KPT];
+        {
+            const uint32_t nb0 = cnt[0];
+#pragma unroll
+            for (int j = 0; j < KPT; j++) { uint32_t idx = j * T + tid; k[j] = idx < nb0 ? __ldcs(logs + idx) : 0ull; }
+        }
+        for (int b = 0; b < QECMC_NBC; b++) {
+            const uint32_t nb = cnt[b];
+            const unsigned long long *src = logs + (uint64_t)b * p.bcap;
+            uint32_t cap = 256;
+            while (cap < 2 * (nb + novf) && cap < (uint32_t)HS) cap <<= 1;
+            for (uint32_t i = tid; i < cap; i += T) hash[i] = 0ull;
+            if (b + 1 < QECMC_NBC) {
+                const uint32_t nb1 = cnt[b + 1];
+                const unsigned long long *src1 = src + p.bcap;
+#pragma unroll
+                for (int j = 0; j < KPT; j++) { uint32_t idx = j * T + tid; kn[j] = idx < nb1 ? __ldcs(src1 + idx) : 0ull; }
+            }
+            __syncthreads();
+            if (nb + novf > (uint32_t)(HS * 0.8)) {
+                if (tid == 0) *p.err = 1;   // would not fit the set: the host redoes the call with per-chain logs
+            } else {
+#pragma unroll
+                for (int j = 0; j < KPT; j++)
+                    if (k[j]) dd_insert(hash, cap - 1, shift, k[j], hist, p.err);
+                for (uint32_t idx = KPT * T + tid; idx < nb; idx += T) dd_insert(hash, cap - 1, shift, __ldcs(src + idx), hist, p.err);
+                for (uint32_t idx = tid; idx < novf; idx += T) {
+                    const unsigned long long kk = ovf[idx];
+                    if (((uint32_t)(kk >> QECMC_LEN_BITS) & (QECMC_NBC - 1)) == (uint32_t)b) dd_insert(hash, cap - 1, shift, kk, hist, p.err);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < KPT; j++) k[j] = kn[j];
+            __syncthreads();
+        }
+        if (p.N_hist)
+            for (int i = tid; i < nh; i += T) p.N_hist[(uint64_t)tab * nh + i] = hist[i];
+        if (tid == 0) {
+            double z = 0;
+            unsigned long long c = 0;
+            for (int n = 0; n < nh; n++)
+                if (hist[n]) { z += (double)hist[n] * exp(-p.beta * (double)n); c += hist[n]; }
+            p.Z[tab] = z;
+            if (p.distinct) atomicAdd(p.distinct, c);
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace qecmc

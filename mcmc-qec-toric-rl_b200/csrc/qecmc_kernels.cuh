@@ -180,6 +180,16 @@ struct StdcParams {
     int insert_mode;               // 4 per-chain key logs + log_dedupe_kernel (default when applicable); 5 early stop: a set per
                                    // chain (probed at once) + a log of the keys new to the chain + dedupe; 2 prefetch + deferred
                                    // probe of the HBM set; 1 asynchronous CAS; diagnostics: 0 synchronous probe, 3 no inserts
+    // insert_mode 6 (table-driven kernel, no early stop, a table's chains inside one CTA): keys go straight into
+    // per-(table, coarse bucket) logs -- the first split of the dedupe is done where the key is produced
+    unsigned long long *blogs;     // [tables][QECMC_NBC][bcap]
+    uint32_t *bcounts;             // [tables][QECMC_NBC] keys per bucket log (capped at bcap)
+    uint32_t bcap;                 // slots per bucket log
+    unsigned long long *ovf;       // [tables][ovf_cap] keys whose bucket log was full
+    uint32_t *ovf_cnt;             // [tables]
+    uint32_t ovf_cap;
+    int tables_per_cta;            // blockDim.x / droplets
+    int *log_err;                  // set to 3 when an overflow log overflows (the host then redoes the wave with mode 4)
     unsigned long long *logs;      // insert_mode 4: [n_chains][log_cap] offered keys, in order
     uint32_t *log_counts;          // [n_chains]
     int64_t log_cap;
@@ -222,6 +232,8 @@ template <> struct ConvStopT<false> {
     __device__ __forceinline__ void after_sample(const StdcParams &, bool, int) {}
     __device__ __forceinline__ uint32_t samples() const { return 0; }
 };
+
+#define QECMC_NBC 128   // coarse buckets per (syndrome, class) table in insert mode 6
 
 enum { MODE_STDC = 0, MODE_STRC = 1, MODE_MEAN = 2 };
 

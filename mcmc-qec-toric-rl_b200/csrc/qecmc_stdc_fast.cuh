@@ -112,7 +112,8 @@ __device__ __forceinline__ void prefetch_l2(const void *addr)
 // epoch counter brought that to 39.98 of 40 but did not raise the issue rate, so it was dropped.
 // Shared memory: the LUTs are static arrays, and for 32-bit row words (L <= 16, at most 512 stabilizers) so are the
 // descriptors and fingerprints, which makes every table address an immediate; the lattice tile is the dynamic part.
-template <int GEOM, typename W, bool REPLAY, int MODE, bool CONV>
+// BLOG = true is the headline specialisation: insert mode 6 known at compile time (no mode dispatch in the sample path).
+template <int GEOM, typename W, bool REPLAY, int MODE, bool CONV, bool BLOG = false>
 __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ? (sizeof(W) == 4 ? 4 : 2) : (sizeof(W) == 4 ? 1 : 3)) stdc_fast_kernel(StdcParams p, FastTables ft, PhiloxKeys keys)
 {
     static_assert(GEOM == TORIC || GEOM == PLANAR, "table-driven kernel covers the two-layer codes");
@@ -202,11 +203,20 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ?
     uint64_t h = lat_hash<W>(g, lat, p.hash_seed);
     const uint64_t cap_mask = p.cap_mask;
     // the early stop needs the probe's answer at once: mode 5 (a set per chain + a log of the keys new to it) or 0 (the class's set)
-    const int imode = MODE == MODE_MEAN ? 3 : (CONV && p.conv_mult != 0.0 ? (p.insert_mode == 5 ? 5 : 0) : p.insert_mode);
+    const int imode = BLOG ? 6 : MODE == MODE_MEAN ? 3 : (CONV && p.conv_mult != 0.0 ? (p.insert_mode == 5 ? 5 : 0) : p.insert_mode);
     // mode 4: `table` is this chain's key log; mode 5: this chain's own set
     unsigned long long *table = imode == 4 ? p.logs + (uint64_t)local * (uint64_t)p.log_cap
                               : p.tables + (uint64_t)(imode == 5 ? local : tab) * (cap_mask + 1);
     uint32_t nlog = 0;
+    // mode 6: this CTA's cursors into the bucket logs of its tables live behind the tile
+    uint32_t *s_cur = reinterpret_cast<uint32_t *>(smem + (((size_t)g.nw * T * sizeof(W) + 15) & ~(size_t)15));
+    // this thread's table: its cursors (shared-memory byte address) and its bucket logs
+    const uint32_t cur_base = (uint32_t)__cvta_generic_to_shared(s_cur) + (uint32_t)(tid / p.droplets) * (QECMC_NBC * 4u);
+    unsigned long long *blog_tab = BLOG ? p.blogs + (uint64_t)tab * QECMC_NBC * p.bcap : nullptr;
+    if (BLOG) {
+        for (int i = tid; i < p.tables_per_cta * QECMC_NBC; i += T) s_cur[i] = 0;
+        __syncthreads();
+    }
 
     uint32_t nacc = 0, noff = 0;
     bool dirty = true;  // the first sample is always new to the chain
@@ -300,7 +310,21 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ?
             left = p.iters;
             acct.sample(n);
             bool is_new = false;
-            if (imode == 4) {
+            if (BLOG) {
+                if (dirty) {
+                    const uint64_t k = make_key(h, n);
+                    const uint32_t b = (uint32_t)(k >> QECMC_LEN_BITS) & (QECMC_NBC - 1);
+                    uint32_t pos;
+                    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(cur_base + b * 4u) : "memory");
+                    if (pos < p.bcap) {
+                        blog_tab[b * p.bcap + pos] = k;
+                    } else {   // rare: the bucket log is full
+                        const uint32_t o = atomicAdd(p.ovf_cnt + tab, 1u);
+                        if (o < p.ovf_cap) p.ovf[(uint64_t)tab * p.ovf_cap + o] = k;
+                        else *p.log_err = 3;
+                    }
+                }
+            } else if (imode == 4) {
                 if (dirty) table[noff] = make_key(h, n);   // fire-and-forget store; log_dedupe_kernel counts later
             } else if (imode == 2) {
                 // Two-phase insert: the sample that produces a key only prefetches its slot's sector into L2 (no
@@ -387,6 +411,12 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ?
             q = atomicCAS(table + slot, 0ull, key);
             slot = (slot + 1u) & smask;
         } while (q != 0ull && q != key);
+    }
+    if (BLOG) {
+        __syncthreads();   // every chain of the CTA has logged its last key
+        const int64_t tab0 = (int64_t)blockIdx.x * p.tables_per_cta;
+        for (int i = tid; i < p.tables_per_cta * QECMC_NBC; i += T)
+            if (tab0 + i / QECMC_NBC < p.n_chains / p.droplets) p.bcounts[tab0 * QECMC_NBC + i] = min(s_cur[i], p.bcap);
     }
     if (imode == 4) p.log_counts[local] = noff;
     if (imode == 5) p.log_counts[local] = nlog;

@@ -698,23 +698,44 @@ def test_chain_xyz_replay_matches_reference_golden_and_oracle(ctx):
 
 # ------------------------------------------------------------------ key logs + dedupe kernel vs the HBM set
 @pytest.mark.parametrize("g,L,droplets,steps", [(O.TORIC, 7, 16, 20000), (O.PLANAR, 9, 64, 6000), (O.TORIC, 15, 7, 9001),
-                                                (O.TORIC, 5, 1, 333)])
+                                                (O.TORIC, 5, 1, 333), (O.TORIC, 9, 64, 12000), (O.TORIC, 15, 32, 4000)])
 def test_log_dedupe_equals_table_set(ctx, g, L, droplets, steps, monkeypatch):
-    """The same native chains counted two ways: per-chain key logs reduced by log_dedupe_kernel (bucketed shared-memory
-    sets; default) and the open-addressing set in HBM.  N(n), the class distributions' inputs, must agree exactly --
-    this exercises the multi-bucket path (tens of thousands of keys per table) that the small replay cases do not."""
+    """The same native chains counted in every way the library has: bucket logs written by the chain kernel + one-pass
+    dedupe (mode 6, the default where a syndrome's chains fill whole CTAs), per-chain key logs reduced by
+    log_dedupe_kernel (mode 4), and the open-addressing set in HBM (modes 2 and 0).  N(n), the class distributions'
+    inputs, must agree exactly -- this exercises the multi-bucket paths (tens of thousands of keys per table) that the
+    small replay cases do not."""
     rng = np.random.default_rng(4000 + L)
     S = 5
     qm = np.stack([rand_lattice(rng, g, L, 0.12).reshape(-1) for _ in range(S)])
     outs = {}
-    for mode in ("4", "2", "0"):
-        monkeypatch.setenv("QECMC_DEBUG_INSERT_MODE", mode)
+    for mode in ("default", "4", "2", "0"):
+        if mode == "default":
+            monkeypatch.delenv("QECMC_DEBUG_INSERT_MODE", raising=False)
+        else:
+            monkeypatch.setenv("QECMC_DEBUG_INSERT_MODE", mode)
         out, st, hist = ctx.stdc(g, g, L, qm, 0.12, 0.3, droplets, steps, seed=99, want_hist=True)
         outs[mode] = (out, st, hist)
     monkeypatch.delenv("QECMC_DEBUG_INSERT_MODE")
-    assert outs["4"][1]["table_slots"] == 0 and outs["2"][1]["table_slots"] > 0      # really two different paths
-    for mode in ("2", "0"):
-        assert np.array_equal(outs["4"][2], outs[mode][2])
-        assert outs["4"][1]["distinct"] == outs[mode][1]["distinct"]
-        assert np.allclose(outs["4"][0], outs[mode][0], rtol=1e-12)
+    assert outs["4"][1]["table_slots"] == 0 and outs["2"][1]["table_slots"] > 0      # really different paths
+    for mode in ("4", "2", "0"):
+        assert np.array_equal(outs["default"][2], outs[mode][2])
+        assert outs["default"][1]["distinct"] == outs[mode][1]["distinct"]
+        assert np.allclose(outs["default"][0], outs[mode][0], rtol=1e-12)
     assert outs["4"][1]["distinct"] > 0.1 * S * O.neq(g) * droplets * steps * 0.1
+
+
+def test_bucket_log_overflow_falls_back(ctx):
+    """Chains at a high sampling rate offer a key at almost every sample; tiny tables make the fixed-capacity bucket logs
+    and their overflow area run over, and the call must then redo itself with per-chain logs and still be exact."""
+    g, L, droplets, steps = O.TORIC, 5, 64, 3000
+    rng = np.random.default_rng(77)
+    qm = np.stack([rand_lattice(rng, g, L, 0.3).reshape(-1) for _ in range(3)])
+    a = ctx.stdc(g, g, L, qm, 0.3, 0.45, droplets, steps, seed=5, want_hist=True)
+    import os
+    os.environ["QECMC_DEBUG_INSERT_MODE"] = "2"
+    try:
+        b = ctx.stdc(g, g, L, qm, 0.3, 0.45, droplets, steps, seed=5, want_hist=True)
+    finally:
+        del os.environ["QECMC_DEBUG_INSERT_MODE"]
+    assert np.array_equal(a[2], b[2]) and a[1]["distinct"] == b[1]["distinct"]
