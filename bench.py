@@ -33,10 +33,10 @@ SAMPLES = L ** 4
 ITERS = 5
 N_EQ = 16
 W_INT = 170.0      # int32 lane-ops per toric/planar depolarizing Metropolis step (agreed figure)
-W_LOG = 8.0        # bytes a chain appends to its key log per offered sample (the chain kernel's only steady HBM traffic)
+W_LOG = 8.0        # bytes a chain appends to a bucket log per offered sample (the chain kernel's only steady HBM traffic)
 # ncu, full-size launch of this exact command (profiles/r01_ncu_fullsize_stdc_v6.csv): warp instructions and DRAM bytes
-NCU_CHAIN = {"file": "profiles/r01_ncu_fullsize_stdc_v7.csv", "warp_inst_per_launch": 95950720865, "dram_bytes_per_launch": 6409024000 + 23494756864,
-             "issue_active_pct": 70.27, "smem_wavefront_pct": 86.35, "steps_per_launch": 148 * 16 * 64 * 50625 * 5}
+NCU_CHAIN = {"file": "profiles/r01_ncu_fullsize_stdc_v8.csv", "warp_inst_per_launch": 90406760592, "dram_bytes_per_launch": 11259394560 + 28711650560,
+             "issue_active_pct": 72.26, "smem_wavefront_pct": 67.68, "steps_per_launch": 148 * 16 * 64 * 50625 * 5}
 
 
 def synth_syndromes(n, seed, L=L, p=P_ERROR):
@@ -324,7 +324,7 @@ def main():
                      "note": "north_star: this path is integer-issue bound, not HBM or tensor bound (SURVEY.md 8d)",
                      "hbm": {"achieved": hbm_alg, "peak": float(peaks.get("hbm_gbs", 6650.0)), "unit": "GB/s",
                              "frac": hbm_alg / float(peaks.get("hbm_gbs", 6650.0)),
-                             "what": "key-log appends, 8 B per offered sample (the dedupe kernel streams them afterwards)",
+                             "what": "bucket-log appends, 8 B per offered sample (the dedupe kernel streams them afterwards)",
                              "peak_source": peak_src},
                      "other_kernels_ms_per_step": (ms - kern_ms) / args.steps, "call_ms": call_ms},
         "chain_stats": {"accept_rate": accepted / (batch * steps_per_syndrome * args.steps),

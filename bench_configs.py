@@ -4,8 +4,9 @@
     python bench_configs.py [--config toric5|rotated25|xzzx21|planar_sweep|all] [--out profiles/xxx.jsonl]
 
 One JSON line per configuration: Metropolis steps/s and syndromes/s on one GPU through the host-buffer C ABI
-(H2D + kernels + D2H inside the timed region), the logical failure rate of the decoded batch, and the oracle port
-timed on the host cores on a bounded sample of the same workload.  These lines are evidence for DESIGN.md; the
+(H2D + kernels + D2H inside the timed region), the logical failure rate of the decoded batch (true classes and hidden
+lattices come from the device workload kernels), and -- the only use of oracle/ here, as in bench.py's cpu_baseline --
+the oracle port timed on the host cores on a bounded sample of the same workload.  These lines are evidence for DESIGN.md; the
 driver's contract line comes from bench.py."""
 import argparse
 import json
@@ -38,14 +39,13 @@ def synth(shape, p, rng, px=None, py=None, pz=None):
     return q
 
 
-def hide_class(O, g, L, qs, rng):
-    """generate_data.py:122-131: remember the class, then apply a random logical operator."""
-    truth = np.array([O.eq_class(g, L, q) for q in qs])
-    out = []
-    for q in qs:
-        nb = O.Stream.mt(int(rng.integers(1, 2**31)))
-        out.append(O.apply_random_logical(g, L, q, nb)[0])
-    return np.stack(out), truth
+def hide_class(ctx, g, L, qs, rng):
+    """generate_data.py:122-131 on the device: remember the class, then apply a random logical operator."""
+    S = qs.shape[0]
+    flat = np.ascontiguousarray(qs.reshape(S, -1))
+    truth = ctx.define_equivalence_class(g, L, flat)
+    hidden, _ = ctx.apply_random_logical(g, L, flat, seed=int(rng.integers(1, 2**31)))
+    return hidden.reshape(qs.shape), truth
 
 
 def timed(fn):
@@ -60,7 +60,7 @@ def timed(fn):
 def run_toric5(ctx, O):
     g, L, S, p = O.TORIC, 5, 100, 0.10
     rng = np.random.default_rng(1)
-    qs, truth = hide_class(O, g, L, synth((S, 2, L, L), p, rng), rng)
+    qs, truth = hide_class(ctx, g, L, synth((S, 2, L, L), p, rng), rng)
     qm = np.ascontiguousarray(qs.reshape(S, -1))
     drop, steps = 10, 5 * L ** 4
     res = {}
@@ -108,7 +108,7 @@ def _pteq_config(ctx, O, name, g, L, kind, bottom, b, S, steps, qs, truth, cpu_l
 def run_rotated25(ctx, O, S=4736, steps=2000):
     g, L, p = O.ROTATED, 25, 0.15
     rng = np.random.default_rng(3)
-    qs, truth = hide_class(O, g, L, synth((S, L, L), p, rng), rng)
+    qs, truth = hide_class(ctx, g, L, synth((S, L, L), p, rng), rng)
     return _pteq_config(ctx, O, "rotated surface code d=25, depolarizing p=0.15, PTEQ Nc=25 iters=10 p_logical=0.5",
                         g, L, 0, p, 0.0, S, steps, qs, truth, 2 * cores(), 12000)
 
@@ -117,7 +117,7 @@ def run_xzzx21(ctx, O, S=4736, steps=2000):
     g, L, p, eta = O.XZZX, 21, 0.15, 100.0
     rng = np.random.default_rng(4)
     pz, px = p * eta / (eta + 1), p / (2 * (eta + 1))
-    qs, truth = hide_class(O, g, L, synth((S, L, L), p, rng, px, px, pz), rng)
+    qs, truth = hide_class(ctx, g, L, synth((S, L, L), p, rng, px, px, pz), rng)
     out = {"biased": _pteq_config(ctx, O, "XZZX d=21, Z-biased eta=100 p=0.15, PTEQ_biased Nc=21", g, L, 2, p, eta, S, steps, qs, truth,
                                   2 * cores(), 1500)}
     pz_tilde = (p / (1 + 1 / eta)) / (1 - p)
@@ -145,7 +145,7 @@ def run_planar_sweep(ctx, O, ps=(0.10, 0.15, 0.20), ds=(7, 11, 15, 21), droplets
             raw = synth((S, 2, d, d), p, rng)
             raw[:, 1, -1, :] = 0
             raw[:, 1, :, -1] = 0
-            qs, truth = hide_class(O, g, d, raw, rng)
+            qs, truth = hide_class(ctx, g, d, raw, rng)
             qm = np.ascontiguousarray(qs.reshape(S, -1))
             if first:   # allocations for this size happen outside the timed call
                 ctx.stdc(g, g, d, qm[:8], p, 0.25, droplets, steps, seed=1)
