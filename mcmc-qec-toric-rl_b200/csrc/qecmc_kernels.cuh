@@ -178,8 +178,8 @@ struct StdcParams {
     const double *u_nb, *u_np;
     unsigned long long *counters;  // [0] accepted [1] offered [2] inserted
     int insert_mode;               // 4 per-chain key logs + log_dedupe_kernel (default when applicable); 5 early stop: a set per
-                                   // chain (probed at once) + a log of the keys new to the chain + dedupe; 2 prefetch + deferred
-                                   // probe of the HBM set; 1 asynchronous CAS; diagnostics: 0 synchronous probe, 3 no inserts
+                                   // chain (probed at once) + a log of the keys new to the chain + dedupe; 6 bucket logs (below);
+                                   // 2 prefetch + deferred probe of the HBM set; 0 synchronous probe; 3 no inserts (diagnostics)
     // insert_mode 6 (table-driven kernel, no early stop, a table's chains inside one CTA): keys go straight into
     // per-(table, coarse bucket) logs -- the first split of the dedupe is done where the key is produced
     unsigned long long *blogs;     // [tables][QECMC_NBC][bcap]

@@ -48,15 +48,6 @@ template <> __device__ __forceinline__ uint32_t gather_fields<uint64_t>(uint64_t
     return qa | (qb << 2) | (qc << 4) | (qd << 6);
 }
 
-// One asynchronous probe of the distinct set: atom.cas with the old word landing in `prev`, which is read a sample
-// later.  Inline PTX pins `prev` as the destination register: with the atomicCAS intrinsic and more than one
-// call site the compiler returned the word in a scratch pair and copied it out right behind the atom, which
-// parks the warp on the memory scoreboard for the whole HBM round trip.
-__device__ __forceinline__ void cas_async(unsigned long long &prev, unsigned long long *addr, unsigned long long key)
-{
-    asm volatile("atom.global.cas.b64 %0, [%1], %2, %3;" : "=l"(prev) : "l"(addr), "l"(0ull), "l"(key));
-}
-
 // The static tables of the 32-bit-word variant live in one struct and are read through ld.shared with an explicit
 // 32-bit base + immediate offset: left to itself the compiler re-derives every table's shared-window address (three
 // instructions each, CTA rank in the cluster included) at every use instead of keeping five bases in registers.
@@ -221,10 +212,10 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ?
     uint32_t nacc = 0, noff = 0;
     bool dirty = true;  // the first sample is always new to the chain
     int left = p.iters;
-    // Distinct-chain accounting by insert mode: 4 (default) appends the key to this chain's log and leaves the counting to
-    // log_dedupe_kernel; 2 prefetches the set's slot at one sample and probes it at the next; 1 issues atom.cas at once
-    // and reads the returned word a sample later (the table modes serve conv_mult and oversized key counts).
-    unsigned long long key = 0, prev = 0;   // key != 0: `key` is waiting for / looking at `slot`; `prev`: mode 1's answer
+    // Distinct-chain accounting by insert mode: 6 / 4 log the key and leave the counting to a dedupe kernel; 5 and 0 probe a
+    // set in HBM at once (early stop); 2 (key counts beyond the dedupe kernels' fan-out) prefetches the set's slot at one
+    // sample and probes it at the next.
+    unsigned long long key = 0;   // mode 2: key != 0 means `key` is waiting to be probed at `slot`
     uint32_t slot = 0;
     const uint32_t smask = (uint32_t)cap_mask;  // host guarantees cap <= 2^32 slots
     ConvStopT<CONV> cs;
@@ -343,25 +334,6 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ?
                     slot = (uint32_t)(key >> QECMC_LEN_BITS) & smask;
                     prefetch_l2(table + slot);
                 }
-            } else if (imode == 1) {
-                bool fire = false;
-                if (key) {
-                    if (prev == 0ull || prev == key) key = 0;
-                    else { slot = (slot + 1u) & smask; fire = true; }
-                }
-                if (dirty) {
-                    if (key) {  // the previous key is still looking for its slot: finish it here
-                        unsigned long long q;
-                        do {
-                            q = atomicCAS(table + slot, 0ull, key);
-                            slot = (slot + 1u) & smask;
-                        } while (q != 0ull && q != key);
-                    }
-                    key = make_key(h, n);
-                    slot = (uint32_t)(key >> QECMC_LEN_BITS) & smask;
-                    fire = true;
-                }
-                if (fire) cas_async(prev, table + slot, key);
             } else if (imode == 0) {
                 if (dirty) is_new = table_insert(table, cap_mask, make_key(h, n));
             } else if (CONV && imode == 5) {
@@ -397,12 +369,6 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ?
         if ((tsteps & 1) && !cs.fin) {
             uint4 r = philox4x32_10(ncalls, 0u, cl, chh, keys);
             step((int)__umulhi(r.x, nstab), r.y, 0.0);
-        }
-    }
-    if (imode == 1 && key) {
-        while (prev != 0ull && prev != key) {
-            slot = (slot + 1u) & smask;
-            prev = atomicCAS(table + slot, 0ull, key);
         }
     }
     if (imode == 2 && key) {
