@@ -200,6 +200,8 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
     uint2 *s_ld = reinterpret_cast<uint2 *>(s_thru + p.Nc * 9 + ((p.Nc * 9) & 1));   // [nstab], 8-byte aligned
     uint16_t *s_ll = reinterpret_cast<uint16_t *>(s_ld + (TABLE ? g.nstab : 0));                    // [patterns <= 16][256]
     __shared__ uint32_t s_patmask[8];
+    __shared__ int s_sw_lane[128], s_sw_a[128], s_sw_b[128], s_sw_rung[128];   // swap sweep: rung-ordered copies, per warp
+    __shared__ double s_sw_u[128];
     // swap sweep: diff[i]^k for |k| <= QECMC_PW_K, made with the same square-and-multiply routine the sweep would call
     // (bit-identical), so a pair costs one table read instead of a multiply loop and, for k < 0, a division
     double *s_pw = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(s_ll) + (TABLE ? 16 * 256 * 2 : 0));
@@ -499,47 +501,64 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
             rr->nbp = base_nb;
             rr->pyp = base_py;
         }
-        double u_sw = 0.0;
-        if (!REPLAY) u_sw = rng.nb();  // lane i's draw decides pair (i, i+1)
-        for (int i = Nc - 2; i >= 0; i--) {
-            uint32_t b_lo = __ballot_sync(0xFFFFFFFFu, valid && r == i);
-            uint32_t b_hi = __ballot_sync(0xFFFFFFFFu, valid && r == i + 1);
-            int l_lo = __ffs((b_lo >> gbase) & gmask) - 1, l_hi = __ffs((b_hi >> gbase) & gmask) - 1;
-            if (l_lo < 0) l_lo = 0;
-            if (l_hi < 0) l_hi = 0;
-            bool swap;
-            if (p.kind == LK_ALPHA) {
-                // mcmc_alpha.py:117-123: PY draw always; float exponent n_eff_hi - n_eff_lo; n_eff stays with the rung
-                int lo_z = __shfl_sync(0xFFFFFFFFu, e_nz, l_lo, G), lo_xy = __shfl_sync(0xFFFFFFFFu, e_nxy, l_lo, G);
-                int hi_z = __shfl_sync(0xFFFFFFFFu, e_nz, l_hi, G), hi_xy = __shfl_sync(0xFFFFFFFFu, e_nxy, l_hi, G);
-                double ne_lo = __dadd_rn((double)lo_z, __dmul_rn(p.alpha, (double)lo_xy));
-                double ne_hi = __dadd_rn((double)hi_z, __dmul_rn(p.alpha, (double)hi_xy));
-                double u;
-                if (REPLAY) u = done ? 1.0 : rng.py();
-                else u = __shfl_sync(0xFFFFFFFFu, u_sw, i, G);
-                swap = u < pow(p.diff[i], __dadd_rn(ne_hi, -ne_lo));
-                if (swap) {  // the lanes trade rungs, so they trade the rung-owned n_eff too
-                    if (gl == l_lo) { e_nz = hi_z; e_nxy = hi_xy; }
-                    if (gl == l_hi) { e_nz = lo_z; e_nxy = lo_xy; }
-                }
-            } else {
-                int ne_lo = __shfl_sync(0xFFFFFFFFu, n, l_lo, G), ne_hi = __shfl_sync(0xFFFFFFFFu, n, l_hi, G);
-                double u = 0.0;
-                if (!REPLAY) u = __shfl_sync(0xFFFFFFFFu, u_sw, i, G);
-                if (p.kind == LK_DEPOL && ne_hi < ne_lo) {
-                    swap = true;  // mcmc.py:146-147: no draw
-                } else {
-                    if (REPLAY) u = done ? 1.0 : rng.nb();  // mcmc_biased.py:154-156 draws always
-                    const int k = ne_hi - ne_lo;
-                    const double pw = (use_pw && k >= -QECMC_PW_K && k <= QECMC_PW_K) ? s_pw[i * (2 * QECMC_PW_K + 1) + k + QECMC_PW_K]
-                                                                                       : numba_pow_dev(p.diff[i], k);
-                    swap = u < pw;
-                }
+        // The sweep is serial over the rung pairs (a replica can fall several rungs in one sweep), so one lane per ladder
+        // walks it on rung-ordered copies in shared memory -- occupant lane and weight of every rung -- carrying the
+        // replica that currently sits on the upper rung of the pair; the other lanes then read their new rung back.  In the
+        // alpha ladder n_eff belongs to the rung (mcmc_alpha.py:126-131 swaps .code and .flag but not .n_eff), so there the
+        // decisions depend on rung-owned values only.
+        {
+            const int wb = (tid >> 5) * 32 + gbase;   // this ladder's slice of the per-warp arrays
+            if (!REPLAY) s_sw_u[(tid >> 5) * 32 + lane] = rng.nb();  // lane i's draw decides pair (i, i+1)
+            if (valid) {
+                s_sw_lane[wb + r] = gl;
+                s_sw_a[wb + r] = p.kind == LK_ALPHA ? e_nz : n;
+                s_sw_b[wb + r] = e_nxy;
             }
-            if (swap && !done) {
-                if (gl == l_lo) r = i + 1;
-                else if (gl == l_hi) r = i;
+            __syncwarp();
+            if (gl == 0 && ladder < p.n_ladders && !done) {
+                int c_lane = s_sw_lane[wb + Nc - 1], c_n = s_sw_a[wb + Nc - 1];
+                for (int i = Nc - 2; i >= 0; i--) {
+                    const int lo_lane = s_sw_lane[wb + i], lo_n = s_sw_a[wb + i];
+                    bool swap;
+                    if (p.kind == LK_ALPHA) {
+                        // mcmc_alpha.py:117-123: PY draw always; float exponent n_eff_hi - n_eff_lo of the two RUNGS
+                        const double ne_lo = __dadd_rn((double)lo_n, __dmul_rn(p.alpha, (double)s_sw_b[wb + i]));
+                        const double ne_hi = __dadd_rn((double)s_sw_a[wb + i + 1], __dmul_rn(p.alpha, (double)s_sw_b[wb + i + 1]));
+                        const double u = REPLAY ? rng.py() : s_sw_u[wb + i];
+                        swap = u < pow(p.diff[i], __dadd_rn(ne_hi, -ne_lo));
+                    } else {
+                        const int ne_lo = lo_n, ne_hi = c_n;
+                        if (p.kind == LK_DEPOL && ne_hi < ne_lo) {
+                            swap = true;  // mcmc.py:146-147: no draw
+                        } else {
+                            const double u = REPLAY ? rng.nb() : s_sw_u[wb + i];  // mcmc_biased.py:154-156 draws always
+                            const int k = ne_hi - ne_lo;
+                            const double pw = (use_pw && k >= -QECMC_PW_K && k <= QECMC_PW_K) ? s_pw[i * (2 * QECMC_PW_K + 1) + k + QECMC_PW_K]
+                                                                                               : numba_pow_dev(p.diff[i], k);
+                            swap = u < pw;
+                        }
+                    }
+                    if (swap) {
+                        s_sw_rung[wb + lo_lane] = i + 1;          // the lower replica moves up; the carried one goes on down
+                    } else {
+                        s_sw_rung[wb + c_lane] = i + 1;           // the carried replica stays on rung i + 1
+                        c_lane = lo_lane;
+                        c_n = lo_n;
+                    }
+                }
+                s_sw_rung[wb + c_lane] = 0;
             }
+            __syncwarp();
+            if (valid && !done) {
+                r = s_sw_rung[wb + gl];
+                if (p.kind == LK_ALPHA) { e_nz = s_sw_a[wb + r]; e_nxy = s_sw_b[wb + r]; }   // n_eff stays with the rung
+            }
+            if (REPLAY) {   // the walking lane consumed the draws: the whole ladder continues from its stream positions
+                ReplayRng *rr = reinterpret_cast<ReplayRng *>(&rng);
+                rr->nbp = __shfl_sync(0xFFFFFFFFu, rr->nbp, 0, G);
+                rr->pyp = __shfl_sync(0xFFFFFFFFu, rr->pyp, 0, G);
+            }
+            __syncwarp();
         }
         if (REPLAY) {
             ReplayRng *rr = reinterpret_cast<ReplayRng *>(&rng);
