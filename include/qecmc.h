@@ -236,6 +236,8 @@ typedef struct qecmc_ptdc_cfg {
     int32_t per_class_inits;
     int64_t steps;              /* already divided by Nc (decoders.py:196) */
     double  p_error;
+    double  conv_mult;          /* PTDC only: early stop of PTDC_droplet (decoders.py:156-161); 0 disables */
+    int64_t *steps_done;        /* optional out (host): [S][n_eq][droplets] Ladder.step calls each droplet made */
 } qecmc_ptdc_cfg;
 int qecmc_ptdc(qecmc_ctx *ctx, const qecmc_ptdc_cfg *cfg, const uint8_t *qm, int64_t S, double *eqdistr, qecmc_stats *stats);
 

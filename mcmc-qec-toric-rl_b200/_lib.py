@@ -62,7 +62,7 @@ class PteqCfg(C.Structure):
 
 class PtdcCfg(C.Structure):
     _fields_ = [("ladder", LadderCfg), ("droplets", C.c_int32), ("per_class_inits", C.c_int32), ("steps", C.c_int64),
-                ("p_error", C.c_double)]
+                ("p_error", C.c_double), ("conv_mult", C.c_double), ("steps_done", C.c_void_p)]
 
 
 class AlphaCfg(C.Structure):
@@ -391,18 +391,20 @@ class Context:
         return st.as_dict(), info
 
     def ptdc(self, geom, L, qm, p_error, p_sampling, droplets, Nc, steps, iters=10, per_class=False, seed=0, u_nb=None,
-             u_py=None):
-        """PTDC over a batch; `steps` is the per-ladder step count (the reference's steps // Nc)."""
+             u_py=None, conv_mult=0.0, want_steps=False):
+        """PTDC over a batch; `steps` is the per-ladder step count (the reference's steps // Nc); conv_mult != 0 is the
+        early stop of PTDC_droplet."""
         _require_u8(qm)
         S, n, n_eq = qm.shape[0], nsites(geom, L), neq(geom)
         assert qm.size == S * (n_eq if per_class else 1) * n
         lc, keep = self._ladder_cfg(geom, L, LADDER_DEPOLARIZING, Nc, iters, p_sampling, 0.0, 0.0, seed, u_nb, u_py,
                                     S * n_eq * droplets)
-        cfg = PtdcCfg(lc, droplets, int(per_class), int(steps), p_error)
+        done = np.zeros((S, n_eq, droplets), np.int64)
+        cfg = PtdcCfg(lc, droplets, int(per_class), int(steps), p_error, float(conv_mult), done.ctypes.data if want_steps else None)
         out = np.zeros((S, n_eq), np.float64)
         st = Stats()
         _check(load().qecmc_ptdc(self._h, C.byref(cfg), qm.ctypes.data, S, out.ctypes.data, C.byref(st)))
-        return out, st.as_dict()
+        return (out, st.as_dict(), done) if want_steps else (out, st.as_dict())
 
     def ptrc(self, geom, L, qm, p_error, p_sampling, droplets, Nc, steps, iters=10, per_class=False, seed=0, u_nb=None,
              u_py=None, want_hist=False):

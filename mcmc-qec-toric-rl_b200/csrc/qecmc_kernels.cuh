@@ -431,6 +431,26 @@ static __global__ void table_hist_kernel(const unsigned long long *__restrict__ 
     }
 }
 
+// PTDC with the early stop and several droplets: one CTA per (syndrome, class) pours the droplets' own sets into the
+// class's set (zeroed by the host); N(n) then comes from table_hist_kernel as usual.
+static __global__ void table_union_kernel(const unsigned long long *__restrict__ ltabs /* [tabs][droplets][cap] */, uint64_t cap,
+                                          int droplets, unsigned long long *__restrict__ utabs /* [tabs][ucap] */, uint64_t ucap,
+                                          int aux_bits)
+{
+    const unsigned long long *src = ltabs + (uint64_t)blockIdx.x * droplets * cap;
+    unsigned long long *dst = utabs + (uint64_t)blockIdx.x * ucap;
+    for (uint64_t i = threadIdx.x; i < (uint64_t)droplets * cap; i += blockDim.x) {
+        const unsigned long long k = src[i];
+        if (!k) continue;
+        uint64_t slot = (k >> aux_bits) & (ucap - 1);
+        while (true) {
+            unsigned long long prev = atomicCAS(dst + slot, 0ull, k);
+            if (prev == 0ull || prev == k) break;
+            slot = (slot + 1) & (ucap - 1);
+        }
+    }
+}
+
 // STRC per (syndrome, class): the order-dependent droplet merge of decoders.py:882-928 (the union of the
 // droplets' distinct shortest / next-shortest sets has N(shortest) / N(next_shortest) members),
 // then Z_E = sum_l m(l) exp(-beta_s * shortest + d_beta * l) * mean_fraction (decoders.py:931-946).

@@ -571,7 +571,7 @@ extern "C" int qecmc_pteq_dev(qecmc_ctx *c, const qecmc_pteq_cfg *cfg, const uin
 // STDC_Nall_n_alpha / STDC_droplet_alpha (decoders.py:510-581, a one-rung alpha "ladder").
 static int dc_common(qecmc_ctx *c, const qecmc_ladder_cfg *lc, int per_class_inits, int droplets, int64_t steps, double beta,
                      const uint8_t *qm, int64_t S, double *eqdistr, int64_t *distinct, qecmc_stats *stats, bool rc = false,
-                     int64_t *N_hist = nullptr, int64_t *m_hist = nullptr)
+                     int64_t *N_hist = nullptr, int64_t *m_hist = nullptr, double conv_mult = 0.0, int64_t *steps_done = nullptr)
 {
     if (!c || !qm || !eqdistr) return set_err(QECMC_ERR_ARG, "NULL argument");
     QTRY(check_ladder_cfg(lc));
@@ -586,16 +586,28 @@ static int dc_common(qecmc_ctx *c, const qecmc_ladder_cfg *lc, int per_class_ini
     LadderDev &d = c->ld;   // device buffers persist in the context: no cudaMalloc / cudaFree per call
     LadderParams p;
     QTRY(setup_ladder(c, lc, g, d, p));
-    // PTDC: one set per (syndrome, class); PTRC: one per (syndrome, class, droplet, rung)
-    uint64_t max_keys = rc ? (uint64_t)steps : (uint64_t)droplets * (uint64_t)steps * (uint64_t)lc->Nc;
+    // PTDC: one set per (syndrome, class) -- with the early stop one per ladder ("new" = new to the droplet), united per class
+    // afterwards; PTRC: one per (syndrome, class, droplet, rung)
+    if (conv_mult < 0.0) return set_err(QECMC_ERR_ARG, "conv_mult must be >= 0");
+    if (conv_mult != 0.0 && (rc || lc->kind != LK_DEPOL)) return set_err(QECMC_ERR_UNSUPPORTED, "the early stop belongs to PTDC");
+    const bool conv = conv_mult != 0.0;
+    uint64_t max_keys = rc ? (uint64_t)steps : (uint64_t)(conv ? 1 : droplets) * (uint64_t)steps * (uint64_t)lc->Nc;
     uint64_t cap = next_pow2(max_keys + max_keys / 4 + 1);
     if (cap < 1024) cap = 1024;
-    const int64_t tabs_per_class = rc ? (int64_t)droplets * lc->Nc : 1;
+    const int64_t tabs_per_class = rc ? (int64_t)droplets * lc->Nc : conv ? (int64_t)droplets : 1;
+    // union tables of the early stop with several droplets: one per (syndrome, class), behind the ladders' own
+    const bool unite = conv && droplets > 1;
+    uint64_t ucap = 0;
+    if (unite) {
+        const uint64_t uk = (uint64_t)droplets * (uint64_t)steps * (uint64_t)lc->Nc;
+        ucap = next_pow2(uk + uk / 4 + 1);
+        if (ucap < 1024) ucap = 1024;
+    }
     const int ns1 = g.nsites + 1;
     size_t fr = 0, tot = 0;
     CUDA_OK(cudaMemGetInfo(&fr, &tot));
     int64_t budget = c->table_budget ? c->table_budget : (int64_t)((double)(fr + c->tables.cap) * 0.85);
-    int64_t per_syndrome = (int64_t)n_eq * tabs_per_class * ((int64_t)cap * 8 + (rc ? (int64_t)ns1 * 12 : 0));
+    int64_t per_syndrome = (int64_t)n_eq * (tabs_per_class * ((int64_t)cap * 8 + (rc ? (int64_t)ns1 * 12 : 0)) + (int64_t)ucap * 8);
     int64_t wave = budget / per_syndrome;
     if (wave < 1) return set_err(QECMC_ERR_NOMEM, "distinct-chain tables need %lld bytes per syndrome, budget is %lld",
                                  (long long)per_syndrome, (long long)budget);
@@ -629,6 +641,8 @@ static int dc_common(qecmc_ctx *c, const qecmc_ladder_cfg *lc, int per_class_ini
     QTRY(stage_replay(c, lc, S * n_eq * droplets, d, p));
     p.acct = rc ? ACCT_RC : ACCT_DC;
     p.steps = steps;
+    p.conv_mult = conv_mult;
+    if (steps_done) QTRY(d.info.ensure((size_t)S * n_eq * droplets * sizeof(long long)));
     DevBuf rc_m, rc_N, rc_Nout, rc_mout, lad_p;
     if (rc) {
         QTRY(rc_m.ensure((size_t)wave * n_eq * tabs_per_class * ns1 * sizeof(unsigned long long)));
@@ -652,15 +666,26 @@ static int dc_common(qecmc_ctx *c, const qecmc_ladder_cfg *lc, int per_class_ini
     int64_t waves = 0;
     for (int64_t s0 = 0; s0 < S; s0 += wave, waves++) {
         int64_t sw = S - s0 < wave ? S - s0 : wave;
-        CUDA_OK(cudaMemsetAsync(c->tables.p, 0, (size_t)sw * n_eq * tabs_per_class * cap * 8, c->stream));
+        CUDA_OK(cudaMemsetAsync(c->tables.p, 0, (size_t)sw * n_eq * (tabs_per_class * cap + ucap) * 8, c->stream));
         if (rc) CUDA_OK(cudaMemsetAsync(rc_m.p, 0, (size_t)sw * n_eq * tabs_per_class * ns1 * sizeof(unsigned long long), c->stream));
         const int64_t l0 = s0 * n_eq * droplets;
         p.n_ladders = sw * n_eq * droplets;
         p.ladder_offset = l0;
         p.lat_in = (const char *)d.lat_out.p + (size_t)l0 * g.nw * wb;
+        p.info = steps_done ? (long long *)d.info.p + l0 : nullptr;
         if (u_nb0) { p.u_nb = u_nb0 + l0 * p.n_nb; p.u_py = u_py0 + l0 * p.n_py; }
         QTRY(launch_ladder(c, p, lc->u_nb != nullptr));
         const int64_t tabs = sw * n_eq;
+        const unsigned long long *class_tables = (const unsigned long long *)c->tables.p;
+        uint64_t class_cap = cap;
+        if (unite) {   // the droplets' sets of a class -> the class's set
+            unsigned long long *ut = (unsigned long long *)c->tables.p + (size_t)sw * n_eq * tabs_per_class * cap;
+            table_union_kernel<<<(unsigned)tabs, 512, 0, c->stream>>>((const unsigned long long *)c->tables.p, cap, droplets, ut, ucap,
+                                                                      p.aux_bits);
+            c->launches++;
+            class_tables = ut;
+            class_cap = ucap;
+        }
         if (rc) {
             table_hist_kernel<<<(unsigned)(tabs * tabs_per_class), 256, ns1 * sizeof(uint32_t), c->stream>>>(
                 (const unsigned long long *)c->tables.p, cap, g.nsites, 0.0, nullptr, (uint32_t *)rc_N.p,
@@ -678,7 +703,7 @@ static int dc_common(qecmc_ctx *c, const qecmc_ladder_cfg *lc, int per_class_ini
         } else {
             QTRY(d.hist.ensure((size_t)tabs * (g.nsites + 1) * sizeof(uint32_t)));
             table_hist_kernel<<<(unsigned)tabs, 512, (g.nsites + 1) * sizeof(uint32_t), c->stream>>>(
-                (const unsigned long long *)c->tables.p, cap, g.nsites, beta, (double *)d.Zd.p + s0 * n_eq, (uint32_t *)d.hist.p,
+                class_tables, class_cap, g.nsites, beta, (double *)d.Zd.p + s0 * n_eq, (uint32_t *)d.hist.p,
                 (unsigned long long *)c->counters.p + 3);
         }
         c->launches++;
@@ -693,6 +718,7 @@ static int dc_common(qecmc_ctx *c, const qecmc_ladder_cfg *lc, int per_class_ini
     if (distinct && lc->kind == LK_ALPHA)
         CUDA_OK(cudaMemcpyAsync(distinct, d.dist.p, (size_t)S * n_eq * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     if (rc && N_hist) CUDA_OK(cudaMemcpyAsync(N_hist, rc_Nout.p, (size_t)S * n_eq * lc->Nc * ns1 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    if (steps_done) CUDA_OK(cudaMemcpyAsync(steps_done, d.info.p, (size_t)S * n_eq * droplets * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     if (rc && m_hist) CUDA_OK(cudaMemcpyAsync(m_hist, rc_mout.p, (size_t)S * n_eq * lc->Nc * ns1 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     unsigned long long cnt[8] = {0};
     CUDA_OK(cudaMemcpyAsync(cnt, c->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
@@ -737,7 +763,8 @@ extern "C" int qecmc_ptdc(qecmc_ctx *c, const qecmc_ptdc_cfg *cfg, const uint8_t
     if (cfg->ladder.kind != LK_DEPOL) return set_err(QECMC_ERR_ARG, "PTDC runs depolarizing ladders");
     if (!(cfg->p_error > 0 && cfg->p_error < 1)) return set_err(QECMC_ERR_ARG, "p_error outside (0,1)");
     const double beta = -log((cfg->p_error / 3) / (1 - cfg->p_error));  // decoders.py:205
-    return dc_common(c, &cfg->ladder, cfg->per_class_inits, cfg->droplets, cfg->steps, beta, qm, S, eqdistr, nullptr, stats);
+    return dc_common(c, &cfg->ladder, cfg->per_class_inits, cfg->droplets, cfg->steps, beta, qm, S, eqdistr, nullptr, stats, false,
+                     nullptr, nullptr, cfg->conv_mult, cfg->steps_done);
 }
 
 extern "C" int qecmc_ptrc(qecmc_ctx *c, const qecmc_ptdc_cfg *cfg, const uint8_t *qm, int64_t S, double *eqdistr,

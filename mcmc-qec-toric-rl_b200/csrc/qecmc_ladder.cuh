@@ -68,6 +68,7 @@ struct LadderParams {
     const uint64_t *log_hash;      // [2 layers][X, Z][32 positions] fingerprints of the logical strings (when hashes are tracked
                                    // on ladders whose top rung proposes logical operators)
     // PTEQ_alpha_with_shortest (decoders_biasednoise.py:114-146); tables = one set per ladder, cap_mask slots
+    double conv_mult;              // ACCT_DC: early stop of PTDC_droplet (decoders.py:156-161); tables are then per ladder
     int track_shortest;
     double *short_v;               // [n_ladders][n_eq] smallest recorded bottom-rung value per class (100000 = none)
     long long *short_n;            // [n_ladders][n_eq] samples at that value
@@ -313,7 +314,11 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
     const bool top_logical = p.p_logical != 0.0;
     const bool track_hash = p.acct >= ACCT_DC || p.track_shortest;
     unsigned long long *table = nullptr;
-    if (p.acct == ACCT_DC && ladder < p.n_ladders) table = p.tables + (uint64_t)(ladder / p.droplets) * (p.cap_mask + 1);
+    // PTDC: the class's set, shared by its droplets -- or, with the early stop ("new" = new to the droplet), the ladder's own
+    if (p.acct == ACCT_DC && ladder < p.n_ladders)
+        table = p.tables + (uint64_t)(p.conv_mult != 0.0 ? ladder : ladder / p.droplets) * (p.cap_mask + 1);
+    int dc_shortest = 2 * L * L;          // group-uniform: shortest chain this droplet has seen, and when to stop
+    double dc_stop = (double)p.steps;
     int last_r = -1;  // ACCT_RC: rung whose set saw this replica's current state
 
     // group-uniform bookkeeping (every lane of the group carries the same values)
@@ -658,6 +663,7 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
         } else if (p.acct == ACCT_DC) {
             // PTDC_droplet (decoders.py:146-155) / STDC_droplet_alpha (decoders.py:521-531): every rung offers its
             // state; a state unchanged since its last offer is already in the set
+            bool is_new = false;
             if (valid && !done && dirty) {
                 uint64_t aux = p.kind == LK_ALPHA ? ((uint64_t)nz | ((uint64_t)(nx + ny) << 11)) : (uint64_t)n;
                 uint64_t amask = (1ull << p.aux_bits) - 1ull;
@@ -668,12 +674,23 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
                     if (curk == key) break;
                     if (curk == 0ull) {
                         unsigned long long prev = atomicCAS(table + slot, 0ull, (unsigned long long)key);
-                        if (prev == 0ull || prev == key) break;
+                        if (prev == 0ull) { is_new = true; break; }
+                        if (prev == key) break;
                     }
                     slot = (slot + 1) & p.cap_mask;
                 }
                 noff++;
                 dirty = false;
+            }
+            if (p.conv_mult != 0.0) {
+                // decoders.py:156-161, rung by rung: a chain new to the droplet and not longer than the shortest so far
+                // moves `stop`; in rung order that leaves shortest = the smallest such length
+                int cand = (is_new && n <= dc_shortest) ? n : 0x7FFFFFFF;
+                for (int o = G >> 1; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xFFFFFFFFu, cand, o, G));
+                if (!done) {
+                    if (cand != 0x7FFFFFFF) { dc_shortest = cand; dc_stop = (double)step * p.conv_mult; }
+                    if ((double)step >= dc_stop && step * 100 >= p.steps) { done = true; steps_used = step + 1; }
+                }
             }
         } else if (p.acct == ACCT_RC) {
             // PTRC_droplet (decoders.py:597-625): every rung keeps its own set of distinct chains and m(n)
@@ -711,6 +728,7 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
         if (p.neff_out) p.neff_out[(size_t)ladder * Nc + r] = make_int2(e_nz, e_nxy);
         if (gl == 0) {
             if (p.tops0_out) p.tops0_out[ladder] = tops0;
+            if (p.acct == ACCT_DC && p.info) p.info[ladder] = steps_used;
             if (p.acct == ACCT_PTEQ) {
                 if (p.info) {
                     p.info[4 * ladder] = steps_used;

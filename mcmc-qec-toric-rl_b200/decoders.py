@@ -133,13 +133,12 @@ def PTDC_batch(init_codes, p_error, p_sampling=None, droplets=4, Nc=None, steps=
                return_float=False):
     """PTDC (decoders.py:168-233) -> uint8 [S, nbr_eq_classes] (truncated percent)."""
     p_sampling = p_sampling or p_error
-    if conv_mult:
-        raise NotImplementedError("conv_mult != 0 is not implemented on the device path")
     code, qm, per_class = _batch(init_codes)
     Nc = Nc or code.system_size
     steps = int(steps) // Nc                       # decoders.py:196
     out, _ = _lib.default_context(device).ptdc(code.geometry, code.system_size, qm, p_error, p_sampling, int(droplets), Nc,
-                                               steps, iters=10, per_class=per_class, seed=_next_seed(seed))
+                                               steps, iters=10, per_class=per_class, seed=_next_seed(seed),
+                                               conv_mult=float(conv_mult))
     return out if return_float else out.astype(np.uint8)
 
 

@@ -393,6 +393,25 @@ def ptxc(mode, geom, L, qm_classes, p_error, p_sampling, droplets, Nc, steps, nb
     return (out, Nh, mh) if want_hist else out
 
 
+def ptdc_conv(geom, L, qm_classes, p_error, p_sampling, droplets, Nc, steps, conv_mult, nb, py, iters=10):
+    """PTDC with the conv_mult early stop (decoders.py:138-233); `steps` = per-ladder step count.
+    -> (class distribution in percent, steps done [n_eq, droplets], N_hist [n_eq, n_sites + 1])"""
+    n_eq = len(qm_classes)
+    n = nsites(geom, L)
+    q = np.ascontiguousarray(np.asarray(qm_classes, np.uint8).reshape(n_eq, n)).reshape(-1)
+    out = np.zeros(n_eq)
+    done = np.zeros((n_eq, droplets), np.int64)
+    Nh = np.zeros((n_eq, n + 1), np.int64)
+    a, b = _stream_array(nb), _stream_array(py)
+    f = lib().qo_ptdc_conv
+    f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_double, C.c_double, C.c_int, C.c_int64, C.c_int64, C.c_double,
+                  _p, _p, _f64p, _p, _p]
+    f.restype = None
+    f(geom, L, n_eq, Nc, q, p_error, p_sampling, droplets, steps, iters, float(conv_mult), C.addressof(a), C.addressof(b), out,
+      done.ctypes.data, Nh.ctypes.data)
+    return out, done, Nh
+
+
 def stdc_batch(geom_code, geom_chain, L, qm, p_error, p_sampling, droplets, steps, seed, iters=5, threads=1):
     """CPU baseline: STDC over many syndromes on `threads` host threads (ctypes drops the GIL)."""
     qm = np.ascontiguousarray(qm, np.uint8)

@@ -1248,6 +1248,70 @@ QO_EXPORT void qo_ptxc(int mode, int geom, int L, int n_eq, int Nc, const uint8_
     free(ladder); free(diff); free(qm); free(flags); free(n_eff); free(Nh); free(mh);
 }
 
+/* PTDC with the early stop of PTDC_droplet (decoders.py:138-165): every droplet keeps its own `samples` dictionary over
+ * all rungs; a chain new to the droplet whose length is <= the shortest seen so far moves `stop` to step * conv_mult, and the
+ * droplet ends once step >= stop and step * 100 >= steps.  The class's Z_E runs over the union of the droplets' samples
+ * (decoders.py:221-231).  steps_done [n_eq * droplets]: Ladder.step calls made; N_out [n_eq][n + 1]: distinct chains per length. */
+QO_EXPORT void qo_ptdc_conv(int geom, int L, int n_eq, int Nc, const uint8_t *qm_init, double p_error, double p_sampling,
+                            int droplets, int64_t steps, int64_t iters, double conv_mult, qo_stream **nb, qo_stream **py,
+                            double *out, int64_t *steps_done, int64_t *N_out)
+{
+    int n = qo_nsites(geom, L);
+    double beta_error = -log((p_error / 3) / (1 - p_error));
+    double *ladder = (double *)malloc(sizeof(double) * (size_t)Nc);
+    double *diff = (double *)calloc((size_t)Nc, sizeof(double));
+    if (Nc == 1) ladder[0] = p_sampling;
+    else {
+        double step = (0.75 - p_sampling) / (double)(Nc - 1);
+        for (int i = 0; i < Nc; i++) { volatile double t = (double)i * step; ladder[i] = t + p_sampling; }
+        ladder[Nc - 1] = 0.75;
+    }
+    for (int i = 0; i + 1 < Nc; i++) diff[i] = (ladder[i] * (1 - ladder[i + 1])) / (ladder[i + 1] * (1 - ladder[i]));
+    uint8_t *qm = (uint8_t *)malloc((size_t)n * Nc);
+    int32_t *flags = (int32_t *)malloc(sizeof(int32_t) * (size_t)Nc);
+    double *n_eff = (double *)calloc((size_t)Nc, sizeof(double));
+    double total = 0;
+    for (int eq = 0; eq < n_eq; eq++) {
+        qo_set *all = qo_set_new(n);
+        for (int d = 0; d < droplets; d++) {
+            qo_set *mine = qo_set_new(n);
+            for (int i = 0; i < Nc; i++) { memcpy(qm + (size_t)i * n, qm_init + (size_t)eq * n, (size_t)n); flags[i] = 0; }
+            flags[Nc - 1] = 1;
+            int64_t tops0 = 0, s = 0;
+            int shortest = 2 * L * L;
+            double stop = (double)steps;
+            for (; s < steps; s++) {
+                qo_ladder_step(0, geom, L, Nc, qm, ladder, diff, 0.0, 0.0, flags, n_eff, &tops0, iters,
+                               nb[eq * droplets + d], py[eq * droplets + d]);
+                for (int i = 0; i < Nc; i++) {
+                    int nw, nw2;
+                    const uint8_t *st = qm + (size_t)i * n;
+                    qo_set_add(mine, st, &nw);
+                    if (nw) {
+                        int length = qo_count_errors(st, n);
+                        int64_t e = qo_set_add(all, st, &nw2);
+                        if (nw2) all->val[3 * e] = length;
+                        if (conv_mult != 0 && length <= shortest) { shortest = length; stop = (double)s * conv_mult; }
+                    }
+                }
+                if (conv_mult != 0 && (double)s >= stop && s * 100 >= steps) { s++; break; }
+            }
+            if (steps_done) steps_done[eq * droplets + d] = s;
+            qo_set_free(mine);
+        }
+        double z = 0;
+        for (int64_t e = 0; e < all->cnt; e++) {
+            z += exp(-beta_error * all->val[3 * e]);
+            if (N_out) N_out[(size_t)eq * (n + 1) + (int)all->val[3 * e]]++;
+        }
+        out[eq] = z;
+        total += z;
+        qo_set_free(all);
+    }
+    for (int eq = 0; eq < n_eq; eq++) out[eq] = out[eq] / total * 100;
+    free(ladder); free(diff); free(qm); free(flags); free(n_eff);
+}
+
 /* ------------------------------------------------------------------ */
 /* CPU baseline driver: a range of syndromes, single-threaded; the      */
 /* Python wrapper fans ranges out over host threads (ctypes drops the   */

@@ -71,6 +71,28 @@ def main():
                 out[k + "q_hidden"] = np.asarray(q2, dtype=np.uint8).reshape(-1)
                 out[k + "eq_hidden"] = np.array(int(ref.models[geom]._define_equivalence_class(np.asarray(q2, dtype=np.uint8))))
                 n += 1
+    # ---- PTDC with the conv_mult early stop (decoders.py:138-233), one ladder per class, droplets = 1 (in process)
+    sys.path.insert(0, HERE)
+    import make_golden as MG
+    m = 0
+    for g2 in ("toric", "planar"):
+        for conv in (2.0, 1.5):
+            q2 = MG.rand_lattice(rng, g2, 5, 0.1)
+            if g2 == "toric":
+                arr = np.array([ref.toric_model._to_class(e, q2) for e in range(16)])
+            else:
+                arr = np.array([c.qubit_matrix for c in MG.class_inits(ref, g2, q2)])
+            seeds = [int(x) for x in rng.integers(1, 2**31, 2)]
+            ref.seed_all(py=seeds[0], nb=seeds[1])
+            res = ref.decoders.PTDC([MG.make_code(ref, g2, a) for a in arr], 0.1, 0.25, droplets=1, Nc=4, steps=2400, conv_mult=conv)
+            k = f"p{m}_"
+            out[k + "geom"] = np.array(g2)
+            out[k + "inits"] = arr.astype(np.uint8)
+            out[k + "conv_mult"] = np.array(conv)
+            out[k + "seeds"] = np.array(seeds)
+            out[k + "out"] = np.asarray(res)
+            m += 1
+    out["n_ptdc_conv"] = np.array(m)
     out["n_cases"] = np.array(n)
     np.savez_compressed(os.path.join(HERE, "golden_workload.npz"), **out)
     print("wrote", n, "cases")

@@ -739,3 +739,30 @@ def test_bucket_log_overflow_falls_back(ctx):
     finally:
         del os.environ["QECMC_DEBUG_INSERT_MODE"]
     assert np.array_equal(a[2], b[2]) and a[1]["distinct"] == b[1]["distinct"]
+
+
+# ------------------------------------------------------------------ PTDC with the conv_mult early stop
+@pytest.mark.parametrize("g,L,Nc,droplets,per_class,conv", [(O.TORIC, 5, 4, 1, False, 2.0), (O.TORIC, 5, 3, 2, False, 1.5),
+                                                             (O.PLANAR, 5, 4, 3, True, 2.0), (O.ROTATED, 5, 4, 2, False, 1.2)])
+def test_ptdc_early_stop_replay_matches_oracle(ctx, g, L, Nc, droplets, per_class, conv):
+    """PTDC_droplet's early stop (decoders.py:156-161): "new" is new to the droplet (a set per ladder on the device, united
+    per class afterwards).  Every droplet must stop after the same number of Ladder.step calls as the oracle's, and the
+    class distributions must agree."""
+    rng = np.random.default_rng(7300 + g + L + Nc)
+    S, steps, iters = 2, 400, 10
+    n_eq = O.neq(g)
+    qs = [rand_lattice(rng, g, L, 0.08) for _ in range(S)]
+    qm = np.stack([O.all_classes(g, L, q) for q in qs]) if per_class else np.stack([q.reshape(-1) for q in qs])
+    u_nb, u_py = _ptxc_streams(rng, g, S * n_eq * droplets, Nc, iters, steps)
+    out, st, done = ctx.ptdc(g, L, qm, 0.1, 0.25, droplets, Nc, steps, iters=iters, per_class=per_class, u_nb=u_nb, u_py=u_py,
+                             conv_mult=conv, want_steps=True)
+    stopped = 0
+    for s in range(S):
+        base = s * n_eq * droplets
+        nb = [O.Stream.replay(u_nb[base + i]) for i in range(n_eq * droplets)]
+        py = [O.Stream.replay(u_py[base + i]) for i in range(n_eq * droplets)]
+        want, wdone, _ = O.ptdc_conv(g, L, O.all_classes(g, L, qs[s]), 0.1, 0.25, droplets, Nc, steps, conv, nb, py, iters=iters)
+        assert np.array_equal(done[s], wdone), (done[s], wdone)
+        np.testing.assert_allclose(out[s], want, rtol=1e-9)
+        stopped += int((wdone < steps).sum())
+    assert stopped > 0, "no droplet stopped early: the case does not exercise the rule"

@@ -256,3 +256,29 @@ def test_generate_writes_the_reference_file_format(ctx, tmp_path):
     assert failed2 == 3 and made2 <= 10000000
     df2 = pd.read_pickle(path)
     assert len(df2) == 1 + 2 * made2
+
+
+# ------------------------------------------------------------------ PTDC with the conv_mult early stop
+def ptdc_conv_cases():
+    z = np.load(os.path.join(HERE, "golden", "golden_workload.npz"))
+    out = []
+    for i in range(int(z["n_ptdc_conv"])):
+        k = f"p{i}_"
+        out.append({f[len(k):]: z[f] for f in z.files if f.startswith(k)})
+    return out
+
+
+PTDC_CONV = ptdc_conv_cases()
+
+
+@pytest.mark.parametrize("i", range(len(PTDC_CONV)))
+def test_oracle_reproduces_reference_ptdc_early_stop(i):
+    """PTDC(..., droplets=1, Nc=4, steps=2400, conv_mult) of the seeded reference (decoders.py:138-233)"""
+    c = PTDC_CONV[i]
+    g = O.GEOM[str(c["geom"])]
+    n_eq = O.neq(g)
+    nb, py = O.Stream.mt(int(c["seeds"][1])), O.Stream.py(int(c["seeds"][0]))
+    out, done, _ = O.ptdc_conv(g, 5, c["inits"], 0.1, 0.25, 1, 4, 2400 // 4, float(c["conv_mult"]), [nb] * n_eq, [py] * n_eq)
+    assert (done < 600).any(), "no ladder stopped early: the vector does not exercise the rule"
+    # the reference truncates to uint8: allow the float result to sit within rounding of a truncation boundary
+    assert np.array_equal(np.floor(out + 1e-9).astype(np.uint8), c["out"]) or np.array_equal(out.astype(np.uint8), c["out"]), (out, c["out"])
