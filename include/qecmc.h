@@ -57,7 +57,7 @@ typedef struct qecmc_stats {
     int64_t accepted;           /* proposals accepted                                  */
     int64_t samples;            /* lattice states offered to the distinct-chain sets   */
     int64_t distinct;           /* distinct chains over all (syndrome, class) sets     */
-    int64_t table_slots;        /* open-addressing slots per (syndrome, class) set     */
+    int64_t table_slots;        /* open-addressing slots per (syndrome, class) set; 0: per-chain key logs, -1: bucket logs */
     int64_t waves;              /* kernel waves the batch was split into               */
     int64_t kernel_launches;    /* CUDA kernels launched by this call                  */
     double  chain_kernel_ms;    /* device time of the chain kernels (CUDA events)      */

@@ -320,9 +320,14 @@ static int launch_stdc_fast(qecmc_ctx *c, StdcParams &p)
     while (T > 64 && (p.n_chains + T - 1) / T < c->prop.multiProcessorCount) T /= 2;
     size_t smem = ((per_chain * T + 15) & ~(size_t)15) + dyn_fixed;
     if (p.insert_mode == 6) {   // per-CTA cursors into the bucket logs, behind the tile
+        // every CTA must be full and hold whole tables: the host made sure a power of two >= max(droplets, 32) divides n_chains
+        const int t_min = p.droplets > 32 ? p.droplets : 32;
+        if (T < t_min) T = t_min;
+        while (T > t_min && p.n_chains % T != 0) T /= 2;
+        smem = ((per_chain * T + 15) & ~(size_t)15) + dyn_fixed;
         if (conv || !static_tab || T % p.droplets != 0 || p.n_chains % T != 0) return set_err(QECMC_ERR_UNSUPPORTED, "internal: bucket-log mode misconfigured");
         p.tables_per_cta = T / p.droplets;
-        smem += (size_t)p.tables_per_cta * QECMC_NBC * 4;
+        smem += (size_t)p.tables_per_cta * p.nbc * 4;
     }
     unsigned grid = (unsigned)((p.n_chains + T - 1) / T);
     if (conv) {
@@ -429,16 +434,20 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
     const bool use_logs = conv_logs || (mode != MODE_MEAN && !conv && (forced_mode < 0 || forced_mode == 4) && fits_dedupe);
     const int64_t log_cap = (cfg->steps + 1) & ~(int64_t)1;
     // Insert mode 6: the table-driven kernel (toric / planar, 32-bit row words, native draws, no early stop) splits the
-    // keys of a table into QECMC_NBC coarse bucket logs as it produces them, when a syndrome's chains fill whole CTAs and
+    // keys of a table into coarse bucket logs as it produces them, when the chains of every wave fill whole CTAs and
     // the per-CTA cursors fit beside the tile; the reduction is then one pass (bucket_dedupe_kernel).
-    const int per_syn_chains = n_eq * cfg->droplets;
+    // nbc coarse buckets per table, sized for ~6000 logged keys each when 30 % of the samples log one (a bucket that
+    // outgrows the dedupe kernel's shared-memory set sends the call back to per-chain logs); the cursors of a CTA's tables
+    // take (T / droplets) * nbc * 4 bytes beside tile and tables
+    int nbc = 1;
+    while (nbc < QECMC_NBC_MAX && (uint64_t)nbc * 20000 < max_keys) nbc <<= 1;
     const bool fast_u32 = (cfg->geom_chain == TORIC || cfg->geom_chain == PLANAR) && cfg->L <= 16;
     bool use_blogs = allow_bucket_logs && use_logs && !conv && !cfg->u_nb && fast_u32 && (forced_mode < 0 || forced_mode == 6) &&
-                     per_syn_chains % 1024 == 0 && 64 % cfg->droplets == 0 && cfg->droplets <= 64;
+                     cfg->droplets <= 1024 && 1024 % cfg->droplets == 0 && (n_eq * cfg->droplets) % 32 == 0;
     if (use_blogs) {
         // the largest CTA the launch will use is 1024 threads: its cursors must fit next to tile and tables
         const size_t used = (size_t)gchain.nw * 4 * 1024 + ((sizeof(FastTabs<8>) + 15) & ~(size_t)15) + 2048;
-        const size_t cursors = (size_t)(1024 / cfg->droplets) * QECMC_NBC * 4;
+        const size_t cursors = (size_t)(1024 / cfg->droplets) * nbc * 4;
         if (used + cursors > c->prop.sharedMemPerBlockOptin) use_blogs = false;
     }
     uint64_t bcap = 0, ovf_cap = 0;
@@ -453,14 +462,14 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
             budget = (int64_t)((double)(fr + c->tables.cap + c->dd_scratch.cap) * 0.85);
         }
         if (use_blogs) {
-            bcap = ((max_keys + QECMC_NBC - 1) / QECMC_NBC + 64 + 1) & ~(uint64_t)1;
+            bcap = ((max_keys + nbc - 1) / nbc + 64 + 1) & ~(uint64_t)1;
             ovf_cap = max_keys / 16 < 1024 ? 1024 : max_keys / 16;
-            per_syndrome = (int64_t)n_eq * (int64_t)(QECMC_NBC * bcap + ovf_cap) * 8;
+            per_syndrome = (int64_t)n_eq * (int64_t)(nbc * bcap + ovf_cap) * 8;
             wave = budget / per_syndrome;
             if (wave < 1)
                 return set_err(QECMC_ERR_NOMEM, "bucket logs need %lld bytes per syndrome, budget is %lld", (long long)per_syndrome, (long long)budget);
             if (wave > S) wave = S;
-            QTRY(c->log_counts.ensure((size_t)wave * n_eq * (QECMC_NBC + 1) * sizeof(uint32_t)));
+            QTRY(c->log_counts.ensure((size_t)wave * n_eq * (nbc + 1) * sizeof(uint32_t)));
             QTRY(c->scratch.ensure(2 * sizeof(int)));
         } else if (use_logs) {
             if ((int64_t)S * n_eq < dd_grid) dd_grid = (int)(S * n_eq);
@@ -533,10 +542,11 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
     if (use_blogs) {   // [bucket logs of the wave | overflow logs of the wave]; counts: [tables][NBC] then [tables]
         p.blogs = (unsigned long long *)c->tables.p;
         p.bcap = (uint32_t)bcap;
-        p.ovf = p.blogs + (size_t)wave * n_eq * QECMC_NBC * bcap;
+        p.nbc = nbc;
+        p.ovf = p.blogs + (size_t)wave * n_eq * nbc * bcap;
         p.ovf_cap = (uint32_t)ovf_cap;
         p.bcounts = (uint32_t *)c->log_counts.p;
-        p.ovf_cnt = p.bcounts + (size_t)wave * n_eq * QECMC_NBC;
+        p.ovf_cnt = p.bcounts + (size_t)wave * n_eq * nbc;
         p.log_err = (int *)c->scratch.p + 1;
     }
     // conv_logs: [per-chain sets of the wave | per-chain logs of the wave]; logs only: the logs start the buffer
@@ -574,6 +584,7 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
         const int64_t tabs = sw * n_eq;
         if (use_blogs) {
             BucketDedupeParams bp;
+            bp.nbc = nbc;
             bp.blogs = p.blogs;
             bp.bcounts = p.bcounts;
             bp.bcap = p.bcap;
@@ -661,7 +672,7 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
         stats->accepted = (int64_t)cnt[0];
         stats->samples = (int64_t)cnt[1];
         stats->distinct = (int64_t)cnt[3];
-        stats->table_slots = (int64_t)cap;
+        stats->table_slots = use_blogs ? -1 : (int64_t)cap;   // -1: bucket logs, 0: per-chain logs, else slots per HBM set
         stats->waves = waves;
         stats->kernel_launches = c->launches;
         stats->chain_kernel_ms = chain_ms;

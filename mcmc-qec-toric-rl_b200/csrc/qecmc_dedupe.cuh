@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(QECMC_DD_THREADS, 1) log_dedupe_kernel(DedupeP
     }
 }
 
-// ---- insert mode 6: the chain kernel already split every table's keys into QECMC_NBC coarse bucket logs, so the
+// ---- insert mode 6: the chain kernel already split every table's keys into coarse bucket logs, so the
 // reduction is a single pass: one CTA per table, bucket after bucket into one shared-memory set of 16384 slots; the next
 // bucket's keys are loaded into registers while the current one is inserted.  Keys that found their bucket log full sit in
 // the table's overflow log and are picked up by scanning it for every bucket (rare, bounded by the overflow capacity).
@@ -219,8 +219,9 @@ __global__ void __launch_bounds__(QECMC_DD_THREADS, 1) log_dedupe_kernel(DedupeP
 #define QECMC_BD_KPT 8
 
 struct BucketDedupeParams {
-    const unsigned long long *blogs;   // [tabs][QECMC_NBC][bcap]
-    const uint32_t *bcounts;           // [tabs][QECMC_NBC]
+    int nbc;                           // coarse buckets per table (power of two)
+    const unsigned long long *blogs;   // [tabs][nbc][bcap]
+    const uint32_t *bcounts;           // [tabs][nbc]
     uint32_t bcap;
     const unsigned long long *ovf;     // [tabs][ovf_cap]
     const uint32_t *ovf_cnt;           // [tabs]
@@ -242,11 +243,13 @@ __global__ void __launch_bounds__(QECMC_BD_THREADS, 1) bucket_dedupe_kernel(Buck
     uint32_t *hist = reinterpret_cast<uint32_t *>(hash + HS);   // [4096]
     const int tid = threadIdx.x;
     const int nh = p.nsites + 1;
-    const int shift = QECMC_LEN_BITS + 7;   // set slots from the fingerprint bits above the 7 coarse-bucket bits
+    int lg = 0;
+    while ((1 << lg) < p.nbc) lg++;
+    const int shift = QECMC_LEN_BITS + lg;   // set slots from the fingerprint bits above the coarse-bucket bits
     for (int64_t tab = blockIdx.x; tab < p.tabs; tab += gridDim.x) {
         for (int i = tid; i < nh; i += T) hist[i] = 0;
-        const uint32_t *cnt = p.bcounts + tab * QECMC_NBC;
-        const unsigned long long *logs = p.blogs + (uint64_t)tab * QECMC_NBC * p.bcap;
+        const uint32_t *cnt = p.bcounts + tab * p.nbc;
+        const unsigned long long *logs = p.blogs + (uint64_t)tab * (uint64_t)p.nbc * p.bcap;
         const uint32_t novf = min(p.ovf_cnt[tab], p.ovf_cap);
         const unsigned long long *ovf = p.ovf + (uint64_t)tab * p.ovf_cap;
         unsigned long long k[KPT], kn[KPT];
@@ -255,13 +258,13 @@ __global__ void __launch_bounds__(QECMC_BD_THREADS, 1) bucket_dedupe_kernel(Buck
 #pragma unroll
             for (int j = 0; j < KPT; j++) { uint32_t idx = j * T + tid; k[j] = idx < nb0 ? __ldcs(logs + idx) : 0ull; }
         }
-        for (int b = 0; b < QECMC_NBC; b++) {
+        for (int b = 0; b < p.nbc; b++) {
             const uint32_t nb = cnt[b];
             const unsigned long long *src = logs + (uint64_t)b * p.bcap;
             uint32_t cap = 256;
             while (cap < 2 * (nb + novf) && cap < (uint32_t)HS) cap <<= 1;
             for (uint32_t i = tid; i < cap; i += T) hash[i] = 0ull;
-            if (b + 1 < QECMC_NBC) {
+            if (b + 1 < p.nbc) {
                 const uint32_t nb1 = cnt[b + 1];
                 const unsigned long long *src1 = src + p.bcap;
 #pragma unroll
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(QECMC_BD_THREADS, 1) bucket_dedupe_kernel(Buck
                 for (uint32_t idx = KPT * T + tid; idx < nb; idx += T) dd_insert(hash, cap - 1, shift, __ldcs(src + idx), hist, p.err);
                 for (uint32_t idx = tid; idx < novf; idx += T) {
                     const unsigned long long kk = ovf[idx];
-                    if (((uint32_t)(kk >> QECMC_LEN_BITS) & (QECMC_NBC - 1)) == (uint32_t)b) dd_insert(hash, cap - 1, shift, kk, hist, p.err);
+                    if (((uint32_t)(kk >> QECMC_LEN_BITS) & (uint32_t)(p.nbc - 1)) == (uint32_t)b) dd_insert(hash, cap - 1, shift, kk, hist, p.err);
                 }
             }
 #pragma unroll

@@ -182,8 +182,9 @@ struct StdcParams {
                                    // 2 prefetch + deferred probe of the HBM set; 0 synchronous probe; 3 no inserts (diagnostics)
     // insert_mode 6 (table-driven kernel, no early stop, a table's chains inside one CTA): keys go straight into
     // per-(table, coarse bucket) logs -- the first split of the dedupe is done where the key is produced
-    unsigned long long *blogs;     // [tables][QECMC_NBC][bcap]
-    uint32_t *bcounts;             // [tables][QECMC_NBC] keys per bucket log (capped at bcap)
+    int nbc;                       // coarse buckets per table: a power of two <= QECMC_NBC_MAX, sized for ~6000 keys each
+    unsigned long long *blogs;     // [tables][nbc][bcap]
+    uint32_t *bcounts;             // [tables][nbc] keys per bucket log (capped at bcap)
     uint32_t bcap;                 // slots per bucket log
     unsigned long long *ovf;       // [tables][ovf_cap] keys whose bucket log was full
     uint32_t *ovf_cnt;             // [tables]
@@ -233,7 +234,7 @@ template <> struct ConvStopT<false> {
     __device__ __forceinline__ uint32_t samples() const { return 0; }
 };
 
-#define QECMC_NBC 128   // coarse buckets per (syndrome, class) table in insert mode 6
+#define QECMC_NBC_MAX 128   // most coarse buckets per (syndrome, class) table in insert mode 6
 
 enum { MODE_STDC = 0, MODE_STRC = 1, MODE_MEAN = 2 };
 

@@ -202,10 +202,10 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ?
     // mode 6: this CTA's cursors into the bucket logs of its tables live behind the tile
     uint32_t *s_cur = reinterpret_cast<uint32_t *>(smem + (((size_t)g.nw * T * sizeof(W) + 15) & ~(size_t)15));
     // this thread's table: its cursors (shared-memory byte address) and its bucket logs
-    const uint32_t cur_base = (uint32_t)__cvta_generic_to_shared(s_cur) + (uint32_t)(tid / p.droplets) * (QECMC_NBC * 4u);
-    unsigned long long *blog_tab = BLOG ? p.blogs + (uint64_t)tab * QECMC_NBC * p.bcap : nullptr;
+    const uint32_t cur_base = (uint32_t)__cvta_generic_to_shared(s_cur) + (uint32_t)(tid / p.droplets) * ((uint32_t)p.nbc * 4u);
+    unsigned long long *blog_tab = BLOG ? p.blogs + (uint64_t)tab * (uint64_t)p.nbc * p.bcap : nullptr;
     if (BLOG) {
-        for (int i = tid; i < p.tables_per_cta * QECMC_NBC; i += T) s_cur[i] = 0;
+        for (int i = tid; i < p.tables_per_cta * p.nbc; i += T) s_cur[i] = 0;
         __syncthreads();
     }
 
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ?
             if (BLOG) {
                 if (dirty) {
                     const uint64_t k = make_key(h, n);
-                    const uint32_t b = (uint32_t)(k >> QECMC_LEN_BITS) & (QECMC_NBC - 1);
+                    const uint32_t b = (uint32_t)(k >> QECMC_LEN_BITS) & (uint32_t)(p.nbc - 1);
                     uint32_t pos;
                     asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(cur_base + b * 4u) : "memory");
                     if (pos < p.bcap) {
@@ -381,8 +381,8 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ?
     if (BLOG) {
         __syncthreads();   // every chain of the CTA has logged its last key
         const int64_t tab0 = (int64_t)blockIdx.x * p.tables_per_cta;
-        for (int i = tid; i < p.tables_per_cta * QECMC_NBC; i += T)
-            if (tab0 + i / QECMC_NBC < p.n_chains / p.droplets) p.bcounts[tab0 * QECMC_NBC + i] = min(s_cur[i], p.bcap);
+        for (int i = tid; i < p.tables_per_cta * p.nbc; i += T)
+            if (tab0 + i / p.nbc < p.n_chains / p.droplets) p.bcounts[tab0 * p.nbc + i] = min(s_cur[i], p.bcap);
     }
     if (imode == 4) p.log_counts[local] = noff;
     if (imode == 5) p.log_counts[local] = nlog;

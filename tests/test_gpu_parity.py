@@ -698,7 +698,9 @@ def test_chain_xyz_replay_matches_reference_golden_and_oracle(ctx):
 
 # ------------------------------------------------------------------ key logs + dedupe kernel vs the HBM set
 @pytest.mark.parametrize("g,L,droplets,steps", [(O.TORIC, 7, 16, 20000), (O.PLANAR, 9, 64, 6000), (O.TORIC, 15, 7, 9001),
-                                                (O.TORIC, 5, 1, 333), (O.TORIC, 9, 64, 12000), (O.TORIC, 15, 32, 4000)])
+                                                (O.TORIC, 5, 1, 333), (O.TORIC, 9, 64, 12000), (O.TORIC, 15, 32, 4000),
+                                                (O.PLANAR, 7, 16, 2401), (O.TORIC, 5, 2, 3000), (O.TORIC, 7, 128, 1500),
+                                                (O.PLANAR, 15, 16, 5000)])
 def test_log_dedupe_equals_table_set(ctx, g, L, droplets, steps, monkeypatch):
     """The same native chains counted in every way the library has: bucket logs written by the chain kernel + one-pass
     dedupe (mode 6, the default where a syndrome's chains fill whole CTAs), per-chain key logs reduced by
@@ -718,6 +720,8 @@ def test_log_dedupe_equals_table_set(ctx, g, L, droplets, steps, monkeypatch):
         outs[mode] = (out, st, hist)
     monkeypatch.delenv("QECMC_DEBUG_INSERT_MODE")
     assert outs["4"][1]["table_slots"] == 0 and outs["2"][1]["table_slots"] > 0      # really different paths
+    bucket_logs = 1024 % droplets == 0 and (O.neq(g) * droplets) % 32 == 0
+    assert outs["default"][1]["table_slots"] == (-1 if bucket_logs else 0)
     for mode in ("4", "2", "0"):
         assert np.array_equal(outs["default"][2], outs[mode][2])
         assert outs["default"][1]["distinct"] == outs[mode][1]["distinct"]
