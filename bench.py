@@ -35,8 +35,8 @@ N_EQ = 16
 W_INT = 170.0      # int32 lane-ops per toric/planar depolarizing Metropolis step (agreed figure)
 W_LOG = 8.0        # bytes a chain appends to a bucket log per offered sample (the chain kernel's only steady HBM traffic)
 # ncu, full-size launch of this exact command (profiles/r01_ncu_fullsize_stdc_v6.csv): warp instructions and DRAM bytes
-NCU_CHAIN = {"file": "profiles/r01_ncu_fullsize_stdc_v8.csv", "warp_inst_per_launch": 90406760592, "dram_bytes_per_launch": 11259394560 + 28711650560,
-             "issue_active_pct": 72.26, "smem_wavefront_pct": 67.68, "steps_per_launch": 148 * 16 * 64 * 50625 * 5}
+NCU_CHAIN = {"file": "profiles/r01_ncu_fullsize_stdc_v10.csv", "warp_inst_per_launch": 89927429188, "dram_bytes_per_launch": 11272329728 + 28721867520,
+             "issue_active_pct": 72.49, "smem_wavefront_pct": 68.23, "steps_per_launch": 148 * 16 * 64 * 50625 * 5}
 
 
 def synth_syndromes(n, seed, L=L, p=P_ERROR):
