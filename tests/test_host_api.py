@@ -151,3 +151,19 @@ def test_dtype_is_enforced_like_the_reference():
         decoders.STDC(code, 0.1, steps=10)
     with pytest.raises(TypeError):
         decoders.STDC(RotSurCode(5), 0.1, steps=10)     # 2-D lattice into the 3-D-only fast path
+
+
+def test_generate_data_noise_models_match_the_reference_formulas():
+    """generate_data.py:57-118: per-qubit Pauli probabilities of the four noise models"""
+    from mcmc_qec_toric_rl_b200 import generate_data as G
+    assert G.noise_probabilities({'code': 'toric', 'noise': 'depolarizing', 'p_error': 0.12}) == (0.12, None)
+    pe, (px, py, pz) = G.noise_probabilities({'code': 'planar', 'noise': 'depolarizing', 'p_error': 0.12})
+    assert pe is None and px == py == pz == 0.12 / 3
+    _, (px, py, pz) = G.noise_probabilities({'code': 'xzzx', 'noise': 'biased', 'p_error': 0.15, 'eta': 100})
+    assert np.isclose(pz, 0.15 * 100 / 101) and np.isclose(px, 0.15 / 202) and px == py
+    _, (px, py, pz) = G.noise_probabilities({'code': 'rotated', 'noise': 'alpha', 'p_error': 0.1, 'alpha': 2})
+    p_tilde = 0.1 + 2 * 0.1 ** 2
+    p = p_tilde / (1 + p_tilde)
+    assert np.isclose(pz, 0.1 * (1 - p)) and np.isclose(px, 0.01 * (1 - p)) and px == py
+    with pytest.raises(AssertionError):
+        G.noise_probabilities({'code': 'toric', 'noise': 'biased', 'p_error': 0.1})
