@@ -230,6 +230,10 @@ int setup_ladder(qecmc_ctx *c, const qecmc_ladder_cfg *cfg, const Geo &g, Ladder
     p.wtab = (const double *)d.wtab.p;
     p.alpha = cfg->param_b;
     p.seed = cfg->seed;
+    {
+        uint32_t k0 = (uint32_t)cfg->seed, k1 = (uint32_t)(cfg->seed >> 32);
+        for (int r = 0; r < 10; r++) { p.keys.k0[r] = k0; p.keys.k1[r] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    }
     p.status = (int *)d.status.p;
     p.hash_seed = c->hash_seed;
     return 0;

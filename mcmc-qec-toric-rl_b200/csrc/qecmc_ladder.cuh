@@ -49,6 +49,7 @@ struct LadderParams {
     double alpha;           // kind 1
     const double *wtab;     // kinds 1, 2: [Nc][4][nsites+1] = px^k, py^k, pz^k, q0^(L*L-k)
     uint64_t seed;
+    PhiloxKeys keys;            // native: the ten Philox round keys of `seed`
     const double *u_nb, *u_py;  // replay: [n_ladders][n_nb], [n_ladders][n_py]
     int n_nb, n_py;
     // PTEQ
@@ -82,38 +83,38 @@ struct LadderParams {
 __host__ __device__ inline int class_raw_to_label(int geom, int raw) { return (geom == XZZX && raw >= 2) ? 5 - raw : raw; }
 
 struct NativeRng {
-    uint32_t k0, k1, id_lo, id_hi, ctr;
+    uint32_t id_lo, id_hi, ctr, tag;   // tag = counter word 1: separate streams of one lane never overlap
     uint4 buf;
     int have;
-    __device__ __forceinline__ void init(uint64_t seed, uint64_t id)
+    __device__ __forceinline__ void init(uint64_t id, uint32_t stream_tag)
     {
-        k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
         id_lo = (uint32_t)id; id_hi = (uint32_t)(id >> 32);
-        ctr = 0; have = 0;
+        ctr = 0; have = 0; tag = stream_tag;
         buf = make_uint4(0, 0, 0, 0);
     }
-    __device__ __forceinline__ uint32_t next32()
+    // k: the ten round keys, precomputed on the host (a kernel parameter: every key is a constant-bank operand)
+    __device__ __forceinline__ uint32_t next32(const PhiloxKeys &k)
     {
-        if (have == 0) { buf = philox4x32_10(ctr++, 0u, id_lo, id_hi, k0, k1); have = 4; }
+        if (have == 0) { buf = philox4x32_10(ctr++, tag, id_lo, id_hi, k); have = 4; }
         uint32_t v = buf.x;
         buf.x = buf.y; buf.y = buf.z; buf.z = buf.w;
         have--;
         return v;
     }
-    __device__ __forceinline__ double nb() { return (double)next32() * 2.3283064365386963e-10; }
-    __device__ __forceinline__ double py() { return nb(); }
+    __device__ __forceinline__ double nb(const PhiloxKeys &k) { return (double)next32(k) * 2.3283064365386963e-10; }
+    __device__ __forceinline__ double py(const PhiloxKeys &k) { return nb(k); }
 };
 
 struct ReplayRng {
     const double *nb_base, *py_base;
     int nbp, pyp, n_nb, n_py;
     int *status;
-    __device__ __forceinline__ double nb()
+    __device__ __forceinline__ double nb(const PhiloxKeys &)
     {
         if (nbp >= n_nb) { *status = 1; nbp++; return 0.0; }
         return nb_base[nbp++];
     }
-    __device__ __forceinline__ double py()
+    __device__ __forceinline__ double py(const PhiloxKeys &)
     {
         if (pyp >= n_py) { *status = 2; pyp++; return 0.0; }
         return py_base[pyp++];
@@ -147,15 +148,15 @@ template <int GEOM, typename RNG> struct LogicalDraw {
     int op[2], xp[2], zp[2];
     // _apply_random_logical draw order: toric_model.py:228-253 (both layer operators first),
     // planar_model.py:271-288, rotated_surface_model.py:331-346, xzzx_model.py:340-357
-    __device__ __forceinline__ void draw(RNG &rng, int L)
+    __device__ __forceinline__ void draw(RNG &rng, int L, const PhiloxKeys &k)
     {
 #pragma unroll
-        for (int l = 0; l < nl; l++) op[l] = (int)(rng.nb() * 4);
+        for (int l = 0; l < nl; l++) op[l] = (int)(rng.nb(k) * 4);
 #pragma unroll
         for (int l = 0; l < nl; l++) {
             xp[l] = zp[l] = 0;
-            if (op[l] == 1 || op[l] == 2) xp[l] = (int)(rng.nb() * L);
-            if (op[l] == 3 || op[l] == 2) zp[l] = (int)(rng.nb() * L);
+            if (op[l] == 1 || op[l] == 2) xp[l] = (int)(rng.nb(k) * L);
+            if (op[l] == 3 || op[l] == 2) zp[l] = (int)(rng.nb(k) * L);
         }
     }
     // fingerprint change of the drawn operator: XOR of the string fingerprints (the fingerprint is GF(2)-linear)
@@ -309,8 +310,15 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
         rr->nbp = rr->pyp = 0;
         rr->status = p.status;
     } else {
-        reinterpret_cast<NativeRng *>(&rng)->init(p.seed, (uint64_t)gladder * 32u + (uint64_t)gl);
+        reinterpret_cast<NativeRng *>(&rng)->init((uint64_t)gladder * 32u + (uint64_t)gl, 0u);
     }
+    // Native mode: what only the top rung draws (logical-move decision, the operator, its accept draw) comes from a
+    // stream of its own.  The main stream then serves every lane exactly two words per iteration and one per sweep, so all
+    // lanes refill together -- one Philox call per warp instead of one per out-of-step lane.  Replay keeps the single
+    // stream (the reference's draw order).
+    RNG rng_top_native;
+    if (!REPLAY) reinterpret_cast<NativeRng *>(&rng_top_native)->init((uint64_t)gladder * 32u + (uint64_t)gl, 1u);
+    RNG &rtop = REPLAY ? rng : rng_top_native;
     const bool top_logical = p.p_logical != 0.0;
     const bool track_hash = p.acct >= ACCT_DC || p.track_shortest;
     unsigned long long *table = nullptr;
@@ -351,12 +359,18 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
                 // draws the operator and broadcasts it, lane j forms the new value of row word j (and j + 32) of the
                 // owner's lattice, the weight change is a warp reduction, the owner decides, and on accept the lanes commit
                 // their words.  Same draws in the same order, same arithmetic as _apply_random_logical + update_chain.
+                // native: every active lane takes its two main-stream words here, whatever it goes on to do
+                uint32_t w_idx = 0, w_acc = 0;
+                if (!REPLAY && active) {
+                    w_idx = reinterpret_cast<NativeRng *>(&rng)->next32(p.keys);
+                    w_acc = reinterpret_cast<NativeRng *>(&rng)->next32(p.keys);
+                }
                 bool logical = false;
                 LogicalDraw<GEOM, RNG> ld;
                 ld.op[0] = ld.op[1] = ld.xp[0] = ld.xp[1] = ld.zp[0] = ld.zp[1] = 0;
                 if (is_top) {
-                    logical = rng.py() < p.p_logical;
-                    if (logical) ld.draw(rng, L);
+                    logical = rtop.py(p.keys) < p.p_logical;
+                    if (logical) ld.draw(rtop, L, p.keys);
                 }
                 uint32_t lm = __ballot_sync(0xFFFFFFFFu, logical);
                 while (lm) {
@@ -399,10 +413,10 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
                     if (lane == src) {
                         if (WEIGHTED) {
                             double pn = chain_weight(wt, ns1, nx + dx, ny + dy, nz + dz);
-                            acc = rng.py() < __ddiv_rn(pn, pb);
+                            acc = rtop.py(p.keys) < __ddiv_rn(pn, pb);
                         } else {
                             if (p.top_accept_all || dE <= 0) acc = true;
-                            else acc = rng.py() < p.thr_top_d[dE + 4 * L];
+                            else acc = rtop.py(p.keys) < p.thr_top_d[dE + 4 * L];
                         }
                         if (acc) {
                             int dcls = 0;
@@ -431,11 +445,11 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
                     if (REPLAY) {
                         ReplayRng *rr = reinterpret_cast<ReplayRng *>(&rng);
                         double u[K];
-                        for (int k = 0; k < K; k++) u[k] = rr->nb();
+                        for (int k = 0; k < K; k++) u[k] = rr->nb(p.keys);
                         propose_replay<GEOM>(g, u, row, col, op);
                         if (track_hash) idx = rco_to_idx<GEOM>(g, row, col, op);
                     } else {
-                        idx = (int)__umulhi(reinterpret_cast<NativeRng *>(&rng)->next32(), (uint32_t)g.nstab);
+                        idx = (int)__umulhi(w_idx, (uint32_t)g.nstab);
                         if (!TABLE) idx_to_rco<GEOM>(g, idx, row, col, op);
                     }
                     Upd<W> u;
@@ -472,14 +486,14 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
                     bool acc;
                     if (WEIGHTED) {
                         double pn = chain_weight(wt, ns1, nx + dx, ny + dy, nz + dz);
-                        acc = rng.py() < __ddiv_rn(pn, pb);
+                        acc = (REPLAY ? rng.py(p.keys) : (double)w_acc * 2.3283064365386963e-10) < __ddiv_rn(pn, pb);
                     } else if (is_top) {
                         if (p.top_accept_all || dE <= 0) acc = true;
-                        else acc = rng.py() < p.thr_top_d[dE + 4 * L];
+                        else acc = (REPLAY ? rng.py(p.keys) : (double)w_acc * 2.3283064365386963e-10) < p.thr_top_d[dE + 4 * L];
                     } else if (REPLAY) {
-                        acc = rng.py() < s_thrd[r * 9 + dE + QECMC_THR_OFF];
+                        acc = rng.py(p.keys) < s_thrd[r * 9 + dE + QECMC_THR_OFF];
                     } else {
-                        acc = reinterpret_cast<NativeRng *>(&rng)->next32() <= s_thru[r * 9 + dE + QECMC_THR_OFF];
+                        acc = w_acc <= s_thru[r * 9 + dE + QECMC_THR_OFF];
                     }
                     if (acc) {
 #pragma unroll
@@ -513,7 +527,7 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
         // decisions depend on rung-owned values only.
         {
             const int wb = (tid >> 5) * 32 + gbase;   // this ladder's slice of the per-warp arrays
-            if (!REPLAY) s_sw_u[(tid >> 5) * 32 + lane] = rng.nb();  // lane i's draw decides pair (i, i+1)
+            if (!REPLAY && valid) s_sw_u[(tid >> 5) * 32 + lane] = rng.nb(p.keys);  // lane i's draw decides pair (i, i+1)
             if (valid) {
                 s_sw_lane[wb + r] = gl;
                 s_sw_a[wb + r] = p.kind == LK_ALPHA ? e_nz : n;
@@ -529,14 +543,14 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
                         // mcmc_alpha.py:117-123: PY draw always; float exponent n_eff_hi - n_eff_lo of the two RUNGS
                         const double ne_lo = __dadd_rn((double)lo_n, __dmul_rn(p.alpha, (double)s_sw_b[wb + i]));
                         const double ne_hi = __dadd_rn((double)s_sw_a[wb + i + 1], __dmul_rn(p.alpha, (double)s_sw_b[wb + i + 1]));
-                        const double u = REPLAY ? rng.py() : s_sw_u[wb + i];
+                        const double u = REPLAY ? rng.py(p.keys) : s_sw_u[wb + i];
                         swap = u < pow(p.diff[i], __dadd_rn(ne_hi, -ne_lo));
                     } else {
                         const int ne_lo = lo_n, ne_hi = c_n;
                         if (p.kind == LK_DEPOL && ne_hi < ne_lo) {
                             swap = true;  // mcmc.py:146-147: no draw
                         } else {
-                            const double u = REPLAY ? rng.nb() : s_sw_u[wb + i];  // mcmc_biased.py:154-156 draws always
+                            const double u = REPLAY ? rng.nb(p.keys) : s_sw_u[wb + i];  // mcmc_biased.py:154-156 draws always
                             const int k = ne_hi - ne_lo;
                             const double pw = (use_pw && k >= -QECMC_PW_K && k <= QECMC_PW_K) ? s_pw[i * (2 * QECMC_PW_K + 1) + k + QECMC_PW_K]
                                                                                                : numba_pow_dev(p.diff[i], k);
