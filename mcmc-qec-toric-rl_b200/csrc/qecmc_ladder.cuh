@@ -413,7 +413,8 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
                     if (lane == src) {
                         if (WEIGHTED) {
                             double pn = chain_weight(wt, ns1, nx + dx, ny + dy, nz + dz);
-                            acc = rtop.py(p.keys) < __ddiv_rn(pn, pb);
+                            if (REPLAY) acc = rtop.py(p.keys) < __ddiv_rn(pn, pb);
+                            else acc = rtop.py(p.keys) * pb < pn;
                         } else {
                             if (p.top_accept_all || dE <= 0) acc = true;
                             else acc = rtop.py(p.keys) < p.thr_top_d[dE + 4 * L];
@@ -486,7 +487,9 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
                     bool acc;
                     if (WEIGHTED) {
                         double pn = chain_weight(wt, ns1, nx + dx, ny + dy, nz + dz);
-                        acc = (REPLAY ? rng.py(p.keys) : (double)w_acc * 2.3283064365386963e-10) < __ddiv_rn(pn, pb);
+                        // replay divides like the reference (bit-exact decisions); native compares u * pb < pn and saves the division
+                        if (REPLAY) acc = rng.py(p.keys) < __ddiv_rn(pn, pb);
+                        else acc = (double)w_acc * 2.3283064365386963e-10 * pb < pn;
                     } else if (is_top) {
                         if (p.top_accept_all || dE <= 0) acc = true;
                         else acc = (REPLAY ? rng.py(p.keys) : (double)w_acc * 2.3283064365386963e-10) < p.thr_top_d[dE + 4 * L];
