@@ -537,17 +537,37 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
                 s_sw_b[wb + r] = e_nxy;
             }
             __syncwarp();
+            // Alpha ladder: the decision of pair (i, i + 1) depends on rung-owned values only, so lane i takes it -- one
+            // pow() per warp instead of one per pair; the reference draws one PY uniform per pair, top pair first
+            // (mcmc_alpha.py:117-123), so pair i reads draw number Nc - 2 - i of this sweep.
+            uint32_t alpha_swaps = 0;
+            if (p.kind == LK_ALPHA) {
+                bool sw = false;
+                if (ladder < p.n_ladders && !done && gl < Nc - 1) {
+                    const int i = gl;
+                    const double ne_lo = __dadd_rn((double)s_sw_a[wb + i], __dmul_rn(p.alpha, (double)s_sw_b[wb + i]));
+                    const double ne_hi = __dadd_rn((double)s_sw_a[wb + i + 1], __dmul_rn(p.alpha, (double)s_sw_b[wb + i + 1]));
+                    double u;
+                    if (REPLAY) {
+                        ReplayRng *rr = reinterpret_cast<ReplayRng *>(&rng);
+                        const int at = rr->pyp + (Nc - 2 - i);
+                        if (at >= rr->n_py) { *rr->status = 2; u = 0.0; }
+                        else u = rr->py_base[at];
+                    } else {
+                        u = s_sw_u[wb + i];
+                    }
+                    sw = u < pow(p.diff[i], __dadd_rn(ne_hi, -ne_lo));
+                }
+                alpha_swaps = (__ballot_sync(0xFFFFFFFFu, sw) >> gbase) & gmask;
+                if (REPLAY && ladder < p.n_ladders && !done) reinterpret_cast<ReplayRng *>(&rng)->pyp += Nc - 1;
+            }
             if (gl == 0 && ladder < p.n_ladders && !done) {
                 int c_lane = s_sw_lane[wb + Nc - 1], c_n = s_sw_a[wb + Nc - 1];
                 for (int i = Nc - 2; i >= 0; i--) {
                     const int lo_lane = s_sw_lane[wb + i], lo_n = s_sw_a[wb + i];
                     bool swap;
                     if (p.kind == LK_ALPHA) {
-                        // mcmc_alpha.py:117-123: PY draw always; float exponent n_eff_hi - n_eff_lo of the two RUNGS
-                        const double ne_lo = __dadd_rn((double)lo_n, __dmul_rn(p.alpha, (double)s_sw_b[wb + i]));
-                        const double ne_hi = __dadd_rn((double)s_sw_a[wb + i + 1], __dmul_rn(p.alpha, (double)s_sw_b[wb + i + 1]));
-                        const double u = REPLAY ? rng.py(p.keys) : s_sw_u[wb + i];
-                        swap = u < pow(p.diff[i], __dadd_rn(ne_hi, -ne_lo));
+                        swap = (alpha_swaps >> i) & 1u;
                     } else {
                         const int ne_lo = lo_n, ne_hi = c_n;
                         if (p.kind == LK_DEPOL && ne_hi < ne_lo) {
