@@ -20,7 +20,7 @@
 namespace qecmc {
 
 enum { LK_DEPOL = 0, LK_ALPHA = 1, LK_BIASED = 2 };
-#define QECMC_PW_K 31   // swap-sweep power table covers weight differences of up to 31 between neighbouring rungs
+#define QECMC_PW_K 31   // swap-sweep power table: 2 * 31 + 1 exponents per rung pair
 enum { ACCT_NONE = 0, ACCT_PTEQ = 1, ACCT_DC = 2, ACCT_RC = 3 };
 
 struct LadderParams {
@@ -208,9 +208,12 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
     // (bit-identical), so a pair costs one table read instead of a multiply loop and, for k < 0, a division
     double *s_pw = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(s_ll) + (TABLE ? 16 * 256 * 2 : 0));
     const bool use_pw = p.kind != LK_ALPHA && p.Nc > 1;
+    // depolarizing ladders only evaluate k = n_hi - n_lo >= 0 (a lighter upper replica swaps without a draw), so their
+    // table covers 0 .. 2 QECMC_PW_K; biased ladders draw always and cover -QECMC_PW_K .. QECMC_PW_K
+    const int pw_off = p.kind == LK_DEPOL ? 0 : QECMC_PW_K;
     if (use_pw)
         for (int e = tid; e < (p.Nc - 1) * (2 * QECMC_PW_K + 1); e += T)
-            s_pw[e] = numba_pow_dev(p.diff[e / (2 * QECMC_PW_K + 1)], e % (2 * QECMC_PW_K + 1) - QECMC_PW_K);
+            s_pw[e] = numba_pow_dev(p.diff[e / (2 * QECMC_PW_K + 1)], e % (2 * QECMC_PW_K + 1) - pw_off);
     if (TABLE) {
         if (tid < 8) s_patmask[tid] = 0;
         __syncthreads();
@@ -575,8 +578,9 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
                         } else {
                             const double u = REPLAY ? rng.nb(p.keys) : s_sw_u[wb + i];  // mcmc_biased.py:154-156 draws always
                             const int k = ne_hi - ne_lo;
-                            const double pw = (use_pw && k >= -QECMC_PW_K && k <= QECMC_PW_K) ? s_pw[i * (2 * QECMC_PW_K + 1) + k + QECMC_PW_K]
-                                                                                               : numba_pow_dev(p.diff[i], k);
+                            const int ki = k + pw_off;
+                            const double pw = (use_pw && ki >= 0 && ki <= 2 * QECMC_PW_K) ? s_pw[i * (2 * QECMC_PW_K + 1) + ki]
+                                                                                           : numba_pow_dev(p.diff[i], k);
                             swap = u < pw;
                         }
                     }
