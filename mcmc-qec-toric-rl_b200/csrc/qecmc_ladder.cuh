@@ -103,6 +103,8 @@ struct NativeRng {
     }
     __device__ __forceinline__ double nb(const PhiloxKeys &k) { return (double)next32(k) * 2.3283064365386963e-10; }
     __device__ __forceinline__ double py(const PhiloxKeys &k) { return nb(k); }
+    // (int)(nb() * m) for the uniform w / 2^32 is floor(w * m / 2^32): the same number without the round trip through double
+    __device__ __forceinline__ int nb_int(const PhiloxKeys &k, int m) { return (int)__umulhi(next32(k), (uint32_t)m); }
 };
 
 struct ReplayRng {
@@ -119,6 +121,7 @@ struct ReplayRng {
         if (pyp >= n_py) { *status = 2; pyp++; return 0.0; }
         return py_base[pyp++];
     }
+    __device__ __forceinline__ int nb_int(const PhiloxKeys &k, int m) { return (int)(nb(k) * m); }
 };
 
 // numba's float64 ** int64 (mcmc.py:149): square-and-multiply, reciprocal for negative exponents
@@ -151,12 +154,12 @@ template <int GEOM, typename RNG> struct LogicalDraw {
     __device__ __forceinline__ void draw(RNG &rng, int L, const PhiloxKeys &k)
     {
 #pragma unroll
-        for (int l = 0; l < nl; l++) op[l] = (int)(rng.nb(k) * 4);
+        for (int l = 0; l < nl; l++) op[l] = rng.nb_int(k, 4);
 #pragma unroll
         for (int l = 0; l < nl; l++) {
             xp[l] = zp[l] = 0;
-            if (op[l] == 1 || op[l] == 2) xp[l] = (int)(rng.nb(k) * L);
-            if (op[l] == 3 || op[l] == 2) zp[l] = (int)(rng.nb(k) * L);
+            if (op[l] == 1 || op[l] == 2) xp[l] = rng.nb_int(k, L);
+            if (op[l] == 3 || op[l] == 2) zp[l] = rng.nb_int(k, L);
         }
     }
     // fingerprint change of the drawn operator: XOR of the string fingerprints (the fingerprint is GF(2)-linear)
