@@ -567,7 +567,45 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
                 alpha_swaps = (__ballot_sync(0xFFFFFFFFu, sw) >> gbase) & gmask;
                 if (REPLAY && ladder < p.n_ladders && !done) reinterpret_cast<ReplayRng *>(&rng)->pyp += Nc - 1;
             }
-            if (gl == 0 && ladder < p.n_ladders && !done) {
+            // Native depolarizing / biased ladders: pair (i, i + 1) swaps iff u_i < diff_i^k, k = n_hi - n_lo, and diff_i^k falls
+            // with k -- so the lane on rung i turns its pair's draw into the largest exponent that still swaps (a search of
+            // the power table, all lanes at once) and the walk over the pairs is left with one compare and one select per
+            // pair: "the carried replica's weight <= n_lo + kmax".  Same decisions as evaluating u < diff^k pair by pair.
+            // A draw below the table's last entry (or a table that does not fall) sends the ladder down the general walk.
+            bool fast_sweep = !REPLAY && p.kind == LK_ALPHA;   // group-uniform
+            uint32_t swaps = alpha_swaps;
+            if (!REPLAY && use_pw) {
+                const int kend = 2 * QECMC_PW_K - pw_off;   // exponents 0 .. kend are tabulated
+                bool big = false;
+                if (valid && !done && r < Nc - 1) {
+                    const double u = s_sw_u[wb + r];
+                    const double *row = s_pw + r * (2 * QECMC_PW_K + 1) + pw_off;   // row[k] = diff_r^k
+                    int cnt = 0;   // number of k in 0 .. kend with u < row[k]
+#pragma unroll
+                    for (int st = 32; st >= 1; st >>= 1) {
+                        const int m = cnt + st;
+                        if (m <= kend + 1 && u < row[m - 1]) cnt = m;
+                    }
+                    big = cnt == kend + 1 || cnt == 0;
+                    s_sw_b[wb + r] = n + cnt - 1;
+                }
+                const uint32_t bigs = (__ballot_sync(0xFFFFFFFFu, big) >> gbase) & gmask;
+                fast_sweep = bigs == 0;
+                __syncwarp();
+                if (fast_sweep && ladder < p.n_ladders && !done) {
+                    // every lane of the ladder walks the pairs on the same (broadcast) reads and ends up with the swap mask
+                    int c_n = s_sw_a[wb + Nc - 1];
+                    uint32_t m = 0;
+                    for (int i = Nc - 2; i >= 0; i--) {
+                        const int lo_n = s_sw_a[wb + i], t = s_sw_b[wb + i];
+                        const bool sw = c_n <= t;
+                        m |= (uint32_t)sw << i;
+                        c_n = sw ? c_n : lo_n;
+                    }
+                    swaps = m;
+                }
+            }
+            if (!fast_sweep && gl == 0 && ladder < p.n_ladders && !done) {
                 int c_lane = s_sw_lane[wb + Nc - 1], c_n = s_sw_a[wb + Nc - 1];
                 for (int i = Nc - 2; i >= 0; i--) {
                     const int lo_lane = s_sw_lane[wb + i], lo_n = s_sw_a[wb + i];
@@ -599,7 +637,14 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
             }
             __syncwarp();
             if (valid && !done) {
-                r = s_sw_rung[wb + gl];
+                if (fast_sweep) {
+                    // from the swap mask: the lower replica of a swapping pair moves up one rung; any other replica falls past
+                    // every swapping pair directly below it
+                    if (r < Nc - 1 && ((swaps >> r) & 1u)) r = r + 1;
+                    else if (r > 0) r -= __clz((int)~(swaps << (32 - r)));
+                } else {
+                    r = s_sw_rung[wb + gl];
+                }
                 if (p.kind == LK_ALPHA) { e_nz = s_sw_a[wb + r]; e_nxy = s_sw_b[wb + r]; }   // n_eff stays with the rung
             }
             if (REPLAY) {   // the walking lane consumed the draws: the whole ladder continues from its stream positions
