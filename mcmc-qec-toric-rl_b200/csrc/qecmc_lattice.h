@@ -302,9 +302,9 @@ template <int GEOM, typename W, typename A> QHD int lat_class(const Geo &g, cons
 
 template <typename W> QHD W rowmask(int pauli, int L)
 {
-    W m = 0;
-    for (int c = 0; c < L; c++) m |= fld<W>(pauli, c);
-    return m;
+    // the Pauli in every one of the L fields: 0b0101.. times the Pauli, cut to 2L bits
+    const W all = (W)((W)(~(W)0 / 3) * (W)pauli);
+    return 2 * L >= (int)(8 * sizeof(W)) ? all : (W)(all & (W)(((W)1 << (2 * L)) - 1));
 }
 
 template <typename W, typename A> QHD int xor_word(A &a, int w, W m)
