@@ -571,12 +571,15 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
             // with k -- so the lane on rung i turns its pair's draw into the largest exponent that still swaps (a search of
             // the power table, all lanes at once) and the walk over the pairs is left with one compare and one select per
             // pair: "the carried replica's weight <= n_lo + kmax".  Same decisions as evaluating u < diff^k pair by pair.
-            // A draw below the table's last entry (or a table that does not fall) sends the ladder down the general walk.
+            // A draw below the table's last entry leaves the exponent open: the pair is marked, swaps outright while k is
+            // inside the table and is evaluated as before beyond it.  A table that does not fall (diff >= 1) sends the ladder
+            // down the general walk.
             bool fast_sweep = !REPLAY && p.kind == LK_ALPHA;   // group-uniform
             uint32_t swaps = alpha_swaps;
             if (!REPLAY && use_pw) {
+                constexpr int OPEN = 1 << 30;
                 const int kend = 2 * QECMC_PW_K - pw_off;   // exponents 0 .. kend are tabulated
-                bool big = false;
+                bool bad = false, open = false;
                 if (valid && !done && r < Nc - 1) {
                     const double u = s_sw_u[wb + r];
                     const double *row = s_pw + r * (2 * QECMC_PW_K + 1) + pw_off;   // row[k] = diff_r^k
@@ -586,21 +589,33 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
                         const int m = cnt + st;
                         if (m <= kend + 1 && u < row[m - 1]) cnt = m;
                     }
-                    big = cnt == kend + 1 || cnt == 0;
-                    s_sw_b[wb + r] = n + cnt - 1;
+                    bad = !(row[1] < 1.0) || cnt == 0;
+                    open = cnt == kend + 1;
+                    s_sw_b[wb + r] = n + cnt - 1 + (open ? OPEN : 0);
                 }
-                const uint32_t bigs = (__ballot_sync(0xFFFFFFFFu, big) >> gbase) & gmask;
-                fast_sweep = bigs == 0;
+                const uint32_t bads = (__ballot_sync(0xFFFFFFFFu, bad) >> gbase) & gmask;
+                const uint32_t opens = (__ballot_sync(0xFFFFFFFFu, open) >> gbase) & gmask;
+                fast_sweep = bads == 0;
                 __syncwarp();
                 if (fast_sweep && ladder < p.n_ladders && !done) {
                     // every lane of the ladder walks the pairs on the same (broadcast) reads and ends up with the swap mask
                     int c_n = s_sw_a[wb + Nc - 1];
                     uint32_t m = 0;
-                    for (int i = Nc - 2; i >= 0; i--) {
-                        const int lo_n = s_sw_a[wb + i], t = s_sw_b[wb + i];
-                        const bool sw = c_n <= t;
-                        m |= (uint32_t)sw << i;
-                        c_n = sw ? c_n : lo_n;
+                    if (opens == 0) {
+                        for (int i = Nc - 2; i >= 0; i--) {
+                            const int lo_n = s_sw_a[wb + i], t = s_sw_b[wb + i];
+                            const bool sw = c_n <= t;
+                            m |= (uint32_t)sw << i;
+                            c_n = sw ? c_n : lo_n;
+                        }
+                    } else {
+                        for (int i = Nc - 2; i >= 0; i--) {
+                            const int lo_n = s_sw_a[wb + i], t = s_sw_b[wb + i];
+                            bool sw = c_n <= t;
+                            if (t >= OPEN && c_n > t - OPEN) sw = s_sw_u[wb + i] < numba_pow_dev(p.diff[i], c_n - lo_n);   // beyond the table
+                            m |= (uint32_t)sw << i;
+                            c_n = sw ? c_n : lo_n;
+                        }
                     }
                     swaps = m;
                 }
