@@ -220,6 +220,7 @@ int setup_ladder(qecmc_ctx *c, const qecmc_ladder_cfg *cfg, const Geo &g, Ladder
     p.kind = cfg->kind;
     p.Nc = cfg->Nc;
     p.G = (int)next_pow2((uint64_t)cfg->Nc);
+    if (p.G < 4) p.G = 4;   // a ladder's lanes fill the top rung's random-word pool: 4 calls = 16 words cover one iteration
     p.iters = cfg->iters;
     p.p_logical = cfg->p_logical;
     p.top_accept_all = t.top_accept_all;

@@ -15,6 +15,7 @@
 // streams in the reference's order and is bit-exact; native mode draws from
 // per-lane Philox4x32-10 streams.
 #pragma once
+#include <type_traits>
 #include "qecmc_device.cuh"
 
 namespace qecmc {
@@ -124,6 +125,19 @@ struct ReplayRng {
     __device__ __forceinline__ int nb_int(const PhiloxKeys &k, int m) { return (int)(nb(k) * m); }
 };
 
+// Native mode, the top rung's own stream (Philox counter word 1 = 1 of the lane's id): its words are produced by the whole
+// ladder at once -- lane j runs call number c0 + j into a shared-memory pool -- and the top lane reads them in order.  Word i
+// of the stream is component i & 3 of call i >> 2, whoever computes it.
+struct TopRng {
+    uint32_t pos;          // words of this lane's stream consumed so far
+    uint32_t end;          // stream position the pool reaches (this lane's pool only while it is the top lane)
+    const uint32_t *pool;  // the word at stream position pos
+    __device__ __forceinline__ uint32_t next32(const PhiloxKeys &) { pos++; return *pool++; }
+    __device__ __forceinline__ double nb(const PhiloxKeys &k) { return (double)next32(k) * 2.3283064365386963e-10; }
+    __device__ __forceinline__ double py(const PhiloxKeys &k) { return nb(k); }
+    __device__ __forceinline__ int nb_int(const PhiloxKeys &k, int m) { return (int)__umulhi(next32(k), (uint32_t)m); }
+};
+
 // numba's float64 ** int64 (mcmc.py:149): square-and-multiply, reciprocal for negative exponents
 __device__ __forceinline__ double numba_pow_dev(double a, int b)
 {
@@ -151,7 +165,7 @@ template <int GEOM, typename RNG> struct LogicalDraw {
     int op[2], xp[2], zp[2];
     // _apply_random_logical draw order: toric_model.py:228-253 (both layer operators first),
     // planar_model.py:271-288, rotated_surface_model.py:331-346, xzzx_model.py:340-357
-    __device__ __forceinline__ void draw(RNG &rng, int L, const PhiloxKeys &k)
+    template <typename R> __device__ __forceinline__ void draw(R &rng, int L, const PhiloxKeys &k)
     {
 #pragma unroll
         for (int l = 0; l < nl; l++) op[l] = rng.nb_int(k, 4);
@@ -205,8 +219,14 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
     uint2 *s_ld = reinterpret_cast<uint2 *>(s_thru + p.Nc * 9 + ((p.Nc * 9) & 1));   // [nstab], 8-byte aligned
     uint16_t *s_ll = reinterpret_cast<uint16_t *>(s_ld + (TABLE ? g.nstab : 0));                    // [patterns <= 16][256]
     __shared__ uint32_t s_patmask[8];
-    __shared__ int s_sw_lane[128], s_sw_a[128], s_sw_b[128], s_sw_rung[128];   // swap sweep: rung-ordered copies, per warp
-    __shared__ double s_sw_u[128];
+    // swap sweep: rung-ordered copies, per warp.  Between sweeps the same 2 KB hold the top rungs' random-word pools
+    // (one Philox call, 16 bytes, per lane).
+    __shared__ __align__(16) int s_sw_all[4 * 128];
+    int *s_sw_w = s_sw_all + (threadIdx.x >> 5) * 128;   // this warp's 512 bytes: four arrays of 32, or 32 pool entries
+    int *s_sw_lane = s_sw_w, *s_sw_a = s_sw_w + 32, *s_sw_b = s_sw_w + 64, *s_sw_rung = s_sw_w + 96;
+    uint4 *s_pool = reinterpret_cast<uint4 *>(s_sw_w);
+    __shared__ double s_sw_u_all[128];
+    double *s_sw_u = s_sw_u_all + (threadIdx.x >> 5) * 32;
     // swap sweep: diff[i]^k for |k| <= QECMC_PW_K, made with the same square-and-multiply routine the sweep would call
     // (bit-identical), so a pair costs one table read instead of a multiply loop and, for k < 0, a division
     double *s_pw = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(s_ll) + (TABLE ? 16 * 256 * 2 : 0));
@@ -322,9 +342,12 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
     // stream of its own.  The main stream then serves every lane exactly two words per iteration and one per sweep, so all
     // lanes refill together -- one Philox call per warp instead of one per out-of-step lane.  Replay keeps the single
     // stream (the reference's draw order).
-    RNG rng_top_native;
-    if (!REPLAY) reinterpret_cast<NativeRng *>(&rng_top_native)->init((uint64_t)gladder * 32u + (uint64_t)gl, 1u);
-    RNG &rtop = REPLAY ? rng : rng_top_native;
+    typedef typename std::conditional<REPLAY, ReplayRng, TopRng>::type TOP;
+    TopRng top_native;
+    top_native.pos = top_native.end = 0;
+    top_native.pool = nullptr;
+    TOP &rtop = *reinterpret_cast<TOP *>(REPLAY ? (void *)&rng : (void *)&top_native);
+    constexpr int TOP_MAXW = 2 + 3 * LogicalDraw<GEOM, RNG>::nl;   // words one iteration of the top rung can take
     const bool top_logical = p.p_logical != 0.0;
     const bool track_hash = p.acct >= ACCT_DC || p.track_shortest;
     unsigned long long *table = nullptr;
@@ -366,6 +389,25 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
                 // owner's lattice, the weight change is a warp reduction, the owner decides, and on accept the lanes commit
                 // their words.  Same draws in the same order, same arithmetic as _apply_random_logical + update_chain.
                 // native: every active lane takes its two main-stream words here, whatever it goes on to do
+                if (!REPLAY && top_logical) {
+                    const bool need = is_top && (int)(top_native.end - top_native.pos) < TOP_MAXW;
+                    if (__any_sync(0xFFFFFFFFu, need)) {
+                        // every ladder of the warp refreshes its pool: G calls from the top lane's stream position on
+                        const uint32_t bt = (__ballot_sync(0xFFFFFFFFu, valid && r == Nc - 1) >> gbase) & gmask;
+                        const int lt = bt ? __ffs(bt) - 1 : 0;
+                        const uint32_t tpos = __shfl_sync(0xFFFFFFFFu, top_native.pos, lt, G);
+                        const uint64_t tid64 = (uint64_t)gladder * 32u + (uint64_t)lt;
+                        const uint32_t c0 = tpos >> 2;
+                        uint4 *mine = s_pool + gbase;
+                        __syncwarp();
+                        mine[gl] = philox4x32_10(c0 + (uint32_t)gl, 1u, (uint32_t)tid64, (uint32_t)(tid64 >> 32), p.keys);
+                        if (gl == lt) {
+                            top_native.pool = reinterpret_cast<const uint32_t *>(mine) + (tpos & 3u);
+                            top_native.end = (c0 + (uint32_t)G) * 4u;
+                        }
+                        __syncwarp();
+                    }
+                }
                 uint32_t w_idx = 0, w_acc = 0;
                 if (!REPLAY && active) {
                     w_idx = reinterpret_cast<NativeRng *>(&rng)->next32(p.keys);
@@ -535,8 +577,9 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
         // alpha ladder n_eff belongs to the rung (mcmc_alpha.py:126-131 swaps .code and .flag but not .n_eff), so there the
         // decisions depend on rung-owned values only.
         {
-            const int wb = (tid >> 5) * 32 + gbase;   // this ladder's slice of the per-warp arrays
-            if (!REPLAY && valid) s_sw_u[(tid >> 5) * 32 + lane] = rng.nb(p.keys);  // lane i's draw decides pair (i, i+1)
+            const int wb = gbase;   // this ladder's slice of the per-warp arrays
+            top_native.end = top_native.pos;   // the arrays overwrite the pool, and another lane may be on top afterwards
+            if (!REPLAY && valid) s_sw_u[lane] = rng.nb(p.keys);  // lane i's draw decides pair (i, i+1)
             if (valid) {
                 s_sw_lane[wb + r] = gl;
                 s_sw_a[wb + r] = p.kind == LK_ALPHA ? e_nz : n;

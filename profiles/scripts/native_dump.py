@@ -12,6 +12,9 @@ res = {}
 cases = [("rot9", _lib.ROTATED, 9, _lib.LADDER_DEPOLARIZING, 0.15, 0.0, None),
          ("rot25", _lib.ROTATED, 25, _lib.LADDER_DEPOLARIZING, 0.15, 0.0, None),
          ("rot5nc3", _lib.ROTATED, 5, _lib.LADDER_DEPOLARIZING, 0.1, 0.0, 3),
+         ("rot5nc2", _lib.ROTATED, 5, _lib.LADDER_DEPOLARIZING, 0.1, 0.0, 2),
+         ("rot5nc1", _lib.ROTATED, 5, _lib.LADDER_DEPOLARIZING, 0.1, 0.0, 1),
+         ("tor5nc2", _lib.TORIC, 5, _lib.LADDER_DEPOLARIZING, 0.1, 0.0, 2),
          ("tor7", _lib.TORIC, 7, _lib.LADDER_DEPOLARIZING, 0.12, 0.0, None),
          ("pla9", _lib.PLANAR, 9, _lib.LADDER_DEPOLARIZING, 0.12, 0.0, None),
          ("xzzx11b", _lib.XZZX, 11, _lib.LADDER_BIASED, 0.15, 30.0, None),
