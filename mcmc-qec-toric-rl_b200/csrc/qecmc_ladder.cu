@@ -224,6 +224,7 @@ int setup_ladder(qecmc_ctx *c, const qecmc_ladder_cfg *cfg, const Geo &g, Ladder
     p.iters = cfg->iters;
     p.p_logical = cfg->p_logical;
     p.top_accept_all = t.top_accept_all;
+    p.serial_sweep = getenv("QECMC_DEBUG_SERIAL_SWEEP") && atoi(getenv("QECMC_DEBUG_SERIAL_SWEEP")) != 0;
     p.thr_d = (const double *)d.thr_d.p;
     p.thr_u = (const uint32_t *)d.thr_u.p;
     p.thr_top_d = (const double *)d.thr_top_d.p;

@@ -29,6 +29,7 @@ struct LadderParams {
     int kind, Nc, G, iters, acct;
     double p_logical;       // top rung: probability of proposing a logical operator
     int top_accept_all;     // kind 0: ladder[Nc-1] >= 0.75 (mcmc.py:30)
+    int serial_sweep;       // tests (QECMC_DEBUG_SERIAL_SWEEP): native mode walks the swap sweep pair by pair like replay does
     int64_t n_ladders, ladder_offset, steps;
     const void *lat_in;     // packed [n_ladders][nw] (init_broadcast) or [n_ladders][Nc][nw]
     int init_broadcast;
@@ -617,9 +618,9 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
             // A draw below the table's last entry leaves the exponent open: the pair is marked, swaps outright while k is
             // inside the table and is evaluated as before beyond it.  A table that does not fall (diff >= 1) sends the ladder
             // down the general walk.
-            bool fast_sweep = !REPLAY && p.kind == LK_ALPHA;   // group-uniform
+            bool fast_sweep = !REPLAY && p.kind == LK_ALPHA && !p.serial_sweep;   // group-uniform
             uint32_t swaps = alpha_swaps;
-            if (!REPLAY && use_pw) {
+            if (!REPLAY && use_pw && !p.serial_sweep) {
                 constexpr int OPEN = 1 << 30;
                 const int kend = 2 * QECMC_PW_K - pw_off;   // exponents 0 .. kend are tabulated
                 bool bad = false, open = false;

@@ -408,6 +408,32 @@ def test_pteq_replay_matches_oracle(ctx, kind, g, L, bottom, b):
         assert np.array_equal(pct[s], want)
 
 
+@pytest.mark.parametrize("kind,g,L,bottom,b,Nc", [(0, O.ROTATED, 9, 0.15, 0.0, None), (0, O.TORIC, 5, 0.1, 0.0, None),
+                                                  (0, O.PLANAR, 7, 0.12, 0.0, 3), (0, O.ROTATED, 5, 0.1, 0.0, 2),
+                                                  (2, O.XZZX, 9, 0.15, 30.0, None), (2, O.XZZX, 7, 0.7, 4.0, None),
+                                                  (1, O.XZZX, 7, 0.17, 0.65, None)])
+def test_native_swap_sweep_equals_the_pair_by_pair_walk(ctx, kind, g, L, bottom, b, Nc, monkeypatch):
+    """Native ladders take the swap decisions of a sweep on all lanes (largest swapping exponent per pair from the power
+    table, compare-and-select walk, rungs from the swap mask).  QECMC_DEBUG_SERIAL_SWEEP makes the same build walk the pairs
+    one by one as mcmc.py:96-103 does (the replay path's code): same seed, same draws => identical results.  The 0.7
+    bottom rung gives the biased ladder tables close to 1, i.e. draws beyond the tabulated exponents."""
+    rng = np.random.default_rng(900 + 7 * kind + g + L)
+    S = 200
+    qm = np.stack([rand_lattice(rng, g, L, 0.12).reshape(-1) for _ in range(S)])
+    kw = dict(param_b=b, steps=300, conv=False, seed=5, p_logical=0.5)
+    if Nc:
+        kw["Nc"] = Nc
+    monkeypatch.delenv("QECMC_DEBUG_SERIAL_SWEEP", raising=False)
+    pct, info = ctx.pteq(g, L, kind, qm, bottom, **kw)
+    monkeypatch.setenv("QECMC_DEBUG_SERIAL_SWEEP", "1")
+    pct1, info1 = ctx.pteq(g, L, kind, qm, bottom, **kw)
+    assert np.array_equal(pct, pct1)
+    for k in ("steps", "since_burn", "tops0", "counts"):
+        assert np.array_equal(info[k], info1[k]), k
+    assert info["stats"]["accepted"] == info1["stats"]["accepted"]
+    assert info["tops0"].sum() > 0 or kind == 0   # replicas did travel the ladder
+
+
 def test_pteq_replay_matches_reference_golden(ctx):
     n = 0
     for c in golden("shipped"):
