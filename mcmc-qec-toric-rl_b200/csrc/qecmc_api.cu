@@ -320,14 +320,15 @@ static int launch_stdc_fast(qecmc_ctx *c, StdcParams &p)
     while (T > 64 && (p.n_chains + T - 1) / T < c->prop.multiProcessorCount) T /= 2;
     size_t smem = ((per_chain * T + 15) & ~(size_t)15) + dyn_fixed;
     if (p.insert_mode == 6) {   // per-CTA cursors into the bucket logs, behind the tile
-        // every CTA must be full and hold whole tables: the host made sure a power of two >= max(droplets, 32) divides n_chains
-        const int t_min = p.droplets > 32 ? p.droplets : 32;
-        if (T < t_min) T = t_min;
-        while (T > t_min && p.n_chains % T != 0) T /= 2;
+        // a CTA holds whole tables: T = (tables per CTA) * droplets, not necessarily a multiple of 32; the last CTA of the
+        // wave may hold fewer tables (its spare threads exit before the first barrier)
+        int tpc = T / p.droplets;
+        if (tpc < 1) tpc = 1;
+        T = tpc * p.droplets;
+        if (conv || !static_tab || T > 1024 || p.n_chains % p.droplets != 0) return set_err(QECMC_ERR_UNSUPPORTED, "internal: bucket-log mode misconfigured");
         smem = ((per_chain * T + 15) & ~(size_t)15) + dyn_fixed;
-        if (conv || !static_tab || T % p.droplets != 0 || p.n_chains % T != 0) return set_err(QECMC_ERR_UNSUPPORTED, "internal: bucket-log mode misconfigured");
-        p.tables_per_cta = T / p.droplets;
-        smem += (size_t)p.tables_per_cta * p.nbc * 4;
+        p.tables_per_cta = tpc;
+        smem += (size_t)tpc * p.nbc * 4;
     }
     unsigned grid = (unsigned)((p.n_chains + T - 1) / T);
     if (conv) {
@@ -434,7 +435,7 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
     const bool use_logs = conv_logs || (mode != MODE_MEAN && !conv && (forced_mode < 0 || forced_mode == 4) && fits_dedupe);
     const int64_t log_cap = (cfg->steps + 1) & ~(int64_t)1;
     // Insert mode 6: the table-driven kernel (toric / planar, 32-bit row words, native draws, no early stop) splits the
-    // keys of a table into coarse bucket logs as it produces them, when the chains of every wave fill whole CTAs and
+    // keys of a table into coarse bucket logs as it produces them, when a table's chains fit one CTA and
     // the per-CTA cursors fit beside the tile; the reduction is then one pass (bucket_dedupe_kernel).
     // nbc coarse buckets per table, sized for ~6000 logged keys each when 30 % of the samples log one (a bucket that
     // outgrows the dedupe kernel's shared-memory set sends the call back to per-chain logs); the cursors of a CTA's tables
@@ -443,11 +444,13 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
     while (nbc < QECMC_NBC_MAX && (uint64_t)nbc * 20000 < max_keys) nbc <<= 1;
     const bool fast_u32 = (cfg->geom_chain == TORIC || cfg->geom_chain == PLANAR) && cfg->L <= 16;
     bool use_blogs = allow_bucket_logs && use_logs && !conv && !cfg->u_nb && fast_u32 && (forced_mode < 0 || forced_mode == 6) &&
-                     cfg->droplets <= 1024 && 1024 % cfg->droplets == 0 && (n_eq * cfg->droplets) % 32 == 0;
+                     cfg->droplets <= 1024;
     if (use_blogs) {
-        // the largest CTA the launch will use is 1024 threads: its cursors must fit next to tile and tables
-        const size_t used = (size_t)gchain.nw * 4 * 1024 + ((sizeof(FastTabs<8>) + 15) & ~(size_t)15) + 2048;
-        const size_t cursors = (size_t)(1024 / cfg->droplets) * nbc * 4;
+        // the largest CTA the launch will use holds 1024 / droplets tables: its cursors must fit next to tile and tables
+        // (256: the kernel's static shared memory)
+        const size_t tpc_max = 1024 / cfg->droplets;
+        const size_t used = (size_t)gchain.nw * 4 * tpc_max * cfg->droplets + 16 + ((sizeof(FastTabs<8>) + 15) & ~(size_t)15) + 256;
+        const size_t cursors = tpc_max * nbc * 4;
         if (used + cursors > c->prop.sharedMemPerBlockOptin) use_blogs = false;
     }
     uint64_t bcap = 0, ovf_cap = 0;
@@ -469,6 +472,17 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
             if (wave < 1)
                 return set_err(QECMC_ERR_NOMEM, "bucket logs need %lld bytes per syndrome, budget is %lld", (long long)per_syndrome, (long long)budget);
             if (wave > S) wave = S;
+            if (wave < S) {
+                // several waves: a wave whose CTAs come to a whole number of rounds over the SMs (one 1024-thread CTA per SM,
+                // 1024 / droplets tables each) leaves no SMs idle behind a short last round
+                const int64_t tpc = 1024 / cfg->droplets, sms = c->prop.multiProcessorCount;
+                int64_t ctas = wave * n_eq / tpc;
+                if (ctas >= sms) {
+                    ctas -= ctas % sms;
+                    const int64_t w2 = ctas * tpc / n_eq;
+                    if (w2 >= 1) wave = w2;
+                }
+            }
             QTRY(c->log_counts.ensure((size_t)wave * n_eq * (nbc + 1) * sizeof(uint32_t)));
             QTRY(c->scratch.ensure(2 * sizeof(int)));
         } else if (use_logs) {

@@ -156,9 +156,13 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ?
         else s_thr[i] = ft.thr[i];
     }
     if (tid < QECMC_THR_N) s_thrd[tid] = p.thr.d[tid];
+    if (BLOG) {   // mode 6: this CTA's cursors into the bucket logs of its tables live behind the tile
+        uint32_t *cur0 = reinterpret_cast<uint32_t *>(smem + (((size_t)g.nw * T * sizeof(W) + 15) & ~(size_t)15));
+        for (int i = tid; i < p.tables_per_cta * p.nbc; i += T) cur0[i] = 0;
+    }
     __syncthreads();
     const int64_t local = (int64_t)blockIdx.x * T + tid;
-    if (local >= p.n_chains) return;
+    if (local >= p.n_chains) return;   // spare threads of the wave's last CTA (whole tables only: n_chains is a multiple of droplets)
     const int64_t gchain = p.chain_offset + local;
     const int n_eq = p.gcode.neq;
     const int64_t tab = local / p.droplets;
@@ -204,10 +208,6 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ?
     // this thread's table: its cursors (shared-memory byte address) and its bucket logs
     const uint32_t cur_base = (uint32_t)__cvta_generic_to_shared(s_cur) + (uint32_t)(tid / p.droplets) * ((uint32_t)p.nbc * 4u);
     unsigned long long *blog_tab = BLOG ? p.blogs + (uint64_t)tab * (uint64_t)p.nbc * p.bcap : nullptr;
-    if (BLOG) {
-        for (int i = tid; i < p.tables_per_cta * p.nbc; i += T) s_cur[i] = 0;
-        __syncthreads();
-    }
 
     uint32_t nacc = 0, noff = 0;
     bool dirty = true;  // the first sample is always new to the chain
@@ -379,9 +379,11 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ?
         } while (q != 0ull && q != key);
     }
     if (BLOG) {
-        __syncthreads();   // every chain of the CTA has logged its last key
+        __syncthreads();   // every chain of the CTA has logged its last key (threads that exited above do not count)
         const int64_t tab0 = (int64_t)blockIdx.x * p.tables_per_cta;
-        for (int i = tid; i < p.tables_per_cta * p.nbc; i += T)
+        const int64_t left = p.n_chains - (int64_t)blockIdx.x * T;
+        const int nact = left < T ? (int)left : T;   // threads still here
+        for (int i = tid; i < p.tables_per_cta * p.nbc; i += nact)
             if (tab0 + i / p.nbc < p.n_chains / p.droplets) p.bcounts[tab0 * p.nbc + i] = min(s_cur[i], p.bcap);
     }
     if (imode == 4) p.log_counts[local] = noff;

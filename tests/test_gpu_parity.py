@@ -726,10 +726,12 @@ def test_chain_xyz_replay_matches_reference_golden_and_oracle(ctx):
 @pytest.mark.parametrize("g,L,droplets,steps", [(O.TORIC, 7, 16, 20000), (O.PLANAR, 9, 64, 6000), (O.TORIC, 15, 7, 9001),
                                                 (O.TORIC, 5, 1, 333), (O.TORIC, 9, 64, 12000), (O.TORIC, 15, 32, 4000),
                                                 (O.PLANAR, 7, 16, 2401), (O.TORIC, 5, 2, 3000), (O.TORIC, 7, 128, 1500),
-                                                (O.PLANAR, 15, 16, 5000)])
+                                                (O.PLANAR, 15, 16, 5000), (O.TORIC, 9, 10, 8000), (O.PLANAR, 11, 3, 7000),
+                                                (O.TORIC, 5, 100, 900), (O.TORIC, 7, 600, 500)])
 def test_log_dedupe_equals_table_set(ctx, g, L, droplets, steps, monkeypatch):
     """The same native chains counted in every way the library has: bucket logs written by the chain kernel + one-pass
-    dedupe (mode 6, the default where a syndrome's chains fill whole CTAs), per-chain key logs reduced by
+    dedupe (mode 6, the default; droplets = 7, 10, 3, 100, 600 give CTAs that are not a multiple of 32 threads and a
+    partly filled last CTA), per-chain key logs reduced by
     log_dedupe_kernel (mode 4), and the open-addressing set in HBM (modes 2 and 0).  N(n), the class distributions'
     inputs, must agree exactly -- this exercises the multi-bucket paths (tens of thousands of keys per table) that the
     small replay cases do not."""
@@ -746,13 +748,35 @@ def test_log_dedupe_equals_table_set(ctx, g, L, droplets, steps, monkeypatch):
         outs[mode] = (out, st, hist)
     monkeypatch.delenv("QECMC_DEBUG_INSERT_MODE")
     assert outs["4"][1]["table_slots"] == 0 and outs["2"][1]["table_slots"] > 0      # really different paths
-    bucket_logs = 1024 % droplets == 0 and (O.neq(g) * droplets) % 32 == 0
-    assert outs["default"][1]["table_slots"] == (-1 if bucket_logs else 0)
+    assert outs["default"][1]["table_slots"] == -1   # bucket logs for any droplets <= 1024 (CTAs of whole tables)
     for mode in ("4", "2", "0"):
         assert np.array_equal(outs["default"][2], outs[mode][2])
         assert outs["default"][1]["distinct"] == outs[mode][1]["distinct"]
         assert np.allclose(outs["default"][0], outs[mode][0], rtol=1e-12)
     assert outs["4"][1]["distinct"] > 0.1 * S * O.neq(g) * droplets * steps * 0.1
+
+
+@pytest.mark.parametrize("droplets", [10, 64])
+def test_waves_under_a_small_table_budget_give_the_same_result(droplets):
+    """A table budget that holds only part of the batch makes the call run in waves (rounded to whole rounds of CTAs over
+    the SMs); chains are seeded by their global index, so the result must not depend on the split."""
+    from mcmc_qec_toric_rl_b200 import _lib
+    g, L, steps, S = O.TORIC, 5, 2000, 700
+    rng = np.random.default_rng(31)
+    qm = np.stack([rand_lattice(rng, g, L, 0.1).reshape(-1) for _ in range(S)])
+    c1 = _lib.Context(0)
+    a = c1.stdc(g, g, L, qm, 0.1, 0.25, droplets, steps, seed=8, want_hist=True)
+    c2 = _lib.Context(0)
+    max_keys = droplets * steps
+    nbc = 1
+    while nbc < 128 and nbc * 20000 < max_keys:
+        nbc *= 2
+    per_syndrome = 16 * (nbc * ((max_keys + nbc - 1) // nbc + 65) + max(1024, max_keys // 16)) * 8
+    c2.set_table_budget(per_syndrome * 333)
+    b = c2.stdc(g, g, L, qm, 0.1, 0.25, droplets, steps, seed=8, want_hist=True)
+    assert a[1]["waves"] == 1 and b[1]["waves"] >= 3 and b[1]["table_slots"] == -1
+    assert np.array_equal(a[2], b[2]) and a[1]["distinct"] == b[1]["distinct"]
+    assert np.allclose(a[0], b[0], rtol=1e-12)
 
 
 def test_bucket_log_overflow_falls_back(ctx):
