@@ -341,7 +341,8 @@ def main():
         cpu_port_rate(1, 1, 2000, 1)  # warm the library
         cpu_drop = 10   # sized for 10-30 s of host work
         rate, dt, steps = cpu_port_rate(n_syn, cpu_drop, samples, cores)
-        line["cpu_baseline"] = {"value": rate, "unit": "steps/s", "cores": cores, "kind": "port",
+        rate1, dt1, _ = cpu_port_rate(1, 1, samples, 1)   # the one-core figure beside the all-core one (~3 s)
+        line["cpu_baseline"] = {"value": rate, "unit": "steps/s", "cores": cores, "kind": "port", "value_1core": rate1,
                                 "sample": f"{n_syn} syndromes x 16 classes x {cpu_drop} chains x {samples} samples x {ITERS} steps "
                                           f"({steps:.3g} Metropolis steps, {dt:.1f} s) with oracle/qec_oracle.c"}
     sys.stdout.flush()
