@@ -80,7 +80,9 @@ def run_toric5(ctx, O):
 
 def _pteq_config(ctx, O, name, g, L, kind, bottom, b, S, steps, qs, truth, cpu_ladders, cpu_steps):
     qm = np.ascontiguousarray(qs.reshape(S, -1))
-    ctx.pteq(g, L, kind, qm[:8], bottom, param_b=b, steps=50, conv=False, seed=1)
+    # warm-up at full size: the context's device buffers (ladder states, n_err history) grow to the batch on first use
+    ctx.pteq(g, L, kind, qm, bottom, param_b=b, steps=50, conv=False, seed=1)
+    ctx.pteq(g, L, kind, qm, bottom, param_b=b, steps=steps, conv=True, seed=1)
     (pct, info), dt = timed(lambda: ctx.pteq(g, L, kind, qm, bottom, param_b=b, steps=steps, conv=False, seed=11))
     msteps = info["stats"]["metropolis_steps"]
     res = {"config": name, "ladders": S, "Nc": L, "ladder_steps": steps, "steps_per_s": msteps / dt, "syndromes_per_s": S / dt,
