@@ -1,4 +1,4 @@
-# new swap sweep: native results must be identical to the previous build's, tests green, timings
+# new swap sweep: native results must be identical to the previous build's (copy the previous libqecmc.so to build/libqecmc_prev.so first), tests green, timings
 QECMC_LIB=/root/repo/build/libqecmc_prev.so python profiles/scripts/native_dump.py /tmp/prev.npz 2>&1 | tail -1
 python profiles/scripts/native_dump.py /tmp/new.npz 2>&1 | tail -1
 python - <<'P'
