@@ -89,7 +89,7 @@ extern "C" int qecmc_device_info(qecmc_ctx *c, qecmc_devinfo *o)
     CUDA_OK(cudaMemGetInfo(&fr, &tot));
     o->total_mem = (int64_t)tot;
     o->free_mem = (int64_t)fr;
-    strncpy(o->name, c->prop.name, sizeof(o->name) - 1);
+    snprintf(o->name, sizeof(o->name), "%s", c->prop.name);   // device names longer than the field are cut
     return 0;
 }
 
