@@ -140,6 +140,56 @@ template <typename W> static int pack_lattices(qecmc_ctx *c, const uint8_t *d_qm
     return 0;
 }
 
+// Two-layer codes (toric, planar): table-driven stabilizer descriptors, shared by the STDC chain kernel and the ladder kernel.
+// descriptor words:  x = sh | w0<<8 | w1<<16 | w2<<24     y = sh2 | f_and<<8 | f_or<<16 | (v==3)<<24
+// slot layout a=(w0,sh) b=(w0,sh2) c=(w1,sh) d=(w2,sh); verified against decode<>() mask by mask
+template <int GEOM, typename W> static int build_stab_desc(qecmc_ctx *c, const Geo &g, const uint2 **out)
+{
+    auto key = std::make_tuple(GEOM, g.L, (int)(sizeof(W) == 8));
+    auto it = c->stab_desc.find(key);
+    if (it != c->stab_desc.end()) { *out = it->second; return 0; }
+    const int L = g.L;
+    std::vector<uint2> tab(g.nstab);
+    for (int idx = 0; idx < g.nstab; idx++) {
+        int row, col, op;
+        idx_to_rco<GEOM>(g, idx, row, col, op);
+        int w0, w1, w2, sh = 2 * col, sh2;
+        bool pa = true, pb = true, pc = true, pd = true;
+        if (GEOM == TORIC) {
+            if (op == 1) { w0 = L + row; sh2 = 2 * (col == 0 ? L - 1 : col - 1); w1 = row; w2 = row == 0 ? L - 1 : row - 1; }
+            else { w0 = row; sh2 = 2 * (col == L - 1 ? 0 : col + 1); w1 = L + row; w2 = L + (row == L - 1 ? 0 : row + 1); }
+        } else {
+            if (op == 1) { w0 = L + row; pa = col < L - 1; pb = col > 0; sh2 = pb ? 2 * (col - 1) : sh; w1 = row; w2 = row + 1; }
+            else { w0 = row; sh2 = 2 * (col + 1); w1 = L + row; pc = row < L - 1; pd = row > 0; w2 = pd ? L + row - 1 : L + 1; }
+        }
+        uint32_t f_and = 0xFF, f_or = 0;
+        bool pres[4] = {pa, pb, pc, pd};
+        for (int i = 0; i < 4; i++)
+            if (!pres[i]) { f_and &= ~(1u << (2 * i)); f_or |= 2u << (2 * i); }
+        tab[idx].x = (uint32_t)sh | ((uint32_t)w0 << 8) | ((uint32_t)w1 << 16) | ((uint32_t)w2 << 24);
+        tab[idx].y = (uint32_t)sh2 | (f_and << 8) | (f_or << 16) | ((op == 3 ? 1u : 0u) << 24);
+        // self-check against the generic geometry
+        Upd<W> u;
+        decode<GEOM, W>(g, row, col, op, u);
+        std::map<int, W> want, got;
+        for (int i = 0; i < 3; i++) if (u.m[i]) want[u.w[i]] ^= u.m[i];
+        W v = (W)op;
+        if (pa) got[w0] ^= (W)(v << sh);
+        if (pb) got[w0] ^= (W)(v << sh2);
+        if (pc) got[w1] ^= (W)(v << sh);
+        if (pd) got[w2] ^= (W)(v << sh);
+        if (want != got || w0 == w1 || w0 == w2 || w1 == w2 || w0 >= g.nw || w1 >= g.nw || w2 >= g.nw)
+            return set_err(QECMC_ERR_UNSUPPORTED, "internal: stabilizer descriptor %d disagrees with the geometry", idx);
+    }
+    uint2 *d = nullptr;
+    CUDA_OK(cudaMalloc(&d, sizeof(uint2) * g.nstab));
+    CUDA_OK(cudaMemcpyAsync(d, tab.data(), sizeof(uint2) * g.nstab, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    c->stab_desc[key] = d;
+    *out = d;
+    return 0;
+}
+
 template <int GEOM, typename W> static int build_stab_hash(qecmc_ctx *c, const Geo &g, uint64_t **out)
 {
     auto key = std::make_tuple(GEOM, g.L, (int)(sizeof(W) == 8));

@@ -157,6 +157,10 @@ template <int GEOM, typename W> int launch_ladder_gw(qecmc_ctx *c, LadderParams 
     const int T = 128;
     size_t smem = (((size_t)p.g.nw * T * sizeof(W) + 15) & ~(size_t)15) + (size_t)p.Nc * 9 * 12 + 16;
     if (GEOM == ROTATED || GEOM == XZZX) smem += (size_t)p.g.nstab * 8 + 16 * 256 * 2;   // step tables of the one-layer codes
+    if ((GEOM == TORIC || GEOM == PLANAR) && !weighted) {                                  // ... and of the two-layer codes
+        smem += (size_t)p.g.nstab * 8 + 512;
+        QTRY((build_stab_desc<GEOM, W>(c, p.g, &p.desc2)));
+    }
     smem += 8 + (size_t)(p.Nc > 1 ? p.Nc - 1 : 0) * (2 * QECMC_PW_K + 1) * 8;            // swap-sweep power table
     if (smem > c->prop.sharedMemPerBlockOptin) return set_err(QECMC_ERR_UNSUPPORTED, "lattice does not fit in shared memory");
     unsigned grid = (unsigned)((p.n_ladders * p.G + T - 1) / T);

@@ -17,6 +17,7 @@
 #pragma once
 #include <type_traits>
 #include "qecmc_device.cuh"
+#include "qecmc_stdc_fast.cuh"   // gather_fields: the two-layer codes' table-driven step
 
 namespace qecmc {
 
@@ -29,6 +30,7 @@ struct LadderParams {
     int kind, Nc, G, iters, acct;
     double p_logical;       // top rung: probability of proposing a logical operator
     int top_accept_all;     // kind 0: ladder[Nc-1] >= 0.75 (mcmc.py:30)
+    const uint2 *desc2;     // toric / planar, depolarizing: stabilizer descriptors of build_stab_desc (qecmc_internal.h)
     int serial_sweep;       // tests (QECMC_DEBUG_SERIAL_SWEEP): native mode walks the swap sweep pair by pair like replay does
     int64_t n_ladders, ladder_offset, steps;
     const void *lat_in;     // packed [n_ladders][nw] (init_broadcast) or [n_ladders][Nc][nw]
@@ -217,8 +219,12 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
     // the Paulis applied to the four slots (a nibble per word); the weight changes (dx, dy, dz and their sum) come from a
     // LUT indexed by (Pauli pattern, the four touched fields).  Both tables are built here from decode<GEOM>().
     constexpr bool TABLE = GEOM == ROTATED || GEOM == XZZX;
+    // Two-layer codes (toric, planar), depolarizing ladders: the descriptors of the STDC chain kernel (three row words, two
+    // shifts, which slots exist) and a 512-entry LUT of the weight change by (Pauli, the four touched fields).
+    constexpr bool TABLE2 = (GEOM == TORIC || GEOM == PLANAR) && !WEIGHTED;
     uint2 *s_ld = reinterpret_cast<uint2 *>(s_thru + p.Nc * 9 + ((p.Nc * 9) & 1));   // [nstab], 8-byte aligned
-    uint16_t *s_ll = reinterpret_cast<uint16_t *>(s_ld + (TABLE ? g.nstab : 0));                    // [patterns <= 16][256]
+    uint16_t *s_ll = reinterpret_cast<uint16_t *>(s_ld + ((TABLE || TABLE2) ? g.nstab : 0));        // [patterns <= 16][256]
+    int8_t *s_dE2 = reinterpret_cast<int8_t *>(s_ll);                                               // TABLE2: [512]
     __shared__ uint32_t s_patmask[8];
     // swap sweep: rung-ordered copies, per warp.  Between sweeps the same 2 KB hold the top rungs' random-word pools
     // (one Philox call, 16 bytes, per lane).
@@ -230,7 +236,7 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
     double *s_sw_u = s_sw_u_all + (threadIdx.x >> 5) * 32;
     // swap sweep: diff[i]^k for |k| <= QECMC_PW_K, made with the same square-and-multiply routine the sweep would call
     // (bit-identical), so a pair costs one table read instead of a multiply loop and, for k < 0, a division
-    double *s_pw = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(s_ll) + (TABLE ? 16 * 256 * 2 : 0));
+    double *s_pw = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(s_ll) + (TABLE ? 16 * 256 * 2 : TABLE2 ? 512 : 0));
     const bool use_pw = p.kind != LK_ALPHA && p.Nc > 1;
     // depolarizing ladders only evaluate k = n_hi - n_lo >= 0 (a lighter upper replica swaps without a draw), so their
     // table covers 0 .. 2 QECMC_PW_K; biased ladders draw always and cover -QECMC_PW_K .. QECMC_PW_K
@@ -238,6 +244,18 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
     if (use_pw)
         for (int e = tid; e < (p.Nc - 1) * (2 * QECMC_PW_K + 1); e += T)
             s_pw[e] = numba_pow_dev(p.diff[e / (2 * QECMC_PW_K + 1)], e % (2 * QECMC_PW_K + 1) - pw_off);
+    if (TABLE2) {
+        for (int i = tid; i < g.nstab; i += T) s_ld[i] = p.desc2[i];
+        for (int e = tid; e < 512; e += T) {
+            const int v = (e >> 8) ? 3 : 1;
+            int d = 0;
+            for (int sl = 0; sl < 4; sl++) {
+                const int q = (e >> (2 * sl)) & 3, nq = q ^ v;   // a missing slot reads as Y: X and Z leave its weight alone
+                d += (q == 0 && nq != 0) - (q != 0 && nq == 0);
+            }
+            s_dE2[e] = (int8_t)d;
+        }
+    }
     if (TABLE) {
         if (tid < 8) s_patmask[tid] = 0;
         __syncthreads();
@@ -500,7 +518,7 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
                         if (track_hash) idx = rco_to_idx<GEOM>(g, row, col, op);
                     } else {
                         idx = (int)__umulhi(w_idx, (uint32_t)g.nstab);
-                        if (!TABLE) idx_to_rco<GEOM>(g, idx, row, col, op);
+                        if (!TABLE && !TABLE2) idx_to_rco<GEOM>(g, idx, row, col, op);
                     }
                     Upd<W> u;
                     W nv[NU];
@@ -518,6 +536,32 @@ __global__ void __launch_bounds__(128, 4) ladder_kernel(LadderParams p)
                         nv[1] = (W)(o1 ^ ((W)((D.y >> 4) & 0xFu) << p1));
                         if (WEIGHTED) { dx = (int)(pk & 15u) - 4; dy = (int)((pk >> 4) & 15u) - 4; dz = (int)((pk >> 8) & 15u) - 4; }
                         else dE = (int)(pk >> 12) - 4;
+                    } else if (TABLE2) {
+                        if (REPLAY && !track_hash) idx = rco_to_idx<GEOM>(g, row, col, op);
+                        const uint2 D = s_ld[idx];
+                        u.w[0] = (int)((D.x >> 8) & 0xFFu);
+                        u.w[1] = (int)((D.x >> 16) & 0xFFu);
+                        u.w[2] = (int)(D.x >> 24);
+                        const W o0 = lat.get(u.w[0]), o1 = lat.get(u.w[1]), o2 = lat.get(u.w[2]);
+                        const uint32_t f = gather_fields<W>(o0, o1, o2, D.x, D.y);
+                        const uint32_t li = GEOM == TORIC ? ((f & 0xFFu) | (D.y >> 16)) : ((f & ((D.y >> 8) & 0xFFu)) | (D.y >> 16));
+                        dE = (int)s_dE2[li];
+                        const uint32_t sh = D.x & 63u, sh2 = D.y & 63u;
+                        const W v = (D.y & 0x01000000u) ? (W)3 : (W)1;
+                        W m0, m1, m2;
+                        if (GEOM == TORIC) {
+                            m1 = (W)(v << sh);
+                            m2 = m1;
+                            m0 = (W)(m1 | (W)(v << sh2));
+                        } else {
+                            const uint32_t fa = D.y >> 8;
+                            m0 = (W)(((fa & 1u) ? (W)(v << sh) : (W)0) | ((fa & 4u) ? (W)(v << sh2) : (W)0));
+                            m1 = (fa & 16u) ? (W)(v << sh) : (W)0;
+                            m2 = (fa & 64u) ? (W)(v << sh) : (W)0;
+                        }
+                        nv[0] = (W)(o0 ^ m0);
+                        nv[1] = (W)(o1 ^ m1);
+                        nv[NU > 2 ? 2 : 0] = (W)(o2 ^ m2);
                     } else {
                         decode<GEOM, W>(g, row, col, op, u);
 #pragma unroll

@@ -12,11 +12,14 @@ ctx = _lib.Context(0)
 rng = np.random.default_rng(3)
 if which == "rotated25":
     g, L, kind, bottom, b = _lib.ROTATED, 25, _lib.LADDER_DEPOLARIZING, 0.15, 0.0
+elif which == "toric15":
+    g, L, kind, bottom, b = _lib.TORIC, 15, _lib.LADDER_DEPOLARIZING, 0.15, 0.0
 elif which == "xzzx21_biased":
     g, L, kind, bottom, b = _lib.XZZX, 21, _lib.LADDER_BIASED, 0.15, 100.0
 else:
     g, L, kind, bottom, b = _lib.XZZX, 21, _lib.LADDER_ALPHA, 0.17474, 0.6447
-q = ((rng.random((S, L * L)) < 0.15) * rng.integers(1, 4, (S, L * L))).astype(np.uint8)
+ns = 2 * L * L if g == _lib.TORIC else L * L
+q = ((rng.random((S, ns)) < 0.15) * rng.integers(1, 4, (S, ns))).astype(np.uint8)
 ctx.pteq(g, L, kind, q[:64], bottom, param_b=b, steps=3, conv=False, seed=1, p_logical=p_logical)      # module load, allocations
 pct, info = ctx.pteq(g, L, kind, q, bottom, param_b=b, steps=steps, conv=False, seed=11, p_logical=p_logical)
 st = info["stats"]
