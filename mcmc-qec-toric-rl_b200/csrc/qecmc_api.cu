@@ -365,7 +365,8 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
     if (mode == MODE_MEAN && cfg->steps < 2) return set_err(QECMC_ERR_ARG, "single_temp needs max_iters >= 2");
     CUDA_OK(cudaSetDevice(c->device));
     c->launches = 0;
-    const bool wide = cfg->L > 16;
+    // tests (QECMC_DEBUG_FORCE_WIDE): 64-bit row words for L <= 16 too, to compare the two word widths on one problem
+    const bool wide = cfg->L > 16 || (getenv("QECMC_DEBUG_FORCE_WIDE") && atoi(getenv("QECMC_DEBUG_FORCE_WIDE")) != 0);
     const size_t wbytes = wide ? 8 : 4;
     const int n_eq = gcode.neq;
     const int nh = gcode.nsites + 1;
@@ -394,7 +395,7 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
     // take (T / droplets) * nbc * 4 bytes beside tile and tables
     int nbc = 1;
     while (nbc < QECMC_NBC_MAX && (uint64_t)nbc * 20000 < max_keys) nbc <<= 1;
-    const bool fast_u32 = (cfg->geom_chain == TORIC || cfg->geom_chain == PLANAR) && cfg->L <= 16;
+    const bool fast_u32 = (cfg->geom_chain == TORIC || cfg->geom_chain == PLANAR) && !wide;
     bool use_blogs = allow_bucket_logs && use_logs && !conv && !cfg->u_nb && fast_u32 && (forced_mode < 0 || forced_mode == 6) &&
                      cfg->droplets <= 1024;
     if (use_blogs) {
@@ -402,6 +403,11 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
         // (256: the kernel's static shared memory)
         const size_t tpc_max = 1024 / cfg->droplets;
         const size_t used = (size_t)gchain.nw * 4 * tpc_max * cfg->droplets + 16 + ((sizeof(FastTabs<8>) + 15) & ~(size_t)15) + 256;
+        // cursors that do not fit: fewer, larger buckets, as long as a bucket stays within the dedupe kernel's set when 35 % of
+        // the samples log a key (beyond that the call falls back to per-chain logs by itself)
+        while (nbc > 1 && used + tpc_max * nbc * 4 > c->prop.sharedMemPerBlockOptin &&
+               (double)max_keys / (nbc / 2) * 0.35 < 0.8 * QECMC_BD_SLOTS)
+            nbc >>= 1;
         const size_t cursors = tpc_max * nbc * 4;
         if (used + cursors > c->prop.sharedMemPerBlockOptin) use_blogs = false;
     }

@@ -779,6 +779,20 @@ def test_waves_under_a_small_table_budget_give_the_same_result(droplets):
     assert np.allclose(a[0], b[0], rtol=1e-12)
 
 
+@pytest.mark.parametrize("g,L", [(O.TORIC, 9), (O.PLANAR, 11), (O.PLANAR, 16)])
+def test_row_word_width_does_not_change_native_results(ctx, g, L, monkeypatch):
+    """QECMC_DEBUG_FORCE_WIDE runs a lattice with L <= 16 through the 64-bit row-word kernels (the ones L > 16 uses): the
+    same seeds must give the same chains, i.e. identical N(n) and distinct counts, as the 32-bit kernels."""
+    rng = np.random.default_rng(640 + L)
+    qm = np.stack([rand_lattice(rng, g, L, 0.12).reshape(-1) for _ in range(6)])
+    monkeypatch.delenv("QECMC_DEBUG_FORCE_WIDE", raising=False)
+    a = ctx.stdc(g, g, L, qm, 0.12, 0.3, 16, 4000, seed=21, want_hist=True)
+    monkeypatch.setenv("QECMC_DEBUG_FORCE_WIDE", "1")
+    b = ctx.stdc(g, g, L, qm, 0.12, 0.3, 16, 4000, seed=21, want_hist=True)
+    assert b[1]["table_slots"] == 0 and a[1]["table_slots"] == -1       # per-chain logs behind the wide kernels, bucket logs otherwise
+    assert np.array_equal(a[2], b[2]) and a[1]["distinct"] == b[1]["distinct"] and a[1]["accepted"] == b[1]["accepted"]
+
+
 def test_bucket_log_overflow_falls_back(ctx):
     """Chains at a high sampling rate offer a key at almost every sample; tiny tables make the fixed-capacity bucket logs
     and their overflow area run over, and the call must then redo itself with per-chain logs and still be exact."""
