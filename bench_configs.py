@@ -133,6 +133,9 @@ def run_planar_sweep(ctx, O, ps=(0.10, 0.15, 0.20), ds=(7, 11, 15, 21), droplets
     """Threshold sweep: STDC, classes reached on device, steps = d^4, one GPU-filling batch per (d, p)."""
     g = O.PLANAR
     info = ctx.device_info()
+    # fix the table budget once: otherwise every call asks the driver for the free memory, which costs ~10 ms on a context
+    # that already holds tens of GB -- more than a whole d=7 batch takes
+    ctx.set_table_budget(int(info["free_mem"] * 0.8))
     rows = []
     for d in ds:
         steps = d ** 4
@@ -149,9 +152,8 @@ def run_planar_sweep(ctx, O, ps=(0.10, 0.15, 0.20), ds=(7, 11, 15, 21), droplets
             raw[:, 1, :, -1] = 0
             qs, truth = hide_class(ctx, g, d, raw, rng)
             qm = np.ascontiguousarray(qs.reshape(S, -1))
-            if first:   # allocations for this size happen outside the timed call
-                ctx.stdc(g, g, d, qm[:8], p, 0.25, droplets, steps, seed=1)
-                ctx.stdc(g, g, d, qm, p, 0.25, droplets, 200, seed=1)
+            if first:   # allocations for this size (key logs of the whole batch at full length) happen outside the timed call
+                ctx.stdc(g, g, d, qm, p, 0.25, droplets, steps, seed=1)
                 first = False
             (out, st), dt = timed(lambda: ctx.stdc(g, g, d, qm, p, 0.25, droplets, steps, seed=5))
             rows.append({"d": d, "p": p, "syndromes": S, "steps_per_s": st["metropolis_steps"] / dt, "syndromes_per_s": S / dt,

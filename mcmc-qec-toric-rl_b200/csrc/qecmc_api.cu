@@ -417,10 +417,16 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
     int64_t per_syndrome = 0, wave = S;
     if (mode != MODE_MEAN) {
         int64_t budget = c->table_budget;
-        if (!budget) {   // cudaMemGetInfo costs milliseconds on a 180 GB device: skipped when the caller fixed the budget
-            size_t fr = 0, tot = 0;
-            CUDA_OK(cudaMemGetInfo(&fr, &tot));
-            budget = (int64_t)((double)(fr + c->tables.cap + c->dd_scratch.cap) * 0.85);
+        if (!budget) {
+            // cudaMemGetInfo costs milliseconds (~10 ms on a context holding tens of GB): asked again only after the
+            // library allocated or freed something; skipped altogether when the caller fixed the budget
+            if (c->free_cached_gen != alloc_generation()) {
+                size_t fr = 0, tot = 0;
+                CUDA_OK(cudaMemGetInfo(&fr, &tot));
+                c->free_cached = fr;
+                c->free_cached_gen = alloc_generation();
+            }
+            budget = (int64_t)((double)(c->free_cached + c->tables.cap + c->dd_scratch.cap) * 0.85);
         }
         if (use_blogs) {
             bcap = ((max_keys + nbc - 1) / nbc + 64 + 1) & ~(uint64_t)1;

@@ -27,12 +27,20 @@ int qecmc_set_err(int code, const char *fmt, ...);
         if (r_ != 0) return r_; \
     } while (0)
 
+// bumped whenever the library allocates or frees device memory: a cached "free memory" figure is good while it stands still
+inline uint64_t &alloc_generation()
+{
+    static uint64_t gen = 0;
+    return gen;
+}
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
     int ensure(size_t bytes)
     {
         if (bytes <= cap) return 0;
+        alloc_generation()++;
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
@@ -43,7 +51,7 @@ struct DevBuf {
     }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p) { cudaFree(p); alloc_generation()++; }
         p = nullptr;
         cap = 0;
     }
@@ -68,6 +76,8 @@ struct qecmc_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaDeviceProp prop;
     int64_t table_budget = 0;
+    size_t free_cached = 0;                 // cudaMemGetInfo's answer at allocation generation free_cached_gen
+    uint64_t free_cached_gen = ~(uint64_t)0;
     DevBuf packed, tables, Z, counters, qm_in, out_f64, out_u32, out_u64, out_i32, replay_a, replay_b, scratch, nhist, mhist,
         shorts, sums;
     std::map<std::tuple<int, int, int>, uint64_t *> stab_hash;  // (geom, L, wide) -> device table
