@@ -420,13 +420,9 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
         if (!budget) {
             // cudaMemGetInfo costs milliseconds (~10 ms on a context holding tens of GB): asked again only after the
             // library allocated or freed something; skipped altogether when the caller fixed the budget
-            if (c->free_cached_gen != alloc_generation()) {
-                size_t fr = 0, tot = 0;
-                CUDA_OK(cudaMemGetInfo(&fr, &tot));
-                c->free_cached = fr;
-                c->free_cached_gen = alloc_generation();
-            }
-            budget = (int64_t)((double)(c->free_cached + c->tables.cap + c->dd_scratch.cap) * 0.85);
+            size_t fr = 0;
+            QTRY(free_device_bytes(c, &fr));
+            budget = (int64_t)((double)(fr + c->tables.cap + c->dd_scratch.cap) * 0.85);
         }
         if (use_blogs) {
             bcap = ((max_keys + nbc - 1) / nbc + 64 + 1) & ~(uint64_t)1;

@@ -215,6 +215,20 @@ template <int GEOM, typename W> static int build_stab_hash(qecmc_ctx *c, const G
     return 0;
 }
 
+// Free device memory as of the library's last allocation or release: cudaMemGetInfo costs milliseconds (~10 ms on a context
+// holding tens of GB), so it is asked again only when the allocation generation has moved.
+static inline int free_device_bytes(qecmc_ctx *c, size_t *fr)
+{
+    if (c->free_cached_gen != alloc_generation()) {
+        size_t f = 0, tot = 0;
+        CUDA_OK(cudaMemGetInfo(&f, &tot));
+        c->free_cached = f;
+        c->free_cached_gen = alloc_generation();
+    }
+    *fr = c->free_cached;
+    return 0;
+}
+
 static inline int pick_threads(size_t bytes_per_chain, size_t fixed, const cudaDeviceProp &prop, int *threads, int *blocks_per_sm,
                                bool allow1024 = false, int regs_per_thread = 0)
 {

@@ -460,8 +460,8 @@ static int pteq_common(qecmc_ctx *c, const qecmc_pteq_cfg *cfg, const uint8_t *q
         if (scap < 1024) scap = 1024;
     }
     if (cfg->use_conv || shortest) {
-        size_t fr = 0, tot = 0;
-        CUDA_OK(cudaMemGetInfo(&fr, &tot));
+        size_t fr = 0;
+        QTRY(free_device_bytes(c, &fr));
         int64_t budget = c->table_budget ? c->table_budget : (int64_t)((double)fr * 0.8);
         wave = budget / ((cfg->use_conv ? cfg->steps * 4 : 0) + (int64_t)scap * 8);
         if (wave < 1) return set_err(QECMC_ERR_NOMEM, "the n_err history of one ladder needs %lld bytes, budget is %lld",
@@ -614,8 +614,8 @@ static int dc_common(qecmc_ctx *c, const qecmc_ladder_cfg *lc, int per_class_ini
         if (ucap < 1024) ucap = 1024;
     }
     const int ns1 = g.nsites + 1;
-    size_t fr = 0, tot = 0;
-    CUDA_OK(cudaMemGetInfo(&fr, &tot));
+    size_t fr = 0;
+    QTRY(free_device_bytes(c, &fr));
     int64_t budget = c->table_budget ? c->table_budget : (int64_t)((double)(fr + c->tables.cap) * 0.85);
     int64_t per_syndrome = (int64_t)n_eq * (tabs_per_class * ((int64_t)cap * 8 + (rc ? (int64_t)ns1 * 12 : 0)) + (int64_t)ucap * 8);
     int64_t wave = budget / per_syndrome;

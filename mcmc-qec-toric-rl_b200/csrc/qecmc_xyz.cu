@@ -195,8 +195,8 @@ extern "C" int qecmc_stdc_general_noise(qecmc_ctx *c, const qecmc_xyz_cfg *cfg, 
     uint64_t max_keys = (uint64_t)cfg->droplets * (uint64_t)cfg->steps;
     uint64_t cap = next_pow2(max_keys + max_keys / 4 + 1);
     if (cap < 1024) cap = 1024;
-    size_t fr = 0, tot = 0;
-    CUDA_OK(cudaMemGetInfo(&fr, &tot));
+    size_t fr = 0;
+    QTRY(free_device_bytes(c, &fr));
     int64_t budget = c->table_budget ? c->table_budget : (int64_t)((double)(fr + c->tables.cap) * 0.85);
     int64_t per_syndrome = (int64_t)n_eq * (int64_t)cap * 16;
     int64_t wave = budget / per_syndrome;
