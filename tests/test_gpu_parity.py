@@ -793,6 +793,19 @@ def test_row_word_width_does_not_change_native_results(ctx, g, L, monkeypatch):
     assert np.array_equal(a[2], b[2]) and a[1]["distinct"] == b[1]["distinct"] and a[1]["accepted"] == b[1]["accepted"]
 
 
+def test_more_droplets_than_a_cta_holds_use_per_chain_logs(ctx, monkeypatch):
+    """droplets > 1024: a table's chains no longer fit one CTA, so the call takes per-chain logs; same counts as the HBM set."""
+    g, L, droplets, steps = O.TORIC, 5, 1100, 300
+    rng = np.random.default_rng(78)
+    qm = np.stack([rand_lattice(rng, g, L, 0.1).reshape(-1) for _ in range(2)])
+    monkeypatch.delenv("QECMC_DEBUG_INSERT_MODE", raising=False)
+    a = ctx.stdc(g, g, L, qm, 0.1, 0.3, droplets, steps, seed=5, want_hist=True)
+    monkeypatch.setenv("QECMC_DEBUG_INSERT_MODE", "2")
+    b = ctx.stdc(g, g, L, qm, 0.1, 0.3, droplets, steps, seed=5, want_hist=True)
+    assert a[1]["table_slots"] == 0 and b[1]["table_slots"] > 0
+    assert np.array_equal(a[2], b[2]) and a[1]["distinct"] == b[1]["distinct"]
+
+
 def test_bucket_log_overflow_falls_back(ctx):
     """Chains at a high sampling rate offer a key at almost every sample; tiny tables make the fixed-capacity bucket logs
     and their overflow area run over, and the call must then redo itself with per-chain logs and still be exact."""
