@@ -73,6 +73,14 @@ int         qecmc_set_stream(qecmc_ctx *ctx, void *cuda_stream);
 int         qecmc_device_info(qecmc_ctx *ctx, qecmc_devinfo *out);
 /* cap (bytes) on the distinct-chain table arena; 0 = 85 % of free device memory */
 int         qecmc_set_table_budget(qecmc_ctx *ctx, int64_t bytes);
+/* Test switches, per context (never read from the environment).  They select between code paths that must give the
+ * same results, so that tests can compare them on one problem; value < 0 restores the default.
+ *   "force_wide"   1: 64-bit row words also for L <= 16
+ *   "insert_mode"  distinct-chain accounting of STDC / STRC: 0 synchronous HBM set, 2 deferred HBM set, 4 per-chain
+ *                  key logs, 6 bucket logs
+ *   "serial_sweep" 1: native ladders walk the swap sweep pair by pair, like replay does
+ * Unknown keys return QECMC_ERR_ARG. */
+int         qecmc_debug_set(qecmc_ctx *ctx, const char *key, int64_t value);
 
 /* ------------------------------------------------------------------------------
  * Single-temperature chains: Chain.update_chain_fast / _update_chain_fast

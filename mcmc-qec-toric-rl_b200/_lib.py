@@ -106,6 +106,7 @@ def load():
     L.qecmc_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     L.qecmc_set_table_budget.argtypes = [C.c_void_p, C.c_int64]
     L.qecmc_device_info.argtypes = [C.c_void_p, C.POINTER(DevInfo)]
+    L.qecmc_debug_set.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
     L.qecmc_chain_update.argtypes = [C.c_void_p, C.POINTER(ChainCfg), C.c_void_p, C.c_int64, C.c_int64, C.POINTER(Stats)]
     L.qecmc_replay_chain.argtypes = [C.c_void_p, C.POINTER(ChainCfg), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -186,6 +187,10 @@ class Context:
 
     def set_table_budget(self, nbytes):
         _check(load().qecmc_set_table_budget(self._h, int(nbytes)))
+
+    def debug_set(self, key, value):
+        """Test switch between code paths that must agree (include/qecmc.h); value < 0 restores the default."""
+        _check(load().qecmc_debug_set(self._h, key.encode(), int(value)))
 
     def device_info(self):
         d = DevInfo()

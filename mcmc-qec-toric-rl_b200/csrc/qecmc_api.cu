@@ -50,6 +50,7 @@ extern "C" void qecmc_destroy(qecmc_ctx *c)
         b->release();
     for (auto &kv : c->stab_hash) cudaFree(kv.second);
     for (auto &kv : c->stab_desc) cudaFree(kv.second);
+    alloc_generation()++;
     c->lut.release();
     c->log_hash.release();
     c->log_counts.release();
@@ -70,6 +71,16 @@ extern "C" int qecmc_set_table_budget(qecmc_ctx *c, int64_t bytes)
 {
     if (!c || bytes < 0) return set_err(QECMC_ERR_ARG, "bad arguments");
     c->table_budget = bytes;
+    return 0;
+}
+
+extern "C" int qecmc_debug_set(qecmc_ctx *c, const char *key, int64_t value)
+{
+    if (!c || !key) return set_err(QECMC_ERR_ARG, "NULL argument");
+    if (!strcmp(key, "force_wide")) c->dbg_force_wide = value > 0;
+    else if (!strcmp(key, "insert_mode")) c->dbg_insert_mode = value < 0 ? -1 : (int)value;
+    else if (!strcmp(key, "serial_sweep")) c->dbg_serial_sweep = value > 0;
+    else return set_err(QECMC_ERR_ARG, "unknown debug key '%s'", key);
     return 0;
 }
 
@@ -345,8 +356,19 @@ struct StdcOut {
     int32_t *short_info = nullptr;       // [S][n_eq][4]         STRC, optional
 };
 
+static int stdc_run_once(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uint8_t *d_qm, int64_t S, const StdcOut &out,
+                         qecmc_stats *stats, bool allow_bucket_logs);
+
+// wave sizes come from a cached free-memory figure: if an allocation fails after all, size once more from a fresh query
 static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uint8_t *d_qm, int64_t S, const StdcOut &out,
                     qecmc_stats *stats, bool allow_bucket_logs = true)
+{
+    if (!c) return set_err(QECMC_ERR_ARG, "NULL argument");
+    return with_fresh_memory_retry(c, [&] { return stdc_run_once(c, cfg, mode, d_qm, S, out, stats, allow_bucket_logs); });
+}
+
+static int stdc_run_once(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uint8_t *d_qm, int64_t S, const StdcOut &out,
+                         qecmc_stats *stats, bool allow_bucket_logs)
 {
     if (!c || !cfg || !d_qm || !out.eqdistr) return set_err(QECMC_ERR_ARG, "NULL argument");
     if (S <= 0) return set_err(QECMC_ERR_ARG, "S must be > 0");
@@ -365,8 +387,8 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
     if (mode == MODE_MEAN && cfg->steps < 2) return set_err(QECMC_ERR_ARG, "single_temp needs max_iters >= 2");
     CUDA_OK(cudaSetDevice(c->device));
     c->launches = 0;
-    // tests (QECMC_DEBUG_FORCE_WIDE): 64-bit row words for L <= 16 too, to compare the two word widths on one problem
-    const bool wide = cfg->L > 16 || (getenv("QECMC_DEBUG_FORCE_WIDE") && atoi(getenv("QECMC_DEBUG_FORCE_WIDE")) != 0);
+    // tests (qecmc_debug_set "force_wide"): 64-bit row words for L <= 16 too, to compare the two word widths on one problem
+    const bool wide = cfg->L > 16 || c->dbg_force_wide;
     const size_t wbytes = wide ? 8 : 4;
     const int n_eq = gcode.neq;
     const int nh = gcode.nsites + 1;
@@ -374,7 +396,7 @@ static int stdc_run(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, const uin
     // Distinct-chain accounting.  Default: per-chain key logs counted afterwards by log_dedupe_kernel (streams through
     // HBM).  The open-addressing tables in HBM remain for the early stop (it needs "new or not" at once) and for key
     // counts beyond what the dedupe kernel's bucket fan-out covers.
-    const int forced_mode = getenv("QECMC_DEBUG_INSERT_MODE") ? atoi(getenv("QECMC_DEBUG_INSERT_MODE")) : -1;
+    const int forced_mode = c->dbg_insert_mode;   // tests (qecmc_debug_set "insert_mode"); -1: the driver chooses
     const uint64_t max_keys = (uint64_t)cfg->droplets * (uint64_t)cfg->steps;
     const bool fits_dedupe = max_keys <= (uint64_t)QECMC_DD_MAX_BUCKETS * QECMC_DD_BUCKET_TARGET && (uint64_t)cfg->steps < (1ull << 32);
     // conv_mult != 0 (early stop, decoders.py:257-263): "new" means new to the DROPLET, so every chain probes a set of

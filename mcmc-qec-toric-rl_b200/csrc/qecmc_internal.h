@@ -45,7 +45,12 @@ struct DevBuf {
         p = nullptr;
         cap = 0;
         cudaError_t e = cudaMalloc(&p, bytes);
-        if (e != cudaSuccess) return set_err(QECMC_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            cudaGetLastError();   // an allocation failure is not sticky: clear it so that the caller can retry smaller
+            return set_err(e == cudaErrorMemoryAllocation ? QECMC_ERR_NOMEM : QECMC_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes,
+                           cudaGetErrorString(e));
+        }
         cap = bytes;
         return 0;
     }
@@ -55,6 +60,14 @@ struct DevBuf {
         p = nullptr;
         cap = 0;
     }
+};
+
+// a call-local device buffer: released when it goes out of scope, on every return path
+struct ScopedDevBuf : DevBuf {
+    ScopedDevBuf() = default;
+    ScopedDevBuf(const ScopedDevBuf &) = delete;
+    ScopedDevBuf &operator=(const ScopedDevBuf &) = delete;
+    ~ScopedDevBuf() { release(); }
 };
 
 // device buffers of the tempering-ladder drivers (qecmc_ladder.cu); they live in the context so that repeated calls
@@ -89,6 +102,8 @@ struct qecmc_ctx {
     cudaEvent_t ev[4];
     uint64_t hash_seed = 0x5EEDC0DE2020ull;
     int64_t launches = 0;
+    // qecmc_debug_set: test switches between code paths that must agree (never read from the environment)
+    int dbg_force_wide = 0, dbg_insert_mode = -1, dbg_serial_sweep = 0;
 };
 
 
@@ -192,6 +207,7 @@ template <int GEOM, typename W> static int build_stab_desc(qecmc_ctx *c, const G
             return set_err(QECMC_ERR_UNSUPPORTED, "internal: stabilizer descriptor %d disagrees with the geometry", idx);
     }
     uint2 *d = nullptr;
+    alloc_generation()++;
     CUDA_OK(cudaMalloc(&d, sizeof(uint2) * g.nstab));
     CUDA_OK(cudaMemcpyAsync(d, tab.data(), sizeof(uint2) * g.nstab, cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -206,6 +222,7 @@ template <int GEOM, typename W> static int build_stab_hash(qecmc_ctx *c, const G
     auto it = c->stab_hash.find(key);
     if (it != c->stab_hash.end()) { *out = it->second; return 0; }
     uint64_t *d = nullptr;
+    alloc_generation()++;
     CUDA_OK(cudaMalloc(&d, sizeof(uint64_t) * g.nstab));
     stab_hash_kernel<GEOM, W><<<(g.nstab + 127) / 128, 128, 0, c->stream>>>(g, c->hash_seed, d);
     c->launches++;
@@ -216,7 +233,20 @@ template <int GEOM, typename W> static int build_stab_hash(qecmc_ctx *c, const G
 }
 
 // Free device memory as of the library's last allocation or release: cudaMemGetInfo costs milliseconds (~10 ms on a context
-// holding tens of GB), so it is asked again only when the allocation generation has moved.
+// holding tens of GB), so it is asked again only when the allocation generation has moved.  The figure is a HINT: memory
+// taken by anyone else on the device (torch tensors between two calls, another context or process) does not move the
+// generation.  The wave-sizing drivers therefore run under with_fresh_memory_retry(): an allocation that fails with
+// QECMC_ERR_NOMEM drops the cached figure and the driver runs once more, sized from a fresh query.
+static inline void forget_free_device_bytes(qecmc_ctx *c) { c->free_cached_gen = ~(uint64_t)0; alloc_generation()++; }
+
+template <typename F> static inline int with_fresh_memory_retry(qecmc_ctx *c, F run)
+{
+    int rc = run();
+    if (rc != QECMC_ERR_NOMEM) return rc;
+    forget_free_device_bytes(c);
+    return run();
+}
+
 static inline int free_device_bytes(qecmc_ctx *c, size_t *fr)
 {
     if (c->free_cached_gen != alloc_generation()) {

@@ -228,7 +228,7 @@ int setup_ladder(qecmc_ctx *c, const qecmc_ladder_cfg *cfg, const Geo &g, Ladder
     p.iters = cfg->iters;
     p.p_logical = cfg->p_logical;
     p.top_accept_all = t.top_accept_all;
-    p.serial_sweep = getenv("QECMC_DEBUG_SERIAL_SWEEP") && atoi(getenv("QECMC_DEBUG_SERIAL_SWEEP")) != 0;
+    p.serial_sweep = c->dbg_serial_sweep;   // tests (qecmc_debug_set "serial_sweep")
     p.thr_d = (const double *)d.thr_d.p;
     p.thr_u = (const uint32_t *)d.thr_u.p;
     p.thr_top_d = (const double *)d.thr_top_d.p;
@@ -357,7 +357,7 @@ extern "C" int qecmc_ladder_run(qecmc_ctx *c, const qecmc_ladder_cfg *cfg, const
     p.steps = steps;
     p.lat_in = d.lat.p;
     p.init_broadcast = io->resume ? 0 : 1;
-    DevBuf flags_in, neff_in, tops0_in;
+    ScopedDevBuf flags_in, neff_in, tops0_in;   // released on every return path
     if (io->resume) {
         QTRY(flags_in.ensure((size_t)S * Nc * sizeof(int)));
         QTRY(tops0_in.ensure((size_t)S * sizeof(long long)));
@@ -389,7 +389,6 @@ extern "C" int qecmc_ladder_run(qecmc_ctx *c, const qecmc_ladder_cfg *cfg, const
     if (rc == 0) rc = cudaEventRecord(c->ev[1], c->stream) == cudaSuccess ? 0 : set_err(QECMC_ERR_CUDA, "cudaEventRecord failed");
     if (rc == 0) rc = check_status(c, d);
     cudaStreamSynchronize(c->stream);
-    flags_in.release(); neff_in.release(); tops0_in.release();
     if (rc) return rc;
     // results
     size_t out_bytes = (size_t)S * Nc * g.nsites;
@@ -433,9 +432,24 @@ extern "C" int qecmc_ladder_run(qecmc_ctx *c, const qecmc_ladder_cfg *cfg, const
 
 // ------------------------------------------------------------------------------------------------
 // PTEQ / PTEQ_biased / PTEQ_alpha (decoders.py:25-89, decoders_biasednoise.py:28-75,175-222)
+static int pteq_once(qecmc_ctx *c, const qecmc_pteq_cfg *cfg, const uint8_t *qm, bool qm_on_device, int64_t S,
+                     uint8_t *eqdistr, int64_t *eq_counts, int64_t *info, bool out_on_device, qecmc_stats *stats,
+                     double *short_len, int64_t *short_n, int64_t *short_unique);
+
+// the wave size comes from a cached free-memory figure: on an allocation failure, size once more from a fresh query
 static int pteq_common(qecmc_ctx *c, const qecmc_pteq_cfg *cfg, const uint8_t *qm, bool qm_on_device, int64_t S,
                        uint8_t *eqdistr, int64_t *eq_counts, int64_t *info, bool out_on_device, qecmc_stats *stats,
                        double *short_len = nullptr, int64_t *short_n = nullptr, int64_t *short_unique = nullptr)
+{
+    if (!c) return set_err(QECMC_ERR_ARG, "NULL argument");
+    return with_fresh_memory_retry(c, [&] {
+        return pteq_once(c, cfg, qm, qm_on_device, S, eqdistr, eq_counts, info, out_on_device, stats, short_len, short_n, short_unique);
+    });
+}
+
+static int pteq_once(qecmc_ctx *c, const qecmc_pteq_cfg *cfg, const uint8_t *qm, bool qm_on_device, int64_t S,
+                     uint8_t *eqdistr, int64_t *eq_counts, int64_t *info, bool out_on_device, qecmc_stats *stats,
+                     double *short_len, int64_t *short_n, int64_t *short_unique)
 {
     if (!c || !cfg || !qm || !eqdistr) return set_err(QECMC_ERR_ARG, "NULL argument");
     const qecmc_ladder_cfg *lc = &cfg->ladder;
@@ -462,7 +476,8 @@ static int pteq_common(qecmc_ctx *c, const qecmc_pteq_cfg *cfg, const uint8_t *q
     if (cfg->use_conv || shortest) {
         size_t fr = 0;
         QTRY(free_device_bytes(c, &fr));
-        int64_t budget = c->table_budget ? c->table_budget : (int64_t)((double)fr * 0.8);
+        // what the context already holds for these two purposes counts as available (as in the STDC / PTDC drivers)
+        int64_t budget = c->table_budget ? c->table_budget : (int64_t)((double)(fr + d.hist.cap + (shortest ? c->tables.cap : 0)) * 0.8);
         wave = budget / ((cfg->use_conv ? cfg->steps * 4 : 0) + (int64_t)scap * 8);
         if (wave < 1) return set_err(QECMC_ERR_NOMEM, "the n_err history of one ladder needs %lld bytes, budget is %lld",
                                      (long long)cfg->steps * 4, (long long)budget);
@@ -579,9 +594,23 @@ extern "C" int qecmc_pteq_dev(qecmc_ctx *c, const qecmc_pteq_cfg *cfg, const uin
 // ------------------------------------------------------------------------------------------------
 // Distinct-chain decoders on ladders: PTDC (decoders.py:138-233) and the EWD-style
 // STDC_Nall_n_alpha / STDC_droplet_alpha (decoders.py:510-581, a one-rung alpha "ladder").
+static int dc_once(qecmc_ctx *c, const qecmc_ladder_cfg *lc, int per_class_inits, int droplets, int64_t steps, double beta,
+                   const uint8_t *qm, int64_t S, double *eqdistr, int64_t *distinct, qecmc_stats *stats, bool rc,
+                   int64_t *N_hist, int64_t *m_hist, double conv_mult, int64_t *steps_done);
+
 static int dc_common(qecmc_ctx *c, const qecmc_ladder_cfg *lc, int per_class_inits, int droplets, int64_t steps, double beta,
                      const uint8_t *qm, int64_t S, double *eqdistr, int64_t *distinct, qecmc_stats *stats, bool rc = false,
                      int64_t *N_hist = nullptr, int64_t *m_hist = nullptr, double conv_mult = 0.0, int64_t *steps_done = nullptr)
+{
+    if (!c) return set_err(QECMC_ERR_ARG, "NULL argument");
+    return with_fresh_memory_retry(c, [&] {
+        return dc_once(c, lc, per_class_inits, droplets, steps, beta, qm, S, eqdistr, distinct, stats, rc, N_hist, m_hist, conv_mult, steps_done);
+    });
+}
+
+static int dc_once(qecmc_ctx *c, const qecmc_ladder_cfg *lc, int per_class_inits, int droplets, int64_t steps, double beta,
+                   const uint8_t *qm, int64_t S, double *eqdistr, int64_t *distinct, qecmc_stats *stats, bool rc,
+                   int64_t *N_hist, int64_t *m_hist, double conv_mult, int64_t *steps_done)
 {
     if (!c || !qm || !eqdistr) return set_err(QECMC_ERR_ARG, "NULL argument");
     QTRY(check_ladder_cfg(lc));
@@ -636,7 +665,7 @@ static int dc_common(qecmc_ctx *c, const qecmc_ladder_cfg *lc, int per_class_ini
     if (wide) QTRY(pack_lattices<uint64_t>(c, (const uint8_t *)d.qm.p, n_in, g, d.lat.p));
     else QTRY(pack_lattices<uint32_t>(c, (const uint8_t *)d.qm.p, n_in, g, d.lat.p));
     // per-class initial states [S][n_eq][nw]
-    DevBuf cls_lat;
+    ScopedDevBuf cls_lat;   // call-local buffers: released on every return path
     const void *class_lat = d.lat.p;
     if (!per_class_inits) {
         QTRY(cls_lat.ensure((size_t)S * n_eq * g.nw * wb));
@@ -653,7 +682,7 @@ static int dc_common(qecmc_ctx *c, const qecmc_ladder_cfg *lc, int per_class_ini
     p.steps = steps;
     p.conv_mult = conv_mult;
     if (steps_done) QTRY(d.info.ensure((size_t)S * n_eq * droplets * sizeof(long long)));
-    DevBuf rc_m, rc_N, rc_Nout, rc_mout, lad_p;
+    ScopedDevBuf rc_m, rc_N, rc_Nout, rc_mout, lad_p;
     if (rc) {
         QTRY(rc_m.ensure((size_t)wave * n_eq * tabs_per_class * ns1 * sizeof(unsigned long long)));
         QTRY(rc_N.ensure((size_t)wave * n_eq * tabs_per_class * ns1 * sizeof(uint32_t)));
@@ -733,8 +762,6 @@ static int dc_common(qecmc_ctx *c, const qecmc_ladder_cfg *lc, int per_class_ini
     unsigned long long cnt[8] = {0};
     CUDA_OK(cudaMemcpyAsync(cnt, c->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
-    cls_lat.release();
-    rc_m.release(); rc_N.release(); rc_Nout.release(); rc_mout.release(); lad_p.release();
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
     fill_stats(c, stats, S * n_eq * droplets * lc->Nc * steps * lc->iters, cnt, ms, waves);

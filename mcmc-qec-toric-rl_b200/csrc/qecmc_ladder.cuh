@@ -31,7 +31,7 @@ struct LadderParams {
     double p_logical;       // top rung: probability of proposing a logical operator
     int top_accept_all;     // kind 0: ladder[Nc-1] >= 0.75 (mcmc.py:30)
     const uint2 *desc2;     // toric / planar, depolarizing: stabilizer descriptors of build_stab_desc (qecmc_internal.h)
-    int serial_sweep;       // tests (QECMC_DEBUG_SERIAL_SWEEP): native mode walks the swap sweep pair by pair like replay does
+    int serial_sweep;       // tests (qecmc_debug_set "serial_sweep"): native mode walks the swap sweep pair by pair like replay does
     int64_t n_ladders, ladder_offset, steps;
     const void *lat_in;     // packed [n_ladders][nw] (init_broadcast) or [n_ladders][Nc][nw]
     int init_broadcast;

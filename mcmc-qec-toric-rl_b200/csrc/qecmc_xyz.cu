@@ -168,8 +168,19 @@ extern "C" int qecmc_chain_update_xyz(qecmc_ctx *c, const qecmc_chain_cfg *cfg, 
     return 0;
 }
 
+static int general_noise_once(qecmc_ctx *c, const qecmc_xyz_cfg *cfg, const uint8_t *qm, int64_t S, double *eqdistr,
+                              double *eqdistr_shortest, int64_t *distinct, qecmc_stats *stats);
+
 extern "C" int qecmc_stdc_general_noise(qecmc_ctx *c, const qecmc_xyz_cfg *cfg, const uint8_t *qm, int64_t S, double *eqdistr,
                                         double *eqdistr_shortest, int64_t *distinct, qecmc_stats *stats)
+{
+    if (!c) return set_err(QECMC_ERR_ARG, "NULL argument");
+    // the wave size comes from a cached free-memory figure: on an allocation failure, size once more from a fresh query
+    return with_fresh_memory_retry(c, [&] { return general_noise_once(c, cfg, qm, S, eqdistr, eqdistr_shortest, distinct, stats); });
+}
+
+static int general_noise_once(qecmc_ctx *c, const qecmc_xyz_cfg *cfg, const uint8_t *qm, int64_t S, double *eqdistr,
+                              double *eqdistr_shortest, int64_t *distinct, qecmc_stats *stats)
 {
     if (!c || !cfg || !qm || !eqdistr) return set_err(QECMC_ERR_ARG, "NULL argument");
     if (S <= 0) return set_err(QECMC_ERR_ARG, "S must be > 0");

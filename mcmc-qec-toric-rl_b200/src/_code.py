@@ -110,6 +110,17 @@ class CodeBase:
         px = p_error / (2 * (eta + 1))
         self.generate_random_error(px, px, pz)
 
+    def generate_alpha_error(self, p_error, alpha):
+        """planar_model.py:79-99: p_tilde = p/(1+p); pz_tilde solves x + 2 x**alpha = p_tilde; then
+        (p_x, p_y, p_z) = (pz_tilde**alpha, pz_tilde**alpha, pz_tilde) * (1 - p_error), i.i.d. per qubit.
+        (The reference's own loop indexes the (2, L, L) planar lattice with two indices and fails for L > 2;
+        this draws every qubit of the code.)"""
+        from scipy import optimize
+        p_tilde = p_error / (1 + p_error)
+        pz_tilde = optimize.fsolve(lambda x: x + 2 * x**alpha - p_tilde, 0.5)[0]
+        p_xy = pz_tilde**alpha * (1 - p_error)
+        self.generate_random_error(p_xy, p_xy, pz_tilde * (1 - p_error))
+
     def _clear_unused(self):
         pass
 

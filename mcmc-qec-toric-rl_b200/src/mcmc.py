@@ -10,6 +10,7 @@ built on it) proposes with:
 """
 import copy
 import itertools
+import random as _pyrandom
 
 import numpy as np
 
@@ -28,6 +29,15 @@ def seed(value):
 
 def _new_stream():
     return ((SEED & 0xFFFFFFFFFF) << 24) ^ next(_chain_ids)
+
+
+def _call_key(stream, calls):
+    """64-bit Philox key of call number `calls` of a host-driven ladder / top-rung chain: (stream, calls) mixed by
+    splitmix64, so the call counter never runs into the seed bits of `stream` and never wraps out of 64 bits."""
+    z = (stream ^ (calls * 0x9E3779B97F4A7C15)) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return z ^ (z >> 31)
 
 
 def fast_path_geometry(code):
@@ -98,7 +108,7 @@ def _single_rung_block(chain, kind, bottom, param_b, iters):
     chain._steps += 1
     out = _lib.default_context().ladder_run(chain.code.geometry, chain.code.system_size, kind, q.reshape(1, -1).copy(), bottom, 1,
                                             1, iters=int(iters), param_b=param_b, p_logical=float(chain.p_logical),
-                                            seed=chain._stream + (chain._steps << 44))
+                                            seed=_call_key(chain._stream, chain._steps))
     chain.code.qubit_matrix = out["rung_states"][0, 0].reshape(q.shape)
     return out
 
@@ -140,7 +150,7 @@ class _LadderBase:
         self._calls += 1
         out = _lib.default_context().ladder_run(code0.geometry, code0.system_size, self._kind, None, self._bottom, self.Nc, 1,
                                                 iters=int(iters), param_b=self._param_b, p_logical=float(self.p_logical),
-                                                seed=self._stream + (self._calls << 44), resume=self._state())
+                                                seed=_call_key(self._stream, self._calls), resume=self._state())
         shape = code0.qubit_matrix.shape
         for i, c in enumerate(self.chains):
             c.code.qubit_matrix = out["rung_states"][0, i].reshape(shape).copy()
@@ -162,31 +172,39 @@ class Ladder(_LadderBase):
         self._setup(init_code, Nc, p_logical, p_bottom, 0.0, p_ladder, [Chain(p, copy.deepcopy(init_code)) for p in p_ladder])
 
     def r_flip(self, ind_lo):
-        raise NotImplementedError("replica swaps run inside Ladder.step on the device")
+        """Swap decision for rungs (ind_lo, ind_lo + 1) from the rungs' current lengths (src/mcmc.py:86-92, 144-149).
+        Host-side (one decision is not GPU work); Ladder.step takes its own decisions on the device."""
+        ne_lo = self.chains[ind_lo].code.count_errors()
+        ne_hi = self.chains[ind_lo + 1].code.count_errors()
+        if ne_hi < ne_lo:
+            return True
+        return _pyrandom.random() < float(self.p_diff[ind_lo]) ** (ne_hi - ne_lo)
 
 
 class MCMCDataReader:
-    """Reader of the workload loop's pickle (src/mcmc.py:118-141): a DataFrame indexed by (data_nr, type)."""
+    """Cursor over a data set written by generate_data.generate (or by the reference): a pickled DataFrame indexed by
+    (data_nr, type).  Same constructor and methods as the reference's reader (src/mcmc.py:118-141); a missing or
+    unreadable file raises instead of leaving a half-built object behind."""
 
     def __init__(self, file_path, size):
         import pandas as pd
-        self.__file_path = file_path
-        self.__size = size
+        self._path, self._size, self._pos = file_path, size, 0
         try:
-            self.__df = pd.read_pickle(file_path)
-            self.__capacity = self.__df.index[-1][0] + 1   # number of data samples in the dataset
-        except Exception:
-            print('No input file for MCMCDataReader')
-        self.__current_index = 0
+            self._frame = pd.read_pickle(file_path)
+        except (OSError, ValueError, EOFError) as exc:
+            raise FileNotFoundError(f"MCMCDataReader: cannot read {file_path!r}: {exc}") from exc
+        last_nr = self._frame.index[-1][0]
+        self._count = int(last_nr) + 1
 
     def full(self):
-        return self.__df.to_numpy().ravel()
+        """Every cell of the frame as one flat object array (params row first)."""
+        return self._frame.to_numpy().ravel()
 
     def has_next(self):
-        return self.__current_index < self.__capacity
+        return self._pos < self._count
 
     def current_index(self):
-        return self.__current_index
+        return self._pos
 
     def get_capacity(self):
-        return self.__capacity
+        return self._count

@@ -6,6 +6,8 @@ import copy
 import numpy as np
 
 from .. import _lib
+import random as _pyrandom
+
 from .mcmc import _LadderBase, _new_stream, _single_rung_block
 
 
@@ -28,6 +30,11 @@ class Chain_alpha:
         # value, which for a chain that started from its own state is the same thing
         self.n_eff = float(out["n_eff"][0, 0])
 
+    def update_chain_fast(self, iters):
+        """mcmc_alpha.py:73-74 reads self.factor, which Chain_alpha never sets (its assignment is commented out,
+        mcmc_alpha.py:21): the reference raises AttributeError here, and so does this mirror."""
+        raise AttributeError("'Chain_alpha' object has no attribute 'factor'")
+
 
 class Ladder_alpha(_LadderBase):
     """Ladder_alpha(pz_tilde_bottom, init_code, alpha, Nc, p_logical=0): src/mcmc_alpha.py:77-137."""
@@ -42,3 +49,8 @@ class Ladder_alpha(_LadderBase):
             self.pz_tilde_diff = (lad[:-1] * (1 - lad[1:])) / (lad[1:] * (1 - lad[:-1]))
         self._setup(init_code, Nc, p_logical, pz_tilde_bottom, alpha, lad,
                     [Chain_alpha(pz, alpha, copy.deepcopy(init_code)) for pz in lad])
+
+    def r_flip(self, ind_lo):
+        """mcmc_alpha.py:117-123: always draws; the exponent is the difference of the rung-owned n_eff values."""
+        lo, hi = self.chains[ind_lo], self.chains[ind_lo + 1]
+        return _pyrandom.random() < (lo.pz_tilde / hi.pz_tilde) ** (hi.n_eff - lo.n_eff)

@@ -22,9 +22,9 @@ run("STDC toric15 + N_hist", lambda: ctx.stdc(_lib.TORIC, _lib.TORIC, L, q, 0.15
 run("STDC toric15 conv_mult=2", lambda: ctx.stdc(_lib.TORIC, _lib.TORIC, L, q, 0.15, 0.25, dr, steps, seed=1, conv_mult=2.0))
 q10 = np.concatenate([q] * 7)[:943]   # 943 syndromes x 16 classes x 10 chains: 147.9 CTAs of 1020 threads (102 tables each)
 run("STDC toric15 droplets=10", lambda: ctx.stdc(_lib.TORIC, _lib.TORIC, L, q10, 0.15, 0.25, 10, steps, seed=1))
-os.environ["QECMC_DEBUG_INSERT_MODE"] = "4"
+ctx.debug_set("insert_mode", 4)
 run("  same, per-chain logs", lambda: ctx.stdc(_lib.TORIC, _lib.TORIC, L, q10, 0.15, 0.25, 10, steps, seed=1))
-del os.environ["QECMC_DEBUG_INSERT_MODE"]
+ctx.debug_set("insert_mode", -1)
 def st_single():
     out = ctx.single_temp(_lib.TORIC, _lib.TORIC, L, np.repeat(q, 8, 0), 0.15, steps)
     return out if isinstance(out, tuple) else (out, {})

@@ -414,7 +414,7 @@ def test_pteq_replay_matches_oracle(ctx, kind, g, L, bottom, b):
                                                   (1, O.XZZX, 7, 0.17, 0.65, None)])
 def test_native_swap_sweep_equals_the_pair_by_pair_walk(ctx, kind, g, L, bottom, b, Nc, monkeypatch):
     """Native ladders take the swap decisions of a sweep on all lanes (largest swapping exponent per pair from the power
-    table, compare-and-select walk, rungs from the swap mask).  QECMC_DEBUG_SERIAL_SWEEP makes the same build walk the pairs
+    table, compare-and-select walk, rungs from the swap mask).  debug_set("serial_sweep") makes the same build walk the pairs
     one by one as mcmc.py:96-103 does (the replay path's code): same seed, same draws => identical results.  The 0.7
     bottom rung gives the biased ladder tables close to 1, i.e. draws beyond the tabulated exponents."""
     rng = np.random.default_rng(900 + 7 * kind + g + L)
@@ -423,10 +423,12 @@ def test_native_swap_sweep_equals_the_pair_by_pair_walk(ctx, kind, g, L, bottom,
     kw = dict(param_b=b, steps=300, conv=False, seed=5, p_logical=0.5)
     if Nc:
         kw["Nc"] = Nc
-    monkeypatch.delenv("QECMC_DEBUG_SERIAL_SWEEP", raising=False)
     pct, info = ctx.pteq(g, L, kind, qm, bottom, **kw)
-    monkeypatch.setenv("QECMC_DEBUG_SERIAL_SWEEP", "1")
-    pct1, info1 = ctx.pteq(g, L, kind, qm, bottom, **kw)
+    ctx.debug_set("serial_sweep", 1)
+    try:
+        pct1, info1 = ctx.pteq(g, L, kind, qm, bottom, **kw)
+    finally:
+        ctx.debug_set("serial_sweep", -1)
     assert np.array_equal(pct, pct1)
     for k in ("steps", "since_burn", "tops0", "counts"):
         assert np.array_equal(info[k], info1[k]), k
@@ -740,13 +742,12 @@ def test_log_dedupe_equals_table_set(ctx, g, L, droplets, steps, monkeypatch):
     qm = np.stack([rand_lattice(rng, g, L, 0.12).reshape(-1) for _ in range(S)])
     outs = {}
     for mode in ("default", "4", "2", "0"):
-        if mode == "default":
-            monkeypatch.delenv("QECMC_DEBUG_INSERT_MODE", raising=False)
-        else:
-            monkeypatch.setenv("QECMC_DEBUG_INSERT_MODE", mode)
-        out, st, hist = ctx.stdc(g, g, L, qm, 0.12, 0.3, droplets, steps, seed=99, want_hist=True)
+        ctx.debug_set("insert_mode", -1 if mode == "default" else int(mode))
+        try:
+            out, st, hist = ctx.stdc(g, g, L, qm, 0.12, 0.3, droplets, steps, seed=99, want_hist=True)
+        finally:
+            ctx.debug_set("insert_mode", -1)
         outs[mode] = (out, st, hist)
-    monkeypatch.delenv("QECMC_DEBUG_INSERT_MODE")
     assert outs["4"][1]["table_slots"] == 0 and outs["2"][1]["table_slots"] > 0      # really different paths
     assert outs["default"][1]["table_slots"] == -1   # bucket logs for any droplets <= 1024 (CTAs of whole tables)
     for mode in ("4", "2", "0"):
@@ -781,14 +782,16 @@ def test_waves_under_a_small_table_budget_give_the_same_result(droplets):
 
 @pytest.mark.parametrize("g,L", [(O.TORIC, 9), (O.PLANAR, 11), (O.PLANAR, 16)])
 def test_row_word_width_does_not_change_native_results(ctx, g, L, monkeypatch):
-    """QECMC_DEBUG_FORCE_WIDE runs a lattice with L <= 16 through the 64-bit row-word kernels (the ones L > 16 uses): the
+    """debug_set("force_wide") runs a lattice with L <= 16 through the 64-bit row-word kernels (the ones L > 16 uses): the
     same seeds must give the same chains, i.e. identical N(n) and distinct counts, as the 32-bit kernels."""
     rng = np.random.default_rng(640 + L)
     qm = np.stack([rand_lattice(rng, g, L, 0.12).reshape(-1) for _ in range(6)])
-    monkeypatch.delenv("QECMC_DEBUG_FORCE_WIDE", raising=False)
     a = ctx.stdc(g, g, L, qm, 0.12, 0.3, 16, 4000, seed=21, want_hist=True)
-    monkeypatch.setenv("QECMC_DEBUG_FORCE_WIDE", "1")
-    b = ctx.stdc(g, g, L, qm, 0.12, 0.3, 16, 4000, seed=21, want_hist=True)
+    ctx.debug_set("force_wide", 1)
+    try:
+        b = ctx.stdc(g, g, L, qm, 0.12, 0.3, 16, 4000, seed=21, want_hist=True)
+    finally:
+        ctx.debug_set("force_wide", -1)
     assert b[1]["table_slots"] == 0 and a[1]["table_slots"] == -1       # per-chain logs behind the wide kernels, bucket logs otherwise
     assert np.array_equal(a[2], b[2]) and a[1]["distinct"] == b[1]["distinct"] and a[1]["accepted"] == b[1]["accepted"]
 
@@ -798,10 +801,12 @@ def test_more_droplets_than_a_cta_holds_use_per_chain_logs(ctx, monkeypatch):
     g, L, droplets, steps = O.TORIC, 5, 1100, 300
     rng = np.random.default_rng(78)
     qm = np.stack([rand_lattice(rng, g, L, 0.1).reshape(-1) for _ in range(2)])
-    monkeypatch.delenv("QECMC_DEBUG_INSERT_MODE", raising=False)
     a = ctx.stdc(g, g, L, qm, 0.1, 0.3, droplets, steps, seed=5, want_hist=True)
-    monkeypatch.setenv("QECMC_DEBUG_INSERT_MODE", "2")
-    b = ctx.stdc(g, g, L, qm, 0.1, 0.3, droplets, steps, seed=5, want_hist=True)
+    ctx.debug_set("insert_mode", 2)
+    try:
+        b = ctx.stdc(g, g, L, qm, 0.1, 0.3, droplets, steps, seed=5, want_hist=True)
+    finally:
+        ctx.debug_set("insert_mode", -1)
     assert a[1]["table_slots"] == 0 and b[1]["table_slots"] > 0
     assert np.array_equal(a[2], b[2]) and a[1]["distinct"] == b[1]["distinct"]
 
@@ -813,12 +818,11 @@ def test_bucket_log_overflow_falls_back(ctx):
     rng = np.random.default_rng(77)
     qm = np.stack([rand_lattice(rng, g, L, 0.3).reshape(-1) for _ in range(3)])
     a = ctx.stdc(g, g, L, qm, 0.3, 0.45, droplets, steps, seed=5, want_hist=True)
-    import os
-    os.environ["QECMC_DEBUG_INSERT_MODE"] = "2"
+    ctx.debug_set("insert_mode", 2)
     try:
         b = ctx.stdc(g, g, L, qm, 0.3, 0.45, droplets, steps, seed=5, want_hist=True)
     finally:
-        del os.environ["QECMC_DEBUG_INSERT_MODE"]
+        ctx.debug_set("insert_mode", -1)
     assert np.array_equal(a[2], b[2]) and a[1]["distinct"] == b[1]["distinct"]
 
 

@@ -167,3 +167,74 @@ def test_generate_data_noise_models_match_the_reference_formulas():
     assert np.isclose(pz, 0.1 * (1 - p)) and np.isclose(px, 0.01 * (1 - p)) and px == py
     with pytest.raises(AssertionError):
         G.noise_probabilities({'code': 'toric', 'noise': 'biased', 'p_error': 0.1})
+
+
+# ------------------------------------------------------------------ host-side mirrors that need no device
+def _ladder_stub(cls, *args):
+    """A ladder object with its rung chains but without touching the device (construction is host-only)."""
+    return cls(*args)
+
+
+def test_ladder_r_flip_follows_the_reference_rules(monkeypatch):
+    """Ladder.r_flip (src/mcmc.py:86-92, 144-149): a lighter upper replica swaps without a draw, otherwise
+    u < p_diff ** (ne_hi - ne_lo); Ladder_biased.r_flip (mcmc_biased.py:107-113) and Ladder_alpha.r_flip
+    (mcmc_alpha.py:117-123) always draw."""
+    import random
+    from mcmc_qec_toric_rl_b200.src.mcmc import Ladder
+    from mcmc_qec_toric_rl_b200.src.mcmc_biased import Ladder_biased
+    from mcmc_qec_toric_rl_b200.src.mcmc_alpha import Ladder_alpha
+    code = Planar_code(5)
+    lad = Ladder(0.1, code, 3, 0.5)
+    lad.chains[0].code.qubit_matrix[0, 0, :3] = 1      # 3 errors on rung 0
+    lad.chains[1].code.qubit_matrix[0, 1, :1] = 2      # 1 error on rung 1
+    draws = []
+    monkeypatch.setattr(random, "random", lambda: draws.append(1) or 0.999999)
+    assert lad.r_flip(0) is True and not draws                       # ne_hi < ne_lo: no draw
+    lad.chains[1].code.qubit_matrix[0, 1, :] = 2                     # 5 errors: now a draw decides
+    want = 0.999999 < lad.p_diff[0] ** (5 - 3)
+    assert lad.r_flip(0) == want and len(draws) == 1
+    monkeypatch.setattr(random, "random", lambda: 0.0)
+    assert lad.r_flip(0) is True
+    lb = Ladder_biased(0.1, xzzx_code(5), 10.0, 3, 0.5)
+    lb.chains[0].code.qubit_matrix[0, :3] = 3
+    monkeypatch.setattr(random, "random", lambda: draws.append(1) or 0.5)
+    n0 = len(draws)
+    assert lb.r_flip(0) == (0.5 < lb.p_diff[0] ** (0 - 3)) and len(draws) == n0 + 1   # draws even though ne_hi < ne_lo
+    la = Ladder_alpha(0.1, xzzx_code(5), 2.0, 3, 0.5)
+    la.chains[1].n_eff = 4.0
+    assert la.r_flip(0) == (0.5 < (la.chains[0].pz_tilde / la.chains[1].pz_tilde) ** 4.0)
+
+
+def test_chain_mirrors_keep_the_reference_attributes():
+    from mcmc_qec_toric_rl_b200.src.mcmc_biased import Chain_biased
+    from mcmc_qec_toric_rl_b200.src.mcmc_alpha import Chain_alpha
+    cb = Chain_biased(0.12, 100.0, xzzx_code(5))
+    assert cb.factor == (0.12 / 3.0) / (1.0 - 0.12) and callable(cb.update_chain_fast)      # mcmc_biased.py:17, 62-63
+    with pytest.raises(AttributeError):                                                     # mcmc_alpha.py:21, 73-74
+        Chain_alpha(0.1, 2.0, xzzx_code(5)).update_chain_fast(10)
+
+
+def test_call_keys_do_not_collide_or_overflow():
+    """The Philox key of call k of a host-driven ladder: distinct across calls and seeds, always < 2^64
+    (the old stream + (calls << 44) overlapped the seed bits and wrapped after 2^20 calls)."""
+    from mcmc_qec_toric_rl_b200.src import mcmc
+    keys = {mcmc._call_key(s, k) for s in (1 << 24, (1 << 24) + (1 << 44), 12345) for k in (0, 1, 2, 1 << 20, (1 << 20) + 1, 5 * 10**7)}
+    assert len(keys) == 18 and all(0 <= k < 1 << 64 for k in keys)
+
+
+def test_generate_alpha_error_rates():
+    """planar_model.py:79-99: pz_tilde solves x + 2 x^alpha = p/(1+p); Z dominates for alpha > 1."""
+    np.random.seed(3)
+    for code in (Planar_code(15), xzzx_code(15)):
+        code.generate_alpha_error(0.3, 2.0)
+        nx, ny, nz = code.chain_lengths()
+        assert code.qubit_matrix.dtype == np.uint8 and nz > 2 * (nx + ny) and nz > 0
+    pc = Planar_code(7)
+    pc.generate_alpha_error(0.5, 1.0)
+    assert not pc.qubit_matrix[1, -1, :].any() and not pc.qubit_matrix[1, :, -1].any()
+
+
+def test_data_reader_raises_on_a_missing_file(tmp_path):
+    from mcmc_qec_toric_rl_b200.src.mcmc import MCMCDataReader
+    with pytest.raises(FileNotFoundError):
+        MCMCDataReader(str(tmp_path / "nope.xz"), 5)
