@@ -134,24 +134,26 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = host_cores()
-    # one step = `cores` syndromes x 16 classes x 4 chains x 50625 samples x 5 steps (bounded sample of the workload)
-    drop = 4
-    n_syn = max(1, min(cores, 64))
+    # same configuration as the GPU arm (16 classes x 64 chains x 15^4 samples x 5 steps per syndrome); the bounded sample
+    # is the number of syndromes per step: one per 16 host threads (a syndrome is 2.6e8 Metropolis steps, ~65 s of one
+    # core; its 16 classes are the parallel jobs)
+    drop = DROPLETS
+    n_syn = max(1, cores // 16)
     for _ in range(args.warmup if args.warmup < 1 else 1):
         cpu_port_rate(max(1, n_syn // 8), 1, 2000, cores)
     t_total, steps_total = 0.0, 0
     for k in range(args.steps):
-        rate, dt, steps = cpu_port_rate(n_syn, drop, SAMPLES, cores, seed=100 + k)
+        rate, dt, steps = cpu_port_rate(n_syn, drop, args.samples, cores, seed=100 + k)
         t_total += dt
         steps_total += steps
     value = steps_total / t_total
-    sample = f"{n_syn} syndromes x 16 classes x {drop} chains x {SAMPLES} samples x {ITERS} steps per bench step"
+    sample = f"{n_syn} syndromes x 16 classes x {drop} chains x {args.samples} samples x {ITERS} steps per bench step"
     line = {
         "impl": "reference", "metric": "metropolis_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "syndromes_per_s": value / (N_EQ * DROPLETS * SAMPLES * ITERS),
-        "config": workload_config(n_syn, args.gpus),
+        "syndromes_per_s": value / (N_EQ * DROPLETS * args.samples * ITERS),
+        "config": workload_config(args.gpus), "syndromes_per_step_per_gpu": n_syn,
         "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -159,9 +161,10 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(batch, n_gpus):
+def workload_config(n_gpus):
+    """identical for both arms (the batch of a step is reported beside it, not inside)"""
     return {"workload": "toric d=15 depolarizing p=0.15, STDC: 16 classes x 64 chains x 15^4 samples x 5 steps, p_sampling=0.25",
-            "syndromes_per_step_per_gpu": batch, "parallelism": f"syndrome-sharded x{n_gpus}, no collective",
+            "parallelism": f"syndrome-sharded x{n_gpus}, no collective",
             "l2": "working set = per-chain key logs (tens of GB, rewritten every step) >> 126 MB L2"}
 
 
@@ -267,7 +270,7 @@ def main():
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record(stream)
-    n_e2e = max(1, min(args.steps, 3))
+    n_e2e = args.steps
     for k in range(n_e2e):
         res, _ = step_e2e(args.warmup + k)
     f1.record(stream)
@@ -303,7 +306,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "syndromes_per_s": value / steps_per_syndrome,
-        "config": workload_config(batch, world),
+        "config": workload_config(world), "syndromes_per_step_per_gpu": batch,
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": int(batch * 2 * L * L),
                 "d2h_bytes_per_step": int(batch * N_EQ * 8), "steps_timed": n_e2e},
         "gpu_launches": int(launches),
@@ -337,9 +340,9 @@ def main():
         line["per_rank_ms"] = {"what": "[timed region, e2e region, chain kernels] per rank", "values": per_rank}
     if not args.no_cpu_baseline and world == 1:
         cores = host_cores()
-        n_syn = max(1, min(cores, 64))
+        n_syn = 3 * max(1, cores // 16)   # sized for 10-30 s of host work: a syndrome's 16 classes are the parallel jobs
         cpu_port_rate(1, 1, 2000, 1)  # warm the library
-        cpu_drop = 10   # sized for 10-30 s of host work
+        cpu_drop = DROPLETS
         rate, dt, steps = cpu_port_rate(n_syn, cpu_drop, samples, cores)
         rate1, dt1, _ = cpu_port_rate(1, 1, samples, 1)   # the one-core figure beside the all-core one (~3 s)
         line["cpu_baseline"] = {"value": rate, "unit": "steps/s", "cores": cores, "kind": "port", "value_1core": rate1,

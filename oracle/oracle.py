@@ -48,6 +48,14 @@ def lib():
         L.qo_stream_next.restype = C.c_double
         L.qo_stream_next.argtypes = [_p]
         L.qo_stream_free.argtypes = [_p]
+        L.qo_stream_philox.restype = _p
+        L.qo_stream_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
+        L.qo_stream_align.argtypes = [_p]
+        L.qo_stream_next_bit.argtypes = [_p]
+        L.qo_philox4x32_10.argtypes = [_p, _p, _p]
+        L.qo_nstab.argtypes = [C.c_int, C.c_int]
+        L.qo_stabilizer_by_index.argtypes = [C.c_int, C.c_int, C.c_int, _p, _p, _p]
+        L.qo_draw_stabilizer.argtypes = [C.c_int, C.c_int, _p, _p, _p, _p]
         L.qo_numba_pow.restype = C.c_double
         L.qo_numba_pow.argtypes = [C.c_double, C.c_int64]
         L.qo_apply_stabilizer.argtypes = [C.c_int, C.c_int, _u8p, C.c_int, C.c_int, C.c_int]
@@ -83,6 +91,9 @@ def lib():
                               C.c_int64, C.c_int64, _p, _p, _f64p, _p, _p]
         L.qo_stdc_batch.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, _u8p, C.c_double, C.c_double,
                                     C.c_int, C.c_int64, C.c_int64, C.c_uint32, C.c_int64, _f64p]
+        L.qo_stdc_class.restype = C.c_double
+        L.qo_stdc_class.argtypes = [C.c_int, C.c_int, C.c_int, _u8p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int64,
+                                    C.c_int64, C.c_uint32, C.c_int64]
         _lib = L
     return _lib
 
@@ -112,6 +123,12 @@ class Stream:
         return cls(lib().qo_stream_mt_pyseed(seed))
 
     @classmethod
+    def philox(cls, key, stream_id, tag=0, call0=0):
+        """Native stream of the product's kernels: Philox4x32-10 words of calls call0, call0 + 1, ... with
+        counter (call, tag, id lo, id hi) and the 64-bit key (oracle/qec_oracle.c, "Native draws")."""
+        return cls(lib().qo_stream_philox(key & 0xFFFFFFFFFFFFFFFF, stream_id, tag & 0xFFFFFFFF, call0 & 0xFFFFFFFF))
+
+    @classmethod
     def replay(cls, u):
         u = np.ascontiguousarray(u, dtype=np.float64)
         return cls(lib().qo_stream_replay(u.ctypes.data, u.size), keep=u)
@@ -131,11 +148,44 @@ class Stream:
     def next(self):
         return lib().qo_stream_next(self.h)
 
+    def next_bit(self):
+        return lib().qo_stream_next_bit(self.h)
+
+    def align(self):
+        lib().qo_stream_align(self.h)
+        return self
+
     def __del__(self):
         try:
             lib().qo_stream_free(self.h)
         except Exception:
             pass
+
+
+def philox4x32_10(ctr, key):
+    """One Philox4x32-10 call of the C oracle: ctr (4 words), key (2 words) -> 4 words."""
+    c = np.ascontiguousarray(ctr, np.uint32)
+    k = np.ascontiguousarray(key, np.uint32)
+    out = np.zeros(4, np.uint32)
+    lib().qo_philox4x32_10(c.ctypes.data, k.ctypes.data, out.ctypes.data)
+    return out
+
+
+def nstab(geom, L):
+    return lib().qo_nstab(geom, L)
+
+
+def stabilizer_by_index(geom, L, idx):
+    """(row, col, op) of stabilizer idx in the canonical numbering the native proposals use."""
+    r, c_, o = C.c_int(), C.c_int(), C.c_int()
+    lib().qo_stabilizer_by_index(geom, L, idx, C.byref(r), C.byref(c_), C.byref(o))
+    return r.value, c_.value, o.value
+
+
+def draw_stabilizer(geom, L, nb):
+    r, c_, o = C.c_int(), C.c_int(), C.c_int()
+    lib().qo_draw_stabilizer(geom, L, nb.h, C.byref(r), C.byref(c_), C.byref(o))
+    return r.value, c_.value, o.value
 
 
 def _flat(qm):
@@ -426,6 +476,24 @@ def stdc_batch(geom_code, geom_chain, L, qm, p_error, p_sampling, droplets, step
             L_.qo_stdc_batch(geom_code, geom_chain, L, hi - lo, q[lo:hi].reshape(-1), p_error, p_sampling,
                              droplets, steps, iters, seed, lo, out[lo:hi].reshape(-1))
 
+    if threads > S:
+        # fewer syndromes than threads: the unit of work is one (syndrome, class) -- same streams, same results
+        Z = np.zeros((S, neq(geom_code)))
+        jobs = [(s, e) for s in range(S) for e in range(neq(geom_code))]
+        lock = threading.Lock()
+
+        def class_runner():
+            while True:
+                with lock:
+                    if not jobs:
+                        return
+                    s, e = jobs.pop()
+                Z[s, e] = L_.qo_stdc_class(geom_code, geom_chain, L, q[s], e, p_error, p_sampling, droplets, steps, iters, seed, s)
+
+        ts = [threading.Thread(target=class_runner) for _ in range(min(threads, len(jobs)))]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        return Z / Z.sum(1, keepdims=True) * 100
     threads = max(1, min(threads, S))
     if threads == 1:
         work(0, S)

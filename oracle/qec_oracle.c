@@ -50,6 +50,13 @@ typedef struct qo_stream {
     int64_t drawn;
     double *record; /* optional log of every draw */
     int64_t record_cap;
+    /* native streams (see "Native draws" below): Philox4x32-10 words instead of MT19937 doubles */
+    int native;
+    uint32_t ph_key[2], ph_ctr[4]; /* ctr[0] = index of the next call */
+    uint32_t ph_buf[4];
+    int ph_have;       /* unread words left in ph_buf */
+    uint32_t bit_word; /* qo_stream_next_bit: the word being handed out bit by bit */
+    int bit_have;
 } qo_stream;
 
 static void mt_init_genrand(qo_stream *s, uint32_t seed)
@@ -123,6 +130,71 @@ QO_EXPORT qo_stream *qo_stream_replay(const double *u, int64_t n)
     return s;
 }
 
+/* ------------------------------------------------------------------ */
+/* Native draws.  The product's kernels do not run MT19937: every chain */
+/* owns a counter-based Philox4x32-10 stream (Salmon, Moraes, Dror,     */
+/* Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11; the      */
+/* round function and the constants below are the published ones, and   */
+/* tests/test_oracle_native.py checks them against the Random123 known- */
+/* answer vectors).  A native stream hands out the four 32-bit words of */
+/* call c, then of call c + 1, ...  The reference's algorithm consumes  */
+/* it through the same qo_stream_next(): a word w stands for the        */
+/* uniform w / 2^32, so "u < threshold" decisions are the reference's   */
+/* own comparisons.  Two things differ from the MT19937 schedule, both  */
+/* distribution-preserving, and both are restated here so that the      */
+/* oracle can be driven word for word like the device:                  */
+/*   * a stabilizer proposal takes ONE word: idx = floor(u * n_stab)    */
+/*     over the canonical numbering of qo_stabilizer_by_index (every    */
+/*     stabilizer equiprobable, as under the reference's 3 or 5 draws); */
+/*   * the rain takes one BIT per site (p = 0.5).                       */
+/* ------------------------------------------------------------------ */
+static void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+QO_EXPORT void qo_philox4x32_10(const uint32_t *ctr, const uint32_t *key, uint32_t *out) { philox4x32_10(ctr, key, out); }
+
+/* key = 64-bit seed; counter = (call index starting at call0, tag, id lo, id hi) */
+QO_EXPORT qo_stream *qo_stream_philox(uint64_t key, uint64_t id, uint32_t tag, uint32_t call0)
+{
+    qo_stream *s = (qo_stream *)calloc(1, sizeof(qo_stream));
+    s->native = 1;
+    s->ph_key[0] = (uint32_t)key; s->ph_key[1] = (uint32_t)(key >> 32);
+    s->ph_ctr[0] = call0; s->ph_ctr[1] = tag; s->ph_ctr[2] = (uint32_t)id; s->ph_ctr[3] = (uint32_t)(id >> 32);
+    return s;
+}
+
+static uint32_t philox_next_word(qo_stream *s)
+{
+    if (s->ph_have == 0) {
+        philox4x32_10(s->ph_ctr, s->ph_key, s->ph_buf);
+        s->ph_ctr[0]++;
+        s->ph_have = 4;
+    }
+    return s->ph_buf[4 - s->ph_have--];
+}
+
+/* drop the unread words of the current call: the next draw starts a new call */
+QO_EXPORT void qo_stream_align(qo_stream *s) { s->ph_have = 0; s->bit_have = 0; }
+
+/* one bit per draw, least significant bit of each word first (native rain) */
+QO_EXPORT int qo_stream_next_bit(qo_stream *s)
+{
+    if (s->bit_have == 0) { s->bit_word = philox_next_word(s); s->bit_have = 32; s->drawn++; }
+    int b = (int)(s->bit_word & 1u);
+    s->bit_word >>= 1;
+    s->bit_have--;
+    return b;
+}
+
 QO_EXPORT void qo_stream_record(qo_stream *s, double *buf, int64_t cap)
 {
     s->record = buf;
@@ -135,7 +207,9 @@ QO_EXPORT void qo_stream_free(qo_stream *s) { free(s); }
 QO_EXPORT double qo_stream_next(qo_stream *s)
 {
     double u;
-    if (s->replay) {
+    if (s->native) {
+        u = (double)philox_next_word(s) * (1.0 / 4294967296.0);
+    } else if (s->replay) {
         u = (s->drawn < s->replay_len) ? s->replay[s->drawn] : 0.0;
     } else {
         uint32_t a = mt_next32(s) >> 5, b = mt_next32(s) >> 6;
@@ -255,8 +329,34 @@ QO_EXPORT int qo_apply_stabilizer(int geom, int L, uint8_t *qm, int row, int col
  * toric_model.py:287-296 (3 draws), planar_model.py:342-352 (3 draws),
  * rotated_surface_model.py:395-408 and xzzx_model.py:439-452 (5 draws,
  * all five always consumed). */
+/* Canonical numbering of a code's stabilizers for native proposals (a product convention, not the reference's):
+ * toric  0 .. L^2-1: op 1 at (idx / L, idx % L); then op 3 likewise;
+ * planar 0 .. L(L-1)-1: op 1 at (idx / L, idx % L), rows 0 .. L-2; then op 3 at (rem / (L-1), rem % (L-1));
+ * rotated / XZZX 0 .. (L-1)^2-1: full plaquettes (op 1) at (idx / (L-1), idx % (L-1)); then the 2(L-1) half
+ * plaquettes (op 3) as (k, side) = (rem / 4, rem % 4) -- the (rows2, cols2) of rotated_surface_model.py:400-407. */
+QO_EXPORT int qo_nstab(int geom, int L)
+{
+    return geom == QO_TORIC ? 2 * L * L : geom == QO_PLANAR ? 2 * L * (L - 1) : L * L - 1;
+}
+
+QO_EXPORT void qo_stabilizer_by_index(int geom, int L, int idx, int *row, int *col, int *op)
+{
+    int nfull = geom == QO_TORIC ? L * L : geom == QO_PLANAR ? L * (L - 1) : (L - 1) * (L - 1);
+    int full = idx < nfull, rem = full ? idx : idx - nfull;
+    *op = full ? 1 : 3;
+    if (geom == QO_TORIC) { *row = rem / L; *col = rem % L; }
+    else if (geom == QO_PLANAR) { int w = full ? L : L - 1; *row = rem / w; *col = rem % w; }
+    else if (full) { *row = rem / (L - 1); *col = rem % (L - 1); }
+    else { *row = rem / 4; *col = rem % 4; }
+}
+
 QO_EXPORT void qo_draw_stabilizer(int geom, int L, qo_stream *nb, int *row, int *col, int *op)
 {
+    if (nb->native) {   /* one word: floor(w * n_stab / 2^32), exact in double */
+        int idx = (int)(qo_stream_next(nb) * qo_nstab(geom, L));
+        qo_stabilizer_by_index(geom, L, idx, row, col, op);
+        return;
+    }
     if (geom == QO_TORIC) {
         *row = (int)(qo_stream_next(nb) * L);
         *col = (int)(qo_stream_next(nb) * L);
@@ -441,7 +541,7 @@ QO_EXPORT void qo_rain(int geom, int L, uint8_t *qm, qo_stream *np_, double p)
     for (int o = 0; o < 2; o++)
         for (int r = 0; r < L; r++)
             for (int c = 0; c < L; c++) {
-                int hit = qo_stream_next(np_) < p;
+                int hit = np_->native ? qo_stream_next_bit(np_) : qo_stream_next(np_) < p;   /* native: p = 0.5 only */
                 if (geom == QO_PLANAR) {
                     if (o == 1 && r == L - 1) hit = 0;
                     if (o == 0 && c == L - 1) hit = 0;
@@ -1318,6 +1418,35 @@ QO_EXPORT void qo_ptdc_conv(int geom, int L, int n_eq, int Nc, const uint8_t *qm
 /* GIL).  One independent NB/NP stream pair per (syndrome, class,       */
 /* droplet), seeded from (seed, global indices).  bench.py times this.  */
 /* ------------------------------------------------------------------ */
+/* One (syndrome, class) of qo_stdc_batch: the unnormalised Z_E of class eq -- the CPU baseline's unit of parallel
+ * work when a step holds fewer syndromes than the host has threads.  Same streams as qo_stdc_batch. */
+QO_EXPORT double qo_stdc_class(int geom_code, int geom_chain, int L, const uint8_t *qm /* [n_sites] */, int eq,
+                               double p_error, double p_sampling, int droplets, int64_t steps, int64_t iters,
+                               uint32_t seed, int64_t s_index)
+{
+    int n = qo_nsites(geom_code, L), n_eq = qo_neq(geom_code);
+    double factor = (p_sampling / 3.0) / (1.0 - p_sampling), beta = -log((p_error / 3) / (1 - p_error));
+    uint8_t *init = (uint8_t *)malloc((size_t)n), *cur = (uint8_t *)malloc((size_t)n);
+    memcpy(init, qm, (size_t)n);
+    qo_to_class(geom_code, L, init, eq);
+    qo_set *all = qo_set_new(n);
+    for (int d = 0; d < droplets; d++) {
+        uint32_t id = (uint32_t)((s_index * n_eq + eq) * droplets + d);
+        qo_stream *nb = qo_stream_mt(seed ^ (2u * id + 1u) * 2654435761u);
+        qo_stream *np_ = qo_stream_mt(seed ^ (2u * id + 2u) * 2246822519u);
+        memcpy(cur, init, (size_t)n);
+        qo_set *s = qo_stdc_droplet(geom_code, geom_chain, L, cur, factor, steps, iters, 1, 0.0, nb, np_, NULL);
+        qo_set_update(all, s);
+        qo_set_free(s);
+        qo_stream_free(nb); qo_stream_free(np_);
+    }
+    double z = 0;
+    for (int64_t e = 0; e < all->cnt; e++) z += exp(-beta * all->val[3 * e]);
+    qo_set_free(all);
+    free(init); free(cur);
+    return z;
+}
+
 QO_EXPORT void qo_stdc_batch(int geom_code, int geom_chain, int L, int64_t S, const uint8_t *qm /* [S][n_sites] */,
                              double p_error, double p_sampling, int droplets, int64_t steps, int64_t iters,
                              uint32_t seed, int64_t s_offset, double *eqdistr /* [S][n_eq] */)

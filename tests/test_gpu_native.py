@@ -1,0 +1,241 @@
+"""GPU parity of the NATIVE (Philox) kernels against the oracle, bit for bit.
+
+Philox4x32-10 is counter based and keyed by the chain's global index, so the exact words a device chain consumes can be
+regenerated on the host: the oracle runs the reference's algorithm on those words (oracle/qec_oracle.c, "Native draws":
+one word per stabilizer proposal over the canonical numbering, one bit per rain site, u = word / 2^32 for every accept
+decision) and the device's distinct-chain histograms N(n), visit histograms m(n), accept counts and final lattices must
+EQUAL the oracle's -- at the BASELINE sizes (toric d=15 with 64 chains per class in the 1024-thread bucket-log
+instantiation, planar d=11, the 64-bit row-word kernels at d=21), not only at d=5.
+
+The second half compares native decoding with the oracle's independent MT19937 runs on the same syndromes: logical
+failure counts within the stated binomial confidence interval (north_star correctness (2))."""
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+RAIN_TAG = 0x80000000
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from mcmc_qec_toric_rl_b200 import _lib
+    return _lib.default_context(0)
+
+
+def rand_lattice(rng, g, L, p=0.15):
+    shape = (2, L, L) if g in (O.TORIC, O.PLANAR) else (L, L)
+    q = ((rng.random(shape) < p) * rng.integers(1, 4, shape)).astype(np.uint8)
+    if g == O.PLANAR:
+        q[1, -1, :] = 0
+        q[1, :, -1] = 0
+    return q
+
+
+def chain_streams(seed, s, n_eq, droplets):
+    """Streams of the chains of syndrome s: chain id = (s * n_eq + eq) * droplets + d (qecmc_stdc_fast.cuh: gchain)."""
+    ids = [(s * n_eq + eq) * droplets + d for eq in range(n_eq) for d in range(droplets)]
+    return [O.Stream.philox(seed, i, 0) for i in ids], [O.Stream.philox(seed, i, RAIN_TAG) for i in ids]
+
+
+def parallel(fn, items, threads=16):
+    """run fn over items on host threads (the oracle's ctypes calls drop the GIL)"""
+    out, lock, todo = {}, threading.Lock(), list(items)
+
+    def work():
+        while True:
+            with lock:
+                if not todo:
+                    return
+                it = todo.pop()
+            out[it] = fn(it)
+
+    ts = [threading.Thread(target=work) for _ in range(min(threads, len(todo)))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    return out
+
+
+def oracle_stdc(g, gc, L, qs, s, p_error, p_sampling, droplets, steps, seed, randomize=True, conv_mult=0.0):
+    n_eq = O.neq(g)
+    nb, np_ = chain_streams(seed, s, n_eq, droplets)
+    return O.stdc(g, gc, L, O.all_classes(g, L, qs[s]), p_error, p_sampling, droplets, steps, nb, np_, randomize=randomize,
+                  conv_mult=conv_mult, want_hist=True)
+
+
+# (geometry, L, syndromes, droplets, samples, syndromes checked against the oracle)
+STDC_CASES = [
+    # the headline instantiation: toric d=15, 16 classes x 64 chains, one 1024-thread CTA per SM (148 syndromes fill the GPU)
+    pytest.param(O.TORIC, 15, 148, 64, 2000, (0, 1, 63, 64, 100, 147), id="toric15-64chains-full-gpu"),
+    pytest.param(O.TORIC, 15, 3, 64, 2500, (0, 1, 2), id="toric15-64chains-small-batch"),
+    pytest.param(O.PLANAR, 11, 40, 64, 2000, (0, 17, 39), id="planar11-64chains"),
+    pytest.param(O.PLANAR, 21, 6, 16, 2000, (0, 3, 5), id="planar21-u64-words"),
+    pytest.param(O.TORIC, 5, 7, 10, 3125, (0, 3, 6), id="toric5-reference-defaults"),
+    pytest.param(O.PLANAR, 15, 5, 16, 3000, (0, 4), id="planar15"),
+    pytest.param(O.TORIC, 9, 4, 3, 4000, (0, 1, 2, 3), id="toric9-3chains"),
+]
+
+
+@pytest.mark.parametrize("g,L,S,droplets,steps,check", STDC_CASES)
+def test_native_stdc_equals_oracle_on_the_same_words(ctx, g, L, S, droplets, steps, check):
+    """STDC (decoders.py:236-322), native draws: N(n) per (syndrome, class) equal to the oracle's, distributions to 1e-9."""
+    rng = np.random.default_rng(7000 + 31 * g + L)
+    p_error, p_sampling, seed = 0.15 if L >= 11 else 0.1, 0.25, 0xC0FFEE + L
+    qs = [rand_lattice(rng, g, L, p_error) for _ in range(S)]
+    qm = np.stack([q.reshape(-1) for q in qs])
+    out, st, hist = ctx.stdc(g, g, L, qm, p_error, p_sampling, droplets, steps, seed=seed, want_hist=True)
+    assert st["metropolis_steps"] == S * O.neq(g) * droplets * steps * 5
+    if g in (O.TORIC, O.PLANAR) and L <= 16:
+        assert st["table_slots"] == -1          # bucket logs written by stdc_fast_kernel<.., BLOG = true>
+    want = parallel(lambda s: oracle_stdc(g, g, L, qs, s, p_error, p_sampling, droplets, steps, seed), check)
+    for s in check:
+        w_out, w_distinct, w_hist = want[s]
+        assert np.array_equal(hist[s].astype(np.int64), w_hist), f"N(n) differs from the oracle at syndrome {s}"
+        assert np.allclose(out[s], w_out, rtol=1e-9, atol=1e-300)
+        assert w_distinct.sum() > O.neq(g) * droplets       # the chains moved
+
+
+@pytest.mark.parametrize("mode", [4, 2, 0])
+def test_native_stdc_other_insert_modes_equal_oracle(ctx, mode):
+    """The per-chain-log, deferred and synchronous HBM-set paths against the oracle (not against each other)."""
+    g, L, S, droplets, steps, seed = O.TORIC, 7, 5, 16, 3000, 77
+    rng = np.random.default_rng(12)
+    qs = [rand_lattice(rng, g, L, 0.1) for _ in range(S)]
+    qm = np.stack([q.reshape(-1) for q in qs])
+    ctx.debug_set("insert_mode", mode)
+    try:
+        out, st, hist = ctx.stdc(g, g, L, qm, 0.1, 0.25, droplets, steps, seed=seed, want_hist=True)
+    finally:
+        ctx.debug_set("insert_mode", -1)
+    for s in (0, 4):
+        w_out, _, w_hist = oracle_stdc(g, g, L, qs, s, 0.1, 0.25, droplets, steps, seed)
+        assert np.array_equal(hist[s].astype(np.int64), w_hist)
+        assert np.allclose(out[s], w_out, rtol=1e-9)
+
+
+@pytest.mark.parametrize("g,L,droplets,conv", [(O.TORIC, 5, 1, 2.0), (O.TORIC, 7, 3, 1.5), (O.PLANAR, 7, 4, 2.0)])
+def test_native_stdc_early_stop_equals_oracle(ctx, g, L, droplets, conv):
+    """conv_mult != 0 (decoders.py:257-263) on native words: same stopping sample per chain, hence the same N(n) and
+    the same number of Metropolis steps."""
+    S, steps, seed = 3, 4000, 5150
+    rng = np.random.default_rng(40 + L)
+    qs = [rand_lattice(rng, g, L, 0.1) for _ in range(S)]
+    qm = np.stack([q.reshape(-1) for q in qs])
+    out, st, hist = ctx.stdc(g, g, L, qm, 0.1, 0.25, droplets, steps, seed=seed, conv_mult=conv, want_hist=True)
+    assert st["metropolis_steps"] < S * O.neq(g) * droplets * steps * 5      # somebody stopped early
+    for s in range(S):
+        w_out, _, w_hist = oracle_stdc(g, g, L, qs, s, 0.1, 0.25, droplets, steps, seed, conv_mult=conv)
+        assert np.array_equal(hist[s].astype(np.int64), w_hist)
+        assert np.allclose(out[s], w_out, rtol=1e-9)
+
+
+@pytest.mark.parametrize("g,L,S,droplets,steps", [(O.TORIC, 15, 148, 64, 1500), (O.PLANAR, 9, 6, 10, 3000), (O.PLANAR, 17, 4, 8, 2000)])
+def test_native_strc_equals_oracle_on_the_same_words(ctx, g, L, S, droplets, steps):
+    """STRC (decoders.py:745-949): m(n) and the (shortest, next shortest, distinct counts) bookkeeping, bit for bit."""
+    rng = np.random.default_rng(8100 + L)
+    p_error, seed = 0.12, 424242 + L
+    qs = [rand_lattice(rng, g, L, p_error) for _ in range(S)]
+    qm = np.stack([q.reshape(-1) for q in qs])
+    out, st, mh, info = ctx.strc(g, g, L, qm, p_error, 0.25, droplets, steps, seed=seed, want_hist=True)
+    n_eq = O.neq(g)
+    check = sorted({0, S // 2, S - 1})
+
+    def run(s):
+        nb, np_ = chain_streams(seed, s, n_eq, droplets)
+        return O.strc(g, g, L, O.all_classes(g, L, qs[s]), p_error, 0.25, droplets, steps, nb, np_, want_hist=True)
+
+    want = parallel(run, check)
+    for s in check:
+        w_out, w_mh, w_info = want[s]
+        assert np.array_equal(mh[s].astype(np.int64), w_mh), f"m(n) differs at syndrome {s}"
+        assert np.array_equal(info[s].astype(np.int64), w_info)
+        assert np.allclose(out[s], w_out, rtol=1e-9)
+
+
+def test_native_single_temp_equals_oracle(ctx):
+    """single_temp (decoders.py:108-135): the mean chain length per class from the same words."""
+    g, L, S, max_iters, seed = O.TORIC, 9, 20, 3000, 99
+    rng = np.random.default_rng(5)
+    qs = [rand_lattice(rng, g, L, 0.1) for _ in range(S)]
+    qm = np.stack([q.reshape(-1) for q in qs])
+    out, st = ctx.single_temp(g, g, L, qm, 0.12, max_iters, seed=seed)
+    for s in (0, 9, 19):
+        nb = [O.Stream.philox(seed, s * 16 + eq, 0) for eq in range(16)]
+        want = O.single_temp(g, g, L, O.all_classes(g, L, qs[s]), 0.12, max_iters, nb)
+        assert np.array_equal(out[s], want)          # sums of integers divided once: exact
+
+
+@pytest.mark.parametrize("g,L", [(O.TORIC, 15), (O.PLANAR, 21), (O.ROTATED, 25), (O.XZZX, 21), (O.ROTATED, 7)])
+def test_native_chain_update_equals_oracle(ctx, g, L):
+    """Chain.update_chain_fast (mcmc.py:45-46, 152-160) with native draws: final lattices and accept counts."""
+    chains, iters, p, seed = 300, 5001, 0.2, 31337
+    rng = np.random.default_rng(60 + L)
+    q0 = np.stack([rand_lattice(rng, g, L, 0.12).reshape(-1) for _ in range(chains)])
+    qm = q0.copy()
+    st = ctx.chain_update(g, L, qm, p, iters, seed=seed)
+    factor, acc = (p / 3.0) / (1.0 - p), 0
+    for ch in (0, 1, 150, 299):
+        want, dE, a = O.update_chain_fast(g, L, q0[ch], factor, iters, O.Stream.philox(seed, ch, 0), trace=True)
+        assert np.array_equal(qm[ch], np.asarray(want).reshape(-1)), ch
+    assert 0 < st["accepted"] < chains * iters
+    # a second call continues the streams where the first stopped (stream_offset)
+    qa, qb = q0[:4].copy(), q0[:4].copy()
+    ctx.chain_update(g, L, qa, p, 1000, seed=seed)
+    ctx.chain_update(g, L, qa, p, 1001, seed=seed, stream_offset=1000)
+    ctx.chain_update(g, L, qb, p, 2001, seed=seed)
+    assert np.array_equal(qa, qb)
+
+
+@pytest.mark.parametrize("g,L,xyz", [(O.PLANAR, 7, True), (O.PLANAR, 9, False), (O.ROTATED, 7, True)])
+def test_native_general_noise_equals_oracle(ctx, g, L, xyz):
+    """STDC_general_noise(_shortest) (decoders.py:325-508) on native words: distinct counts and both distributions."""
+    S, droplets, steps, seed = 3, 4, 3000, 2718
+    rng = np.random.default_rng(3 + L)
+    qs = [rand_lattice(rng, g, L, 0.1) for _ in range(S)]
+    qm = np.stack([q.reshape(-1) for q in qs])
+    p_xyz = np.array([0.02, 0.03, 0.07])
+    p_sampling = np.array([0.06, 0.05, 0.09]) if xyz else 0.25
+    out, out_s, distinct, st = ctx.stdc_general_noise(g, g, L, qm, p_xyz, p_sampling, droplets, steps, seed=seed)
+    n_eq = O.neq(g)
+    for s in range(S):
+        nb = [O.Stream.philox(seed, (s * n_eq + eq) * droplets + d, 0) for eq in range(n_eq) for d in range(droplets)]
+        w, w_s, w_d = O.stdc_general_noise(g, g, L, O.all_classes(g, L, qs[s]), p_xyz, p_sampling, droplets, steps, nb)
+        assert np.array_equal(distinct[s], w_d)
+        assert np.allclose(out[s], w, rtol=1e-9) and np.allclose(out_s[s], w_s, rtol=1e-9)
+
+
+# ------------------------------------------------------------------ native vs the oracle's own MT19937 runs
+def _binomial_gap_ok(f_a, f_b, n, z=3.0):
+    """two failure counts out of n trials each (same syndromes, independent randomness): |difference| within z sigma of
+    the pooled binomial, plus one count for discreteness"""
+    p_hat = (f_a + f_b) / (2.0 * n)
+    sigma = np.sqrt(2.0 * p_hat * (1.0 - p_hat) * n)
+    return abs(int(f_a) - int(f_b)) <= z * sigma + 1, sigma
+
+
+def test_toric_d15_failure_rate_within_binomial_ci_of_the_oracle(ctx):
+    """BASELINE config 1 (toric d=15, p = 0.15, STDC, p_sampling 0.25), 200 syndromes: the native decode and the oracle's
+    MT19937 decode of the SAME syndromes (droplets 16, 5000 samples per chain) agree on the logical failure count within 3
+    sigma of the pooled binomial (stated CI), pick the same class on >= 85 % of the syndromes, and their class
+    distributions differ by less than 4 percentage points on average.  (Both decoders disagree with each other exactly
+    where a syndrome is ambiguous -- at p = 0.15 the toric code is close to threshold.)"""
+    g, L, S, droplets, steps = O.TORIC, 15, 200, 16, 5000
+    rng = np.random.default_rng(20251)
+    qs, truth = [], []
+    for _ in range(S):
+        q = rand_lattice(rng, g, L, 0.15)
+        truth.append(O.eq_class(g, L, q))
+        q2, _ = O.apply_random_logical(g, L, q, O.Stream.mt(int(rng.integers(1 << 30))))    # generate_data.py:131
+        qs.append(np.asarray(q2, np.uint8).reshape(-1))
+    qm, truth = np.stack(qs), np.array(truth)
+    gpu, st = ctx.stdc(g, g, L, qm, 0.15, 0.25, droplets, steps, seed=5)
+    ref = O.stdc_batch(g, g, L, qm, 0.15, 0.25, droplets, steps, seed=17, threads=16)
+    f_gpu, f_ref = int((gpu.argmax(1) != truth).sum()), int((ref.argmax(1) != truth).sum())
+    ok, sigma = _binomial_gap_ok(f_gpu, f_ref, S)
+    assert ok, (f_gpu, f_ref, sigma)
+    assert 0 < f_gpu < 0.5 * S and 0 < f_ref < 0.5 * S, (f_gpu, f_ref)
+    assert (gpu.argmax(1) == ref.argmax(1)).mean() >= 0.85
+    assert np.abs(gpu - ref).mean() < 4.0
