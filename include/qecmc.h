@@ -78,7 +78,10 @@ int         qecmc_set_table_budget(qecmc_ctx *ctx, int64_t bytes);
  *   "force_wide"   1: 64-bit row words also for L <= 16
  *   "insert_mode"  distinct-chain accounting of STDC / STRC: 0 synchronous HBM set, 2 deferred HBM set, 4 per-chain
  *                  key logs, 6 bucket logs
- *   "serial_sweep" 1: native ladders walk the swap sweep pair by pair, like replay does
+ *   "serial_sweep" 1: native ladders walk the swap sweep pair by pair, like replay does (warp-per-ladder kernel)
+ *   "ladder_kernel" 1: native ladders run on the warp-per-ladder kernel replay uses, not on the rung-major one
+ *   "pt_grid"      cap on the rung-major kernel's grid, so that ladders queue up behind few CTAs
+ *   "pt_lt"        lanes sharing one top-rung replica in the rung-major tempering kernel (2, 4, 8, ...)
  * Unknown keys return QECMC_ERR_ARG. */
 int         qecmc_debug_set(qecmc_ctx *ctx, const char *key, int64_t value);
 

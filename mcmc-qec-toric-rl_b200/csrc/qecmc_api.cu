@@ -80,6 +80,9 @@ extern "C" int qecmc_debug_set(qecmc_ctx *c, const char *key, int64_t value)
     if (!strcmp(key, "force_wide")) c->dbg_force_wide = value > 0;
     else if (!strcmp(key, "insert_mode")) c->dbg_insert_mode = value < 0 ? -1 : (int)value;
     else if (!strcmp(key, "serial_sweep")) c->dbg_serial_sweep = value > 0;
+    else if (!strcmp(key, "pt_lt")) c->dbg_pt_lt = value > 0 ? (int)value : 0;
+    else if (!strcmp(key, "pt_grid")) c->dbg_pt_grid = value > 0 ? (int)value : 0;
+    else if (!strcmp(key, "ladder_kernel")) c->dbg_ladder_kernel = value > 0 ? (int)value : 0;
     else return set_err(QECMC_ERR_ARG, "unknown debug key '%s'", key);
     return 0;
 }

@@ -73,12 +73,12 @@ struct ScopedDevBuf : DevBuf {
 // device buffers of the tempering-ladder drivers (qecmc_ladder.cu); they live in the context so that repeated calls
 // reuse them
 struct LadderDev {
-    DevBuf log_hash, short_v, short_n, short_u;
+    DevBuf log_hash, short_v, short_n, short_u, pw, queue;
     DevBuf thr_d, thr_u, thr_top_d, diff, wtab, lat, lat_out, flags, neff, tops0, snap_lat, snap_flags, snap_tops0, hist, eqc,
         info, pct, status, u_nb, u_py, qm, bytes_out, Zd, dist;
     ~LadderDev()
     {
-        for (DevBuf *b : {&log_hash, &short_v, &short_n, &short_u, &thr_d, &thr_u, &thr_top_d, &diff, &wtab, &lat, &lat_out, &flags, &neff, &tops0, &snap_lat,
+        for (DevBuf *b : {&log_hash, &short_v, &short_n, &short_u, &pw, &queue, &thr_d, &thr_u, &thr_top_d, &diff, &wtab, &lat, &lat_out, &flags, &neff, &tops0, &snap_lat,
                           &snap_flags, &snap_tops0, &hist, &eqc, &info, &pct, &status, &u_nb, &u_py, &qm, &bytes_out, &Zd, &dist})
             b->release();
     }
@@ -104,7 +104,21 @@ struct qecmc_ctx {
     int64_t launches = 0;
     // qecmc_debug_set: test switches between code paths that must agree (never read from the environment)
     int dbg_force_wide = 0, dbg_insert_mode = -1, dbg_serial_sweep = 0;
+    int dbg_pt_lt = 0;          // lanes per top-rung replica in the rung-major tempering kernel (0: default)
+    int dbg_pt_grid = 0;        // cap on the rung-major kernel's grid (tests: makes ladders queue behind few CTAs)
+    int dbg_ladder_kernel = 0;  // 1: native ladders on the warp-per-ladder (replay) kernel instead of the rung-major one
 };
+
+// rung-major tempering kernel (qecmc_pt.cu): CTA shape chosen for a ladder configuration
+namespace qecmc { struct LadderParams; }
+struct PtPlan {
+    int NLC = 0, T = 0, lt = 0;      // ladders per CTA, threads per CTA, lanes per top-rung replica
+    size_t smem = 0;
+    int blocks_per_sm = 0, max_grid = 0;
+};
+int qecmc_pt_plan(qecmc_ctx *c, const qecmc::LadderParams &lp, PtPlan *out);
+int qecmc_pt_launch(qecmc_ctx *c, const qecmc::LadderParams &lp, const PtPlan &pl, int grid, uint32_t step0, void *hist,
+                    int64_t hist_stride);
 
 
 using namespace qecmc;

@@ -206,6 +206,26 @@ int launch_ladder(qecmc_ctx *c, LadderParams &p, bool replay)
     }
 }
 
+// what launch_ladder_g / launch_ladder_gw prepare per geometry, for the rung-major kernel: class changes of the logical
+// operators and (two-layer depolarizing ladders) the stabilizer descriptors
+int prepare_pt(qecmc_ctx *c, LadderParams &p)
+{
+    const bool wide = p.g.L > 16, weighted = p.kind != LK_DEPOL;
+    switch (p.g.geom) {
+    case TORIC:
+        class_deltas<TORIC>(p.g, p.cls_delta);
+        if (!weighted) { if (wide) QTRY((build_stab_desc<TORIC, uint64_t>(c, p.g, &p.desc2))); else QTRY((build_stab_desc<TORIC, uint32_t>(c, p.g, &p.desc2))); }
+        break;
+    case PLANAR:
+        class_deltas<PLANAR>(p.g, p.cls_delta);
+        if (!weighted) { if (wide) QTRY((build_stab_desc<PLANAR, uint64_t>(c, p.g, &p.desc2))); else QTRY((build_stab_desc<PLANAR, uint32_t>(c, p.g, &p.desc2))); }
+        break;
+    case ROTATED: class_deltas<ROTATED>(p.g, p.cls_delta); break;
+    default: class_deltas<XZZX>(p.g, p.cls_delta); break;
+    }
+    return 0;
+}
+
 // fills the configuration-only part of LadderParams and uploads the tables
 int setup_ladder(qecmc_ctx *c, const qecmc_ladder_cfg *cfg, const Geo &g, LadderDev &d, LadderParams &p)
 {
@@ -216,6 +236,12 @@ int setup_ladder(qecmc_ctx *c, const qecmc_ladder_cfg *cfg, const Geo &g, Ladder
     QTRY(upload(c, d.thr_u, t.thr_u));
     QTRY(upload(c, d.thr_top_d, t.thr_top_d));
     QTRY(upload(c, d.diff, t.diff));
+    {   // swap-sweep power table of the rung-major kernel: diff^k by numba's square-and-multiply (mcmc.py:149), k = 0 .. 2K
+        std::vector<double> pw((size_t)(cfg->Nc > 1 ? cfg->Nc - 1 : 1) * (2 * QECMC_PW_K + 1), 0.0);
+        for (int i = 0; i + 1 < cfg->Nc; i++)
+            for (int k = 0; k <= 2 * QECMC_PW_K; k++) pw[(size_t)i * (2 * QECMC_PW_K + 1) + k] = numba_pow(t.diff[i], k);
+        QTRY(upload(c, d.pw, pw));
+    }
     QTRY(upload(c, d.wtab, t.wtab));
     QTRY(d.status.ensure(sizeof(int)));
     CUDA_OK(cudaMemsetAsync(d.status.p, 0, sizeof(int), c->stream));
@@ -233,6 +259,7 @@ int setup_ladder(qecmc_ctx *c, const qecmc_ladder_cfg *cfg, const Geo &g, Ladder
     p.thr_u = (const uint32_t *)d.thr_u.p;
     p.thr_top_d = (const double *)d.thr_top_d.p;
     p.diff = (const double *)d.diff.p;
+    p.pw = (const double *)d.pw.p;
     p.wtab = (const double *)d.wtab.p;
     p.alpha = cfg->param_b;
     p.seed = cfg->seed;
@@ -385,7 +412,21 @@ extern "C" int qecmc_ladder_run(qecmc_ctx *c, const qecmc_ladder_cfg *cfg, const
         p.snap_tops0 = (long long *)d.snap_tops0.p;
     }
     CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
-    int rc = launch_ladder(c, p, cfg->u_nb != nullptr);
+    // native draws without per-step snapshots run on the rung-major kernel (qecmc_pt.cuh); replay keeps the reference's
+    // draw order on the warp-per-ladder kernel
+    const bool use_pt = !cfg->u_nb && !io->snap_states && steps > 0 && !c->dbg_ladder_kernel;
+    int rc;
+    if (use_pt) {
+        PtPlan pl;
+        rc = prepare_pt(c, p);
+        if (rc == 0) rc = qecmc_pt_plan(c, p, &pl);
+        if (rc == 0) {
+            const int64_t want = (S + pl.NLC - 1) / pl.NLC;
+            rc = qecmc_pt_launch(c, p, pl, (int)(want < pl.max_grid ? want : pl.max_grid), 0u, nullptr, 0);
+        }
+    } else {
+        rc = launch_ladder(c, p, cfg->u_nb != nullptr);
+    }
     if (rc == 0) rc = cudaEventRecord(c->ev[1], c->stream) == cudaSuccess ? 0 : set_err(QECMC_ERR_CUDA, "cudaEventRecord failed");
     if (rc == 0) rc = check_status(c, d);
     cudaStreamSynchronize(c->stream);
@@ -473,7 +514,10 @@ static int pteq_once(qecmc_ctx *c, const qecmc_pteq_cfg *cfg, const uint8_t *qm,
         scap = next_pow2((uint64_t)cfg->steps + (uint64_t)cfg->steps / 4 + 1);
         if (scap < 1024) scap = 1024;
     }
-    if (cfg->use_conv || shortest) {
+    // native draws run on the rung-major kernel (qecmc_pt.cuh): one launch for the whole batch, ladders handed to the CTAs
+    // from a queue, the n_err history sized by the RESIDENT ladders (2 bytes per Ladder.step, 4 for alpha ladders)
+    const bool use_pt = !lc->u_nb && !shortest && !c->dbg_ladder_kernel;
+    if (!use_pt && (cfg->use_conv || shortest)) {
         size_t fr = 0;
         QTRY(free_device_bytes(c, &fr));
         // what the context already holds for these two purposes counts as available (as in the STDC / PTDC drivers)
@@ -522,7 +566,33 @@ static int pteq_once(qecmc_ctx *c, const qecmc_pteq_cfg *cfg, const uint8_t *qm,
     CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
     int64_t waves = 0;
     const double *u_nb0 = p.u_nb, *u_py0 = p.u_py;
-    for (int64_t s0 = 0; s0 < S; s0 += wave, waves++) {
+    if (use_pt) {
+        QTRY(prepare_pt(c, p));
+        PtPlan pl;
+        QTRY(qecmc_pt_plan(c, p, &pl));
+        int64_t grid = (S + pl.NLC - 1) / pl.NLC;
+        if (grid > pl.max_grid) grid = pl.max_grid;
+        const int64_t hb = lc->kind == LK_ALPHA ? 4 : 2;
+        if (cfg->use_conv) {
+            size_t fr = 0;
+            QTRY(free_device_bytes(c, &fr));
+            const int64_t budget = c->table_budget ? c->table_budget : (int64_t)((double)(fr + d.hist.cap) * 0.8);
+            const int64_t per_cta = (int64_t)pl.NLC * cfg->steps * hb;
+            if (grid * per_cta > budget) grid = budget / per_cta;   // fewer resident ladders: the queue feeds them all the same
+            if (grid < 1) return set_err(QECMC_ERR_NOMEM, "the n_err history of %d resident ladders needs %lld bytes, budget is %lld",
+                                         pl.NLC, (long long)per_cta, (long long)budget);
+            QTRY(d.hist.ensure((size_t)(grid * per_cta)));
+        }
+        p.n_ladders = S;
+        p.ladder_offset = 0;
+        p.lat_in = d.lat.p;
+        p.eq_counts = (long long *)d.eqc.p;
+        p.info = (long long *)d.info.p;
+        p.percent = d_pct;
+        QTRY(qecmc_pt_launch(c, p, pl, (int)grid, 0u, cfg->use_conv ? d.hist.p : nullptr, cfg->steps));
+        waves = 1;
+    }
+    for (int64_t s0 = 0; !use_pt && s0 < S; s0 += wave, waves++) {
         int64_t sw = S - s0 < wave ? S - s0 : wave;
         p.n_ladders = sw;
         p.ladder_offset = s0;

@@ -50,6 +50,7 @@ struct LadderParams {
     const double *thr_top_d;// [8L+1]   kind 0 top rung: pow(factor_top, dE), dE = -4L..4L (a toric logical
                             //          acts on both layers: up to 2(2L-1) qubits)
     const double *diff;     // [Nc-1]   p_diff (kind 0, 2) or pz_tilde[i]/pz_tilde[i+1] (kind 1)
+    const double *pw;       // [Nc-1][2 QECMC_PW_K + 1] diff^k, k = 0 .. 2 QECMC_PW_K (rung-major kernel; numba's square-and-multiply)
     double alpha;           // kind 1
     const double *wtab;     // kinds 1, 2: [Nc][4][nsites+1] = px^k, py^k, pz^k, q0^(L*L-k)
     uint64_t seed;

@@ -50,6 +50,8 @@ def lib():
         L.qo_stream_free.argtypes = [_p]
         L.qo_stream_philox.restype = _p
         L.qo_stream_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
+        L.qo_stream_ladder_native.restype = _p
+        L.qo_stream_ladder_native.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
         L.qo_stream_align.argtypes = [_p]
         L.qo_stream_next_bit.argtypes = [_p]
         L.qo_philox4x32_10.argtypes = [_p, _p, _p]
@@ -127,6 +129,12 @@ class Stream:
         """Native stream of the product's kernels: Philox4x32-10 words of calls call0, call0 + 1, ... with
         counter (call, tag, id lo, id hi) and the 64-bit key (oracle/qec_oracle.c, "Native draws")."""
         return cls(lib().qo_stream_philox(key & 0xFFFFFFFFFFFFFFFF, stream_id, tag & 0xFFFFFFFF, call0 & 0xFFFFFFFF))
+
+    @classmethod
+    def ladder_native(cls, key, ladder_id, step0=0):
+        """Native words of one tempering ladder, addressed by (Ladder.step, purpose, rung, iteration): pass it as BOTH the
+        nb and the py stream of Ladder.step / pteq / ptxc / stdc_alpha (oracle/qec_oracle.c, ladder_step_native)."""
+        return cls(lib().qo_stream_ladder_native(key & 0xFFFFFFFFFFFFFFFF, ladder_id, step0 & 0xFFFFFFFF))
 
     @classmethod
     def replay(cls, u):

@@ -57,6 +57,7 @@ typedef struct qo_stream {
     int ph_have;       /* unread words left in ph_buf */
     uint32_t bit_word; /* qo_stream_next_bit: the word being handed out bit by bit */
     int bit_have;
+    uint32_t lad_step; /* native == 2: index of the next Ladder.step of this ladder (see ladder_step_native) */
 } qo_stream;
 
 static void mt_init_genrand(qo_stream *s, uint32_t seed)
@@ -180,6 +181,17 @@ static uint32_t philox_next_word(qo_stream *s)
         s->ph_have = 4;
     }
     return s->ph_buf[4 - s->ph_have--];
+}
+
+/* A LADDER-native stream (native == 2) carries no position: ladder_step_native addresses every word it needs by
+ * (Ladder.step index, purpose, rung, iteration), so the words do not depend on how many draws were made before.
+ * key = the call's seed, id = the ladder's global index, step0 = Ladder.step calls already made on this ladder. */
+QO_EXPORT qo_stream *qo_stream_ladder_native(uint64_t key, uint64_t id, uint32_t step0)
+{
+    qo_stream *s = qo_stream_philox(key, id, 0, 0);
+    s->native = 2;
+    s->lad_step = step0;
+    return s;
 }
 
 /* drop the unread words of the current call: the next draw starts a new call */
@@ -671,6 +683,123 @@ QO_EXPORT void qo_update_chain_weighted(int kind, int geom, int L, uint8_t *qm, 
 }
 
 /* ------------------------------------------------------------------ */
+/* Ladder.step on native words.  The algorithm is the reference's        */
+/* (Chain / Chain_alpha / Chain_biased .update_chain on every rung, then */
+/* the top-to-bottom swap sweep, mcmc.py:19-43,94-103, mcmc_alpha.py:    */
+/* 27-70,117-137, mcmc_biased.py:21-59,107-124); only where each uniform */
+/* comes from differs.  Word k of Philox call (c0, tag) under the         */
+/* ladder's key and id, tag = purpose << 8 | rung:                        */
+/*   purpose 0, c0 = s * ceil(iters / 2) + it / 2: stabilizer proposal    */
+/*     (word 2 (it & 1)) and accept draw (word 2 (it & 1) + 1) of         */
+/*     iteration `it` of the rung in Ladder.step number s;                */
+/*   purpose 1, c0 = s * iters + it (top rung, p_logical != 0): word 0    */
+/*     decides logical vs stabilizer (u < p_logical), word 1 is the       */
+/*     accept draw of a logical move, word 2 carries the operators        */
+/*     (bits 31:30 layer 0, bits 29:28 the toric code's layer 1);         */
+/*   purpose 2, same c0: words 0..3 = X_pos, Z_pos of layer 0, then of    */
+/*     layer 1 (floor(u L)); as in the reference a position is only       */
+/*     drawn for operator 1 / 2 (X_pos) and 3 / 2 (Z_pos), else it is 0;  */
+/*   purpose 3, c0 = s: word 0 is the swap draw of pair (rung, rung + 1). */
+/* Weighted chains accept iff u * pb < pn (the product's form of          */
+/* u < pn / pb: one rounding instead of a division), pb frozen per block. */
+/* ------------------------------------------------------------------ */
+static void lad_words(const qo_stream *st, uint32_t c0, int purpose, int rung, uint32_t w[4])
+{
+    uint32_t ctr[4] = {c0, (uint32_t)(purpose << 8 | rung), st->ph_ctr[2], st->ph_ctr[3]};
+    philox4x32_10(ctr, st->ph_key, w);
+}
+
+static void ladder_step_native(int kind, int geom, int L, int Nc, uint8_t *qm, const double *ladder,
+                               const double *diff, double param_b, double p_logical, int32_t *flags,
+                               double *n_eff, int64_t *tops0, int64_t iters, qo_stream *st)
+{
+    const int n = qo_nsites(geom, L), nstab = qo_nstab(geom, L);
+    const uint32_t s = st->lad_step++, H = (uint32_t)((iters + 1) / 2);
+    const double U = 1.0 / 4294967296.0, num = (double)L * (double)L;
+    uint8_t *save = (uint8_t *)malloc((size_t)n);
+    for (int i = 0; i < Nc; i++) {
+        uint8_t *q = qm + (size_t)i * n;
+        const int is_top = (i == Nc - 1) && p_logical != 0;
+        double factor = 0, px = 0, py_ = 0, pz = 0, q0 = 0, pb = 0, p = ladder[i];
+        int64_t c[3];
+        if (kind == 0) {
+            factor = (p / 3.0) / (1.0 - p);
+        } else {
+            if (kind == 1) {
+                double pz_tilde = ladder[i], p_tilde = pz_tilde + 2 * pow(pz_tilde, param_b), pp = p_tilde / (1 + p_tilde);
+                pz = pz_tilde * (1 - pp);
+                px = py_ = pow(pz_tilde, param_b) * (1 - pp);
+            } else {
+                pz = p * param_b / (param_b + 1);
+                px = py_ = p / (2 * (param_b + 1));
+            }
+            q0 = 1 - px - py_ - pz;
+            qo_count_xyz(q, n, c);
+            pb = pow(px, (double)c[0]) * pow(py_, (double)c[1]) * pow(pz, (double)c[2]) * pow(q0, num - (double)c[0] - (double)c[1] - (double)c[2]);
+        }
+        for (int64_t it = 0; it < iters; it++) {
+            uint32_t w[4], t[4], pos[4];
+            lad_words(st, s * H + (uint32_t)(it >> 1), 0, i, w);
+            double u_acc = (double)w[2 * (it & 1) + 1] * U;
+            int logical = 0, d;
+            memcpy(save, q, (size_t)n);
+            if (is_top) {
+                lad_words(st, s * (uint32_t)iters + (uint32_t)it, 1, i, t);
+                logical = (double)t[0] * U < p_logical;
+            }
+            if (logical) {
+                u_acc = (double)t[1] * U;
+                lad_words(st, s * (uint32_t)iters + (uint32_t)it, 2, i, pos);
+                d = 0;
+                for (int layer = 0; layer < (geom == QO_TORIC ? 2 : 1); layer++) {
+                    int op = (int)((t[2] >> (30 - 2 * layer)) & 3u);
+                    int X_pos = (op == 1 || op == 2) ? (int)(((uint64_t)pos[2 * layer] * (uint64_t)L) >> 32) : 0;
+                    int Z_pos = (op == 3 || op == 2) ? (int)(((uint64_t)pos[2 * layer + 1] * (uint64_t)L) >> 32) : 0;
+                    d += qo_apply_logical(geom, L, q, op, layer, X_pos, Z_pos);
+                }
+            } else {
+                int row, col, op;
+                qo_stabilizer_by_index(geom, L, (int)(((uint64_t)w[2 * (it & 1)] * (uint64_t)nstab) >> 32), &row, &col, &op);
+                d = qo_apply_stabilizer(geom, L, q, row, col, op);
+            }
+            int acc;
+            if (kind == 0) {
+                if (is_top && (p >= 0.75 || d <= 0)) acc = 1;   /* mcmc.py:30-31: no draw needed */
+                else acc = u_acc < pow(factor, (double)d);
+            } else {
+                qo_count_xyz(q, n, c);
+                double pn = pow(px, (double)c[0]) * pow(py_, (double)c[1]) * pow(pz, (double)c[2]) *
+                            pow(q0, num - (double)c[0] - (double)c[1] - (double)c[2]);
+                acc = u_acc * pb < pn;
+                if (acc && kind == 1) n_eff[i] = (double)c[2] + param_b * (double)(c[0] + c[1]);
+            }
+            if (!acc) memcpy(q, save, (size_t)n);
+        }
+    }
+    for (int i = Nc - 2; i >= 0; i--) {
+        uint8_t *lo = qm + (size_t)i * n, *hi = lo + n;
+        uint32_t w[4];
+        lad_words(st, s, 3, i, w);
+        const double u = (double)w[0] * U;
+        int swap;
+        if (kind == 1) {
+            swap = u < pow(ladder[i] / ladder[i + 1], n_eff[i + 1] - n_eff[i]);
+        } else {
+            int ne_lo = qo_count_errors(lo, n), ne_hi = qo_count_errors(hi, n);
+            if (kind == 0 && ne_hi < ne_lo) swap = 1;
+            else swap = u < qo_numba_pow(diff[i], (int64_t)ne_hi - ne_lo);
+        }
+        if (swap) {
+            memcpy(save, lo, (size_t)n); memcpy(lo, hi, (size_t)n); memcpy(hi, save, (size_t)n);
+            int32_t f = flags[i]; flags[i] = flags[i + 1]; flags[i + 1] = f;
+        }
+    }
+    free(save);
+    flags[Nc - 1] = 1;
+    if (flags[0] == 1) { (*tops0)++; flags[0] = 0; }
+}
+
+/* ------------------------------------------------------------------ */
 /* Ladders (parallel tempering)                                        */
 /* ------------------------------------------------------------------ */
 /* kind: 0 depolarizing (mcmc.py:49-103), 1 alpha (mcmc_alpha.py:77-137),
@@ -684,6 +813,10 @@ QO_EXPORT void qo_ladder_step(int kind, int geom, int L, int Nc, uint8_t *qm, co
                               double *n_eff, int64_t *tops0, int64_t iters, qo_stream *nb, qo_stream *py)
 {
     int n = qo_nsites(geom, L);
+    if (nb->native == 2) {   /* native words: same algorithm, positional draws */
+        ladder_step_native(kind, geom, L, Nc, qm, ladder, diff, param_b, p_logical, flags, n_eff, tops0, iters, nb);
+        return;
+    }
     for (int i = 0; i < Nc; i++) {
         double pl = (i == Nc - 1) ? p_logical : 0.0;
         uint8_t *q = qm + (size_t)i * n;
@@ -1048,7 +1181,13 @@ QO_EXPORT void qo_stdc_alpha(int geom, int L, int n_eq, const uint8_t *qm_init, 
         qo_set *seen = qo_set_new(n);
         double z = 0, n_eff = 0;
         for (int64_t s = 0; s < steps; s++) {
-            qo_update_chain_weighted(0, geom, L, qm, pz_tilde_sampling, alpha, 0.0, iters, nb, py, &n_eff);
+            if (nb->native == 2) {   /* native words: the chain is a one-rung alpha ladder (no swap partner) */
+                int32_t fl = 1;
+                int64_t t0 = 0;
+                qo_ladder_step(1, geom, L, 1, qm, &pz_tilde_sampling, NULL, alpha, 0.0, &fl, &n_eff, &t0, iters, nb, py);
+            } else {
+                qo_update_chain_weighted(0, geom, L, qm, pz_tilde_sampling, alpha, 0.0, iters, nb, py, &n_eff);
+            }
             int nw;
             qo_set_add(seen, qm, &nw);
             if (nw) {
