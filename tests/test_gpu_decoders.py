@@ -101,11 +101,13 @@ def test_single_temp_prefers_true_class(api):
 def test_pteq_all_codes(api, cls_name, L):
     dec, _, _ = api
     cls = getattr(dec, cls_name)
-    codes, truth = _workload(cls, L, 0.08, 24, 5)
+    # 96 syndromes: at p = 0.08, d = 5 the oracle on the reference's MT19937 streams decodes 85-90 % of them (toric, the
+    # hardest of the four; 45 failures of 400), so 0.75 is > 3 sigma below the expected success rate
+    codes, truth = _workload(cls, L, 0.08, 96, 5)
     pct, info = dec.PTEQ_batch(codes, 0.08, steps=60000, seed=11, return_info=True)
-    assert pct.shape == (24, cls(L).nbr_eq_classes) and pct.dtype == np.uint8
+    assert pct.shape == (96, cls(L).nbr_eq_classes) and pct.dtype == np.uint8
     assert (pct.sum(1) <= 100).all() and (pct.sum(1) >= 100 - pct.shape[1]).all()      # truncation loses < 1 per class
-    assert (pct.argmax(1) == truth).mean() >= 0.8
+    assert (pct.argmax(1) == truth).mean() >= 0.75
     assert info["converged"].mean() >= 0.7
     one = dec.PTEQ(codes[0], 0.08, steps=60000)
     assert one.shape == (pct.shape[1],) and one.dtype == np.uint8
