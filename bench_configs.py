@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Secondary measurements: the BASELINE.json configs other than the headline one (which bench.py times).
 
-    python bench_configs.py [--config toric5|rotated25|xzzx21|planar_sweep|all] [--out profiles/xxx.jsonl]
+    python bench_configs.py [--config toric5|rotated25|xzzx21|planar_points|all] [--out profiles/xxx.jsonl]
+    torchrun --nproc-per-node N bench_configs.py --config planar_sweep [--syndromes 1000000]    (BASELINE config 5, sharded)
+    torchrun --nproc-per-node N bench_configs.py --config toric15_strong [--syndromes 10000]    (config 2, strong scaling)
 
 One JSON line per configuration: Metropolis steps/s and syndromes/s on one GPU through the host-buffer C ABI
 (H2D + kernels + D2H inside the timed region), the logical failure rate of the decoded batch (true classes and hidden
@@ -162,16 +164,137 @@ def run_planar_sweep(ctx, O, ps=(0.10, 0.15, 0.20), ds=(7, 11, 15, 21), droplets
     return {"config": "planar code threshold sweep, STDC, 4 classes x 16 chains, steps = d^4, p_sampling = 0.25", "points": rows}
 
 
+def _dist_env():
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    return rank, world, local
+
+
+def _run_sharded(name, text, params_of, points, per_point, chunk_of, steps_per_syndrome, out_path, warm):
+    """Common driver of the two multi-GPU workloads: one process per GPU (torchrun), the (point, chunk) items balanced by
+    cost over the ranks, each decoded by generate_data.generate_batch with the lattices resident in HBM from the error
+    draw to the failure count, and the failure counts + class distributions gathered on the host at the end."""
+    import torch
+    import torch.distributed as dist
+    from mcmc_qec_toric_rl_b200 import _lib, generate_data, sharding
+    rank, world, local = _dist_env()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = _lib.default_context(local)
+    info = ctx.device_info()
+    ctx.set_table_budget(int(info["free_mem"] * 0.8))
+    for pt in warm:                                            # module load and first allocations, untimed
+        generate_data.generate_batch(params_of(pt), 64, seed=1, device=local)
+
+    def decode_chunk(pt, n, item):
+        res = generate_data.generate_batch(params_of(pt), n, seed=1000003 * (item + 1), device=local)
+        return res["failures"], res["distr"].astype(np.float32)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    # the gather inside run_sweep_sharded is part of the job; the decode time alone is taken per rank before it
+    local_t = {}
+
+    def timed_chunk(pt, n, item):
+        out = decode_chunk(pt, n, item)
+        torch.cuda.synchronize()
+        local_t["decode_s"] = time.perf_counter() - t0
+        return out
+    curve = sharding.run_sweep_sharded(points, per_point, chunk_of, timed_chunk, rank=rank, world=world)
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3, local_t.get("decode_s", 0.0), wall], dtype=torch.float64, device="cuda")
+    per_rank = None
+    if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = [[round(float(x), 3) for x in a.tolist()] for a in allt]
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    seconds, decode_s, wall = [float(x) for x in t.tolist()]
+    n_total = sum(o["syndromes"] for o in curve)
+    steps_total = float(sum(o["syndromes"] * steps_per_syndrome(o["point"]) for o in curve))
+    line = None
+    if rank == 0:
+        rows = []
+        for o in curve:
+            row = dict(o["point"], syndromes=o["syndromes"], failures=o["failures"], logical_failure_rate=o["rate"], sigma=o["sigma"])
+            if o["extra"] is not None:
+                row["mean_class_distribution"] = [round(float(x), 3) for x in o["extra"].mean(0)]
+            rows.append(row)
+        line = {"name": name, "config": text, "n_gpus": world, "syndromes": n_total, "seconds": seconds, "syndromes_per_s": n_total / seconds,
+                "metropolis_steps": steps_total, "steps_per_s": steps_total / seconds, "decode_seconds_max_over_ranks": decode_s,
+                "gathered": "failure counts and float32 class distributions of every syndrome (all_gather_object of host arrays)",
+                "gathered_bytes": int(sum(o["extra"].nbytes for o in curve if o["extra"] is not None)),
+                "timing": "CUDA events on rank-local default streams around decode + gather, max over ranks",
+                "per_rank_seconds": per_rank, "curve": rows, "device": info["name"]}
+        print(json.dumps(line), flush=True)
+        if out_path:
+            with open(out_path, "a") as f:
+                f.write(json.dumps(line) + "\n")
+    if world > 1:
+        dist.destroy_process_group()
+    return line
+
+
+def run_planar_sweep_sharded(args):
+    """BASELINE config 5: planar threshold sweep d in {7,11,15,21}, p in [0.10,0.20], `--syndromes` in total (default 1e6),
+    STDC with 4 classes x 16 chains, d^4 samples per chain, p_sampling 0.25 (generate_data.py:53-261 per syndrome)."""
+    ds, ps, droplets = (7, 11, 15, 21), [round(0.10 + 0.01 * i, 2) for i in range(11)], 16
+    points = [dict(d=d, p=p) for d in ds for p in ps]
+    per_point = -(-args.syndromes // len(points))
+    fill = 148 * 1024 // (4 * droplets)
+
+    def params_of(pt):
+        return dict(code="planar", method="STDC", size=pt["d"], noise="depolarizing", p_error=pt["p"], p_sampling=0.25,
+                    droplets=droplets, steps=pt["d"] ** 4)
+
+    def chunk_of(pt):                                           # about the same work per item, never less than a full GPU
+        return fill * max(1, int(round((15.0 / pt["d"]) ** 4)))
+    return _run_sharded("planar_sweep", "planar code threshold sweep d in {7,11,15,21} x p in {0.10..0.20}, STDC, 4 classes x 16 chains, "
+                        "d^4 samples x 5 steps per chain, p_sampling 0.25; errors drawn, labelled, hidden, decoded and scored on the device",
+                        params_of, points, per_point, chunk_of, lambda pt: 4 * droplets * pt["d"] ** 4 * 5, args.out,
+                        [dict(d=d, p=0.15) for d in ds])
+
+
+def run_toric15_strong(args):
+    """BASELINE config 2 as a fixed job (strong scaling): `--syndromes` (default 10000) toric d=15 p=0.15 syndromes,
+    16 classes x 64 chains x 15^4 samples x 5 steps, split evenly over the ranks."""
+    _, world, _ = _dist_env()
+    pt = dict(d=15, p=0.15)
+
+    def params_of(pt):
+        return dict(code="toric", method="STDC", size=15, p_error=0.15, p_sampling=0.25, droplets=64, steps=15 ** 4)
+    share = -(-args.syndromes // world)
+    return _run_sharded("toric15_strong", "toric d=15 depolarizing p=0.15, STDC 16 classes x 64 chains x 15^4 samples x 5 steps; fixed job "
+                        "split over the ranks (strong scaling)", params_of, [pt], args.syndromes, share,
+                        lambda pt: 16 * 64 * 15 ** 4 * 5, args.out, [pt])
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="all")
     ap.add_argument("--out", default="")
+    ap.add_argument("--gpus", type=int, default=1, help="informational: the rank count comes from torchrun's WORLD_SIZE")
+    ap.add_argument("--syndromes", type=int, default=0, help="total syndromes of the sharded workloads")
     args = ap.parse_args()
+    if args.config == "planar_sweep":
+        args.syndromes = args.syndromes or 1000000
+        return run_planar_sweep_sharded(args)
+    if args.config == "toric15_strong":
+        args.syndromes = args.syndromes or 10000
+        return run_toric15_strong(args)
     from mcmc_qec_toric_rl_b200 import _lib
     from oracle import oracle as O
     O.lib()
     ctx = _lib.Context(0)
-    runs = {"toric5": run_toric5, "rotated25": run_rotated25, "xzzx21": run_xzzx21, "planar_sweep": run_planar_sweep}
+    runs = {"toric5": run_toric5, "rotated25": run_rotated25, "xzzx21": run_xzzx21, "planar_points": run_planar_sweep}
     todo = list(runs) if args.config == "all" else [args.config]
     lines = []
     for name in todo:

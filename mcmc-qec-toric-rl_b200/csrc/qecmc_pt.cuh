@@ -365,6 +365,44 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
 #pragma unroll
                 for (int i = 0; i < NU; i++) mycol[(size_t)uw[i] * NREP] = nv[i];
             };
+            // the same proposal as XOR masks only (no reads): uw[] and mk[]; the words are distinct or their masks zero
+            auto stab_masks = [&](int idx, W *mk) {
+                if (TABLE) {
+                    const uint2 D = s_ld[idx];
+                    uw[0] = (int)(D.x & 0xFFu);
+                    uw[1] = (int)((D.x >> 8) & 0xFFu);
+                    mk[0] = (W)((W)(D.y & 0xFu) << ((D.x >> 16) & 0xFFu));
+                    mk[1] = (W)((W)((D.y >> 4) & 0xFu) << (D.x >> 24));
+                } else if (TABLE2) {
+                    const uint2 D = s_ld[idx];
+                    uw[0] = (int)((D.x >> 8) & 0xFFu);
+                    uw[1] = (int)((D.x >> 16) & 0xFFu);
+                    uw[NU > 2 ? 2 : 0] = (int)(D.x >> 24);
+                    const uint32_t sh = D.x & 63u, sh2 = D.y & 63u;
+                    const W v = (D.y & 0x01000000u) ? (W)3 : (W)1;
+                    W m0, m1, m2;
+                    if (GEOM == TORIC) {
+                        m1 = (W)(v << sh);
+                        m2 = m1;
+                        m0 = (W)(m1 | (W)(v << sh2));
+                    } else {
+                        const uint32_t fa = D.y >> 8;
+                        m0 = (W)(((fa & 1u) ? (W)(v << sh) : (W)0) | ((fa & 4u) ? (W)(v << sh2) : (W)0));
+                        m1 = (fa & 16u) ? (W)(v << sh) : (W)0;
+                        m2 = (fa & 64u) ? (W)(v << sh) : (W)0;
+                    }
+                    mk[0] = m0;
+                    mk[1] = m1;
+                    mk[NU > 2 ? 2 : 0] = m2;
+                } else {
+                    int row, colq, op;
+                    idx_to_rco<GEOM>(g, idx, row, colq, op);
+                    Upd<W> u;
+                    decode<GEOM, W>(g, row, colq, op, u);
+#pragma unroll
+                    for (int i = 0; i < NU; i++) { uw[i] = u.w[i]; mk[i] = u.m[i]; }
+                }
+            };
 
             if (rung_warp) {
                 for (int it = 0; it < p.iters; it++) {
@@ -387,7 +425,7 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
                 // rung's proposal / accept words, [H, H + iters) the logical-or-stabilizer decisions, [H + iters, H + 2 iters)
                 // the logical operators' positions.  The serial part below then holds no generator arithmetic.
                 uint4 *draws = s_draw + (size_t)l * (H + 2u * (uint32_t)p.iters);
-                const uint32_t ncalls = H + 2u * (uint32_t)p.iters;
+                const uint32_t ncalls = H + (GEOM == XZZX ? 1u : 2u) * (uint32_t)p.iters;   // the XZZX logicals take no position
                 for (uint32_t c = (uint32_t)sub; c < ncalls; c += (uint32_t)LT) {
                     uint32_t c0, tag;
                     if (c < H) { c0 = step * H + c; tag = (uint32_t)my_r; }
@@ -397,6 +435,102 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
                 }
                 __syncwarp(gm);
                 const bool walk = !WEIGHTED && p.top_accept_all;
+                if (walk) {
+                    // A depolarizing ladder's top rung sits at p = 0.75 and accepts every proposal (mcmc.py:30).  All of the block's
+                    // moves are then XOR masks, which commute: lane `sub` applies to the row words it owns (w = sub mod LT) its
+                    // share of every move, with no reads of other lanes' words and no synchronisation inside the block; the weight
+                    // is recounted once at the end.
+                    for (int it = 0; it < p.iters; it++) {
+                        const uint4 Tw = draws[H + it];
+                        if ((double)Tw.x * U32 < p.p_logical) {
+                            const int op0 = (int)(Tw.z >> 30), op1 = NLAY == 2 ? (int)((Tw.z >> 28) & 3u) : 0;
+                            int x0 = 0, z0 = 0, x1 = 0, z1 = 0;
+                            if (GEOM != XZZX) {
+                                const uint4 P = draws[H + p.iters + it];
+                                x0 = (op0 == 1 || op0 == 2) ? (int)__umulhi(P.x, (uint32_t)L) : 0;
+                                z0 = (op0 == 3 || op0 == 2) ? (int)__umulhi(P.y, (uint32_t)L) : 0;
+                                x1 = (op1 == 1 || op1 == 2) ? (int)__umulhi(P.z, (uint32_t)L) : 0;
+                                z1 = (op1 == 3 || op1 == 2) ? (int)__umulhi(P.w, (uint32_t)L) : 0;
+                            }
+                            for (int w = sub; w < g.nw; w += LT) {
+                                const W m = logical_mask<GEOM, W>(g, w, op0, op1, x0, z0, x1, z1);
+                                if (m) mycol[(size_t)w * NREP] ^= m;
+                            }
+                            st1 ^= (uint32_t)(p.cls_delta[op0] ^ (NLAY == 2 ? p.cls_delta[4 + op1] : 0));
+                        } else {
+                            const uint4 Rw = draws[it >> 1];
+                            W mk[NU];
+                            stab_masks((int)__umulhi((it & 1) ? Rw.z : Rw.x, nstab), mk);
+#pragma unroll
+                            for (int i = 0; i < NU; i++)
+                                if ((uw[i] & (LT - 1)) == sub && mk[i]) mycol[(size_t)uw[i] * NREP] ^= mk[i];
+                        }
+                    }
+                } else if (WEIGHTED && GEOM == XZZX) {
+                    // The XZZX logical operators have fixed supports (xzzx_model.py:340-357): X on the antidiagonal, Z on the diagonal.
+                    // Every lane of the group keeps the two diagonals of the replica as packed words (A: field L-1-w of row w at bit
+                    // 2w; Dg: field w of row w, without the centre qubit, which A carries), so a logical proposal is evaluated from
+                    // registers -- no row reads, no reduction -- and only an accepted one touches the rows (each lane its own).
+                    const bool odd = (L & 1) != 0;
+                    const int cw = (L - 1) >> 1;
+                    W A = 0, Dg = 0;
+                    for (int w = sub; w < g.nw; w += LT) {
+                        const W v = mycol[(size_t)w * NREP];
+                        A |= (W)(((v >> (2 * (L - 1 - w))) & (W)3) << (2 * w));
+                        if (!(odd && w == cw)) Dg |= (W)(((v >> (2 * w)) & (W)3) << (2 * w));
+                    }
+                    for (int o = LT >> 1; o > 0; o >>= 1) {
+                        A |= (W)__shfl_xor_sync(gm, A, o);
+                        Dg |= (W)__shfl_xor_sync(gm, Dg, o);
+                    }
+                    const W M1 = rowmask<W>(1, L), CZ = odd ? fld<W>(3, cw) : (W)0, M3d = (W)(rowmask<W>(3, L) ^ CZ);
+                    for (int it = 0; it < p.iters; it++) {
+                        const uint4 Tw = draws[H + it];
+                        const bool logical = (double)Tw.x * U32 < p.p_logical;
+                        uint32_t w_acc;
+                        int ex, ey, ez, op0 = 0;
+                        W An = A, Dn = Dg;
+                        if (logical) {
+                            op0 = (int)(Tw.z >> 30);
+                            const bool px = op0 == 1 || op0 == 2, pz = op0 == 3 || op0 == 2;
+                            An = (W)(A ^ (px ? M1 : (W)0) ^ (pz ? CZ : (W)0));
+                            Dn = (W)(Dg ^ (pz ? M3d : (W)0));
+                            ex = popc(xmap(An)) - popc(xmap(A)) + popc(xmap(Dn)) - popc(xmap(Dg));
+                            ey = popc(ymap(An)) - popc(ymap(A)) + popc(ymap(Dn)) - popc(ymap(Dg));
+                            ez = popc(zmap(An)) - popc(zmap(A)) + popc(zmap(Dn)) - popc(zmap(Dg));
+                            w_acc = Tw.y;
+                        } else {
+                            const uint4 Rw = draws[it >> 1];
+                            propose((int)__umulhi((it & 1) ? Rw.z : Rw.x, nstab));
+                            ex = dx; ey = dy; ez = dz;
+                            w_acc = (it & 1) ? Rw.w : Rw.y;
+                        }
+                        const bool acc = (double)w_acc * U32 * pb < chain_weight(wt, ns1, nx + ex, ny + ey, nz + ez);
+                        if (acc) {
+                            if (logical) {
+                                for (int w = sub; w < g.nw; w += LT) {
+                                    const W m = logical_mask<GEOM, W>(g, w, op0, 0, 0, 0, 0, 0);
+                                    if (m) mycol[(size_t)w * NREP] ^= m;
+                                }
+                                A = An; Dg = Dn;
+                                st1 ^= (uint32_t)p.cls_delta[op0];
+                            } else {
+                                if (sub == 0) commit();
+#pragma unroll
+                                for (int i = 0; i < NU; i++) {   // an untouched spare word refreshes its fields with what they were
+                                    const int w = uw[i];
+                                    const W v = nv[i];
+                                    A = (W)((A & ~((W)3 << (2 * w))) | (((v >> (2 * (L - 1 - w))) & (W)3) << (2 * w)));
+                                    if (!(odd && w == cw)) Dg = (W)((Dg & ~((W)3 << (2 * w))) | (((v >> (2 * w)) & (W)3) << (2 * w)));
+                                }
+                            }
+                            nx += ex; ny += ey; nz += ez; e_nz = nz; e_nxy = nx + ny;
+                            n += ex + ey + ez;
+                            if (sub == 0) nacc++;
+                        }
+                        __syncwarp(gm);   // the group's stores are visible before its next loads
+                    }
+                } else
                 for (int it = 0; it < p.iters; it++) {
                     const uint4 Tw = draws[H + it];
                     const bool logical = (double)Tw.x * U32 < p.p_logical;
@@ -410,15 +544,7 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
                         const int x1 = (op1 == 1 || op1 == 2) ? (int)__umulhi(P.z, (uint32_t)L) : 0;
                         const int z1 = (op1 == 3 || op1 == 2) ? (int)__umulhi(P.w, (uint32_t)L) : 0;
                         const uint32_t dcls = (uint32_t)(p.cls_delta[op0] ^ (NLAY == 2 ? p.cls_delta[4 + op1] : 0));
-                        if (walk) {
-                            // a depolarizing ladder's top rung sits at p = 0.75 and accepts every proposal (mcmc.py:30): the
-                            // operator is applied outright; the weight is recounted once after the last iteration
-                            for (int w = sub; w < g.nw; w += LT) {
-                                const W m = logical_mask<GEOM, W>(g, w, op0, op1, x0, z0, x1, z1);
-                                if (m) mycol[(size_t)w * NREP] ^= m;
-                            }
-                            st1 ^= dcls;
-                        } else {
+                        {
                             int ddx = 0, ddy = 0, ddz = 0;
                             for (int w = sub; w < g.nw; w += LT) {
                                 const W m = logical_mask<GEOM, W>(g, w, op0, op1, x0, z0, x1, z1);
@@ -458,9 +584,7 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
                     } else {
                         const uint4 Rw = draws[it >> 1];
                         const uint32_t w_idx = (it & 1) ? Rw.z : Rw.x, w_acc = (it & 1) ? Rw.w : Rw.y;
-                        if (walk) {
-                            if (sub == 0) { propose((int)__umulhi(w_idx, nstab)); commit(); }
-                        } else {
+                        {
                             propose((int)__umulhi(w_idx, nstab));
                             bool acc;
                             if (WEIGHTED) acc = (double)w_acc * U32 * pb < chain_weight(wt, ns1, nx + dx, ny + dy, nz + dz);
@@ -540,8 +664,19 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
                     m = s_mask[buf * NLC + ml];
                 } else if (Nc > 1) {
                     int c_n = s_n[(Nc - 1) * NLC + ml];
-                    for (int i = Nc - 2; i >= 0; i--) {
-                        const int lo_n = s_n[i * NLC + ml], t = s_t[i * NLC + ml];
+                    for (int base = Nc - 2; base >= 0; base -= 8) {
+                    int lo8[8], t8[8];   // the operands of eight pairs at once: the walk itself is a compare and a select per pair
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int ii = base - j < 0 ? 0 : base - j;
+                        lo8[j] = s_n[ii * NLC + ml];
+                        t8[j] = s_t[ii * NLC + ml];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int i = base - j;
+                        if (i < 0) break;
+                        const int lo_n = lo8[j], t = t8[j];
                         bool sw = c_n <= t;
                         if (t >= QECMC_PT_BAD && !(t >= QECMC_PT_OPEN && c_n <= t - QECMC_PT_OPEN)) {
                             // beyond the table (or no usable table): evaluate the pair as the reference does
@@ -556,6 +691,7 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
                         }
                         m |= (uint32_t)sw << i;
                         c_n = sw ? c_n : lo_n;
+                    }
                     }
                     s_mask[buf * NLC + ml] = m;
                 }

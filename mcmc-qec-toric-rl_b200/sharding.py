@@ -50,3 +50,54 @@ def decode_sharded(decode_fn, codes, rank=None, world=None, group=None):
 def count_failures(distributions, true_classes):
     """generate_data.py:187-189: a decode fails when argmax of the class distribution differs from the true class."""
     return int((np.argmax(distributions, axis=1) != np.asarray(true_classes)).sum())
+
+
+def sweep_chunks(points, syndromes_per_point, chunk):
+    """Cut every point of a threshold sweep (a dict with at least 'd') into work items of at most `chunk` syndromes.
+    -> list of (point_index, n_syndromes, cost) with cost ~ n * d^4 (an STDC sample budget of d^4 per chain)."""
+    items = []
+    for i, pt in enumerate(points):
+        left = int(syndromes_per_point)
+        while left > 0:
+            n = min(int(chunk(pt) if callable(chunk) else chunk), left)
+            items.append((i, n, float(n) * float(pt['d']) ** 4))
+            left -= n
+    return items
+
+
+def run_sweep_sharded(points, syndromes_per_point, chunk, decode_chunk, rank=None, world=None, group=None):
+    """Threshold sweep of generate_data.py's workload (:53-261), sharded: the (point, chunk) work items are balanced by
+    cost over the ranks (shard_by_cost), every rank runs `decode_chunk(point, n, item_index) -> (failures, extra)` on
+    its items, and the per-point failure counts (generate_data.py:187-189) -- plus whatever `extra` arrays the decoder
+    returns, concatenated per point -- are gathered on the host of every rank.  No collective on the data path.
+    -> list of dict(point, syndromes, failures, rate, sigma, extra) in point order."""
+    import torch.distributed as dist
+    if world is None:
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if rank is None:
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+    items = sweep_chunks(points, syndromes_per_point, chunk)
+    mine = shard_by_cost([c for (_, _, c) in items], world)[rank]
+    # largest first inside the rank as well: the long d = 21 items do not end up at the tail
+    local = []
+    for j in sorted(mine, key=lambda j: -items[j][2]):
+        i, n, _ = items[j]
+        failures, extra = decode_chunk(points[i], n, j)
+        local.append((j, i, n, int(failures), extra))
+    if world == 1:
+        parts = [local]
+    else:
+        parts = [None] * world
+        dist.all_gather_object(parts, local, group=group)
+    out = [dict(point=pt, syndromes=0, failures=0, extra=[]) for pt in points]
+    for (j, i, n, f, extra) in sorted(sum(parts, []), key=lambda t: t[0]):
+        out[i]['syndromes'] += n
+        out[i]['failures'] += f
+        if extra is not None:
+            out[i]['extra'].append(extra)
+    for o in out:
+        n = max(o['syndromes'], 1)
+        o['rate'] = o['failures'] / n
+        o['sigma'] = float(np.sqrt(max(o['rate'] * (1 - o['rate']), 0.0) / n))
+        o['extra'] = np.concatenate(o['extra'], axis=0) if o['extra'] else None
+    return out

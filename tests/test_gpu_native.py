@@ -219,9 +219,11 @@ def _binomial_gap_ok(f_a, f_b, n, z=3.0):
 def test_toric_d15_failure_rate_within_binomial_ci_of_the_oracle(ctx):
     """BASELINE config 1 (toric d=15, p = 0.15, STDC, p_sampling 0.25), 200 syndromes: the native decode and the oracle's
     MT19937 decode of the SAME syndromes (droplets 16, 5000 samples per chain) agree on the logical failure count within 3
-    sigma of the pooled binomial (stated CI), pick the same class on >= 85 % of the syndromes, and their class
-    distributions differ by less than 4 percentage points on average.  (Both decoders disagree with each other exactly
-    where a syndrome is ambiguous -- at p = 0.15 the toric code is close to threshold.)"""
+    sigma of the pooled binomial (stated CI).  At p = 0.15 the toric code is close to threshold and 5000 samples leave
+    every STDC estimate noisy, so two runs of the ORACLE ITSELF with different seeds disagree on most syndromes; that
+    oracle-vs-oracle scatter is the yardstick for the per-class distributions: the native-vs-oracle mean absolute
+    difference may exceed it by at most 20 % + 0.5 points, and the share of syndromes on which both pick the same class
+    may fall short of the oracle-vs-oracle share by at most 3 binomial sigma + 2 points."""
     g, L, S, droplets, steps = O.TORIC, 15, 200, 16, 5000
     rng = np.random.default_rng(20251)
     qs, truth = [], []
@@ -233,12 +235,16 @@ def test_toric_d15_failure_rate_within_binomial_ci_of_the_oracle(ctx):
     qm, truth = np.stack(qs), np.array(truth)
     gpu, st = ctx.stdc(g, g, L, qm, 0.15, 0.25, droplets, steps, seed=5)
     ref = O.stdc_batch(g, g, L, qm, 0.15, 0.25, droplets, steps, seed=17, threads=16)
-    f_gpu, f_ref = int((gpu.argmax(1) != truth).sum()), int((ref.argmax(1) != truth).sum())
+    ref2 = O.stdc_batch(g, g, L, qm, 0.15, 0.25, droplets, steps, seed=23, threads=16)
+    f_gpu, f_ref, f_ref2 = (int((x.argmax(1) != truth).sum()) for x in (gpu, ref, ref2))
     ok, sigma = _binomial_gap_ok(f_gpu, f_ref, S)
     assert ok, (f_gpu, f_ref, sigma)
-    assert f_gpu > 0 and f_ref > 0, (f_gpu, f_ref)
-    assert (gpu.argmax(1) == ref.argmax(1)).mean() >= 0.85
-    assert np.abs(gpu - ref).mean() < 4.0
+    assert _binomial_gap_ok(f_gpu, f_ref2, S)[0], (f_gpu, f_ref2)
+    assert 0 < f_gpu < S and 0 < f_ref < S, (f_gpu, f_ref)
+    d_go, d_oo = np.abs(gpu - ref).mean(), np.abs(ref - ref2).mean()
+    assert d_go <= 1.2 * d_oo + 0.5, (d_go, d_oo)
+    a_go, a_oo = (gpu.argmax(1) == ref.argmax(1)).mean(), (ref.argmax(1) == ref2.argmax(1)).mean()
+    assert a_go >= a_oo - 3.0 * np.sqrt(max(a_oo * (1 - a_oo), 1e-9) / S) - 0.02, (a_go, a_oo)
 
 
 # ------------------------------------------------------------------ tempering ladders on native words

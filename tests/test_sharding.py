@@ -63,3 +63,53 @@ def test_decode_sharded_gloo_world2():
         assert np.array_equal(out[:, 0], np.arange(11)) and np.array_equal(out[:, 1], 2 * np.arange(11))
         assert np.array_equal(out[:, 2], np.array([0] * 6 + [1] * 5))   # rank 0 decoded 6 syndromes, rank 1 five
     assert np.array_equal(res[0], res[1])
+
+
+def test_sweep_chunks_cover_every_point():
+    pts = [dict(d=d, p=p) for d in (7, 21) for p in (0.1, 0.2)]
+    items = sharding.sweep_chunks(pts, 1000, lambda pt: 300 if pt['d'] == 7 else 128)
+    for i, pt in enumerate(pts):
+        sizes = [n for (j, n, c) in items if j == i]
+        assert sum(sizes) == 1000 and max(sizes) <= (300 if pt['d'] == 7 else 128)
+    assert all(abs(c - n * pts[i]['d'] ** 4) < 1e-6 for (i, n, c) in items)
+
+
+def _sweep_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pts = [dict(d=d, p=p) for d in (7, 11, 15, 21) for p in (0.10, 0.15, 0.20)]
+    seen = []
+
+    def fake(pt, n, item):           # stand-in decoder: "fails" on every (d)-th syndrome of the item, remembers who ran it
+        seen.append((pt['d'], n))
+        return n // pt['d'], np.full((n, 2), rank, dtype=np.int16)
+    out = sharding.run_sweep_sharded(pts, 500, 64, fake)
+    cost = sum(n * d ** 4 for d, n in seen)
+    dist.destroy_process_group()
+    q.put((rank, [(o['syndromes'], o['failures'], o['rate'], o['sigma'], o['extra'].shape, int(o['extra'][:, 0].sum())) for o in out], cost))
+
+
+def test_run_sweep_sharded_gloo_world2():
+    """Config 5's control flow on CPU: two ranks, cost-balanced items, host-side gather of failure counts and arrays."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_sweep_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = {}
+    for _ in procs:
+        r, rows, cost = q.get(timeout=120)
+        res[r] = (rows, cost)
+    [p.join(timeout=60) for p in procs]
+    assert res[0][0] == res[1][0]                                   # every rank holds the whole gathered curve
+    ds = [d for d in (7, 11, 15, 21) for _ in range(3)]
+    for d, (n, f, rate, sigma, shape, ranksum) in zip(ds, res[0][0]):
+        assert n == 500 and shape == (500, 2)
+        assert f == 7 * (64 // d) + (500 - 7 * 64) // d             # 7 items of 64 and one of 52
+        assert abs(rate - f / 500) < 1e-12 and abs(sigma - np.sqrt(rate * (1 - rate) / 500)) < 1e-12
+    c0, c1 = res[0][1], res[1][1]
+    assert abs(c0 - c1) <= 0.1 * (c0 + c1)                          # the two ranks carry about the same cost
+    assert 0 < sum(r[5] for r in res[0][0]) < 12 * 500              # both ranks contributed rows
