@@ -32,11 +32,19 @@ DROPLETS = 64
 SAMPLES = L ** 4
 ITERS = 5
 N_EQ = 16
-W_INT = 170.0      # int32 lane-ops per toric/planar depolarizing Metropolis step (agreed figure)
+W_INT = 170.0      # SURVEY.md 8d's pre-implementation estimate of int32 lane-ops per toric/planar step (kept for reference only)
 W_LOG = 8.0        # bytes a chain appends to a bucket log per offered sample (the chain kernel's only steady HBM traffic)
-# ncu, full-size launch of this exact command (profiles/r01_ncu_fullsize_stdc_v6.csv): warp instructions and DRAM bytes
-NCU_CHAIN = {"file": "profiles/r01_ncu_fullsize_stdc_v10.csv", "warp_inst_per_launch": 89927429188, "dram_bytes_per_launch": 11272329728 + 28721867520,
-             "issue_active_pct": 72.49, "smem_wavefront_pct": 68.23, "steps_per_launch": 148 * 16 * 64 * 50625 * 5}
+NCU_SUMMARY = "profiles/r02_ncu_summary.json"   # written by profiles/scripts/ncu_summary.py from ncu captures of this command
+
+
+def ncu_summary():
+    """Per-kernel ncu figures of the last committed capture (git sha inside): the chain kernel's counted lane-ops per step
+    (thread instructions executed / Metropolis steps), issue-slot and active-lane utilisation, pipes, DRAM bytes."""
+    try:
+        with open(os.path.join(ROOT, NCU_SUMMARY)) as f:
+            return json.load(f)
+    except Exception:
+        return {"git_sha": None, "kernels": {}}
 
 
 def synth_syndromes(n, seed, L=L, p=P_ERROR):
@@ -295,12 +303,21 @@ def main():
     peaks, peak_src = measured_peaks()
     sm_max_mhz = float(peaks.get("sm_max_mhz", 1965.0))
     peak_ops = info["sm_count"] * 128 * sm_max_mhz * 1e6            # int32 lane-ops/s, one GPU
-    kern_steps_per_s = batch * steps_per_syndrome * args.steps / (kern_ms * 1e-3)   # per GPU, chain kernel only
-    achieved_ops = kern_steps_per_s * W_INT
-    slots_meas = NCU_CHAIN["warp_inst_per_launch"] * 32 / NCU_CHAIN["steps_per_launch"]
-    achieved_meas = kern_steps_per_s * slots_meas
+    kern_steps_per_s = batch * steps_per_syndrome * args.steps / (kern_ms * 1e-3)   # per GPU, chain kernel only (CUDA events)
+    ncu = ncu_summary()
+    ck = ncu["kernels"].get("chain", {})
+    full_size = samples == SAMPLES and ck.get("steps_per_launch") == batch * steps_per_syndrome
+    # useful lane-ops per Metropolis step = thread instructions the chain kernel executes per step (ncu, predicated-off and
+    # idle lanes excluded); issue slots per step = warp instructions x 32 / steps (idle lanes included)
+    useful = ck.get("thread_inst_per_step")
+    slots = ck.get("issue_slots_per_step")
+    achieved = kern_steps_per_s * useful if useful else None
     hbm_alg = (offered / args.steps) * W_LOG / ((kern_ms / args.steps) * 1e-3) / 1e9  # GB/s, rank 0
-    full_size = samples == SAMPLES and batch * steps_per_syndrome == NCU_CHAIN["steps_per_launch"]
+    keep = ("duration_ms", "issue_slot_utilisation", "active_lane_utilisation", "lanes_per_inst", "issue_slots_per_step",
+            "thread_inst_per_step", "pipe_alu_pct", "pipe_fma_pct", "pipe_lsu_pct", "pipe_fp64_pct", "smem_wavefront_pct",
+            "dram_read_bytes", "dram_write_bytes", "registers", "warps_active_pct", "stall_barrier", "stall_wait",
+            "stall_short_scoreboard", "kernel", "source")
+    others = {k: {f: v[f] for f in keep if f in v} for k, v in ncu["kernels"].items() if k != "chain"}
     line = {
         "metric": "metropolis_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -311,25 +328,32 @@ def main():
                 "d2h_bytes_per_step": int(batch * N_EQ * 8), "steps_timed": n_e2e},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "alu", "achieved": achieved_meas / 1e12, "peak": peak_ops / 1e12, "unit": "Tlaneop/s",
-                     "frac": achieved_meas / peak_ops,
-                     "traffic": NCU_CHAIN["dram_bytes_per_launch"] if full_size else None,
-                     "what": "achieved = steps/s of the chain kernel x the issue slots it spends per step, measured by ncu "
-                             "(smsp__inst_executed x 32 lanes / steps; " + NCU_CHAIN["file"] + "); peak = SMs x 128 int32 lanes x max SM clock",
-                     "lane_slots_per_step": slots_meas, "issue_active_pct_ncu": NCU_CHAIN["issue_active_pct"],
-                     "smem_wavefront_pct_ncu": NCU_CHAIN["smem_wavefront_pct"],
-                     "at_agreed_170_laneops": {"achieved": achieved_ops / 1e12, "frac": achieved_ops / peak_ops,
-                                               "note": "SURVEY.md 8d's pre-implementation estimate of 170 lane-ops per step; the kernel "
-                                                       "needs fewer, so this figure exceeds 1 and says nothing about headroom"},
-                     "kernel": "stdc_fast_kernel<TORIC,u32,native,STDC>", "kernel_ms_per_launch": kern_ms / (args.steps * waves),
-                     "units_per_launch": batch * steps_per_syndrome / waves, "algorithmic_laneops_per_step": W_INT,
+        "roofline": {"bound": "alu", "achieved": achieved / 1e12 if achieved else None, "peak": peak_ops / 1e12, "unit": "Tlaneop/s",
+                     "frac": achieved / peak_ops if achieved else None,
+                     "traffic": (ck.get("dram_read_bytes", 0) + ck.get("dram_write_bytes", 0)) if full_size and ck else None,
+                     "what": "achieved = steps/s of the chain kernel (CUDA events, this run) x useful lane-ops per step (thread "
+                             "instructions executed per Metropolis step, counted by ncu on this command at ncu.git_sha: idle and "
+                             "predicated-off lanes do not count); peak = SMs x 128 int32 lanes x max SM clock",
+                     "useful_laneops_per_step": useful, "issue_slots_per_step": slots,
+                     "issue_slot_utilisation": (kern_steps_per_s * slots / peak_ops) if slots else None,
+                     "active_lane_utilisation": (kern_steps_per_s * useful / peak_ops) if useful else None,
+                     "pipes_pct_of_peak": {k: ck.get(k) for k in ("pipe_alu_pct", "pipe_fma_pct", "pipe_lsu_pct", "smem_wavefront_pct")},
+                     "ncu": {"file": NCU_SUMMARY, "git_sha": ncu.get("git_sha"), "capture": ck.get("source"),
+                             "issue_slot_utilisation": ck.get("issue_slot_utilisation"),
+                             "active_lane_utilisation": ck.get("active_lane_utilisation"), "kernel_ms": ck.get("duration_ms")},
+                     "survey_8d_estimate": {"laneops_per_step": W_INT, "frac": kern_steps_per_s * W_INT / peak_ops,
+                                            "note": "SURVEY.md 8d's pre-implementation figure; the kernel needs a third of it, "
+                                                    "so this exceeds 1 and says nothing about headroom"},
+                     "kernel": "stdc_fast_kernel<TORIC,u32,native,STDC,BLOG>", "kernel_ms_per_launch": kern_ms / (args.steps * waves),
+                     "units_per_launch": batch * steps_per_syndrome / waves,
                      "peak_source": f"{info['sm_count']} SMs x 128 int32 lanes x {sm_max_mhz:.0f} MHz ({peak_src} max SM clock)",
                      "note": "north_star: this path is integer-issue bound, not HBM or tensor bound (SURVEY.md 8d)",
                      "hbm": {"achieved": hbm_alg, "peak": float(peaks.get("hbm_gbs", 6650.0)), "unit": "GB/s",
                              "frac": hbm_alg / float(peaks.get("hbm_gbs", 6650.0)),
                              "what": "bucket-log appends, 8 B per offered sample (the dedupe kernel streams them afterwards)",
                              "peak_source": peak_src},
-                     "other_kernels_ms_per_step": (ms - kern_ms) / args.steps, "call_ms": call_ms},
+                     "other_kernels_ms_per_step": (ms - kern_ms) / args.steps, "call_ms": call_ms,
+                     "other_kernels_ncu": others},
         "chain_stats": {"accept_rate": accepted / (batch * steps_per_syndrome * args.steps),
                         "offered_per_sample": offered / (batch * N_EQ * DROPLETS * samples * args.steps),
                         "distinct_per_sample": distinct / (batch * N_EQ * DROPLETS * samples * args.steps),

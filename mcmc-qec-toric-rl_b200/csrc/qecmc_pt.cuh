@@ -66,7 +66,8 @@ struct PtParams {
 
 // manager state per ladder, [field][ladder] in shared memory
 enum { PA_ACTIVE = 0, PA_LIDX, PA_STEP, PA_TOPS0, PA_SINCE, PA_BURN, PA_CSTART, PA_CSTREAK, PA_WA, PA_WB, PA_WC,
-       PA_S2A, PA_S2A_HI, PA_S2B, PA_S2B_HI, PA_S4A, PA_S4A_HI, PA_S4B, PA_S4B_HI, PA_FIN, PA_NEXT, PA_CONV, PA_EQC, PA_NF = PA_EQC + 16 };
+       PA_S2A, PA_S2A_HI, PA_S2B, PA_S2B_HI, PA_S4A, PA_S4A_HI, PA_S4B, PA_S4B_HI, PA_FIN, PA_NEXT, PA_CONV, PA_BOTCLS, PA_HA, PA_HB, PA_PEND,
+       PA_EQC, PA_NF = PA_EQC + 16 };
 #define QECMC_PT_FLAG 0x100u
 #define QECMC_PT_OPEN (1 << 30)
 #define QECMC_PT_BAD (1 << 29)
@@ -225,10 +226,12 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
     const bool is_mgr = warp == 0 && lane < NLC;                                   // lane = ladder it manages
     const uint32_t gm = LT >= 32 ? 0xFFFFFFFFu : (((1u << LT) - 1u) << (lane / LT * LT));   // the lanes sharing this top replica
     const uint32_t H = (uint32_t)((p.iters + 1) >> 1);
+    // (double)x * 2^-32 < p_logical for a 32-bit draw x  <=>  x < ceil(p_logical * 2^32) (the scaling is exact)
+    const uint64_t plog = p.p_logical >= 1.0 ? (1ull << 32) : (uint64_t)ceil(p.p_logical * 4294967296.0);
     const uint32_t nstab = (uint32_t)g.nstab;
     const double *wt = WEIGHTED ? p.wtab + (size_t)(worker ? my_r : 0) * 4 * ns1 : nullptr;
     int e_nz = 0, e_nxy = 0;     // alpha ladders: the RUNG's n_eff = e_nz + alpha * e_nxy (mcmc_alpha.py:22,56 -- not swapped, :126-131)
-    uint32_t nacc = 0;
+    uint32_t nacc = 0, nacc_s = 0;   // accepted moves: confirmed, and of the step in flight
 
     // (re)start ladder `lidx` of the launch in this thread's ladder slot: replica r starts in column r
     auto init_ladder = [&](uint32_t lidx, int buf) {
@@ -267,6 +270,107 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
         s_acc[PA_TOPS0 * NLC + lane] = p.tops0_in ? (uint32_t)p.tops0_in[lidx] : 0u;
     };
 
+    // PTEQ's accounting of one completed Ladder.step (decoders.py:56-82; decoders_biasednoise.py:196-215 records the bottom
+    // rung's n_eff), from what the bottom-rung thread took down in phase C; decides whether the ladder ends.  With `defer`
+    // the thread runs it at the top of the NEXT step, beside the other warps' Metropolis block: the ladder then takes one
+    // step more than it needed, which nothing reads (the call returns counts, not lattices).
+    const bool defer = p.acct == ACCT_PTEQ && Nc > 1 && !p.lat_out && !p.flags_out && !p.neff_out;
+    auto account = [&](int ml) {
+        const uint32_t lidx = s_acc[PA_LIDX * NLC + ml];
+        const uint32_t step = s_acc[PA_STEP * NLC + ml] - 1u;            // steps completed before the one accounted here
+        const uint32_t tops0 = s_acc[PA_TOPS0 * NLC + ml];
+        s_acc[PA_PEND * NLC + ml] = 0;
+        bool fin = false;
+        int converged = 0;
+        if (p.acct == ACCT_PTEQ) {
+            const int cur = class_raw_to_label(GEOM, (int)s_acc[PA_BOTCLS * NLC + ml]);   // the tracked bits are the XOR-linear raw class
+            const uint32_t h_a = s_acc[PA_HA * NLC + ml], h_b = p.kind == LK_ALPHA ? s_acc[PA_HB * NLC + ml] : 0u;
+            uint32_t since = s_acc[PA_SINCE * NLC + ml];
+            const uint32_t burn = s_acc[PA_BURN * NLC + ml];
+            if (tops0 >= (uint32_t)p.tops_burn) {
+                since = step - burn;
+                s_acc[(PA_EQC + cur) * NLC + ml]++;
+                if (p.use_conv) {
+                    auto ld64 = [&](int f) { return (long long)((uint64_t)s_acc[f * NLC + ml] | ((uint64_t)s_acc[(f + 1) * NLC + ml] << 32)); };
+                    auto st64 = [&](int f, long long v) { s_acc[f * NLC + ml] = (uint32_t)v; s_acc[(f + 1) * NLC + ml] = (uint32_t)((uint64_t)v >> 32); };
+                    long long S2a = ld64(PA_S2A), S2b = ld64(PA_S2B), S4a = ld64(PA_S4A), S4b = ld64(PA_S4B);
+                    const size_t hrow = ((size_t)blockIdx.x * NLC + ml) * (size_t)p.hist_stride;
+                    uint16_t *h16 = reinterpret_cast<uint16_t *>(p.hist) + hrow;
+                    uint32_t *h32 = reinterpret_cast<uint32_t *>(p.hist) + hrow;
+                    const bool wide_hist = p.kind == LK_ALPHA;
+                    if (wide_hist) h32[since] = h_a | (h_b << 16); else h16[since] = (uint16_t)h_a;
+                    // history windows [l/4, l/2) and [3l/4, l) of conv_crit_error_based_PT (decoders.py:93-105)
+                    const uint32_t wl = since + 1, nC = (uint32_t)(3ull * wl / 4), nB = wl / 2, nA = wl / 4;
+                    const uint32_t wA = s_acc[PA_WA * NLC + ml], wB = s_acc[PA_WB * NLC + ml], wC = s_acc[PA_WC * NLC + ml];
+                    S4a += h_a; S4b += h_b;
+                    // the three window edges move by at most one entry per step; their loads are issued together
+                    uint32_t vC = 0, vB = 0, vA = 0;
+                    if (wide_hist) {
+                        if (nC > wC) vC = __ldcg(h32 + wC);
+                        if (nB > wB) vB = __ldcg(h32 + wB);
+                        if (nA > wA) vA = __ldcg(h32 + wA);
+                    } else {
+                        if (nC > wC) vC = __ldcg(h16 + wC);
+                        if (nB > wB) vB = __ldcg(h16 + wB);
+                        if (nA > wA) vA = __ldcg(h16 + wA);
+                    }
+                    if (nC > wC) { S4a -= vC & 0xFFFFu; S4b -= vC >> 16; }
+                    if (nB > wB) { S2a += vB & 0xFFFFu; S2b += vB >> 16; }
+                    if (nA > wA) { S2a -= vA & 0xFFFFu; S2b -= vA >> 16; }
+                    s_acc[PA_WA * NLC + ml] = nA; s_acc[PA_WB * NLC + ml] = nB; s_acc[PA_WC * NLC + ml] = nC;
+                    st64(PA_S2A, S2a); st64(PA_S2B, S2b); st64(PA_S4A, S4a); st64(PA_S4B, S4b);
+                    if (tops0 >= (uint32_t)p.TOPS) {
+                        const long long lq = (long long)since + 1;
+                        double q2, q4;
+                        if (p.kind == LK_ALPHA) {
+                            q2 = ((double)S2a + p.alpha * (double)S2b) / (double)(lq / 2 - lq / 4);
+                            q4 = ((double)S4a + p.alpha * (double)S4b) / (double)(lq - 3 * lq / 4);
+                        } else {
+                            q2 = (double)S2a / (double)(lq / 2 - lq / 4);
+                            q4 = (double)S4a / (double)(lq - 3 * lq / 4);
+                        }
+                        const uint32_t streak = s_acc[PA_CSTREAK * NLC + ml];
+                        if (fabs(q2 - q4) < p.eps) {
+                            if ((long long)streak >= p.SEQ) { fin = true; converged = 1; }
+                            s_acc[PA_CSTREAK * NLC + ml] = tops0 - s_acc[PA_CSTART * NLC + ml];
+                        } else {
+                            s_acc[PA_CSTREAK * NLC + ml] = 0;
+                            s_acc[PA_CSTART * NLC + ml] = tops0;
+                        }
+                    }
+                }
+                s_acc[PA_SINCE * NLC + ml] = since;
+            } else {
+                s_acc[PA_BURN * NLC + ml] = burn + 1;
+                if (p.use_conv && tops0 >= (uint32_t)p.TOPS) {   // TOPS <= tops_burn is refused by the reference's callers; kept for symmetry
+                    s_acc[PA_CSTREAK * NLC + ml] = 0;
+                    s_acc[PA_CSTART * NLC + ml] = tops0;
+                }
+            }
+        }
+        if ((long long)step + 1 >= p.steps) fin = true;
+        if (fin) {
+            if (p.acct == ACCT_PTEQ) {
+                const uint32_t since = s_acc[PA_SINCE * NLC + ml];
+                if (p.info) {
+                    p.info[4 * (size_t)lidx] = (long long)step + 1;
+                    p.info[4 * (size_t)lidx + 1] = since;
+                    p.info[4 * (size_t)lidx + 2] = tops0;
+                    p.info[4 * (size_t)lidx + 3] = converged;
+                }
+                for (int e = 0; e < g.neq; e++) {   // decoders.py:89: (eq[since_burn] / (since_burn + 1) * 100).astype(np.uint8)
+                    const uint32_t cnt = s_acc[(PA_EQC + e) * NLC + ml];
+                    if (p.eq_counts) p.eq_counts[(size_t)lidx * g.neq + e] = cnt;
+                    if (p.percent) p.percent[(size_t)lidx * g.neq + e] = (uint8_t)(int)((double)cnt / (double)(since + 1) * 100);
+                }
+            }
+            if (p.tops0_out) p.tops0_out[lidx] = tops0;
+            const unsigned int nxt = atomicAdd(p.queue, 1u);
+            s_acc[PA_NEXT * NLC + ml] = (long long)nxt < p.n_ladders ? nxt : 0xFFFFFFFFu;
+            s_acc[PA_FIN * NLC + ml] = 1;
+        }
+    };
+
     __syncthreads();
     if (is_mgr) {
         const int64_t lidx = (int64_t)blockIdx.x * NLC + lane;
@@ -285,7 +389,11 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
         // =====================================================================================================
         // phase A: `iters` Metropolis steps on every rung (Ladder.update_ladder, mcmc.py:81-83)
         // =====================================================================================================
+        __syncwarp();   // a top group's leader wrote the group's slot and flag in phase C
         const bool active = worker && s_acc[PA_ACTIVE * NLC + l] != 0;
+        // the previous step's accounting, by the thread that took its inputs down (the bottom rung's), while the other warps
+        // are already in this step's block
+        if (defer && active && my_r == 0 && sub == 0 && s_acc[PA_PEND * NLC + l]) account(l);
         if (active) {
             const uint32_t lidx = s_acc[PA_LIDX * NLC + l];
             const uint64_t gid = (uint64_t)p.ladder_offset + lidx;
@@ -416,7 +524,7 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
                         commit();
                         if (WEIGHTED) { nx += dx; ny += dy; nz += dz; e_nz = nz; e_nxy = nx + ny; }
                         n += dE;
-                        nacc++;
+                        nacc_s++;
                     }
                 }
             } else {
@@ -440,9 +548,13 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
                     // moves are then XOR masks, which commute: lane `sub` applies to the row words it owns (w = sub mod LT) its
                     // share of every move, with no reads of other lanes' words and no synchronisation inside the block; the weight
                     // is recounted once at the end.
+                    // Logical operators are XOR-linear too: the block's logical moves are gathered into two column masks and two
+                    // sets of rows (per layer) and reach the rows once, together with the recount.
+                    W colA = 0, colB = 0;
+                    uint32_t rowsA = 0, rowsB = 0;
                     for (int it = 0; it < p.iters; it++) {
                         const uint4 Tw = draws[H + it];
-                        if ((double)Tw.x * U32 < p.p_logical) {
+                        if ((uint64_t)Tw.x < plog) {
                             const int op0 = (int)(Tw.z >> 30), op1 = NLAY == 2 ? (int)((Tw.z >> 28) & 3u) : 0;
                             int x0 = 0, z0 = 0, x1 = 0, z1 = 0;
                             if (GEOM != XZZX) {
@@ -452,9 +564,21 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
                                 x1 = (op1 == 1 || op1 == 2) ? (int)__umulhi(P.z, (uint32_t)L) : 0;
                                 z1 = (op1 == 3 || op1 == 2) ? (int)__umulhi(P.w, (uint32_t)L) : 0;
                             }
-                            for (int w = sub; w < g.nw; w += LT) {
-                                const W m = logical_mask<GEOM, W>(g, w, op0, op1, x0, z0, x1, z1);
-                                if (m) mycol[(size_t)w * NREP] ^= m;
+                            // the terms of logical_mask (qecmc_lattice.h), operator by operator
+                            if (GEOM == TORIC) {
+                                if (op0 == 1 || op0 == 2) rowsA ^= 1u << x0;
+                                if (op0 == 3 || op0 == 2) colA ^= fld<W>(3, z0);
+                                if (op1 == 1 || op1 == 2) colB ^= fld<W>(1, x1);
+                                if (op1 == 3 || op1 == 2) rowsB ^= 1u << z1;
+                            } else if (GEOM == PLANAR) {
+                                if (op0 == 1 || op0 == 3) rowsA ^= 1u << x0;
+                                if (op0 == 2 || op0 == 3) colA ^= fld<W>(3, z0);
+                            } else if (GEOM == ROTATED) {
+                                if (op0 == 1 || op0 == 3) colA ^= fld<W>(1, x0);
+                                if (op0 == 2 || op0 == 3) rowsA ^= 1u << z0;
+                            } else {
+                                if (op0 == 1 || op0 == 2) rowsA ^= 1u;
+                                if (op0 == 3 || op0 == 2) rowsA ^= 2u;
                             }
                             st1 ^= (uint32_t)(p.cls_delta[op0] ^ (NLAY == 2 ? p.cls_delta[4 + op1] : 0));
                         } else {
@@ -466,38 +590,65 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
                                 if ((uw[i] & (LT - 1)) == sub && mk[i]) mycol[(size_t)uw[i] * NREP] ^= mk[i];
                         }
                     }
+                    int cnt = 0;
+                    for (int w = sub; w < g.nw; w += LT) {
+                        W m;
+                        if (GEOM == TORIC) m = w < L ? (W)((((rowsA >> w) & 1u) ? rowmask<W>(1, L) : (W)0) ^ colA)
+                                                     : (W)(colB ^ (((rowsB >> (w - L)) & 1u) ? rowmask<W>(3, L) : (W)0));
+                        else if (GEOM == PLANAR) m = w < L ? (W)((((rowsA >> w) & 1u) ? rowmask<W>(1, L) : (W)0) ^ colA) : (W)0;
+                        else if (GEOM == ROTATED) m = (W)(colA ^ (((rowsA >> w) & 1u) ? rowmask<W>(3, L) : (W)0));
+                        else m = (W)(((rowsA & 1u) ? fld<W>(1, L - 1 - w) : (W)0) ^ ((rowsA & 2u) ? fld<W>(3, w) : (W)0));
+                        const W v = (W)(mycol[(size_t)w * NREP] ^ m);
+                        if (m) mycol[(size_t)w * NREP] = v;
+                        cnt += weight<W>(v);
+                    }
+                    for (int o = LT >> 1; o > 0; o >>= 1) cnt += __shfl_xor_sync(gm, cnt, o);
+                    n = cnt;
+                    if (sub == 0) nacc_s += (uint32_t)p.iters;
                 } else if (WEIGHTED && GEOM == XZZX) {
                     // The XZZX logical operators have fixed supports (xzzx_model.py:340-357): X on the antidiagonal, Z on the diagonal.
                     // Every lane of the group keeps the two diagonals of the replica as packed words (A: field L-1-w of row w at bit
-                    // 2w; Dg: field w of row w, without the centre qubit, which A carries), so a logical proposal is evaluated from
-                    // registers -- no row reads, no reduction -- and only an accepted one touches the rows (each lane its own).
+                    // 2w; Dg: field w of row w; the centre qubit, which lies on both, apart in c0) together with their Pauli counts.
+                    // X on a diagonal swaps its counts I <-> X and Y <-> Z, Z swaps I <-> Z and X <-> Y, so a logical proposal is
+                    // evaluated from a handful of registers -- no row reads, no reduction -- and only an accepted one touches the
+                    // rows (each lane its own).  An accepted stabilizer refreshes the fields of its two rows and recounts.
                     const bool odd = (L & 1) != 0;
-                    const int cw = (L - 1) >> 1;
+                    const int cw = (L - 1) >> 1, nd = L - (odd ? 1 : 0);
+                    const W CM = odd ? (W)((W)3 << (2 * cw)) : (W)0;
                     W A = 0, Dg = 0;
                     for (int w = sub; w < g.nw; w += LT) {
                         const W v = mycol[(size_t)w * NREP];
                         A |= (W)(((v >> (2 * (L - 1 - w))) & (W)3) << (2 * w));
-                        if (!(odd && w == cw)) Dg |= (W)(((v >> (2 * w)) & (W)3) << (2 * w));
+                        Dg |= (W)(((v >> (2 * w)) & (W)3) << (2 * w));
                     }
                     for (int o = LT >> 1; o > 0; o >>= 1) {
                         A |= (W)__shfl_xor_sync(gm, A, o);
                         Dg |= (W)__shfl_xor_sync(gm, Dg, o);
                     }
-                    const W M1 = rowmask<W>(1, L), CZ = odd ? fld<W>(3, cw) : (W)0, M3d = (W)(rowmask<W>(3, L) ^ CZ);
+                    int c0 = odd ? (int)((A >> (2 * cw)) & (W)3) : 0;
+                    A &= (W)~CM;
+                    Dg &= (W)~CM;
+                    int aX = popc(xmap(A)), aY = popc(ymap(A)), aZ = popc(zmap(A));
+                    int dX = popc(xmap(Dg)), dY = popc(ymap(Dg)), dZ = popc(zmap(Dg));
+                    const W M1 = (W)(rowmask<W>(1, L) & ~CM), M3 = (W)(rowmask<W>(3, L) & ~CM);
                     for (int it = 0; it < p.iters; it++) {
                         const uint4 Tw = draws[H + it];
-                        const bool logical = (double)Tw.x * U32 < p.p_logical;
+                        const bool logical = (uint64_t)Tw.x < plog;
                         uint32_t w_acc;
-                        int ex, ey, ez, op0 = 0;
-                        W An = A, Dn = Dg;
+                        int ex = 0, ey = 0, ez = 0, op0 = 0, cn = c0;
+                        bool px = false, pz = false;
                         if (logical) {
                             op0 = (int)(Tw.z >> 30);
-                            const bool px = op0 == 1 || op0 == 2, pz = op0 == 3 || op0 == 2;
-                            An = (W)(A ^ (px ? M1 : (W)0) ^ (pz ? CZ : (W)0));
-                            Dn = (W)(Dg ^ (pz ? M3d : (W)0));
-                            ex = popc(xmap(An)) - popc(xmap(A)) + popc(xmap(Dn)) - popc(xmap(Dg));
-                            ey = popc(ymap(An)) - popc(ymap(A)) + popc(ymap(Dn)) - popc(ymap(Dg));
-                            ez = popc(zmap(An)) - popc(zmap(A)) + popc(zmap(Dn)) - popc(zmap(Dg));
+                            px = op0 == 1 || op0 == 2;
+                            pz = op0 == 3 || op0 == 2;
+                            if (px) { ex += nd - aX - aY - aZ - aX; ey += aZ - aY; ez += aY - aZ; }
+                            if (pz) { ez += nd - dX - dY - dZ - dZ; ex += dY - dX; ey += dX - dY; }
+                            if (odd) {
+                                cn = c0 ^ (px ? 1 : 0) ^ (pz ? 3 : 0);
+                                ex += (cn == 1) - (c0 == 1);
+                                ey += (cn == 2) - (c0 == 2);
+                                ez += (cn == 3) - (c0 == 3);
+                            }
                             w_acc = Tw.y;
                         } else {
                             const uint4 Rw = draws[it >> 1];
@@ -512,7 +663,9 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
                                     const W m = logical_mask<GEOM, W>(g, w, op0, 0, 0, 0, 0, 0);
                                     if (m) mycol[(size_t)w * NREP] ^= m;
                                 }
-                                A = An; Dg = Dn;
+                                if (px) { const int t = nd - aX - aY - aZ, u = aY; aX = t; aY = aZ; aZ = u; A ^= M1; }
+                                if (pz) { const int t = nd - dX - dY - dZ, u = dX; dZ = t; dX = dY; dY = u; Dg ^= M3; }
+                                c0 = cn;
                                 st1 ^= (uint32_t)p.cls_delta[op0];
                             } else {
                                 if (sub == 0) commit();
@@ -521,19 +674,24 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
                                     const int w = uw[i];
                                     const W v = nv[i];
                                     A = (W)((A & ~((W)3 << (2 * w))) | (((v >> (2 * (L - 1 - w))) & (W)3) << (2 * w)));
-                                    if (!(odd && w == cw)) Dg = (W)((Dg & ~((W)3 << (2 * w))) | (((v >> (2 * w)) & (W)3) << (2 * w)));
+                                    Dg = (W)((Dg & ~((W)3 << (2 * w))) | (((v >> (2 * w)) & (W)3) << (2 * w)));
+                                    if (odd && w == cw) c0 = (int)((v >> (2 * cw)) & (W)3);
                                 }
+                                A &= (W)~CM;
+                                Dg &= (W)~CM;
+                                aX = popc(xmap(A)); aY = popc(ymap(A)); aZ = popc(zmap(A));
+                                dX = popc(xmap(Dg)); dY = popc(ymap(Dg)); dZ = popc(zmap(Dg));
                             }
                             nx += ex; ny += ey; nz += ez; e_nz = nz; e_nxy = nx + ny;
                             n += ex + ey + ez;
-                            if (sub == 0) nacc++;
+                            if (sub == 0) nacc_s++;
                         }
                         __syncwarp(gm);   // the group's stores are visible before its next loads
                     }
                 } else
                 for (int it = 0; it < p.iters; it++) {
                     const uint4 Tw = draws[H + it];
-                    const bool logical = (double)Tw.x * U32 < p.p_logical;
+                    const bool logical = (uint64_t)Tw.x < plog;
                     if (logical) {
                         const uint4 P = draws[H + p.iters + it];
                         // operators and positions as _apply_random_logical draws them (a position only for operator 1 / 2
@@ -578,7 +736,7 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
                                 if (WEIGHTED) { nx += ddx; ny += ddy; nz += ddz; e_nz = nz; e_nxy = nx + ny; }
                                 n += d;
                                 st1 ^= dcls;
-                                if (sub == 0) nacc++;
+                                if (sub == 0) nacc_s++;
                             }
                         }
                     } else {
@@ -590,20 +748,13 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
                             if (WEIGHTED) acc = (double)w_acc * U32 * pb < chain_weight(wt, ns1, nx + dx, ny + dy, nz + dz);
                             else acc = (p.top_accept_all || dE <= 0) ? true : ((double)w_acc * U32 < p.thr_top_d[dE + 4 * L]);
                             if (acc) {
-                                if (sub == 0) { commit(); nacc++; }
+                                if (sub == 0) { commit(); nacc_s++; }
                                 if (WEIGHTED) { nx += dx; ny += dy; nz += dz; e_nz = nz; e_nxy = nx + ny; }
                                 n += dE;
                             }
                         }
                     }
                     __syncwarp(gm);   // the group's stores are visible before its next loads
-                }
-                if (walk) {
-                    int cnt = 0;
-                    for (int w = sub; w < g.nw; w += LT) cnt += weight<W>(mycol[(size_t)w * NREP]);
-                    for (int o = LT >> 1; o > 0; o >>= 1) cnt += __shfl_xor_sync(gm, cnt, o);
-                    n = cnt;
-                    if (sub == 0) nacc += (uint32_t)p.iters;
                 }
                 if (sub == 0) s_state[NREP + col] = st1;
             }
@@ -651,11 +802,10 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
             __syncthreads();
         }
         // =====================================================================================================
-        // phase B: the manager of each ladder -- swap sweep (mcmc.py:96-99), flags and tops0 (:100-103), accounting
+        // phase B: the manager of each ladder walks the swap sweep (mcmc.py:96-99) -- nothing else sits between the barriers
         // =====================================================================================================
         if (warp == 0) {
-            bool alive = false;
-            if (is_mgr && s_acc[PA_ACTIVE * NLC + lane]) {
+            if (is_mgr && s_acc[PA_ACTIVE * NLC + lane] && !s_acc[PA_FIN * NLC + lane]) {
                 const int ml = lane;
                 const uint32_t lidx = s_acc[PA_LIDX * NLC + ml];
                 uint32_t m = 0;
@@ -665,152 +815,100 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
                 } else if (Nc > 1) {
                     int c_n = s_n[(Nc - 1) * NLC + ml];
                     for (int base = Nc - 2; base >= 0; base -= 8) {
-                    int lo8[8], t8[8];   // the operands of eight pairs at once: the walk itself is a compare and a select per pair
+                        int lo8[8], t8[8];   // the operands of eight pairs at once: the walk itself is a compare and a select per pair
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const int ii = base - j < 0 ? 0 : base - j;
-                        lo8[j] = s_n[ii * NLC + ml];
-                        t8[j] = s_t[ii * NLC + ml];
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const int i = base - j;
-                        if (i < 0) break;
-                        const int lo_n = lo8[j], t = t8[j];
-                        bool sw = c_n <= t;
-                        if (t >= QECMC_PT_BAD && !(t >= QECMC_PT_OPEN && c_n <= t - QECMC_PT_OPEN)) {
-                            // beyond the table (or no usable table): evaluate the pair as the reference does
-                            const int k = c_n - lo_n;
-                            if (p.kind == LK_DEPOL && k < 0) sw = true;
-                            else {
-                                const uint64_t gid = (uint64_t)p.ladder_offset + lidx;
-                                const uint4 Sw = philox4x32_10(p.step0 + s_acc[PA_STEP * NLC + ml], (3u << 8) | (uint32_t)i, (uint32_t)gid,
-                                                               (uint32_t)(gid >> 32), p.keys);
-                                sw = (double)Sw.x * U32 < numba_pow_dev(p.diff[i], k);
-                            }
+                        for (int j = 0; j < 8; j++) {
+                            const int ii = base - j < 0 ? 0 : base - j;
+                            lo8[j] = s_n[ii * NLC + ml];
+                            t8[j] = s_t[ii * NLC + ml];
                         }
-                        m |= (uint32_t)sw << i;
-                        c_n = sw ? c_n : lo_n;
-                    }
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const int i = base - j;
+                            if (i < 0) break;
+                            const int lo_n = lo8[j], t = t8[j];
+                            bool sw = c_n <= t;
+                            if (t >= QECMC_PT_BAD && !(t >= QECMC_PT_OPEN && c_n <= t - QECMC_PT_OPEN)) {
+                                // beyond the table (or no usable table): evaluate the pair as the reference does
+                                const int k = c_n - lo_n;
+                                if (p.kind == LK_DEPOL && k < 0) sw = true;
+                                else {
+                                    const uint64_t gid = (uint64_t)p.ladder_offset + lidx;
+                                    const uint4 Sw = philox4x32_10(p.step0 + s_acc[PA_STEP * NLC + ml], (3u << 8) | (uint32_t)i, (uint32_t)gid,
+                                                                   (uint32_t)(gid >> 32), p.keys);
+                                    sw = (double)Sw.x * U32 < numba_pow_dev(p.diff[i], k);
+                                }
+                            }
+                            m |= (uint32_t)sw << i;
+                            c_n = sw ? c_n : lo_n;
+                        }
                     }
                     s_mask[buf * NLC + ml] = m;
                 }
-                const int src_top = pt_src_rung(m, Nc - 1), src_bot = pt_src_rung(m, 0);
-                const int col_top = (int)s_slot[(size_t)buf * NREP + src_top * NLC + ml] * NLC + ml;
-                const int col_bot = (int)s_slot[(size_t)buf * NREP + src_bot * NLC + ml] * NLC + ml;
-                s_state[NREP + col_top] |= QECMC_PT_FLAG;                       // self.chains[-1].flag = 1
-                uint32_t sb1 = s_state[NREP + col_bot];
-                uint32_t tops0 = s_acc[PA_TOPS0 * NLC + ml];
-                if (sb1 & QECMC_PT_FLAG) { tops0++; sb1 &= ~QECMC_PT_FLAG; s_state[NREP + col_bot] = sb1; }
-                s_acc[PA_TOPS0 * NLC + ml] = tops0;
-                const uint32_t step = s_acc[PA_STEP * NLC + ml];                // steps completed before this one
-                bool fin = false;
-                int converged = 0;
-                if (p.acct == ACCT_PTEQ) {
-                    // decoders.py:56-82 (PTEQ), decoders_biasednoise.py:196-215 (PTEQ_alpha records the bottom rung's n_eff)
-                    const int cur = class_raw_to_label(GEOM, (int)(sb1 & 15u));   // the tracked bits are the XOR-linear raw class
-                    uint32_t h_a, h_b = 0;
-                    if (p.kind == LK_ALPHA) { h_a = (uint32_t)s_n[ml]; h_b = (uint32_t)s_t[ml]; }
-                    else h_a = (uint32_t)s_n[src_bot * NLC + ml];
-                    uint32_t since = s_acc[PA_SINCE * NLC + ml], burn = s_acc[PA_BURN * NLC + ml];
-                    auto ld64 = [&](int f) { return (long long)((uint64_t)s_acc[f * NLC + ml] | ((uint64_t)s_acc[(f + 1) * NLC + ml] << 32)); };
-                    auto st64 = [&](int f, long long v) { s_acc[f * NLC + ml] = (uint32_t)v; s_acc[(f + 1) * NLC + ml] = (uint32_t)((uint64_t)v >> 32); };
-                    long long S2a = ld64(PA_S2A), S2b = ld64(PA_S2B), S4a = ld64(PA_S4A), S4b = ld64(PA_S4B);
-                    const size_t hrow = ((size_t)blockIdx.x * NLC + ml) * (size_t)p.hist_stride;
-                    uint16_t *h16 = reinterpret_cast<uint16_t *>(p.hist) + hrow;
-                    uint32_t *h32 = reinterpret_cast<uint32_t *>(p.hist) + hrow;
-                    const bool wide_hist = p.kind == LK_ALPHA;
-                    if (tops0 >= (uint32_t)p.tops_burn) {
-                        since = step - burn;
-                        s_acc[(PA_EQC + cur) * NLC + ml]++;
-                        if (p.use_conv) {
-                            if (wide_hist) h32[since] = h_a | (h_b << 16); else h16[since] = (uint16_t)h_a;
-                            // history windows [l/4, l/2) and [3l/4, l) of conv_crit_error_based_PT (decoders.py:93-105)
-                            const uint32_t wl = since + 1, nC = (uint32_t)(3ull * wl / 4), nB = wl / 2, nA = wl / 4;
-                            uint32_t wA = s_acc[PA_WA * NLC + ml], wB = s_acc[PA_WB * NLC + ml], wC = s_acc[PA_WC * NLC + ml];
-                            S4a += h_a; S4b += h_b;
-                            auto hget = [&](uint32_t i, uint32_t &a, uint32_t &b) {
-                                if (wide_hist) { const uint32_t v = __ldcg(h32 + i); a = v & 0xFFFFu; b = v >> 16; }
-                                else { a = __ldcg(h16 + i); b = 0; }
-                            };
-                            uint32_t a, b;
-                            if (nC > wC) { hget(wC, a, b); S4a -= a; S4b -= b; }
-                            if (nB > wB) { hget(wB, a, b); S2a += a; S2b += b; }
-                            if (nA > wA) { hget(wA, a, b); S2a -= a; S2b -= b; }
-                            s_acc[PA_WA * NLC + ml] = nA; s_acc[PA_WB * NLC + ml] = nB; s_acc[PA_WC * NLC + ml] = nC;
-                            st64(PA_S2A, S2a); st64(PA_S2B, S2b); st64(PA_S4A, S4a); st64(PA_S4B, S4b);
-                        }
-                        s_acc[PA_SINCE * NLC + ml] = since;
-                    } else {
-                        s_acc[PA_BURN * NLC + ml] = burn + 1;
-                    }
-                    if (p.use_conv && tops0 >= (uint32_t)p.TOPS) {
-                        const long long lq = (long long)since + 1;
-                        double q2, q4;
-                        if (p.kind == LK_ALPHA) {
-                            q2 = ((double)S2a + p.alpha * (double)S2b) / (double)(lq / 2 - lq / 4);
-                            q4 = ((double)S4a + p.alpha * (double)S4b) / (double)(lq - 3 * lq / 4);
-                        } else {
-                            q2 = (double)S2a / (double)(lq / 2 - lq / 4);
-                            q4 = (double)S4a / (double)(lq - 3 * lq / 4);
-                        }
-                        uint32_t streak = s_acc[PA_CSTREAK * NLC + ml];
-                        if (fabs(q2 - q4) < p.eps) {
-                            if ((long long)streak >= p.SEQ) { fin = true; converged = 1; }
-                            s_acc[PA_CSTREAK * NLC + ml] = tops0 - s_acc[PA_CSTART * NLC + ml];
-                        } else {
-                            s_acc[PA_CSTREAK * NLC + ml] = 0;
-                            s_acc[PA_CSTART * NLC + ml] = tops0;
-                        }
-                    }
-                }
-                s_acc[PA_STEP * NLC + ml] = step + 1;
-                if ((long long)step + 1 >= p.steps) fin = true;
-                if (fin) {
-                    if (p.acct == ACCT_PTEQ) {
-                        const uint32_t since = s_acc[PA_SINCE * NLC + ml];
-                        if (p.info) {
-                            p.info[4 * (size_t)lidx] = (long long)step + 1;
-                            p.info[4 * (size_t)lidx + 1] = since;
-                            p.info[4 * (size_t)lidx + 2] = tops0;
-                            p.info[4 * (size_t)lidx + 3] = converged;
-                        }
-                        for (int e = 0; e < g.neq; e++) {   // decoders.py:89: (eq[since_burn] / (since_burn + 1) * 100).astype(np.uint8)
-                            const uint32_t cnt = s_acc[(PA_EQC + e) * NLC + ml];
-                            if (p.eq_counts) p.eq_counts[(size_t)lidx * g.neq + e] = cnt;
-                            if (p.percent) p.percent[(size_t)lidx * g.neq + e] = (uint8_t)(int)((double)cnt / (double)(since + 1) * 100);
-                        }
-                    }
-                    if (p.tops0_out) p.tops0_out[lidx] = tops0;
-                    const unsigned int nxt = atomicAdd(p.queue, 1u);
-                    s_acc[PA_FIN * NLC + ml] = 1;
-                    s_acc[PA_NEXT * NLC + ml] = (long long)nxt < p.n_ladders ? nxt : 0xFFFFFFFFu;
-                    alive = (long long)nxt < p.n_ladders;
-                } else {
-                    alive = true;
-                }
+                s_acc[PA_STEP * NLC + ml]++;        // Ladder.step calls completed, this one included
             }
-            const uint32_t fins = __ballot_sync(0xFFFFFFFFu, is_mgr && s_acc[PA_FIN * NLC + (lane < NLC ? lane : 0)] != 0);
-            const bool any = __any_sync(0xFFFFFFFFu, alive);
-            if (lane == 0) { s_alive = any; s_anyfin = fins != 0; }
+            if (defer) {
+                // what the deferred accounting decided (it ran beside the block just ended) is known before barrier (2)
+                const int ml = lane < NLC ? lane : 0;
+                const bool act = is_mgr && s_acc[PA_ACTIVE * NLC + ml] != 0, finl = act && s_acc[PA_FIN * NLC + ml] != 0;
+                const uint32_t fins = __ballot_sync(0xFFFFFFFFu, finl);
+                const bool any = __any_sync(0xFFFFFFFFu, act && (!finl || s_acc[PA_NEXT * NLC + ml] != 0xFFFFFFFFu));
+                if (lane == 0) { s_alive = any; s_anyfin = fins != 0; }
+            }
         }
-        __syncthreads();   // (2) swap masks, flags and the managers' verdicts are published
+        __syncthreads();   // (2) the swap masks are published
         // =====================================================================================================
-        // phase C: every rung thread reads its new column off the swap mask
+        // phase C: every rung thread reads its new column off the swap mask; the thread of the top rung raises the flag of the
+        // replica that arrived there, the thread of the bottom rung counts and clears the flag of the one that arrived at the
+        // bottom (mcmc.py:100-103) and takes down what PTEQ's accounting of this step needs
         // =====================================================================================================
-        const bool anyfin = s_anyfin != 0, alive = s_alive != 0;
         int newcol = 0;
-        if (active) {
+        const bool stepping = active && s_acc[PA_FIN * NLC + l] == 0;
+        if (stepping) nacc += nacc_s;   // a ladder the deferred accounting ended ran this block for nothing
+        nacc_s = 0;
+        if (stepping) {
             const uint32_t m = s_mask[buf * NLC + l];
             const int src = pt_src_rung(m, my_r);
             const uint8_t ns = s_slot[(size_t)buf * NREP + src * NLC + l];
             newcol = (int)ns * NLC + l;
-            if (sub == 0) s_slot[(size_t)(buf ^ 1) * NREP + my_r * NLC + l] = ns;
+            if (sub == 0) {
+                s_slot[(size_t)(buf ^ 1) * NREP + my_r * NLC + l] = ns;
+                if (my_r == Nc - 1) s_state[NREP + newcol] |= QECMC_PT_FLAG;        // self.chains[-1].flag = 1
+                if (my_r == 0) {
+                    uint32_t sb1 = s_state[NREP + newcol];
+                    uint32_t tops0 = s_acc[PA_TOPS0 * NLC + l];
+                    if (sb1 & QECMC_PT_FLAG) { tops0++; sb1 &= ~QECMC_PT_FLAG; s_state[NREP + newcol] = sb1; }
+                    s_acc[PA_TOPS0 * NLC + l] = tops0;
+                    if (p.acct == ACCT_PTEQ) {
+                        s_acc[PA_BOTCLS * NLC + l] = sb1 & 15u;
+                        if (p.kind == LK_ALPHA) {
+                            s_acc[PA_HA * NLC + l] = (uint32_t)s_n[l];
+                            s_acc[PA_HB * NLC + l] = (uint32_t)s_t[l];
+                        } else {
+                            s_acc[PA_HA * NLC + l] = (uint32_t)s_n[src * NLC + l];
+                        }
+                        s_acc[PA_PEND * NLC + l] = 1;
+                    }
+                    if (!defer) account(l);
+                }
+            }
         }
+        if (!defer) {
+            __syncthreads();
+            if (warp == 0) {
+                const int ml = lane < NLC ? lane : 0;
+                const bool act = is_mgr && s_acc[PA_ACTIVE * NLC + ml] != 0, finl = act && s_acc[PA_FIN * NLC + ml] != 0;
+                const uint32_t fins = __ballot_sync(0xFFFFFFFFu, finl);
+                const bool any = __any_sync(0xFFFFFFFFu, act && (!finl || s_acc[PA_NEXT * NLC + ml] != 0xFFFFFFFFu));
+                if (lane == 0) { s_alive = any; s_anyfin = fins != 0; }
+            }
+            __syncthreads();
+        }
+        const bool anyfin = s_anyfin != 0, alive = s_alive != 0;
         if (anyfin) {
             // a ladder ended: write what the caller asked for in rung order, then hand its columns to the next ladder
             const bool mine = active && s_acc[PA_FIN * NLC + l] != 0;
-            if (mine) {
+            if (mine && !defer) {
                 const uint32_t lidx = s_acc[PA_LIDX * NLC + l];
                 if (p.lat_out) {
                     W *o = reinterpret_cast<W *>(p.lat_out) + ((size_t)lidx * Nc + my_r) * g.nw;
@@ -826,7 +924,7 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
                 }
             }
             __syncthreads();   // (3) rare: the old columns have been read before the new ladder overwrites them
-            if (is_mgr && s_acc[PA_FIN * NLC + lane]) {
+            if (is_mgr && s_acc[PA_ACTIVE * NLC + lane] && s_acc[PA_FIN * NLC + lane]) {
                 const uint32_t nxt = s_acc[PA_NEXT * NLC + lane];
                 if (nxt != 0xFFFFFFFFu) init_manager(nxt);
                 else { s_acc[PA_ACTIVE * NLC + lane] = 0; s_acc[PA_FIN * NLC + lane] = 0; }
