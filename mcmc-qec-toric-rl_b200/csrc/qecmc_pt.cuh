@@ -91,8 +91,10 @@ template <typename W> __host__ __device__ inline PtLayout pt_layout(const Geo &g
     size_t off = 0;
     o.tile = off; off += ((size_t)g.nw * NREP * sizeof(W) + 15) & ~(size_t)15;
     o.state = off; off += 2 * NREP * 4;
-    o.sn = off; off += NREP * 4;
-    o.st = off; off += NREP * 4;
+    // eight rungs of padding in front of each sweep array: the manager reads the operands of eight pairs at a time without
+    // clamping (the threshold padding holds "swaps whatever is carried", so a pair below rung 0 changes nothing)
+    o.sn = off + 8 * (size_t)NLC * 4; off += (8 * (size_t)NLC + NREP) * 4;
+    o.st = off + 8 * (size_t)NLC * 4; off += (8 * (size_t)NLC + NREP) * 4;
     o.mask = off; off += 2 * (size_t)NLC * 4;
     o.acc = off; off += (size_t)PA_NF * NLC * 4;
     o.thru = off; off += (((size_t)Nc * 9 * 4) + 7) & ~(size_t)7;
@@ -147,6 +149,7 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
     // ---------------- tables (once per CTA; the CTA is persistent) ----------------
     if (!WEIGHTED)
         for (int i = tid; i < Nc * 9; i += blockDim.x) s_thru[i] = p.thr_u[i];
+    for (int i = tid; i < 8 * NLC; i += blockDim.x) { s_t[-1 - i] = QECMC_PT_BAD - 1; s_n[-1 - i] = 0; }
     if (TABLE2) {
         for (int i = tid; i < g.nstab; i += blockDim.x) s_ld[i] = p.desc2[i];
         for (int e = tid; e < 512; e += blockDim.x) {
@@ -217,13 +220,16 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
     }
 
     // ---------------- roles ----------------
-    const bool rung_warp = warp < lay.NRW;
+    // The top-rung warps come FIRST in the CTA: their serial blocks are the critical path of a step, and the scheduler
+    // favours the older (lower-numbered) warps of a CTA when several are ready.
+    const int rwarp = warp - lay.NTW;                                              // index among the rung warps
+    const bool rung_warp = warp >= lay.NTW;
     const int LT = p.lt, TPW = 32 / LT;
     const int sub = rung_warp ? 0 : lane % LT;                                     // lane within a top replica's group
-    const int l = rung_warp ? lane % NLC : (warp - lay.NRW) * TPW + lane / LT;     // this thread's ladder within the CTA
-    const int my_r = rung_warp ? warp * RPW + lane / NLC : Nc - 1;                 // this thread's rung
+    const int l = rung_warp ? lane % NLC : warp * TPW + lane / LT;                 // this thread's ladder within the CTA
+    const int my_r = rung_warp ? rwarp * RPW + lane / NLC : Nc - 1;                 // this thread's rung
     const bool worker = rung_warp ? my_r < NR : l < NLC;
-    const bool is_mgr = warp == 0 && lane < NLC;                                   // lane = ladder it manages
+    const bool is_mgr = rwarp == 0 && lane < NLC;                                  // lane = ladder it manages
     const uint32_t gm = LT >= 32 ? 0xFFFFFFFFu : (((1u << LT) - 1u) << (lane / LT * LT));   // the lanes sharing this top replica
     const uint32_t H = (uint32_t)((p.iters + 1) >> 1);
     // (double)x * 2^-32 < p_logical for a 32-bit draw x  <=>  x < ceil(p_logical * 2^32) (the scaling is exact)
@@ -268,6 +274,8 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
         s_acc[PA_ACTIVE * NLC + lane] = 1;
         s_acc[PA_LIDX * NLC + lane] = lidx;
         s_acc[PA_TOPS0 * NLC + lane] = p.tops0_in ? (uint32_t)p.tops0_in[lidx] : 0u;
+        s_mask[lane] = 0;          // alpha ladders OR their pair decisions into the step's mask: a new ladder starts from none
+        s_mask[NLC + lane] = 0;
     };
 
     // PTEQ's accounting of one completed Ladder.step (decoders.py:56-82; decoders_biasednoise.py:196-215 records the bottom
@@ -804,7 +812,7 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
         // =====================================================================================================
         // phase B: the manager of each ladder walks the swap sweep (mcmc.py:96-99) -- nothing else sits between the barriers
         // =====================================================================================================
-        if (warp == 0) {
+        if (rwarp == 0) {
             if (is_mgr && s_acc[PA_ACTIVE * NLC + lane] && !s_acc[PA_FIN * NLC + lane]) {
                 const int ml = lane;
                 const uint32_t lidx = s_acc[PA_LIDX * NLC + ml];
@@ -815,32 +823,43 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
                 } else if (Nc > 1) {
                     int c_n = s_n[(Nc - 1) * NLC + ml];
                     for (int base = Nc - 2; base >= 0; base -= 8) {
-                        int lo8[8], t8[8];   // the operands of eight pairs at once: the walk itself is a compare and a select per pair
+                        // the operands of eight pairs at once (immediate offsets; rungs below 0 read the padding): the walk itself
+                        // is then a compare and a select per pair, the eight decisions gathered in a byte
+                        const int *qn = s_n + base * NLC + ml, *qt = s_t + base * NLC + ml;
+                        int lo8[8], t8[8];
 #pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            const int ii = base - j < 0 ? 0 : base - j;
-                            lo8[j] = s_n[ii * NLC + ml];
-                            t8[j] = s_t[ii * NLC + ml];
-                        }
+                        for (int j = 0; j < 8; j++) { lo8[j] = qn[-j * NLC]; t8[j] = qt[-j * NLC]; }
+                        int any = 0;
 #pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            const int i = base - j;
-                            if (i < 0) break;
-                            const int lo_n = lo8[j], t = t8[j];
-                            bool sw = c_n <= t;
-                            if (t >= QECMC_PT_BAD && !(t >= QECMC_PT_OPEN && c_n <= t - QECMC_PT_OPEN)) {
-                                // beyond the table (or no usable table): evaluate the pair as the reference does
-                                const int k = c_n - lo_n;
-                                if (p.kind == LK_DEPOL && k < 0) sw = true;
-                                else {
-                                    const uint64_t gid = (uint64_t)p.ladder_offset + lidx;
-                                    const uint4 Sw = philox4x32_10(p.step0 + s_acc[PA_STEP * NLC + ml], (3u << 8) | (uint32_t)i, (uint32_t)gid,
-                                                                   (uint32_t)(gid >> 32), p.keys);
-                                    sw = (double)Sw.x * U32 < numba_pow_dev(p.diff[i], k);
-                                }
+                        for (int j = 0; j < 8; j++) any |= t8[j];
+                        if ((any & (QECMC_PT_BAD | QECMC_PT_OPEN)) == 0) {
+                            uint32_t bits = 0;
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const bool sw = c_n <= t8[j];
+                                bits |= sw ? (0x80u >> j) : 0u;
+                                c_n = sw ? c_n : lo8[j];
                             }
-                            m |= (uint32_t)sw << i;
-                            c_n = sw ? c_n : lo_n;
+                            m |= base >= 7 ? bits << (base - 7) : bits >> (7 - base);   // pair base - j sits at bit 7 - j
+                        } else {
+                            // a draw beyond the power table (or no usable table) in this chunk: pair by pair, exact where needed
+                            for (int j = 0; j < 8 && base - j >= 0; j++) {
+                                const int i = base - j;
+                                const int lo_n = s_n[i * NLC + ml], t = s_t[i * NLC + ml];
+                                bool sw = c_n <= t;
+                                if (t >= QECMC_PT_BAD && !(t >= QECMC_PT_OPEN && c_n <= t - QECMC_PT_OPEN)) {
+                                    const int k = c_n - lo_n;
+                                    if (p.kind == LK_DEPOL && k < 0) sw = true;
+                                    else {
+                                        const uint64_t gid = (uint64_t)p.ladder_offset + lidx;
+                                        const uint4 Sw = philox4x32_10(p.step0 + s_acc[PA_STEP * NLC + ml], (3u << 8) | (uint32_t)i, (uint32_t)gid,
+                                                                       (uint32_t)(gid >> 32), p.keys);
+                                        sw = (double)Sw.x * U32 < numba_pow_dev(p.diff[i], k);
+                                    }
+                                }
+                                m |= (uint32_t)sw << i;
+                                c_n = sw ? c_n : lo_n;
+                            }
                         }
                     }
                     s_mask[buf * NLC + ml] = m;
@@ -895,7 +914,7 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
         }
         if (!defer) {
             __syncthreads();
-            if (warp == 0) {
+            if (rwarp == 0) {
                 const int ml = lane < NLC ? lane : 0;
                 const bool act = is_mgr && s_acc[PA_ACTIVE * NLC + ml] != 0, finl = act && s_acc[PA_FIN * NLC + ml] != 0;
                 const uint32_t fins = __ballot_sync(0xFFFFFFFFu, finl);
