@@ -181,15 +181,24 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
                 nib[k] = (uint32_t)(u.m[k] >> pos[k]) & 0xFu;
             }
             const uint32_t pat = nib[0] | (nib[1] << 4);
-            s_ld[i] = make_uint2((uint32_t)u.w[0] | ((uint32_t)u.w[1] << 8) | (pos[0] << 16) | (pos[1] << 24), pat);
+            // bit 31 of the second word: the stabilizer touches a qubit of the diagonal or the antidiagonal (the supports of
+            // the XZZX logical operators, whose Pauli counts the top rung caches)
+            uint32_t diag = 0;
+            for (int k = 0; k < 2; k++)
+                for (int fq = 0; fq < 2; fq++)
+                    if ((nib[k] >> (2 * fq)) & 3u) {
+                        const int cq = (int)(pos[k] >> 1) + fq;
+                        if (cq == u.w[k] || cq == g.L - 1 - u.w[k]) diag = 0x80000000u;
+                    }
+            s_ld[i] = make_uint2((uint32_t)u.w[0] | ((uint32_t)u.w[1] << 8) | (pos[0] << 16) | (pos[1] << 24), pat | diag);
             atomicOr(&s_patmask[pat >> 5], 1u << (pat & 31));
         }
         __syncthreads();
         for (int i = tid; i < g.nstab; i += blockDim.x) {
-            const uint32_t pat = s_ld[i].y & 0xFFu;
+            const uint32_t pat = s_ld[i].y & 0xFFu, diag = s_ld[i].y & 0x80000000u;
             uint32_t id = __popc(s_patmask[pat >> 5] & ((1u << (pat & 31)) - 1u));
             for (uint32_t wq = 0; wq < (pat >> 5); wq++) id += __popc(s_patmask[wq]);
-            s_ld[i].y = pat | (id << 8);
+            s_ld[i].y = pat | (id << 8) | diag;
         }
         for (int e = tid; e < 16 * 256; e += blockDim.x) {
             int want = e >> 8, pat = -1;
@@ -421,6 +430,7 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
             W nv[NU];
             int uw[NU];
             int dE, dx, dy, dz;
+            uint32_t dflag = 0;   // one-layer codes: the proposed stabilizer touches a diagonal qubit
             auto propose = [&](int idx) {
                 dE = dx = dy = dz = 0;
                 if (TABLE) {
@@ -430,7 +440,8 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
                     const uint32_t p0 = (D.x >> 16) & 0xFFu, p1 = D.x >> 24;
                     const W o0 = mycol[(size_t)uw[0] * NREP], o1 = mycol[(size_t)uw[1] * NREP];
                     const uint32_t f = ((uint32_t)(o0 >> p0) & 0xFu) | (((uint32_t)(o1 >> p1) & 0xFu) << 4);
-                    const uint32_t pk = s_ll[((D.y >> 8) << 8) + f];
+                    const uint32_t pk = s_ll[(((D.y >> 8) & 0xFFu) << 8) + f];
+                    dflag = D.y >> 31;
                     nv[0] = (W)(o0 ^ ((W)(D.y & 0xFu) << p0));
                     nv[1] = (W)(o1 ^ ((W)((D.y >> 4) & 0xFu) << p1));
                     if (WEIGHTED) { dx = (int)(pk & 15u) - 4; dy = (int)((pk >> 4) & 15u) - 4; dz = (int)((pk >> 8) & 15u) - 4; }
@@ -677,6 +688,7 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
                                 st1 ^= (uint32_t)p.cls_delta[op0];
                             } else {
                                 if (sub == 0) commit();
+                                if (dflag) {
 #pragma unroll
                                 for (int i = 0; i < NU; i++) {   // an untouched spare word refreshes its fields with what they were
                                     const int w = uw[i];
@@ -689,6 +701,7 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
                                 Dg &= (W)~CM;
                                 aX = popc(xmap(A)); aY = popc(ymap(A)); aZ = popc(zmap(A));
                                 dX = popc(xmap(Dg)); dY = popc(ymap(Dg)); dZ = popc(zmap(Dg));
+                                }
                             }
                             nx += ex; ny += ey; nz += ez; e_nz = nz; e_nxy = nx + ny;
                             n += ex + ey + ez;
