@@ -113,6 +113,7 @@ struct qecmc_ctx {
 namespace qecmc { struct LadderParams; }
 struct PtPlan {
     int NLC = 0, T = 0, lt = 0;      // ladders per CTA, threads per CTA, lanes per top-rung replica
+    int small_cta = 0;               // the instantiation compiled for CTAs of at most 448 threads
     size_t smem = 0;
     int blocks_per_sm = 0, max_grid = 0;
 };

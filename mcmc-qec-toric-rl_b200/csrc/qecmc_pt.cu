@@ -13,9 +13,19 @@ template <int GEOM, typename W, bool WEIGHTED, int NLC> int plan_one(qecmc_ctx *
     const PtLayout lay = pt_layout<W>(lp.g, lp.Nc, NLC, lt, lp.p_logical != 0.0, TABLE, TABLE2, lp.iters);
     out->NLC = 0;
     if (lay.T > 1024 || lay.total > c->prop.sharedMemPerBlockOptin) return 0;
-    CUDA_OK(cudaFuncSetAttribute(pt_kernel<GEOM, W, WEIGHTED, NLC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
     int nb = 0;
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pt_kernel<GEOM, W, WEIGHTED, NLC>, lay.T, lay.total));
+    out->small_cta = 0;
+    if constexpr (sizeof(W) == 8 && NLC == 16) {
+        if (lay.T <= 448) {   // the instantiation compiled for CTAs of at most 448 threads (72 registers)
+            out->small_cta = 1;
+            CUDA_OK(cudaFuncSetAttribute(pt_kernel<GEOM, W, WEIGHTED, NLC, 448>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+            CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pt_kernel<GEOM, W, WEIGHTED, NLC, 448>, lay.T, lay.total));
+        }
+    }
+    if (!out->small_cta) {
+        CUDA_OK(cudaFuncSetAttribute(pt_kernel<GEOM, W, WEIGHTED, NLC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pt_kernel<GEOM, W, WEIGHTED, NLC>, lay.T, lay.total));
+    }
     if (nb < 1) return 0;
     out->NLC = NLC;
     out->T = lay.T;
@@ -41,6 +51,12 @@ template <int GEOM, typename W, bool WEIGHTED> int plan_gw(qecmc_ctx *c, const L
 
 template <int GEOM, typename W, bool WEIGHTED, int NLC> void launch_one(qecmc_ctx *c, const PtParams &p, const PtPlan &pl, int grid)
 {
+    if constexpr (sizeof(W) == 8 && NLC == 16) {
+        if (pl.small_cta) {
+            pt_kernel<GEOM, W, WEIGHTED, NLC, 448><<<grid, pl.T, pl.smem, c->stream>>>(p);
+            return;
+        }
+    }
     pt_kernel<GEOM, W, WEIGHTED, NLC><<<grid, pl.T, pl.smem, c->stream>>>(p);
 }
 

@@ -115,8 +115,10 @@ __device__ __forceinline__ int pt_src_rung(uint32_t m, int q)
     return q + __ffs((int)~(m >> q)) - 1;
 }
 
-template <int GEOM, typename W, bool WEIGHTED, int NLC>
-__global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
+// MAXT: the largest CTA the instantiation is launched with.  Two CTAs share an SM whenever they fit, so a CTA of at most 448
+// threads (e.g. XZZX d = 21: 10 rung warps + 4 top-rung warps) may use 72 registers per thread instead of 64.
+template <int GEOM, typename W, bool WEIGHTED, int NLC, int MAXT = 1024>
+__global__ void __launch_bounds__(MAXT, MAXT <= 512 ? 2 : 1) pt_kernel(PtParams p)
 {
     constexpr int RPW = 32 / NLC;
     constexpr bool TABLE = GEOM == ROTATED || GEOM == XZZX;
@@ -244,7 +246,16 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
     // (double)x * 2^-32 < p_logical for a 32-bit draw x  <=>  x < ceil(p_logical * 2^32) (the scaling is exact)
     const uint64_t plog = p.p_logical >= 1.0 ? (1ull << 32) : (uint64_t)ceil(p.p_logical * 4294967296.0);
     const uint32_t nstab = (uint32_t)g.nstab;
-    const double *wt = WEIGHTED ? p.wtab + (size_t)(worker ? my_r : 0) * 4 * ns1 : nullptr;
+    // weight tables of this thread's rung: 32-bit offsets into p.wtab (the base stays in uniform registers; a per-thread
+    // 64-bit pointer is rematerialised with a dozen instructions at every use under the register cap)
+    const uint32_t wo = WEIGHTED ? (uint32_t)(worker ? my_r : 0) * 4u * (uint32_t)ns1 : 0u;
+    auto chain_weight_r = [&](int cx, int cy, int cz) {   // chain_weight (qecmc_ladder.cuh) on this rung's tables
+        const double *wb = p.wtab;
+        const uint32_t u1 = (uint32_t)ns1;
+        double a = __dmul_rn(wb[wo + (uint32_t)cx], wb[wo + u1 + (uint32_t)cy]);
+        a = __dmul_rn(a, wb[wo + 2u * u1 + (uint32_t)cz]);
+        return __dmul_rn(a, wb[wo + 3u * u1 + (uint32_t)(cx + cy + cz)]);
+    };
     int e_nz = 0, e_nxy = 0;     // alpha ladders: the RUNG's n_eff = e_nz + alpha * e_nxy (mcmc_alpha.py:22,56 -- not swapped, :126-131)
     uint32_t nacc = 0, nacc_s = 0;   // accepted moves: confirmed, and of the step in flight
 
@@ -422,7 +433,7 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
             int n = (int)st0, nx = 0, ny = 0, nz = 0;
             if (WEIGHTED) { nx = st0 & 1023; ny = (st0 >> 10) & 1023; nz = st0 >> 20; n = nx + ny + nz; }
             double pb = 0.0;
-            if (WEIGHTED) pb = chain_weight(wt, ns1, nx, ny, nz);   // frozen for the block
+            if (WEIGHTED) pb = chain_weight_r(nx, ny, nz);   // frozen for the block
             uint32_t st1 = rung_warp ? 0u : s_state[NREP + col];     // top rung: the replica's class changes with logical moves
             uint4 R = make_uint4(0, 0, 0, 0);
 
@@ -537,7 +548,7 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
                     const uint32_t w_idx = (it & 1) ? R.z : R.x, w_acc = (it & 1) ? R.w : R.y;
                     propose((int)__umulhi(w_idx, nstab));
                     bool acc;
-                    if (WEIGHTED) acc = (double)w_acc * U32 * pb < chain_weight(wt, ns1, nx + dx, ny + dy, nz + dz);
+                    if (WEIGHTED) acc = (double)w_acc * U32 * pb < chain_weight_r(nx + dx, ny + dy, nz + dz);
                     else acc = w_acc <= s_thru[my_r * 9 + dE + QECMC_THR_OFF];
                     if (acc) {
                         commit();
@@ -675,7 +686,7 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
                             ex = dx; ey = dy; ez = dz;
                             w_acc = (it & 1) ? Rw.w : Rw.y;
                         }
-                        const bool acc = (double)w_acc * U32 * pb < chain_weight(wt, ns1, nx + ex, ny + ey, nz + ez);
+                        const bool acc = (double)w_acc * U32 * pb < chain_weight_r(nx + ex, ny + ey, nz + ez);
                         if (acc) {
                             if (logical) {
                                 for (int w = sub; w < g.nw; w += LT) {
@@ -747,7 +758,7 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
                             }
                             const int d = ddx + ddy + ddz;
                             bool acc;
-                            if (WEIGHTED) acc = (double)Tw.y * U32 * pb < chain_weight(wt, ns1, nx + ddx, ny + ddy, nz + ddz);
+                            if (WEIGHTED) acc = (double)Tw.y * U32 * pb < chain_weight_r(nx + ddx, ny + ddy, nz + ddz);
                             else acc = (p.top_accept_all || d <= 0) ? true : ((double)Tw.y * U32 < p.thr_top_d[d + 4 * L]);
                             if (acc) {
                                 for (int w = sub; w < g.nw; w += LT) {
@@ -766,7 +777,7 @@ __global__ void __launch_bounds__(1024, 1) pt_kernel(PtParams p)
                         {
                             propose((int)__umulhi(w_idx, nstab));
                             bool acc;
-                            if (WEIGHTED) acc = (double)w_acc * U32 * pb < chain_weight(wt, ns1, nx + dx, ny + dy, nz + dz);
+                            if (WEIGHTED) acc = (double)w_acc * U32 * pb < chain_weight_r(nx + dx, ny + dy, nz + dz);
                             else acc = (p.top_accept_all || dE <= 0) ? true : ((double)w_acc * U32 < p.thr_top_d[dE + 4 * L]);
                             if (acc) {
                                 if (sub == 0) { commit(); nacc_s++; }

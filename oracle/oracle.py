@@ -84,6 +84,7 @@ def lib():
         L.qo_pteq.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _u8p, _f64p, _f64p, C.c_double, C.c_double,
                               C.c_int, C.c_int, C.c_int, C.c_double, C.c_int64, C.c_int64, C.c_int, _p, _p,
                               _i64p, _p, _p, _u8p]
+        L.qo_set_fast_windows.argtypes = [C.c_int]
         L.qo_pteq_ex.restype = C.c_int64
         L.qo_pteq_ex.argtypes = L.qo_pteq.argtypes + [_f64p, _i64p, _i64p]
         L.qo_update_chain_fast_xyz.argtypes = [C.c_int, C.c_int, _u8p, _f64p, C.c_int64, _p]

@@ -1213,6 +1213,9 @@ QO_EXPORT void qo_stdc_alpha(int geom, int L, int n_eq, const uint8_t *qm_init, 
 /* qo_pteq_ex additionally keeps PTEQ_alpha_with_shortest's bookkeeping (decoders_biasednoise.py:114-146) when
  * short_len != NULL: per class the smallest recorded bottom-rung value, how many samples hit it (short_n) and how
  * many distinct bottom-rung states were seen at it (short_unique). */
+static int qo_fast_windows = 0;
+QO_EXPORT void qo_set_fast_windows(int on) { qo_fast_windows = on; }
+
 QO_EXPORT int64_t qo_pteq_ex(int kind, int geom, int L, int Nc, const uint8_t *qm0, const double *ladder,
                              const double *diff, double param_b, double p_logical, int SEQ, int TOPS,
                              int tops_burn, double eps, int64_t steps, int64_t iters, int use_conv,
@@ -1235,6 +1238,8 @@ QO_EXPORT int64_t qo_pteq_ex(int kind, int geom, int L, int Nc, const uint8_t *q
     }
     flags[Nc - 1] = 1;
     int64_t tops0 = 0, since_burn = 0, resulting_burn_in = 0, conv_start = 0, conv_streak = 0;
+    int64_t w_a2 = 0, w_b2 = 0, w_a4 = 0, w_b4 = 0;   /* window edges [a2, b2) and [a4, b4) of the running sums */
+    double w_S2 = 0, w_S4 = 0;
     int64_t hcap = 1024;
     double *hist = (double *)calloc((size_t)hcap, sizeof(double));
     memset(eq_counts, 0, sizeof(int64_t) * (size_t)n_eq);
@@ -1268,12 +1273,29 @@ QO_EXPORT int64_t qo_pteq_ex(int kind, int geom, int L, int Nc, const uint8_t *q
         } else {
             resulting_burn_in++;
         }
+        /* The two windows of conv_crit_error_based_PT as running sums.  For the depolarizing and biased ladders the history
+           holds integers (error counts), whose sums are exact in double in any order: the running sums ARE the sums the
+           reference recomputes from scratch at every step (decoders.py:93-105), at O(1) instead of O(history) per step.
+           The alpha ladders' history holds n_eff = nz + alpha * nxy (not integers): they keep the literal recomputation
+           unless qo_set_fast_windows(1) was called (long measurement runs only; the sums then differ in the last bits). */
+        if (use_conv && tops0 >= tops_burn && (kind != 1 || qo_fast_windows)) {
+            int64_t l = since_burn + 1;
+            while (w_b2 < l / 2) w_S2 += hist[w_b2++];
+            while (w_a2 < l / 4) w_S2 -= hist[w_a2++];
+            while (w_b4 < l) w_S4 += hist[w_b4++];
+            while (w_a4 < 3 * l / 4) w_S4 -= hist[w_a4++];
+        }
         if (use_conv && tops0 >= TOPS) {
             /* conv_crit_error_based_PT: decoders.py:93-105 */
             int64_t l = since_burn + 1;
             double q2 = 0, q4 = 0;
-            for (int64_t k = l / 4; k < l / 2; k++) q2 += hist[k];
-            for (int64_t k = 3 * l / 4; k < l; k++) q4 += hist[k];
+            if ((kind != 1 || qo_fast_windows) && tops0 >= tops_burn) {
+                q2 = w_S2;
+                q4 = w_S4;
+            } else {
+                for (int64_t k = l / 4; k < l / 2; k++) q2 += hist[k];
+                for (int64_t k = 3 * l / 4; k < l; k++) q4 += hist[k];
+            }
             q2 /= (double)(l / 2 - l / 4);
             q4 /= (double)(l - 3 * l / 4);
             double err = fabs(q2 - q4);

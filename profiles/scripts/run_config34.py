@@ -95,7 +95,7 @@ def main():
         cap, n = int(sys.argv[3]), int(sys.argv[4])
         threads = int(sys.argv[5]) if len(sys.argv) > 5 else len(os.sched_getaffinity(0))
         qs, truth = syndromes(cfg, n)          # the generator is sequential: the first n of any S are the same syndromes
-        O.lib()
+        O.lib().qo_set_fast_windows(1)   # alpha ladders: running window sums instead of the O(history) recomputation per step
 
         def one(i):
             pct, w = O.pteq(kind, g, L, qs[i].reshape(L, L), cfg["bottom"], O.Stream.mt(7000 + i), O.Stream.py(9000 + i), param_b=cfg["b"], steps=cap)

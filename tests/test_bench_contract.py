@@ -32,3 +32,25 @@ def test_product_arm_refuses_to_run_without_a_gpu():
                          capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode != 0
     assert "CUDA" in (out.stderr + out.stdout)
+
+
+def test_roofline_figures_come_from_a_committed_ncu_capture():
+    """bench.py holds no ncu constants: the chain kernel's counted lane-ops per step, issue-slot and active-lane
+    utilisation are read from profiles/r02_ncu_summary.json, which profiles/scripts/ncu_summary.py rebuilds from the
+    committed ncu exports (the git sha of the capture rides along)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    s = bench.ncu_summary()
+    assert s["git_sha"]
+    ck = s["kernels"]["chain"]
+    assert "stdc_fast_kernel" in ck["kernel"] and os.path.exists(os.path.join(ROOT, "profiles", os.path.basename(ck["source"])))
+    assert ck["steps_per_launch"] == 148 * 16 * 64 * 15 ** 4 * 5
+    assert 40 < ck["thread_inst_per_step"] < ck["issue_slots_per_step"] < 120       # useful lane-ops <= issue slots
+    assert 0 < ck["active_lane_utilisation"] < ck["issue_slot_utilisation"] < 1
+    for k in ("dedupe", "ladder_rotated25", "ladder_xzzx21_biased"):
+        assert 0 < s["kernels"][k]["issue_slot_utilisation"] < 1, k
+    # the summary is reproducible from the committed export
+    sys.path.insert(0, os.path.join(ROOT, "profiles", "scripts"))
+    import ncu_summary
+    again = ncu_summary.read(os.path.join(ROOT, "profiles", "r02_ncu_fullsize_stdc.csv"), "stdc_fast_kernel")
+    assert again["warp_inst"] == ck["warp_inst"] and again["thread_inst"] == ck["thread_inst"]
