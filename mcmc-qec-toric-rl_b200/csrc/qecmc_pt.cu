@@ -96,7 +96,10 @@ template <int GEOM, typename W, bool WEIGHTED> int launch_gw(qecmc_ctx *c, const
 
 int qecmc_pt_plan(qecmc_ctx *c, const LadderParams &lp, PtPlan *out)
 {
-    int lt = c->dbg_pt_lt > 0 ? c->dbg_pt_lt : 8;
+    // lanes per top-rung replica: a depolarizing top rung that accepts everything (mcmc.py:30) is a set of commuting XOR masks,
+    // cheap enough for 4 lanes (fewer top warps: rotated d=25 1.32e11 against 1.27e11 steps/s with 8); a top rung that
+    // evaluates its proposals is the critical path of the step and takes 8 (XZZX d=21 biased: 6.0e10 against 5.0e10 with 4)
+    int lt = c->dbg_pt_lt > 0 ? c->dbg_pt_lt : (lp.kind == LK_DEPOL && lp.top_accept_all ? 4 : 8);
     if (lt > 32) lt = 32;
     while (lt & (lt - 1)) lt &= lt - 1;   // power of two
     if (lt < 1) lt = 1;

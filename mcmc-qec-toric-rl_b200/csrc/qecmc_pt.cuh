@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 512 ? 2 : 1) pt_kernel(PtParams 
             int uw[NU];
             int dE, dx, dy, dz;
             uint32_t dflag = 0;   // one-layer codes: the proposed stabilizer touches a diagonal qubit
-            // one-layer codes: the proposal from its descriptor (which the XZZX top rung loads one iteration ahead)
+            // one-layer codes: the proposal from its descriptor
             auto propose_tab = [&](const uint2 D) {
                 uw[0] = (int)(D.x & 0xFFu);
                 uw[1] = (int)((D.x >> 8) & 0xFFu);
@@ -665,29 +665,9 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 512 ? 2 : 1) pt_kernel(PtParams 
                     int aX = popc(xmap(A)), aY = popc(ymap(A)), aZ = popc(zmap(A));
                     int dX = popc(xmap(Dg)), dY = popc(ymap(Dg)), dZ = popc(zmap(Dg));
                     const W M1 = (W)(rowmask<W>(1, L) & ~CM), M3 = (W)(rowmask<W>(3, L) & ~CM);
-                    // The draws, the logical-or-stabilizer decision and the stabilizer's descriptor do not depend on the chain:
-                    // those of iteration it + 1 are fetched while iteration it runs (the group barrier at the end of an iteration
-                    // keeps the compiler from moving the loads up by itself).
-                    uint32_t nTx = 0, nTy = 0, nTz = 0, nWacc = 0;
-                    bool nlog = false;
-                    uint2 nD = make_uint2(0, 0);
-                    auto fetch = [&](int it) {
-                        const uint4 T = draws[H + it];
-                        nTx = T.x; nTy = T.y; nTz = T.z;
-                        nlog = (uint64_t)T.x < plog;
-                        if (!nlog) {
-                            const uint4 Rn = draws[it >> 1];
-                            nWacc = (it & 1) ? Rn.w : Rn.y;
-                            nD = s_ld[__umulhi((it & 1) ? Rn.z : Rn.x, nstab)];
-                        }
-                    };
-                    fetch(0);
                     for (int it = 0; it < p.iters; it++) {
-                        const uint4 Tw = make_uint4(nTx, nTy, nTz, 0u);
-                        const bool logical = nlog;
-                        const uint32_t cur_wacc = nWacc;
-                        const uint2 curD = nD;
-                        if (it + 1 < p.iters) fetch(it + 1);
+                        const uint4 Tw = draws[H + it];
+                        const bool logical = (uint64_t)Tw.x < plog;
                         uint32_t w_acc;
                         int ex = 0, ey = 0, ez = 0, op0 = 0, cn = c0;
                         bool px = false, pz = false;
@@ -705,9 +685,12 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 512 ? 2 : 1) pt_kernel(PtParams 
                             }
                             w_acc = Tw.y;
                         } else {
-                            propose_tab(curD);
+                            // (fetching the next iteration's draws and descriptor ahead was measured: 5.8e10 against 6.0e10
+                            // steps/s -- the extra live registers spill)
+                            const uint4 Rw = draws[it >> 1];
+                            propose((int)__umulhi((it & 1) ? Rw.z : Rw.x, nstab));
                             ex = dx; ey = dy; ez = dz;
-                            w_acc = cur_wacc;
+                            w_acc = (it & 1) ? Rw.w : Rw.y;
                         }
                         const bool acc = (double)w_acc * U32 * pb < chain_weight_r(nx + ex, ny + ey, nz + ez);
                         if (acc) {

@@ -282,3 +282,30 @@ def test_oracle_reproduces_reference_ptdc_early_stop(i):
     assert (done < 600).any(), "no ladder stopped early: the vector does not exercise the rule"
     # the reference truncates to uint8: allow the float result to sit within rounding of a truncation boundary
     assert np.array_equal(np.floor(out + 1e-9).astype(np.uint8), c["out"]) or np.array_equal(out.astype(np.uint8), c["out"]), (out, c["out"])
+
+
+@pytest.mark.gpu
+def test_threshold_sweep_through_the_sharded_driver(ctx):
+    """Config 5's driver on one GPU (world size 1; the two-rank control flow is tests/test_sharding.py): every (d, p) point
+    gets its syndromes through generate_batch, the gathered failure counts equal argmax != eq_true recomputed from the
+    gathered distributions, and the failure rate rises with p at fixed d."""
+    from mcmc_qec_toric_rl_b200 import generate_data as G, sharding
+    points = [dict(d=d, p=p) for d in (5, 7) for p in (0.04, 0.12, 0.20)]
+    truth = {}
+
+    def decode_chunk(pt, n, item):
+        params = dict(code='planar', method='STDC', size=pt['d'], noise='depolarizing', p_error=pt['p'], p_sampling=0.25,
+                      droplets=4, steps=pt['d'] ** 4, mwpm_init=False)
+        res = G.generate_batch(params, n, seed=1000 + item)
+        truth[item] = res['eq_true']
+        return res['failures'], np.concatenate([res['distr'], res['eq_true'][:, None].astype(np.float64)], axis=1)
+    curve = sharding.run_sweep_sharded(points, 300, 128, decode_chunk, rank=0, world=1)
+    assert [o['syndromes'] for o in curve] == [300] * 6
+    for o in curve:
+        distr, eq_true = o['extra'][:, :4], o['extra'][:, 4].astype(np.int64)
+        assert o['failures'] == int((distr.argmax(1) != eq_true).sum())
+        assert abs(o['rate'] - o['failures'] / 300) < 1e-12
+    for d0 in (0, 3):
+        rates = [curve[d0 + k]['rate'] for k in range(3)]
+        assert rates[0] < rates[1] < rates[2], rates
+        assert rates[0] < 0.1 and rates[2] > 0.15, rates
