@@ -281,9 +281,9 @@ static int launch_stdc_fast(qecmc_ctx *c, StdcParams &p)
     const size_t tabs_bytes = !static_tab ? 0 : conv ? ((sizeof(FastTabs<1>) + 15) & ~(size_t)15) : ((sizeof(FastTabs<8>) + 15) & ~(size_t)15);
     size_t stat = 512 * 5 + 128;
     size_t dyn_fixed = static_tab ? tabs_bytes : (size_t)p.gchain.nstab * 16 + 16;
-    QTRY(pick_threads(per_chain, stat + dyn_fixed + 256, c->prop, &T, &nb, static_tab && !conv, conv ? 56 : 64));
+    QTRY(pick_threads(per_chain, stat + dyn_fixed + 256, c->prop, &T, &nb, !conv, conv ? 56 : 64, !static_tab && !conv));
     // a small batch is spread over the SMs rather than packed into a few large CTAs
-    while (T > 64 && (p.n_chains + T - 1) / T < c->prop.multiProcessorCount) T /= 2;
+    while (T > 64 && (p.n_chains + T - 1) / T < c->prop.multiProcessorCount) T = (T / 2 + 31) & ~31;
     size_t smem = ((per_chain * T + 15) & ~(size_t)15) + dyn_fixed;
     if (p.insert_mode == 6) {   // per-CTA cursors into the bucket logs, behind the tile
         // a CTA holds whole tables: T = (tables per CTA) * droplets, not necessarily a multiple of 32; the last CTA of the
