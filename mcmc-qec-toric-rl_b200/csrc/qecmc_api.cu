@@ -281,9 +281,11 @@ static int launch_stdc_fast(qecmc_ctx *c, StdcParams &p)
     const size_t tabs_bytes = !static_tab ? 0 : conv ? ((sizeof(FastTabs<1>) + 15) & ~(size_t)15) : ((sizeof(FastTabs<8>) + 15) & ~(size_t)15);
     size_t stat = 512 * 5 + 128;
     size_t dyn_fixed = static_tab ? tabs_bytes : (size_t)p.gchain.nstab * 16 + 16;
-    QTRY(pick_threads(per_chain, stat + dyn_fixed + 256, c->prop, &T, &nb, !conv, conv ? 56 : 64, !static_tab && !conv));
+    // (64-bit row words: ONE CTA of 608-800 threads per SM instead of two of 256 was measured -- the per-SM rate rose 6 % with
+    // 56 % more threads, and CTAs of odd sizes quantise badly over the SMs; descriptors with ready byte offsets changed nothing)
+    QTRY(pick_threads(per_chain, stat + dyn_fixed + 256, c->prop, &T, &nb, static_tab && !conv, conv ? 56 : 64));
     // a small batch is spread over the SMs rather than packed into a few large CTAs
-    while (T > 64 && (p.n_chains + T - 1) / T < c->prop.multiProcessorCount) T = (T / 2 + 31) & ~31;
+    while (T > 64 && (p.n_chains + T - 1) / T < c->prop.multiProcessorCount) T /= 2;
     size_t smem = ((per_chain * T + 15) & ~(size_t)15) + dyn_fixed;
     if (p.insert_mode == 6) {   // per-CTA cursors into the bucket logs, behind the tile
         // a CTA holds whole tables: T = (tables per CTA) * droplets, not necessarily a multiple of 32; the last CTA of the

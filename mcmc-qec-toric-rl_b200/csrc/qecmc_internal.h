@@ -275,20 +275,13 @@ static inline int free_device_bytes(qecmc_ctx *c, size_t *fr)
 }
 
 static inline int pick_threads(size_t bytes_per_chain, size_t fixed, const cudaDeviceProp &prop, int *threads, int *blocks_per_sm,
-                               bool allow1024 = false, int regs_per_thread = 0, bool one_cta_any_size = false)
+                               bool allow1024 = false, int regs_per_thread = 0)
 {
     // largest resident chain count per SM within the shared-memory budget, 256-thread CTAs preferred
     size_t budget = prop.sharedMemPerMultiprocessor;
     int best_T = 0, best_res = 0;
     // candidates in order of preference: a later one wins only with strictly more resident chains
-    int cand[40], nc = 0;
-    for (int T : {1024, 256, 128, 64}) cand[nc++] = T;
-    // 64-bit row words: lattices of 272-336 bytes leave two 256-thread CTAs (512 chains) per SM; ONE CTA of whatever whole
-    // number of warps fits beside the tables holds 608 (d = 21) to 800 (d = 17) chains
-    if (one_cta_any_size)
-        for (int T = 992; T > 256; T -= 32) cand[nc++] = T;
-    for (int ci = 0; ci < nc; ci++) {
-        const int T = cand[ci];
+    for (int T : {1024, 256, 128, 64}) {
         if (T == 1024 && !allow1024) continue;
         size_t per_block = bytes_per_chain * T + fixed + 1024;  // +1 KiB reserved per CTA
         if (bytes_per_chain * T + fixed > prop.sharedMemPerBlockOptin) continue;

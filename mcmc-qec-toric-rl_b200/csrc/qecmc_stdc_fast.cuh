@@ -105,7 +105,7 @@ __device__ __forceinline__ void prefetch_l2(const void *addr)
 // descriptors and fingerprints, which makes every table address an immediate; the lattice tile is the dynamic part.
 // BLOG = true is the headline specialisation: insert mode 6 known at compile time (no mode dispatch in the sample path).
 template <int GEOM, typename W, bool REPLAY, int MODE, bool CONV, bool BLOG = false>
-__global__ void __launch_bounds__(!CONV ? 1024 : 256, CONV ? (sizeof(W) == 4 ? 4 : 2) : 1) stdc_fast_kernel(StdcParams p, FastTables ft, PhiloxKeys keys)
+__global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ? (sizeof(W) == 4 ? 4 : 2) : (sizeof(W) == 4 ? 1 : 3)) stdc_fast_kernel(StdcParams p, FastTables ft, PhiloxKeys keys)
 {
     static_assert(GEOM == TORIC || GEOM == PLANAR, "table-driven kernel covers the two-layer codes");
     constexpr bool STATIC_TAB = sizeof(W) == 4;
