@@ -219,7 +219,9 @@ typedef struct qecmc_pteq_cfg {
     int32_t SEQ, TOPS, tops_burn;
     int32_t use_conv;    /* 1: conv_criteria='error_based' (decoders.py:93-105); 0: run all `steps` */
     double  eps;
-    int64_t steps;       /* cap on Ladder.step calls per syndrome */
+    int64_t steps;       /* cap on Ladder.step calls per syndrome (steps * iters < 2^32).  The history the criterion needs is
+                          * 2 bytes per step (4 for alpha ladders) per ladder IN FLIGHT: with native draws a finished ladder
+                          * hands its place to the next one of the batch, so the reference's default of 50000000 runs */
 } qecmc_pteq_cfg;
 
 /* eqdistr [S][n_eq] uint8 = (class counts / (since_burn + 1) * 100) truncated, as the reference returns;

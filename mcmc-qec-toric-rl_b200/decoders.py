@@ -109,8 +109,10 @@ def PTEQ_batch(init_codes, p, Nc=None, SEQ=2, TOPS=10, tops_burn=2, eps=0.1, ste
                _param_b=0.0):
     """PTEQ (decoders.py:25-89) for a list of code objects -> uint8 [S, nbr_eq_classes] (truncated percent).
 
-    `steps` caps the Ladder.step calls per syndrome; with conv_criteria='error_based' the device keeps 4 bytes of
-    history per step and ladder, so pass a realistic cap (the reference's default of 5e7 preallocates the same way)."""
+    `steps` caps the Ladder.step calls per syndrome.  With conv_criteria='error_based' the device keeps 2 bytes of history
+    per step (4 for alpha ladders) for every ladder in flight -- a finished ladder hands its place to the next one of the
+    batch -- so the reference's default cap of 5e7 runs (with fewer ladders resident), it just takes as long as its slowest
+    ladder."""
     code, qm, per_class = _batch(init_codes)
     if per_class:
         raise TypeError("PTEQ takes a single code object per syndrome")
