@@ -104,6 +104,19 @@ def single_temp(init_code, p, max_iters):
 
 
 # ------------------------------------------------------------------------------------------------ PTEQ / PTDC
+def conv_crit_error_based_PT(nbr_errors_bottom_chain, since_burn, tops_accepted, SEQ, eps):
+    """The reference's convergence test on a host array (decoders.py:91-104): the history of the bottom rung's length has
+    since_burn + 1 valid entries; its second and fourth quarters must agree within eps.  -> (agree, agree and
+    tops_accepted >= SEQ).  The device evaluates the same windows as running integer sums inside the tempering kernel; this
+    helper is for callers that keep their own history."""
+    n = int(since_burn) + 1
+    hist = np.asarray(nbr_errors_bottom_chain)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        gap = abs(np.mean(hist[n // 4: n // 2]) - np.mean(hist[3 * n // 4: n])) if n >= 2 else float("nan")
+    agree = bool(gap < eps)
+    return agree, bool(agree and tops_accepted >= SEQ)
+
+
 def PTEQ_batch(init_codes, p, Nc=None, SEQ=2, TOPS=10, tops_burn=2, eps=0.1, steps=50000000, iters=10,
                conv_criteria='error_based', seed=None, device=0, return_info=False, _kind=_lib.LADDER_DEPOLARIZING,
                _param_b=0.0):

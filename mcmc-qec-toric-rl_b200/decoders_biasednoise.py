@@ -1,6 +1,10 @@
 """Biased / alpha-noise parallel-tempering decoders with the reference's signatures (decoders_biasednoise.py)."""
 from . import _lib
-from .decoders import PTEQ_batch
+from .decoders import PTEQ_batch, conv_crit_error_based_PT
+
+# the biased and alpha ladders use the same test on their own history (decoders_biasednoise.py:79-90, 226-237)
+conv_crit_error_based_PT_biased = conv_crit_error_based_PT
+conv_crit_error_based_PT_alpha = conv_crit_error_based_PT
 
 
 def PTEQ_biased_batch(init_codes, p, eta=0.5, Nc=None, SEQ=2, TOPS=10, tops_burn=2, eps=0.1, steps=50000000, iters=10,

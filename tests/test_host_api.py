@@ -238,3 +238,18 @@ def test_data_reader_raises_on_a_missing_file(tmp_path):
     from mcmc_qec_toric_rl_b200.src.mcmc import MCMCDataReader
     with pytest.raises(FileNotFoundError):
         MCMCDataReader(str(tmp_path / "nope.xz"), 5)
+
+
+def test_convergence_criterion_helper():
+    """conv_crit_error_based_PT (decoders.py:91-104) on host arrays: quarters 2 and 4 of the valid part of the history."""
+    from mcmc_qec_toric_rl_b200 import decoders, decoders_biasednoise
+    hist = np.zeros(64)
+    hist[:40] = [5] * 10 + [7] * 10 + [9] * 10 + [7] * 10          # since_burn = 39: Q2 = hist[10:20] = 7, Q4 = hist[30:40] = 7
+    assert decoders.conv_crit_error_based_PT(hist, 39, 3, 2, 0.1) == (True, True)
+    assert decoders.conv_crit_error_based_PT(hist, 39, 1, 2, 0.1) == (True, False)
+    hist[30:40] = 7.2
+    assert decoders.conv_crit_error_based_PT(hist, 39, 3, 2, 0.1) == (False, False)
+    assert decoders.conv_crit_error_based_PT(hist, 39, 3, 2, 0.25) == (True, True)
+    assert decoders.conv_crit_error_based_PT(hist, 0, 3, 2, 0.1) == (False, False)     # one entry: empty quarters
+    assert decoders_biasednoise.conv_crit_error_based_PT_alpha is decoders.conv_crit_error_based_PT
+    assert decoders_biasednoise.conv_crit_error_based_PT_biased is decoders.conv_crit_error_based_PT
