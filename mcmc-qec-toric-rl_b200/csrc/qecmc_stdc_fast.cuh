@@ -122,6 +122,10 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ?
     int8_t *s_dE = STATIC_TAB ? tb.dE : s_dE_dyn;
     const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(smem_all);
     const uint32_t tbaseA = tbase + (threadIdx.x & (REP - 1)) * 16u;   // this lane's copy of A
+    // the accept path's tables (B, hs, dE) are addressed from a copy of the base the compiler cannot re-derive: left to itself it
+    // rebuilds the shared-window address (S2UR + UMOV + ULEA) inside the branch, three issue slots for a handful of lanes
+    uint32_t tbase_acc;
+    asm volatile("mov.u32 %0, %1;" : "=r"(tbase_acc) : "r"(tbase));
     const uint32_t tbaseT = tbase + (threadIdx.x & (REP - 1)) * 4u;    // ... and of thr
     const int T = blockDim.x, tid = threadIdx.x;
     const Geo g = p.gchain;
@@ -209,8 +213,9 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ?
     const uint32_t cur_base = (uint32_t)__cvta_generic_to_shared(s_cur) + (uint32_t)(tid / p.droplets) * ((uint32_t)p.nbc * 4u);
     unsigned long long *blog_tab = BLOG ? p.blogs + (uint64_t)tab * (uint64_t)p.nbc * p.bcap : nullptr;
 
-    uint32_t nacc = 0, noff = 0;
-    bool dirty = true;  // the first sample is always new to the chain
+    // "the state changed since the last sample" = the accept counter moved: no flag of its own to set on the accept path
+    // (which a warp runs for 2-5 active lanes); the first sample is always new to the chain
+    uint32_t nacc = 0, noff = 0, nacc_seen = 0xFFFFFFFFu;
     int left = p.iters;
     // Distinct-chain accounting by insert mode: 6 / 4 log the key and leave the counting to a dedupe kernel; 5 and 0 probe a
     // set in HBM at once (early stop); 2 (key counts beyond the dedupe kernels' fan-out) prefetches the set's slot at one
@@ -264,7 +269,7 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ?
         else acc = r_acc <= s_thr[li];
         if (acc) {
             if (STATIC_TAB) {
-                const uint4 B = lds_v4<offsetof(Tabs, B)>(tbase + (uint32_t)idx * 16u);
+                const uint4 B = lds_v4<offsetof(Tabs, B)>(tbase_acc + (uint32_t)idx * 16u);
                 *p0 = (W)(o0 ^ (W)B.x);
                 *p1 = (W)(o1 ^ (W)B.y);
                 *p2 = (W)(o2 ^ (W)B.z);
@@ -287,20 +292,20 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ?
                 *p2 = (W)(o2 ^ m2);
             }
             if (STATIC_TAB) {
-                n += lds_s8<offsetof(Tabs, dE)>(tbase + li);
-                const uint2 hv = lds_v2<offsetof(Tabs, hs)>(tbase + (uint32_t)idx * 8u);
+                n += lds_s8<offsetof(Tabs, dE)>(tbase_acc + li);
+                const uint2 hv = lds_v2<offsetof(Tabs, hs)>(tbase_acc + (uint32_t)idx * 8u);
                 h ^= (uint64_t)hv.x | ((uint64_t)hv.y << 32);
             } else {
                 n += (int)s_dE[li];
                 h ^= s_hs[idx];
             }
-            dirty = true;
             nacc++;
         }
         if (--left == 0) {
             left = p.iters;
             acct.sample(n);
             bool is_new = false;
+            const bool dirty = nacc != nacc_seen;
             if (BLOG) {
                 if (dirty) {
                     const uint64_t k = make_key(h, n);
@@ -344,7 +349,7 @@ __global__ void __launch_bounds__((!CONV && sizeof(W) == 4) ? 1024 : 256, CONV ?
                 }
             }
             noff += dirty;
-            dirty = false;
+            nacc_seen = nacc;
             cs.after_sample(p, is_new, n);
         }
     };
