@@ -443,19 +443,13 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 512 ? 2 : 1) pt_kernel(PtParams 
             int dE, dx, dy, dz;
             uint32_t dflag = 0;   // one-layer codes: the proposed stabilizer touches a diagonal qubit
             // one-layer codes: the proposal from its descriptor
-            // descriptor and LUT bases as shared-memory addresses the compiler cannot re-derive: in the top-rung code, where
-            // they are not otherwise live, it rebuilds the carve-up offsets with ~15 instructions per proposal
-            uint32_t ld_addr = (uint32_t)__cvta_generic_to_shared(s_ld), ll_addr = (uint32_t)__cvta_generic_to_shared(s_ll);
-            asm volatile("mov.u32 %0, %1;" : "=r"(ld_addr) : "r"(ld_addr));
-            asm volatile("mov.u32 %0, %1;" : "=r"(ll_addr) : "r"(ll_addr));
             auto propose_tab = [&](const uint2 D) {
                 uw[0] = (int)(D.x & 0xFFu);
                 uw[1] = (int)((D.x >> 8) & 0xFFu);
                 const uint32_t p0 = (D.x >> 16) & 0xFFu, p1 = D.x >> 24;
                 const W o0 = mycol[(size_t)uw[0] * NREP], o1 = mycol[(size_t)uw[1] * NREP];
                 const uint32_t f = ((uint32_t)(o0 >> p0) & 0xFu) | (((uint32_t)(o1 >> p1) & 0xFu) << 4);
-                uint32_t pk;
-                asm("ld.shared.u16 %0, [%1];" : "=r"(pk) : "r"(ll_addr + (((((D.y >> 8) & 0xFFu) << 8) + f) << 1)));
+                const uint32_t pk = s_ll[(((D.y >> 8) & 0xFFu) << 8) + f];
                 dflag = D.y >> 31;
                 nv[0] = (W)(o0 ^ ((W)(D.y & 0xFu) << p0));
                 nv[1] = (W)(o1 ^ ((W)((D.y >> 4) & 0xFu) << p1));
@@ -466,7 +460,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 512 ? 2 : 1) pt_kernel(PtParams 
             auto propose = [&](int idx) {
                 dE = dx = dy = dz = 0;
                 if (TABLE) {
-                    propose_tab(lds_v2<0>(ld_addr + (uint32_t)idx * 8u));
+                    propose_tab(s_ld[idx]);
                 } else if (TABLE2) {
                     const uint2 D = s_ld[idx];
                     uw[0] = (int)((D.x >> 8) & 0xFFu);
