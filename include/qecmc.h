@@ -358,6 +358,24 @@ int qecmc_count_failures(qecmc_ctx *ctx, const void *distr, int32_t dtype, int32
 int qecmc_count_failures_dev(qecmc_ctx *ctx, const void *d_distr, int32_t dtype, int32_t use_argmin, int32_t n_eq, int64_t S,
                              const int32_t *d_eq_true, int32_t *d_choice, int64_t *failures);
 
+/* ------------------------------------------------------------------------------
+ * Class-sorted minimum-weight perfect matching start states for planar chains (host code, no device work):
+ * MWPM(code).solve() and class_sorted_mwpm(code) of src/mwpm.py (:408-415, :417-438, :462-475; regular_mwpm :479-487
+ * is define_equivalence_class of mode 0's output).  The reference hands its defect graph (generate_edges :66-133,
+ * generate_edges_constrained :136-229) to the external blossom5 binary (:376-405); this solves the same graphs in
+ * process (dense primal-dual blossom algorithm), one syndrome per host thread.
+ *   qm                 [S][2][L][L] error chains; the syndrome is Planar_code.syndrom() of each (planar_model.py:134-153).
+ *                      NULL: the defects are given instead
+ *   vertex_defects     [S][L-1][L], plaquette_defects [S][L][L-1] (0 / non-zero), used when qm is NULL
+ *   mode               0: solve() -> out [S][2][L][L], weights [S][2] = matching weight per layer
+ *                      1: class_sorted_mwpm -> out [S][4][2][L][L] in class order, weights [S][2][2] = weight of
+ *                         solve_layer(layer, parity)
+ *   weights            optional
+ *   threads            host threads (0: all)
+ * ------------------------------------------------------------------------------ */
+int qecmc_mwpm_planar(int32_t L, int64_t S, const uint8_t *qm, const uint8_t *vertex_defects, const uint8_t *plaquette_defects,
+                      int32_t mode, uint8_t *out, int32_t *weights, int32_t threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -142,6 +142,8 @@ def load():
     L.qecmc_count_failures.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
                                        C.c_void_p, C.POINTER(C.c_int64)]
     L.qecmc_count_failures_dev.argtypes = L.qecmc_count_failures.argtypes
+    L.qecmc_mwpm_planar.argtypes = [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_int32]
     _lib = L
     return L
 
@@ -576,6 +578,36 @@ class Context:
                                                C.c_void_p(d_eq_true_ptr), C.c_void_p(d_choice_ptr) if d_choice_ptr else None,
                                                C.byref(fails)))
         return int(fails.value)
+
+
+def mwpm_planar(L, qm=None, vertex_defects=None, plaquette_defects=None, class_sorted=True, threads=0):
+    """qecmc_mwpm_planar: host-side matching (no device, no context).  qm [S][2][L][L] error chains, or the two defect
+    arrays [S][L-1][L] / [S][L][L-1].  Returns (chains, weights): class_sorted -> chains [S][4][2][L][L] in class order,
+    weights [S][2][2] = weight of solve_layer(layer, parity); else chains [S][2][L][L] = MWPM.solve(), weights [S][2]."""
+    if qm is not None:
+        qm = np.ascontiguousarray(qm, dtype=np.uint8).reshape(-1, 2, L, L)
+        S = qm.shape[0]
+        v = p = None
+    else:
+        v = np.ascontiguousarray(np.asarray(vertex_defects) != 0, dtype=np.uint8).reshape(-1, L - 1, L)
+        p = np.ascontiguousarray(np.asarray(plaquette_defects) != 0, dtype=np.uint8).reshape(-1, L, L - 1)
+        S = v.shape[0]
+        if p.shape[0] != S:
+            raise ValueError("vertex_defects and plaquette_defects disagree on the batch size")
+    out = np.zeros((S, 4, 2, L, L) if class_sorted else (S, 2, L, L), np.uint8)
+    w = np.zeros((S, 2, 2) if class_sorted else (S, 2), np.int32)
+    _check(load().qecmc_mwpm_planar(L, S, qm.ctypes.data if qm is not None else None, v.ctypes.data if v is not None else None,
+                                    p.ctypes.data if p is not None else None, int(bool(class_sorted)), out.ctypes.data,
+                                    w.ctypes.data, int(threads)))
+    return out, w
+
+
+def host_planar_class(qm):
+    """Planar_code.define_equivalence_class (planar_model.py:379-390) of host lattices [S][2][L][L] -> int [S]."""
+    q = np.asarray(qm)
+    x = ((q[:, 0, :, 0] == 1) | (q[:, 0, :, 0] == 2)).sum(axis=1) % 2
+    z = ((q[:, 0, 0, :] == 3) | (q[:, 0, 0, :] == 2)).sum(axis=1) % 2
+    return (x + 2 * z).astype(np.int32)
 
 
 def _require_u8(a):

@@ -9,8 +9,10 @@ GPU-generated files unchanged.
 Per batch the device draws the errors (generate_random_error), labels them (define_equivalence_class -> eq_true),
 hides the class (apply_random_logical), decodes, and counts ``argmax != eq_true`` (argmin for "ST"); lattices stay in
 HBM between those steps for the decoders that have a device-pointer entry (STDC, PTEQ family), the others take the
-hidden lattices through their host-buffer ``*_batch`` entry.  MWPM initialisation and the MWPM / eMWPM methods need
-the external blossom5 solver and are out of scope.
+hidden lattices through their host-buffer ``*_batch`` entry.  ``params['mwpm_init']`` (generate_data.py:126-128, planar
+only) starts every class's chains from its class-constrained minimum-weight matching (src/mwpm.py, matched on the host
+by the native library); ``mwpm_batch`` scores the matching decoders themselves ("MWPM" / "eMWPM",
+generate_data_noise_models.py:123-146).
 """
 import numpy as np
 
@@ -18,6 +20,7 @@ from . import _lib
 from . import decoders as _dec
 from . import decoders_biasednoise as _decb
 from .src import mcmc as _mcmc
+from .src import mwpm as _mwpm
 from .src.toric_model import Toric_code
 from .src.planar_model import Planar_code
 from .src.rotated_surface_model import RotSurCode
@@ -64,12 +67,40 @@ def _wrap(code_cls, size, qm):
     return out
 
 
+def mwpm_start_states(params, qubit):
+    """generate_data.py:126-128 (`mwpm_init`): the per-class start chains class_sorted_mwpm gives for every error chain
+    of the batch (numpy [S, n_sites]) -> [S, 4, n_sites], matched on the host (csrc/qecmc_mwpm.cu)."""
+    assert params['code'] == 'planar'
+    L = params['size']
+    return _mwpm.class_sorted_mwpm_batch(qubit.reshape(-1, 2, L, L), L).reshape(qubit.shape[0], 4, -1)
+
+
+def mwpm_batch(params, qubit, eq_true=None):
+    """The matching decoders as a workload (generate_data_noise_models.py:123-146), host only: "MWPM" = class of the
+    unconstrained matching (regular_mwpm), "eMWPM" = the class whose constrained matching is shortest (enhanced_mwpm,
+    depolarizing rule; ties go to the lowest class here, the reference draws among them).
+    -> dict(choice=[S], failures=int or None)"""
+    assert params['code'] == 'planar'
+    L = params['size']
+    qm = np.ascontiguousarray(qubit, dtype=np.uint8).reshape(-1, 2, L, L)
+    if params['method'] == 'MWPM':
+        sol = _lib.mwpm_planar(L, qm=qm, class_sorted=False)[0]
+        choice = _lib.host_planar_class(sol)
+    elif params['method'] == 'eMWPM':
+        chains = _lib.mwpm_planar(L, qm=qm, class_sorted=True)[0]
+        choice = np.count_nonzero(chains.reshape(qm.shape[0], 4, -1), axis=2).argmin(axis=1)
+    else:
+        raise ValueError("mwpm_batch scores 'MWPM' or 'eMWPM'")
+    choice = choice.astype(np.int32)
+    return dict(choice=choice, failures=None if eq_true is None else int((choice != np.asarray(eq_true)).sum()))
+
+
 def decode_batch(params, hidden, seed=None, device=0):
-    """Decoder dispatch of generate_data.py:137-201 on a batch of hidden lattices (numpy [S, n_sites]).
-    -> (distributions [S, n_eq], use_argmin)"""
+    """Decoder dispatch of generate_data.py:137-201 on a batch of hidden lattices (numpy [S, n_sites]), or of per-class
+    start chains (numpy [S, n_eq, n_sites], the `mwpm_init` route).  -> (distributions [S, n_eq], use_argmin)"""
     method, noise = params['method'], params.get('noise', 'depolarizing')
     code_cls, size = _CODES[params['code']], params['size']
-    codes = _wrap(code_cls, size, hidden)
+    codes = [_wrap(code_cls, size, h) for h in hidden] if hidden.ndim == 3 else _wrap(code_cls, size, hidden)
     kw = dict(seed=seed, device=device)
     if method == 'PTEQ':
         if noise == 'depolarizing':
@@ -106,7 +137,7 @@ def decode_batch(params, hidden, seed=None, device=0):
         return _dec.STRC_batch(codes, params['p_error'], p_sampling=params['p_sampling'], steps=params['steps'],
                                droplets=params['droplets'], **kw), False
     if method in ('MWPM', 'eMWPM'):
-        raise NotImplementedError("MWPM needs the external blossom5 solver (src/mwpm.py:391); out of scope")
+        raise ValueError("MWPM / eMWPM score the matching itself (generate_data_noise_models.py:123-146): use mwpm_batch")
     raise ValueError(f"unknown method {method!r}")
 
 
@@ -115,8 +146,7 @@ def generate_batch(params, S, seed=0, device=0):
     failures=int).  The STDC and depolarizing-PTEQ paths keep the lattices on the device from error generation to
     failure counting; the others stage the hidden lattices through the host-buffer decoder entry."""
     import torch
-    if params.get('mwpm_init'):
-        raise NotImplementedError("mwpm_init needs the external blossom5 solver (src/mwpm.py:391); out of scope")
+    mwpm_init = bool(params.get('mwpm_init'))
     ctx = _lib.default_context(device)
     geom = _lib.GEOM_NAMES[params['code']]
     L = params['size']
@@ -133,7 +163,17 @@ def generate_batch(params, S, seed=0, device=0):
         method, noise = params['method'], params.get('noise', 'depolarizing')
         use_argmin = False
         d_choice = torch.empty(S, dtype=torch.int32, device=dev)
-        if method == 'STDC' and geom in (_lib.TORIC, _lib.PLANAR):
+        if mwpm_init:
+            # generate_data.py:126-128: start every class's chains from its minimum-weight matching instead of the
+            # hidden error (no apply_random_logical: the matchings carry no trace of the error's class)
+            starts = mwpm_start_states(params, d_q.cpu().numpy())
+            distr, use_argmin = decode_batch(params, starts, seed=seed + 1, device=device)
+            ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+            scored = np.ascontiguousarray(distr[:, :n_eq])
+            d_scored = torch.from_numpy(scored).to(dev)
+            failures = ctx.count_failures_dev(d_scored.data_ptr(), _lib.DISTR_U8 if scored.dtype == np.uint8 else _lib.DISTR_F64,
+                                              n_eq, S, d_true.data_ptr(), d_choice.data_ptr(), use_argmin=use_argmin)
+        elif method == 'STDC' and geom in (_lib.TORIC, _lib.PLANAR):
             d_out = torch.empty((S, n_eq), dtype=torch.float64, device=dev)
             code0 = _CODES[params['code']](L)
             ctx.stdc_dev(geom, _mcmc.fast_path_geometry(code0), L, d_hidden.data_ptr(), S, d_out.data_ptr(), params['p_error'],

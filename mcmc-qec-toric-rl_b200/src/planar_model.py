@@ -35,6 +35,23 @@ class Planar_code(CodeBase):
                 t[(r, c, 3)] = (s, [3] * len(s))
         return t
 
+    def __init__(self, size):
+        super().__init__(size)
+        self.plaquette_defects = np.zeros((size, size - 1), dtype=bool)    # planar_model.py:15-16
+        self.vertex_defects = np.zeros((size - 1, size), dtype=bool)
+
+    def syndrom(self):
+        """planar_model.py:134-153: vertex defects [L-1][L] from Y / Z errors, plaquette defects [L][L-1] from X / Y
+        errors, kept on the object for src/mwpm.py; returns the per-stabilizer dict of the other codes as well."""
+        q = self.qubit_matrix
+        yz = (q == 2) | (q == 3)
+        self.vertex_defects = (yz[0, 1:, :] ^ yz[0, :-1, :]) ^ (yz[1, :-1, :] ^ np.roll(yz[1, :-1, :], 1, axis=1))
+        xy = (q == 1) | (q == 2)
+        self.plaquette_defects = (xy[0, :, 1:] ^ xy[0, :, :-1]) ^ (xy[1, :, :-1] ^ np.roll(xy[1, :, :-1], 1, axis=0))
+        return super().syndrome()
+
+    syndrome = syndrom
+
     def _clear_unused(self):
         self.qubit_matrix[1, -1, :] = 0             # layer 1 lives in [0:L-1, 0:L-1] (planar_model.py:36-37)
         self.qubit_matrix[1, :, -1] = 0
