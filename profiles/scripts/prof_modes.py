@@ -32,3 +32,11 @@ try:
     run("single_temp toric15", st_single)
 except Exception as e:
     print("single_temp:", e)
+def st_single_full():
+    # 9472 syndromes x 16 classes = 151 552 chains = 1024 per SM: the size at which single_temp fills the GPU
+    out = ctx.single_temp(_lib.TORIC, _lib.TORIC, L, np.repeat(q, 64, 0), 0.15, 4000)
+    return out if isinstance(out, tuple) else (out, {})
+try:
+    run("single_temp toric15 x64", st_single_full)
+except Exception as e:
+    print("single_temp x64:", e)
