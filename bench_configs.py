@@ -164,12 +164,15 @@ def run_planar_sweep(ctx, O, ps=(0.10, 0.15, 0.20), ds=(7, 11, 15, 21), droplets
     return {"config": "planar code threshold sweep, STDC, 4 classes x 16 chains, steps = d^4, p_sampling = 0.25", "points": rows}
 
 
+AB_OLD_SIZING = False
+
+
 def _dist_env():
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
     return rank, world, local
 
 
-def _run_sharded(name, text, params_of, points, per_point, chunk_of, steps_per_syndrome, out_path, warm):
+def _run_sharded(name, text, params_of, points, per_point, chunk_of, steps_per_syndrome, out_path, warm, rounds_of=None):
     """Common driver of the two multi-GPU workloads: one process per GPU (torchrun), the (point, chunk) items balanced by
     cost over the ranks, each decoded by generate_data.generate_batch with the lattices resident in HBM from the error
     draw to the failure count, and the failure counts + class distributions gathered on the host at the end."""
@@ -183,8 +186,28 @@ def _run_sharded(name, text, params_of, points, per_point, chunk_of, steps_per_s
     ctx = _lib.default_context(local)
     info = ctx.device_info()
     ctx.set_table_budget(int(info["free_mem"] * 0.8))
+    if AB_OLD_SIZING:
+        ctx.debug_set("packed", 0)
+        rounds_of = None
+    planned = {}
     for pt in warm:                                            # module load and first allocations, untimed
         generate_data.generate_batch(params_of(pt), 64, seed=1, device=local)
+        if rounds_of is not None:
+            # size the items of this distance from the library's own plan (qecmc_last_plan): whole rounds of full-size CTAs
+            # over the SMs, within what one wave may hold in the table budget -- no SM idles behind a short last round
+            par = params_of(pt)
+            wave_cap, round_chains = ctx.last_plan()
+            per_round = max(1, round_chains // ((16 if par["code"] == "toric" else 4) * par["droplets"]))
+            want = per_round * rounds_of(pt)
+            n = want if wave_cap >= want else (wave_cap // per_round * per_round if wave_cap >= per_round else wave_cap)
+            planned[pt["d"]] = int(max(64, n))
+    if planned:
+        ds_sorted = sorted(planned)
+        t = torch.tensor([planned[d] for d in ds_sorted], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)           # every rank cuts the same items
+        planned = {d: int(v) for d, v in zip(ds_sorted, t.tolist())}
+        chunk_of = lambda pt: planned[pt["d"]]                  # noqa: E731
 
     def decode_chunk(pt, n, item):
         res = generate_data.generate_batch(params_of(pt), n, seed=1000003 * (item + 1), device=local)
@@ -234,6 +257,8 @@ def _run_sharded(name, text, params_of, points, per_point, chunk_of, steps_per_s
                 "gathered_bytes": int(sum(o["extra"].nbytes for o in curve if o["extra"] is not None)),
                 "timing": "CUDA events on rank-local default streams around decode + gather, max over ranks",
                 "per_rank_seconds": per_rank, "curve": rows, "device": info["name"]}
+        if planned:
+            line["syndromes_per_item"] = planned
         print(json.dumps(line), flush=True)
         if out_path:
             with open(out_path, "a") as f:
@@ -260,7 +285,7 @@ def run_planar_sweep_sharded(args):
     return _run_sharded("planar_sweep", "planar code threshold sweep d in {7,11,15,21} x p in {0.10..0.20}, STDC, 4 classes x 16 chains, "
                         "d^4 samples x 5 steps per chain, p_sampling 0.25; errors drawn, labelled, hidden, decoded and scored on the device",
                         params_of, points, per_point, chunk_of, lambda pt: 4 * droplets * pt["d"] ** 4 * 5, args.out,
-                        [dict(d=d, p=0.15) for d in ds])
+                        [dict(d=d, p=0.15) for d in ds], rounds_of=lambda pt: max(1, int(round((15.0 / pt["d"]) ** 4))))
 
 
 def run_toric15_strong(args):
@@ -283,7 +308,11 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--gpus", type=int, default=1, help="informational: the rank count comes from torchrun's WORLD_SIZE")
     ap.add_argument("--syndromes", type=int, default=0, help="total syndromes of the sharded workloads")
+    ap.add_argument("--ab-old-sizing", action="store_true",
+                    help="A/B switch of the planar sweep: fixed items of 2368 syndromes and the 64-bit row-word kernel for d = 21")
     args = ap.parse_args()
+    global AB_OLD_SIZING
+    AB_OLD_SIZING = args.ab_old_sizing
     if args.config == "planar_sweep":
         args.syndromes = args.syndromes or 1000000
         return run_planar_sweep_sharded(args)

@@ -73,6 +73,11 @@ int         qecmc_set_stream(qecmc_ctx *ctx, void *cuda_stream);
 int         qecmc_device_info(qecmc_ctx *ctx, qecmc_devinfo *out);
 /* cap (bytes) on the distinct-chain table arena; 0 = 85 % of free device memory */
 int         qecmc_set_table_budget(qecmc_ctx *ctx, int64_t bytes);
+/* How the most recent qecmc_stdc / qecmc_strc / qecmc_single_temp call (host or _dev form) was sized, for callers that cut a
+ * long job into batches: wave_capacity = syndromes one wave may hold within the table budget (the call splits a larger batch
+ * into waves), round_chains = chains one round of CTAs over all SMs holds at the kernel's full CTA size.  A batch of
+ * min(wave_capacity, k * round_chains / (classes * droplets)) syndromes leaves no SM idle behind a short last round. */
+int         qecmc_last_plan(qecmc_ctx *ctx, int64_t *wave_capacity, int64_t *round_chains);
 /* Test switches, per context (never read from the environment).  They select between code paths that must give the
  * same results, so that tests can compare them on one problem; value < 0 restores the default.
  *   "force_wide"   1: 64-bit row words also for L <= 16
@@ -81,6 +86,8 @@ int         qecmc_set_table_budget(qecmc_ctx *ctx, int64_t bytes);
  *   "serial_sweep" 1: native ladders walk the swap sweep pair by pair, like replay does (warp-per-ladder kernel)
  *   "ladder_kernel" 1: native ladders run on the warp-per-ladder kernel replay uses, not on the rung-major one
  *   "pt_grid"      cap on the rung-major kernel's grid, so that ladders queue up behind few CTAs
+ *   "packed"       0: two-layer codes with 17 <= L <= 24 stay on the 64-bit row-word chain kernel instead of the packed-lattice
+ *                  one; 2 / 4 / 8: interleaved copies of its hot tables
  *   "pt_lt"        lanes sharing one top-rung replica in the rung-major tempering kernel (2, 4, 8, ...)
  * Unknown keys return QECMC_ERR_ARG. */
 int         qecmc_debug_set(qecmc_ctx *ctx, const char *key, int64_t value);

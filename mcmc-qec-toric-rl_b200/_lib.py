@@ -107,6 +107,7 @@ def load():
     L.qecmc_set_table_budget.argtypes = [C.c_void_p, C.c_int64]
     L.qecmc_device_info.argtypes = [C.c_void_p, C.POINTER(DevInfo)]
     L.qecmc_debug_set.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+    L.qecmc_last_plan.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.qecmc_chain_update.argtypes = [C.c_void_p, C.POINTER(ChainCfg), C.c_void_p, C.c_int64, C.c_int64, C.POINTER(Stats)]
     L.qecmc_replay_chain.argtypes = [C.c_void_p, C.POINTER(ChainCfg), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -193,6 +194,13 @@ class Context:
     def debug_set(self, key, value):
         """Test switch between code paths that must agree (include/qecmc.h); value < 0 restores the default."""
         _check(load().qecmc_debug_set(self._h, key.encode(), int(value)))
+
+    def last_plan(self):
+        """(wave_capacity, round_chains) of the most recent STDC-family call: syndromes one wave may hold within the table
+        budget, chains one round of full-size CTAs over all SMs holds."""
+        w, r = C.c_int64(0), C.c_int64(0)
+        _check(load().qecmc_last_plan(self._h, C.byref(w), C.byref(r)))
+        return int(w.value), int(r.value)
 
     def device_info(self):
         d = DevInfo()

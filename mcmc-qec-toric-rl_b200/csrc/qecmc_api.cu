@@ -2,6 +2,7 @@
 // memory, wave scheduling of the distinct-chain tables, host<->device staging.
 #include "qecmc_internal.h"
 #include "qecmc_stdc_fast.cuh"
+#include "qecmc_stdc_pk.cuh"
 #include "qecmc_dedupe.cuh"
 
 using namespace qecmc;
@@ -82,8 +83,17 @@ extern "C" int qecmc_debug_set(qecmc_ctx *c, const char *key, int64_t value)
     else if (!strcmp(key, "serial_sweep")) c->dbg_serial_sweep = value > 0;
     else if (!strcmp(key, "pt_lt")) c->dbg_pt_lt = value > 0 ? (int)value : 0;
     else if (!strcmp(key, "pt_grid")) c->dbg_pt_grid = value > 0 ? (int)value : 0;
+    else if (!strcmp(key, "packed")) c->dbg_packed = value < 0 ? -1 : (int)value;
     else if (!strcmp(key, "ladder_kernel")) c->dbg_ladder_kernel = value > 0 ? (int)value : 0;
     else return set_err(QECMC_ERR_ARG, "unknown debug key '%s'", key);
+    return 0;
+}
+
+extern "C" int qecmc_last_plan(qecmc_ctx *c, int64_t *wave_capacity, int64_t *round_chains)
+{
+    if (!c) return set_err(QECMC_ERR_ARG, "ctx is NULL");
+    if (wave_capacity) *wave_capacity = c->plan_wave_cap;
+    if (round_chains) *round_chains = c->plan_round_chains;
     return 0;
 }
 
@@ -261,6 +271,67 @@ static int build_fast_lut(qecmc_ctx *c, const Thr &t, FastTables &ft)
     return 0;
 }
 
+// interleaved copies of the packed-lattice kernel's hot tables (tests: qecmc_debug_set "packed" = 2 / 4 / 8)
+static int pk_copies(const qecmc_ctx *c) { return c->dbg_packed == 2 || c->dbg_packed == 8 ? c->dbg_packed : 4; }
+
+// packed-lattice kernel in bucket-log mode: whole tables per CTA beside the tables and the cursors (0: none fits)
+static int pk_tables_per_cta(const Geo &g, int rep, int droplets, int nbc, size_t room)
+{
+    const PkGeo q = pk_geo(g);
+    const PkLayout lay = pk_layout(g.nstab, rep);
+    const size_t per_table = (size_t)q.nwp * 4 * droplets + (size_t)nbc * 4;
+    if (lay.tile + 16 + per_table > room) return 0;
+    int tpc = (int)((room - lay.tile - 16) / per_table);
+    if (tpc * droplets > 1024) tpc = 1024 / droplets;
+    return tpc;
+}
+
+// 17 <= L <= 24, native draws, no early stop: the packed-lattice kernel (qecmc_stdc_pk.cuh), one CTA per SM with as many
+// chains as fit beside the tables
+template <int GEOM, int MODE, int REP>
+static int launch_stdc_pk_rep(qecmc_ctx *c, StdcParams &p, const FastTables &ft, const PhiloxKeys &keys)
+{
+    const PkGeo q = pk_geo(p.gchain);
+    const PkLayout lay = pk_layout(p.gchain.nstab, REP);
+    const size_t per_chain = (size_t)q.nwp * 4;
+    const size_t room = c->prop.sharedMemPerBlockOptin;
+    if (lay.tile + per_chain * 64 > room) return set_err(QECMC_ERR_UNSUPPORTED, "internal: packed tables do not fit");
+    int T = (int)((room - lay.tile) / per_chain);
+    if (T > 1024) T = 1024;
+    T &= ~31;
+    const int64_t sms = c->prop.multiProcessorCount;
+    size_t smem;
+    if (p.insert_mode == 6) {
+        // a CTA holds whole tables (their bucket-log cursors live behind the tile): T = tables * droplets
+        int tpc = pk_tables_per_cta(p.gchain, REP, p.droplets, p.nbc, room);
+        if (tpc < 1 || p.n_chains % p.droplets != 0) return set_err(QECMC_ERR_UNSUPPORTED, "internal: bucket-log mode misconfigured");
+        c->plan_round_chains = (int64_t)tpc * p.droplets * sms;
+        const int64_t tabs = p.n_chains / p.droplets;
+        if ((tabs + tpc - 1) / tpc < sms) {   // a small batch is spread over the SMs
+            const int t2 = (int)((tabs + sms - 1) / sms);
+            if (t2 < tpc) tpc = t2 < 1 ? 1 : t2;
+        }
+        T = tpc * p.droplets;
+        p.tables_per_cta = tpc;
+        smem = lay.tile + ((per_chain * T + 15) & ~(size_t)15) + (size_t)tpc * p.nbc * 4;
+    } else {
+        c->plan_round_chains = (int64_t)T * sms;
+        // a small batch is spread over the SMs rather than packed into a few large CTAs
+        if ((p.n_chains + T - 1) / T < sms) {
+            int t2 = (int)(((p.n_chains + sms - 1) / sms + 31) & ~(int64_t)31);
+            if (t2 < 64) t2 = 64;
+            if (t2 < T) T = t2;
+        }
+        smem = lay.tile + per_chain * T;
+    }
+    CUDA_OK(cudaFuncSetAttribute(stdc_pk_kernel<GEOM, MODE, REP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)((p.n_chains + T - 1) / T);
+    stdc_pk_kernel<GEOM, MODE, REP><<<grid, T, smem, c->stream>>>(p, ft, keys);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 template <int GEOM, typename W, bool REPLAY, int MODE>
 static int launch_stdc_fast(qecmc_ctx *c, StdcParams &p)
 {
@@ -269,6 +340,17 @@ static int launch_stdc_fast(qecmc_ctx *c, StdcParams &p)
     QTRY(build_fast_lut(c, p.thr, ft));
     PhiloxKeys keys;
     make_philox_keys(p.seed, keys);
+    if constexpr (sizeof(W) == 8 && !REPLAY) {
+        // tests (qecmc_debug_set "packed"): 0 keeps these sizes on the 64-bit row-word kernel; 1 / 2 / 4 pick the number of
+        // interleaved copies of the hot tables
+        const bool pk_mode = MODE == MODE_MEAN || p.insert_mode == 4 || p.insert_mode == 2 || p.insert_mode == 6;
+        if (p.conv_mult == 0.0 && pk_supported(p.gchain) && p.gchain.L == p.gcode.L && c->dbg_packed != 0 && pk_mode) {
+            const int rep = pk_copies(c);
+            if (rep == 2) return launch_stdc_pk_rep<GEOM, MODE, 2>(c, p, ft, keys);
+            if (rep == 8) return launch_stdc_pk_rep<GEOM, MODE, 8>(c, p, ft, keys);
+            return launch_stdc_pk_rep<GEOM, MODE, 4>(c, p, ft, keys);
+        }
+    }
     int T = 0, nb = 0;
     size_t per_chain = (size_t)p.gchain.nw * sizeof(W);
     // static part: LUTs (512 * 5 + 72 B) and, for 32-bit row words, expanded descriptor (2 x 16 B) + fingerprint arrays of 512 entries;
@@ -284,6 +366,7 @@ static int launch_stdc_fast(qecmc_ctx *c, StdcParams &p)
     // (64-bit row words: ONE CTA of 608-800 threads per SM instead of two of 256 was measured -- the per-SM rate rose 6 % with
     // 56 % more threads, and CTAs of odd sizes quantise badly over the SMs; descriptors with ready byte offsets changed nothing)
     QTRY(pick_threads(per_chain, stat + dyn_fixed + 256, c->prop, &T, &nb, static_tab && !conv, conv ? 56 : 64));
+    c->plan_round_chains = (int64_t)T * nb * c->prop.multiProcessorCount;
     // a small batch is spread over the SMs rather than packed into a few large CTAs
     while (T > 64 && (p.n_chains + T - 1) / T < c->prop.multiProcessorCount) T /= 2;
     size_t smem = ((per_chain * T + 15) & ~(size_t)15) + dyn_fixed;
@@ -293,6 +376,7 @@ static int launch_stdc_fast(qecmc_ctx *c, StdcParams &p)
         int tpc = T / p.droplets;
         if (tpc < 1) tpc = 1;
         T = tpc * p.droplets;
+        c->plan_round_chains = (int64_t)(1024 / p.droplets) * p.droplets * c->prop.multiProcessorCount;
         if (conv || !static_tab || T > 1024 || p.n_chains % p.droplets != 0) return set_err(QECMC_ERR_UNSUPPORTED, "internal: bucket-log mode misconfigured");
         smem = ((per_chain * T + 15) & ~(size_t)15) + dyn_fixed;
         p.tables_per_cta = tpc;
@@ -423,9 +507,17 @@ static int stdc_run_once(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, cons
     int nbc = 1;
     while (nbc < QECMC_NBC_MAX && (uint64_t)nbc * 20000 < max_keys) nbc <<= 1;
     const bool fast_u32 = (cfg->geom_chain == TORIC || cfg->geom_chain == PLANAR) && !wide;
-    bool use_blogs = allow_bucket_logs && use_logs && !conv && !cfg->u_nb && fast_u32 && (forced_mode < 0 || forced_mode == 6) &&
+    // 17 <= L <= 24: the packed-lattice kernel (qecmc_stdc_pk.cuh) writes bucket logs as well
+    const bool fast_pk = (cfg->geom_chain == TORIC || cfg->geom_chain == PLANAR) && wide && pk_supported(gchain) && gchain.L == gcode.L &&
+                         c->dbg_packed != 0;
+    const int pk_rep = pk_copies(c);
+    bool use_blogs = allow_bucket_logs && use_logs && !conv && !cfg->u_nb && (fast_u32 || fast_pk) && (forced_mode < 0 || forced_mode == 6) &&
                      cfg->droplets <= 1024;
-    if (use_blogs) {
+    int64_t blog_tpc = 1024 / (cfg->droplets > 0 ? cfg->droplets : 1);   // tables per full CTA (wave rounding)
+    if (use_blogs && fast_pk) {
+        blog_tpc = pk_tables_per_cta(gchain, pk_rep, cfg->droplets, nbc, c->prop.sharedMemPerBlockOptin);
+        if (blog_tpc < 1) use_blogs = false;
+    } else if (use_blogs) {
         // the largest CTA the launch will use holds 1024 / droplets tables: its cursors must fit next to tile and tables
         // (256: the kernel's static shared memory)
         const size_t tpc_max = 1024 / cfg->droplets;
@@ -458,11 +550,12 @@ static int stdc_run_once(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, cons
             wave = budget / per_syndrome;
             if (wave < 1)
                 return set_err(QECMC_ERR_NOMEM, "bucket logs need %lld bytes per syndrome, budget is %lld", (long long)per_syndrome, (long long)budget);
+            c->plan_wave_cap = wave;
             if (wave > S) wave = S;
             if (wave < S) {
                 // several waves: a wave whose CTAs come to a whole number of rounds over the SMs (one 1024-thread CTA per SM,
                 // 1024 / droplets tables each) leaves no SMs idle behind a short last round
-                const int64_t tpc = 1024 / cfg->droplets, sms = c->prop.multiProcessorCount;
+                const int64_t tpc = blog_tpc, sms = c->prop.multiProcessorCount;
                 int64_t ctas = wave * n_eq / tpc;
                 if (ctas >= sms) {
                     ctas -= ctas % sms;
@@ -484,6 +577,7 @@ static int stdc_run_once(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, cons
             if (wave < 1)
                 return set_err(QECMC_ERR_NOMEM, "key logs need %lld bytes per syndrome plus %lld bytes of scratch, budget is %lld",
                                (long long)per_syndrome, (long long)scratch_bytes, (long long)budget);
+            c->plan_wave_cap = wave;
             if (wave > S) wave = S;
             QTRY(c->dd_scratch.ensure((size_t)scratch_bytes));
             QTRY(c->log_counts.ensure((size_t)wave * n_eq * cfg->droplets * sizeof(uint32_t)));
@@ -498,6 +592,7 @@ static int stdc_run_once(qecmc_ctx *c, const qecmc_stdc_cfg *cfg, int mode, cons
             if (wave < 1)
                 return set_err(QECMC_ERR_NOMEM, "distinct-chain tables need %lld bytes per syndrome, budget is %lld",
                                (long long)per_syndrome, (long long)budget);
+            c->plan_wave_cap = wave;
             if (wave > S) wave = S;
         }
         QTRY(c->tables.ensure((size_t)wave * per_syndrome));

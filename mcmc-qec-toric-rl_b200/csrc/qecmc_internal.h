@@ -102,10 +102,14 @@ struct qecmc_ctx {
     cudaEvent_t ev[4];
     uint64_t hash_seed = 0x5EEDC0DE2020ull;
     int64_t launches = 0;
+    // sizing of the most recent STDC-family call (qecmc_last_plan): syndromes one wave may hold within the table budget,
+    // chains one round of CTAs over the SMs holds at the kernel's full CTA size
+    int64_t plan_wave_cap = 0, plan_round_chains = 0;
     // qecmc_debug_set: test switches between code paths that must agree (never read from the environment)
     int dbg_force_wide = 0, dbg_insert_mode = -1, dbg_serial_sweep = 0;
     int dbg_pt_lt = 0;          // lanes per top-rung replica in the rung-major tempering kernel (0: default)
     int dbg_pt_grid = 0;        // cap on the rung-major kernel's grid (tests: makes ladders queue behind few CTAs)
+    int dbg_packed = -1;        // packed-lattice chain kernel for 17 <= L <= 24: -1 default, 0 off, 1 / 2 / 4 table copies
     int dbg_ladder_kernel = 0;  // 1: native ladders on the warp-per-ladder (replay) kernel instead of the rung-major one
 };
 

@@ -72,7 +72,11 @@ STDC_CASES = [
     pytest.param(O.TORIC, 15, 148, 64, 2000, (0, 1, 63, 64, 100, 147), id="toric15-64chains-full-gpu"),
     pytest.param(O.TORIC, 15, 3, 64, 2500, (0, 1, 2), id="toric15-64chains-small-batch"),
     pytest.param(O.PLANAR, 11, 40, 64, 2000, (0, 17, 39), id="planar11-64chains"),
-    pytest.param(O.PLANAR, 21, 6, 16, 2000, (0, 3, 5), id="planar21-u64-words"),
+    pytest.param(O.PLANAR, 21, 6, 16, 2000, (0, 3, 5), id="planar21-packed-lattice"),
+    pytest.param(O.TORIC, 17, 4, 8, 1500, (0, 3), id="toric17-packed-lattice"),
+    pytest.param(O.PLANAR, 19, 3, 8, 1500, (0, 2), id="planar19-packed-lattice"),
+    pytest.param(O.TORIC, 24, 2, 4, 1200, (0, 1), id="toric24-packed-lattice"),
+    pytest.param(O.PLANAR, 25, 2, 4, 1000, (0, 1), id="planar25-u64-words"),
     pytest.param(O.TORIC, 5, 7, 10, 3125, (0, 3, 6), id="toric5-reference-defaults"),
     pytest.param(O.PLANAR, 15, 5, 16, 3000, (0, 4), id="planar15"),
     pytest.param(O.TORIC, 9, 4, 3, 4000, (0, 1, 2, 3), id="toric9-3chains"),
@@ -94,8 +98,50 @@ def test_native_stdc_equals_oracle_on_the_same_words(ctx, g, L, S, droplets, ste
     for s in check:
         w_out, w_distinct, w_hist = want[s]
         assert np.array_equal(hist[s].astype(np.int64), w_hist), f"N(n) differs from the oracle at syndrome {s}"
-        assert np.allclose(out[s], w_out, rtol=1e-9, atol=1e-300)
+        # (L = 24 at p = 0.15: every exp(-beta n) underflows, the reference's 0 / 0 -- NaN on both sides)
+        assert np.allclose(out[s], w_out, rtol=1e-9, atol=1e-300, equal_nan=True)
         assert w_distinct.sum() > O.neq(g) * droplets       # the chains moved
+
+
+@pytest.mark.parametrize("g,L", [(O.PLANAR, 17), (O.PLANAR, 20), (O.PLANAR, 21), (O.PLANAR, 22), (O.TORIC, 18), (O.TORIC, 21),
+                                 (O.TORIC, 23)])
+def test_packed_lattice_kernel_equals_the_64_bit_row_word_kernel(ctx, g, L):
+    """Two-layer codes with 17 <= L <= 24 run on the packed-lattice chain kernel (qecmc_stdc_pk.cuh); debug_set("packed", 0)
+    keeps them on the 64-bit row-word kernel.  Same draws, same step: N(n), m(n), mean lengths and distributions are
+    identical -- for every number of table copies, for per-chain logs and for the deferred HBM set, for a batch that fills
+    several CTAs and for one that does not."""
+    rng = np.random.default_rng(300 + L)
+    S, droplets, steps, seed = (150 if L == 21 else 9), 16, 600, 9000 + L
+    qm = np.stack([rand_lattice(rng, g, L, 0.14).reshape(-1) for _ in range(S)])
+
+    def run_all():
+        a = ctx.stdc(g, g, L, qm, 0.14, 0.25, droplets, steps, seed=seed, want_hist=True)
+        b = ctx.strc(g, g, L, qm[:5], 0.14, 0.25, 6, steps, seed=seed + 1, want_hist=True)
+        c = ctx.single_temp(g, g, L, qm[:7], 0.12, 700, seed=seed + 2)
+        ctx.debug_set("insert_mode", 2)
+        try:
+            d = ctx.stdc(g, g, L, qm[:4], 0.14, 0.25, 5, steps, seed=seed + 3, want_hist=True)
+        finally:
+            ctx.debug_set("insert_mode", -1)
+        return a, b, c, d
+
+    ctx.debug_set("packed", 0)
+    try:
+        ref = run_all()
+    finally:
+        ctx.debug_set("packed", -1)
+    for rep in (-1, 2, 8):
+        ctx.debug_set("packed", rep)
+        try:
+            got = run_all()
+        finally:
+            ctx.debug_set("packed", -1)
+        same = lambda x, y: np.array_equal(x, y, equal_nan=True)    # a class without weight: 0 / 0 on both sides
+        assert same(got[0][2], ref[0][2]) and same(got[0][0], ref[0][0])
+        assert got[0][1]["accepted"] == ref[0][1]["accepted"] and got[0][1]["distinct"] == ref[0][1]["distinct"]
+        assert same(got[1][2], ref[1][2]) and same(got[1][3], ref[1][3]) and same(got[1][0], ref[1][0])
+        assert same(got[2][0], ref[2][0])
+        assert same(got[3][2], ref[3][2]) and same(got[3][0], ref[3][0])
 
 
 @pytest.mark.parametrize("mode", [4, 2, 0])
