@@ -306,22 +306,22 @@ static int launch_stdc_pk_rep(qecmc_ctx *c, StdcParams &p, const FastTables &ft,
         int tpc = pk_tables_per_cta(p.gchain, REP, p.droplets, p.nbc, room);
         if (tpc < 1 || p.n_chains % p.droplets != 0) return set_err(QECMC_ERR_UNSUPPORTED, "internal: bucket-log mode misconfigured");
         c->plan_round_chains = (int64_t)tpc * p.droplets * sms;
+        // the launch takes ceil(tables / (tpc * SMs)) rounds of CTAs over the SMs: spread the tables evenly over that many
+        // rounds (smaller CTAs) instead of leaving most SMs idle behind a short last round -- a small batch included
         const int64_t tabs = p.n_chains / p.droplets;
-        if ((tabs + tpc - 1) / tpc < sms) {   // a small batch is spread over the SMs
-            const int t2 = (int)((tabs + sms - 1) / sms);
-            if (t2 < tpc) tpc = t2 < 1 ? 1 : t2;
-        }
+        const int64_t rounds = (tabs + (int64_t)tpc * sms - 1) / ((int64_t)tpc * sms);
+        const int t2 = (int)((tabs + rounds * sms - 1) / (rounds * sms));
+        if (t2 < tpc) tpc = t2 < 1 ? 1 : t2;
         T = tpc * p.droplets;
         p.tables_per_cta = tpc;
         smem = lay.tile + ((per_chain * T + 15) & ~(size_t)15) + (size_t)tpc * p.nbc * 4;
     } else {
         c->plan_round_chains = (int64_t)T * sms;
-        // a small batch is spread over the SMs rather than packed into a few large CTAs
-        if ((p.n_chains + T - 1) / T < sms) {
-            int t2 = (int)(((p.n_chains + sms - 1) / sms + 31) & ~(int64_t)31);
-            if (t2 < 64) t2 = 64;
-            if (t2 < T) T = t2;
-        }
+        // the same balancing over whole rounds of CTAs, in warps
+        const int64_t rounds = (p.n_chains + (int64_t)T * sms - 1) / ((int64_t)T * sms);
+        int t2 = (int)(((p.n_chains + rounds * sms - 1) / (rounds * sms) + 31) & ~(int64_t)31);
+        if (t2 < 64) t2 = 64;
+        if (t2 < T) T = t2;
         smem = lay.tile + per_chain * T;
     }
     CUDA_OK(cudaFuncSetAttribute(stdc_pk_kernel<GEOM, MODE, REP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
