@@ -154,6 +154,27 @@ def test_packed_lattice_kernel_equals_the_64_bit_row_word_kernel(ctx, g, L):
             assert same(got[4][2], ref[4][2]) and same(got[4][0], ref[4][0])
 
 
+def test_last_plan_sizes_a_batch_that_fills_whole_rounds(ctx):
+    """qecmc_last_plan: after a call, how many syndromes one wave may hold and how many chains one round of full-size CTAs
+    holds -- a batch of that many syndromes runs as one wave, and the figures do not depend on the size of the call."""
+    g, L, droplets, steps = O.PLANAR, 21, 16, 2000
+    rng = np.random.default_rng(77)
+    qm = np.stack([rand_lattice(rng, g, L, 0.12).reshape(-1) for _ in range(40)])
+    ctx.stdc(g, g, L, qm[:3], 0.12, 0.25, droplets, steps, seed=3)
+    wave_small, round_small = ctx.last_plan()
+    _, st = ctx.stdc(g, g, L, qm, 0.12, 0.25, droplets, steps, seed=3)[:2]
+    wave_cap, round_chains = ctx.last_plan()
+    assert round_chains == round_small and abs(wave_cap - wave_small) <= 0.02 * wave_cap    # (free memory moves a little)
+    assert wave_cap >= 40 and st["waves"] == 1
+    sms = ctx.device_info()["sm_count"]
+    assert round_chains % (sms * droplets) == 0                  # whole tables per CTA, one CTA per SM
+    assert 16 * 32 * sms <= round_chains <= 1024 * sms            # the packed-lattice kernel keeps >= 16 warps per SM at d = 21
+    g2, L2 = O.TORIC, 15
+    q2 = np.stack([rand_lattice(rng, g2, L2, 0.12).reshape(-1) for _ in range(4)])
+    ctx.stdc(g2, g2, L2, q2, 0.12, 0.25, 64, 500, seed=3)
+    assert ctx.last_plan()[1] == 1024 * sms                       # the headline kernel: one 1024-thread CTA per SM
+
+
 @pytest.mark.parametrize("mode", [4, 2, 0])
 def test_native_stdc_other_insert_modes_equal_oracle(ctx, mode):
     """The per-chain-log, deferred and synchronous HBM-set paths against the oracle (not against each other)."""
