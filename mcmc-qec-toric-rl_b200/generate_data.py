@@ -202,9 +202,30 @@ def generate_batch(params, S, seed=0, device=0):
     return out
 
 
-def generate(file_path, params, nbr_datapoints=10**6, fixed_errors=None, batch=256, seed=None, device=0, verbose=True):
+def auto_batch(params, device=0):
+    """Syndromes per batch that fill the GPU for this workload: for the STDC family (STDC, STRC, ST) a whole number of rounds
+    of the chain kernel's CTAs within one wave of the table budget, read from the library's plan of the most recent call
+    (qecmc_last_plan); for the tempering decoders one resident ladder per slot of the tempering kernel's grid."""
+    ctx = _lib.default_context(device)
+    sms = ctx.device_info()["sm_count"]
+    if params['method'] in ('STDC', 'STRC', 'ST'):
+        wave_cap, round_chains = ctx.last_plan()
+        chains = _lib.neq(_lib.GEOM_NAMES[params['code']]) * (1 if params['method'] == 'ST' else int(params['droplets']))
+        per_round = max(1, round_chains // chains)
+        if wave_cap <= 0 or round_chains <= 0:
+            return 256
+        return int(max(64, min(wave_cap // per_round * per_round if wave_cap >= per_round else wave_cap, 8 * per_round)))
+    return 32 * sms
+
+
+def generate(file_path, params, nbr_datapoints=10**6, fixed_errors=None, batch=None, seed=None, device=0, verbose=True):
     """generate_data.py:19-261.  Extra keyword arguments (batch, seed, device) have no reference counterpart: the
-    reference decodes one syndrome at a time, unseeded."""
+    reference decodes one syndrome at a time, unseeded.  batch = None sizes the batches itself: a first batch of 256, then
+    whatever fills the GPU for this workload (auto_batch) -- a planar d = 7 round holds 49 728 syndromes, and batches of 256
+    would leave the device idle."""
+    auto = batch is None
+    if auto:
+        batch = 256
     import pandas as pd
     names = ['data_nr', 'type']
     frames = [pd.DataFrame([[params]], index=pd.MultiIndex.from_product([[-1], np.arange(1)], names=names), columns=['data'])]
@@ -230,6 +251,11 @@ def generate(file_path, params, nbr_datapoints=10**6, fixed_errors=None, batch=2
             if fixed_errors is not None and failed_syndroms == fixed_errors:
                 S = s + 1
                 break
+        if auto and i == 0:
+            batch = auto_batch(params, device)
+            if fixed_errors is not None:        # a batch is decoded whole: do not overshoot the failure target by much
+                seen = max(failed_syndroms, 1) / float(S)
+                batch = int(max(256, min(batch, 1.5 * fixed_errors / seen)))
         rows, idx = rows[:2 * S], idx[:2 * S]
         frames.append(pd.DataFrame(rows, index=pd.MultiIndex.from_tuples(idx, names=names), columns=['data']))
         i += S

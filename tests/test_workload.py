@@ -256,6 +256,14 @@ def test_generate_writes_the_reference_file_format(ctx, tmp_path):
     assert failed2 == 3 and made2 <= 10000000
     df2 = pd.read_pickle(path)
     assert len(df2) == 1 + 2 * made2
+    # batch=None: the loop sizes its batches from the library's plan (a first batch of 256, then whole rounds of CTAs)
+    planar = dict(code='planar', method='STDC', size=5, noise='depolarizing', p_error=0.1, p_sampling=0.25, droplets=4,
+                  steps=200, mwpm_init=False)
+    failed3, made3 = G.generate(path, planar, nbr_datapoints=3000, seed=6, verbose=False)
+    assert made3 == 3000 and len(pd.read_pickle(path)) == 1 + 2 * 3000
+    sms = ctx.device_info()["sm_count"]
+    assert G.auto_batch(planar) % (sms * 1024 // (4 * 4)) == 0          # whole rounds of 1024-thread CTAs, 4 classes x 4 chains
+    assert G.auto_batch(dict(planar, method='PTEQ')) == 32 * sms
 
 
 # ------------------------------------------------------------------ PTDC with the conv_mult early stop
