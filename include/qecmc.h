@@ -377,6 +377,8 @@ int qecmc_count_failures_dev(qecmc_ctx *ctx, const void *d_distr, int32_t dtype,
  *   mode               0: solve() -> out [S][2][L][L], weights [S][2] = matching weight per layer
  *                      1: class_sorted_mwpm -> out [S][4][2][L][L] in class order, weights [S][2][2] = weight of
  *                         solve_layer(layer, parity)
+ *                      | 2 (tests): solve the reference's graphs as written, one ancilla node per defect, instead of the
+ *                         equivalent problem on half the nodes -- same weights, eight times the work
  *   weights            optional
  *   threads            host threads (0: all)
  * ------------------------------------------------------------------------------ */

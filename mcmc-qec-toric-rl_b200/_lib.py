@@ -588,7 +588,7 @@ class Context:
         return int(fails.value)
 
 
-def mwpm_planar(L, qm=None, vertex_defects=None, plaquette_defects=None, class_sorted=True, threads=0):
+def mwpm_planar(L, qm=None, vertex_defects=None, plaquette_defects=None, class_sorted=True, threads=0, unreduced=False):
     """qecmc_mwpm_planar: host-side matching (no device, no context).  qm [S][2][L][L] error chains, or the two defect
     arrays [S][L-1][L] / [S][L][L-1].  Returns (chains, weights): class_sorted -> chains [S][4][2][L][L] in class order,
     weights [S][2][2] = weight of solve_layer(layer, parity); else chains [S][2][L][L] = MWPM.solve(), weights [S][2]."""
@@ -605,7 +605,7 @@ def mwpm_planar(L, qm=None, vertex_defects=None, plaquette_defects=None, class_s
     out = np.zeros((S, 4, 2, L, L) if class_sorted else (S, 2, L, L), np.uint8)
     w = np.zeros((S, 2, 2) if class_sorted else (S, 2), np.int32)
     _check(load().qecmc_mwpm_planar(L, S, qm.ctypes.data if qm is not None else None, v.ctypes.data if v is not None else None,
-                                    p.ctypes.data if p is not None else None, int(bool(class_sorted)), out.ctypes.data,
+                                    p.ctypes.data if p is not None else None, int(bool(class_sorted)) | (2 if unreduced else 0), out.ctypes.data,
                                     w.ctypes.data, int(threads)))
     return out, w
 

@@ -4,9 +4,10 @@
 // (:136-229), eliminate_defect_pair (:232-288), eliminate_border_defect (:291-316), solve_layer (:319-373), solve
 // (:408-415), generate_classes (:417-438), class_sorted_mwpm (:462-475) and regular_mwpm (:479-487).  The reference writes
 // the defect graph to a text file and runs the external blossom5 binary on it (:376-405); here the matching is solved in
-// process by a dense O(n^3) primal-dual blossom algorithm, one syndrome per host thread.  The graphs are the reference's
-// own (same nodes, same edges, same weights), so the matching WEIGHT is the reference's; which of several minimum-weight
-// matchings comes out is the solver's choice there and here.
+// process by a dense O(n^3) primal-dual blossom algorithm, one syndrome per host thread.  The optimisation problems are the
+// reference's own (its graphs with the ancillas folded away, solve_layer_reduced below; mode | 2 solves the graphs as the
+// reference writes them), so the matching WEIGHT is the reference's; which of several minimum-weight matchings comes out
+// is the solver's choice there and here.
 //
 // This is an initialiser that runs once per syndrome before the chains start (decoders.py:272-279 take the list of
 // per-class codes it returns); it is not on the Metropolis path and stays on the host like the reference's.
@@ -351,10 +352,71 @@ struct PlanarMwpm {
             else for (int i = a.c + 1; i < L; i++) corr[idx(0, a.r, i)] ^= op;
         }
     }
+    // The same optimisation problem on half the nodes.  In the reference's graphs every defect owns an ancilla it alone may
+    // reach (at the cost of its border distance) and the ancillas of a border are joined to each other for free, so a perfect
+    // matching is: a set M of defects sent to the border + a pairing of the rest, with |M| of fixed parity per border (free
+    // graph: |M| = N mod 2 overall).  Two defects of M are as good as joined by an edge of weight b_i + b_j "through the
+    // border"; an odd |M| needs one more node per border that any of its defects may take alone.  The matching then runs on
+    // N + (0..2) nodes instead of 2 N + (0..2) -- an eighth of the O(n^3) work -- and has the same minimum weight.
+    long long solve_layer_reduced(int layer, int parity, uint8_t *corr) const
+    {
+        const std::vector<Coord> &d = def[layer];
+        const int nd = (int)d.size();
+        std::vector<int> side(nd), bd(nd);
+        int n_side[2] = {0, 0};
+        for (int s = 0; s < nd; s++) {
+            const int b0 = (layer == 0 ? d[s].r : d[s].c) + 1;
+            if (parity < 0) side[s] = !(b0 * 2 < L);          // generate_edges, mwpm.py:106-110
+            else side[s] = b0 * 2 > L;                        // generate_edges_constrained, mwpm.py:156
+            bd[s] = side[s] ? L - b0 : b0;
+            n_side[side[s]]++;
+        }
+        struct Border { int side; bool far; };
+        std::vector<Border> borders;
+        if (parity < 0) { if (nd & 1) borders.push_back({-1, false}); }
+        else
+            for (int b = 0; b < 2; b++)
+                if ((n_side[b] + (parity == 1)) & 1) borders.push_back({b, n_side[b] == 0});   // far: the parity edges, mwpm.py:170-182
+        Graph gr;
+        gr.ndef = nd;
+        gr.nodes = nd + (int)borders.size();
+        std::vector<char> virt((size_t)nd * nd, 0);
+        for (int i = 0; i < nd; i++)
+            for (int j = i + 1; j < nd; j++) {
+                int w = manhattan(d[i], d[j]);
+                if ((parity < 0 || side[i] == side[j]) && bd[i] + bd[j] < w) { w = bd[i] + bd[j]; virt[(size_t)i * nd + j] = 1; }
+                gr.edges.push_back({i, j, w});
+            }
+        for (int k = 0; k < (int)borders.size(); k++)
+            for (int s = 0; s < nd; s++) {
+                if (borders[k].far) gr.edges.push_back({s, nd + k, L - bd[s]});
+                else if (borders[k].side < 0 || borders[k].side == side[s]) gr.edges.push_back({s, nd + k, bd[s]});
+            }
+        std::vector<std::pair<int, int>> pairs;
+        long long w;
+        if (!min_weight_perfect_matching(gr, pairs, w)) return -1;
+        for (const auto &pr : pairs) {
+            const int i = pr.first, j = pr.second;
+            if (j >= nd) {
+                const Border &b = borders[j - nd];
+                eliminate_border(d[i], layer, b.far ? b.side : side[i], corr);
+            } else if (virt[(size_t)i * nd + j]) {
+                eliminate_border(d[i], layer, side[i], corr);
+                eliminate_border(d[j], layer, side[j], corr);
+            } else {
+                eliminate_pair(d[i], d[j], layer, corr);
+            }
+        }
+        return w;
+    }
+
+    bool reduced = true;   // false: the reference's own graphs, ancillas and all (tests: same weights)
+
     // MWPM.solve_layer (mwpm.py:319-373); parity < 0: unconstrained.  corr is XORed into; returns the matching weight
     // (-1: no perfect matching)
     long long solve_layer(int layer, int parity, uint8_t *corr) const
     {
+        if (reduced) return solve_layer_reduced(layer, parity, corr);
         const std::vector<Coord> &d = def[layer];
         const Graph gr = parity < 0 ? edges_free(d, layer, L) : edges_constrained(d, layer, L, parity);
         std::vector<std::pair<int, int>> pairs;
@@ -402,6 +464,8 @@ static int mwpm_one(int L, const uint8_t *qm, const uint8_t *vdef, const uint8_t
     const size_t n = (size_t)2 * L * L;
     PlanarMwpm m;
     m.L = L;
+    m.reduced = !(mode & 2);
+    mode &= 1;
     if (qm) planar_defects(qm, L, m.def[0], m.def[1]);
     else {
         for (int r = 0; r < L - 1; r++)
@@ -464,10 +528,10 @@ using namespace qecmc;
 extern "C" int qecmc_mwpm_planar(int32_t L, int64_t S, const uint8_t *qm, const uint8_t *vertex_defects,
                                  const uint8_t *plaquette_defects, int32_t mode, uint8_t *out, int32_t *weights, int32_t threads)
 {
-    if (L < 2 || L > 32 || S < 0 || !out || (mode != 0 && mode != 1)) return set_err(QECMC_ERR_ARG, "bad arguments");
+    if (L < 2 || L > 32 || S < 0 || !out || mode < 0 || mode > 3) return set_err(QECMC_ERR_ARG, "bad arguments");
     if (!qm && (!vertex_defects || !plaquette_defects))
         return set_err(QECMC_ERR_ARG, "either qm or both defect arrays must be given");
-    const size_t n = (size_t)2 * L * L, nout = mode == 1 ? 4 * n : n, nw = mode == 1 ? 4 : 2;
+    const size_t n = (size_t)2 * L * L, nout = (mode & 1) ? 4 * n : n, nw = (mode & 1) ? 4 : 2;
     const size_t nv = (size_t)(L - 1) * L;
     int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
     if (nt < 1) nt = 1;

@@ -100,6 +100,26 @@ def test_native_matching_against_the_oracle_on_random_syndromes(L, p, n):
                 assert wf[s, layer] <= w[s, layer].min()
 
 
+@pytest.mark.parametrize("L,p,n", [(4, 0.25, 60), (5, 0.3, 60), (7, 0.2, 40), (9, 0.1, 30), (13, 0.2, 10), (21, 0.15, 3)])
+def test_folded_graph_has_the_weights_of_the_reference_graph(L, p, n):
+    """The library matches on the defects alone (border-to-border pairs as edges of weight b_i + b_j, one extra node per
+    border whose count of border matches must be odd); `unreduced` solves the reference's graphs as written, one ancilla per
+    defect.  Same minimum weights, valid chains in the right classes either way."""
+    rng = np.random.default_rng(2000 + L)
+    qm = np.stack([_random_error(rng, L, p) for _ in range(n)])
+    for class_sorted in (True, False):
+        a, wa = _lib.mwpm_planar(L, qm=qm, class_sorted=class_sorted)
+        b, wb = _lib.mwpm_planar(L, qm=qm, class_sorted=class_sorted, unreduced=True)
+        assert np.array_equal(wa, wb)
+        for s in range(n):
+            if class_sorted:
+                _check_chains(qm[s], b[s])
+                for cls in range(4):
+                    assert _z_part(a[s, cls]) == _z_part(b[s, cls]) and _x_part(a[s, cls]) == _x_part(b[s, cls])
+            else:
+                assert _z_part(a[s]) == _z_part(b[s]) == wa[s, 0] and _x_part(a[s]) == _x_part(b[s]) == wa[s, 1]
+
+
 def test_layers_without_defects_take_the_reference_logicals():
     L = 5
     chains, w = _lib.mwpm_planar(L, qm=np.zeros((1, 2, L, L), np.uint8))
