@@ -67,8 +67,10 @@ def run_toric5(ctx, O):
     drop, steps = 10, 5 * L ** 4
     res = {}
     for name, fn in (("STDC", ctx.stdc), ("STRC", ctx.strc)):
-        fn(g, g, L, qm, p, 0.25, drop, steps, seed=1)     # warm-up at full size (allocations, module load)
-        (out, st), dt = timed(lambda: fn(g, g, L, qm, p, 0.25, drop, steps, seed=7))
+        for w in range(2):                                # warm-up at full size (allocations, module load, memory query)
+            fn(g, g, L, qm, p, 0.25, drop, steps, seed=1 + w)
+        # a 4 ms problem: the best of three calls (host-side jitter is a large part of a single one)
+        (out, st), dt = min((timed(lambda: fn(g, g, L, qm, p, 0.25, drop, steps, seed=7)) for _ in range(3)), key=lambda t: t[1])
         res[name] = {"steps_per_s": st["metropolis_steps"] / dt, "syndromes_per_s": S / dt, "seconds": dt,
                      "logical_failure_rate": float((out.argmax(1) != truth).mean())}
     t0 = time.perf_counter()
@@ -146,6 +148,14 @@ def run_planar_sweep(ctx, O, ps=(0.10, 0.15, 0.20), ds=(7, 11, 15, 21), droplets
             cap *= 2
         fit = int(info["free_mem"] * 0.8) // (4 * cap * 8)
         S = max(8, min(fit, (info["sm_count"] * 1024) // (4 * droplets)))
+        # one batch = whole rounds of the kernel's CTAs within one wave, from the library's plan of a small probe call
+        probe = synth((64, 2, d, d), 0.1, np.random.default_rng(1))
+        probe[:, 1, -1, :] = 0
+        probe[:, 1, :, -1] = 0
+        ctx.stdc(g, g, d, np.ascontiguousarray(probe.reshape(64, -1)), 0.1, 0.25, droplets, steps, seed=1)
+        wave_cap, round_chains = ctx.last_plan()
+        per_round = max(1, round_chains // (4 * droplets))
+        S = int(per_round if wave_cap >= per_round else wave_cap)
         first = True
         for p in ps:
             rng = np.random.default_rng(50 + d)
