@@ -9,6 +9,7 @@ from .. import _lib
 import random as _pyrandom
 
 from .mcmc import _LadderBase, _new_stream, _single_rung_block
+from .mcmc import MCMCDataReader  # noqa: F401  (the reference repeats the reader in this module)
 
 
 class Chain_alpha:

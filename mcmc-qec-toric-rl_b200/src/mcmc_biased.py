@@ -8,6 +8,7 @@ from .. import _lib
 import random as _pyrandom
 
 from .mcmc import Chain, _LadderBase, _new_stream, _single_rung_block, fast_path_geometry
+from .mcmc import MCMCDataReader  # noqa: F401  (the reference repeats the reader in this module)
 
 
 class Chain_biased:

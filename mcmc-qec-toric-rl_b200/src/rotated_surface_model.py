@@ -16,6 +16,12 @@ class RotSurCode(CodeBase):
     nbr_eq_classes = 4           # rotated_surface_model.py:9
     layers = 1
 
+    def generate_known_error(self, p_error, eta):
+        """rotated_surface_model.py:79-82: two fixed X errors (the arguments are ignored there as well)."""
+        self.qubit_matrix[2, 2] = 1
+        self.qubit_matrix[1, 0] = 1
+        self.syndrome()
+
     @classmethod
     @functools.lru_cache(maxsize=None)
     def _stabilizer_table(cls, L):
